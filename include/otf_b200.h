@@ -1,0 +1,170 @@
+/*
+ * otf_b200.h — C ABI of libotf_b200.so: B200 (sm_100a) kernels for the on-the-fly
+ * Real-ESRGAN-style second-order degradation path of traiNNer-redux.
+ *
+ * This is the drop-in boundary.  The reference has no FFI for
+ * this path — it is pure Python calling ATen — so each entry point below names
+ * the reference *function* it replaces (file:line relative to the reference
+ * tree).  A maintainer binds these with ctypes; the shipped
+ * binding is trainner_redux_b200/_lib.py.
+ *
+ * Conventions
+ *  - every pointer named *_dev / img / out is a DEVICE pointer to fp32 data in
+ *    dense NCHW order unless stated; the caller owns all memory;
+ *  - nothing here allocates persistent device memory, synchronises the device
+ *    or the stream, or reads results back to the host;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL =
+ *    the legacy default stream);
+ *  - return value: 0 (OTF_OK) or a negative OTF_ERR_* code; the message for the
+ *    last error on the calling thread is available from otf_last_error();
+ *  - the library is reentrant; it keeps no mutable global state except the
+ *    per-thread error string and a lazily resolved driver entry point.
+ */
+#ifndef OTF_B200_H_
+#define OTF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTF_ABI_VERSION 1
+
+enum {
+    OTF_OK = 0,
+    OTF_ERR_BAD_ARG = -1,     /* null pointer, non-positive extent, even kernel size ... */
+    OTF_ERR_UNSUPPORTED = -2, /* shape outside what the kernels are built for          */
+    OTF_ERR_CUDA = -3,        /* a CUDA runtime call or launch failed                   */
+    OTF_ERR_WORKSPACE = -4    /* caller-provided workspace too small                    */
+};
+
+/* resize modes — traiNNer/data/degradations.py:1004-1021 (`resize_pt`) */
+enum {
+    OTF_RESIZE_BILINEAR_AA = 0, /* F.interpolate(mode="bilinear", antialias=True)      */
+    OTF_RESIZE_BICUBIC_AA = 1,  /* F.interpolate(mode="bicubic",  antialias=True), a=-0.5 */
+    OTF_RESIZE_AREA = 2,        /* adaptive average pooling                             */
+    OTF_RESIZE_NEAREST_EXACT = 3,
+    OTF_RESIZE_BICUBIC = 4      /* non-antialiased bicubic, a=-0.75 (tail of "lanczos") */
+};
+
+/* flags for the noise tails: degradations.py:626-632 */
+enum {
+    OTF_NOISE_CLIP = 1,
+    OTF_NOISE_ROUNDS = 2,
+    OTF_NOISE_FIELD_ONLY = 4 /* write the noise field itself (generate_*_noise_pt), no add/tail */
+};
+
+int otf_abi_version(void);
+const char* otf_last_error(void);
+/* Compute capability of the current device as major*10+minor (100 on B200), or <0. */
+int otf_device_cc(void);
+
+/* ---- a1: filter2d — traiNNer/utils/img_process_util.py:8-32 -------------------
+ * out[b,c,y,x] = sum_{i,j<K} reflect_pad(img)[b,c,y+i,x+j] * kernel[kb,i,j],
+ * kb = b (kernel_batch == B) or 0 (kernel_batch == 1).  K odd, K//2 < min(H,W).
+ * `support_dev` (int32[kernel_batch], written by the call; may be NULL) receives
+ * the true half-width of each kernel (largest |offset| with a non-zero tap); the
+ * kernel only iterates over that support. K <= 21 runs the register-blocked
+ * path; larger odd K runs the generic path.  `img` and `out` must not alias. */
+int otf_filter2d_f32(const float* img, int B, int C, int H, int W,
+                     const float* kernel, int kernel_batch, int K,
+                     int32_t* support_dev, float* out, void* stream);
+
+/* ---- 1-D correlation with reflect padding along one axis ----------------------
+ * Building block of USMSharp (exactly separable 51x51 Gaussian) and of the
+ * Lanczos prefilter in degradations.py:982-998.  `taps_host` is a HOST array of
+ * `ntaps` (odd, <= 127) fp32 taps; axis 0 = vertical (H), 1 = horizontal (W). */
+int otf_sepconv_reflect_f32(const float* img, int planes, int H, int W,
+                            const float* taps_host, int ntaps, int axis,
+                            float* out, void* stream);
+
+/* ---- a2: USMSharp.forward — traiNNer/utils/img_process_util.py:45-55 ----------
+ * taps_host: the 1-D Gaussian whose outer product is the module's `kernel`
+ * buffer (cv2.getGaussianKernel(radius, sigma) as fp32).  workspace_dev must
+ * hold otf_usm_workspace_bytes(planes,H,W) bytes. */
+int64_t otf_usm_workspace_bytes(int planes, int H, int W);
+int otf_usm_sharp_f32(const float* img, int planes, int H, int W,
+                      const float* taps_host, int ntaps, float weight, float threshold,
+                      void* workspace_dev, int64_t workspace_bytes, float* out, void* stream);
+
+/* ---- a3: resize_pt — traiNNer/data/degradations.py:1004-1021 ------------------
+ * Separable resampling with ATen's index/weight rules (SURVEY.md §8a "R"),
+ * followed by clamp(0,1) when `clamp01` != 0 (resize_pt always clamps). */
+int otf_resize_f32(const float* img, int planes, int H, int W,
+                   float* out, int OH, int OW, int mode, int clamp01, void* stream);
+
+/* ---- a4: Gaussian noise — degradations.py:569-633 -----------------------------
+ * out = tail(img + mix(N*sigma[b]/255, G*sigma[b]/255, gray[b])).
+ * sigma_dev, gray_dev: fp32[B] (gray_dev may be NULL = colour noise only).
+ * Either inject the standard-normal fields (noise_color_dev fp32[B,C,H,W],
+ * noise_gray_dev fp32[H,W] — ONE field shared by the batch) or pass NULL for
+ * both and give a Philox4x32-10 (seed, offset) pair. flags: OTF_NOISE_*. */
+int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int W,
+                           const float* sigma_dev, const float* gray_dev,
+                           const float* noise_color_dev, const float* noise_gray_dev,
+                           uint64_t seed, uint64_t offset, int flags,
+                           float* out, void* stream);
+/* Fill out[n] with Philox standard normals / uniforms (distribution tests). */
+int otf_philox_normal_f32(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+int otf_philox_uniform_f32(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- a5: Poisson noise — degradations.py:762-842 ------------------------------
+ * Two launches behind one call: (1) per-sample 256-bit presence masks of the
+ * 8-bit-quantised colour and gray images -> vals = 2^ceil(log2(#distinct));
+ * (2) sampling + mixing + tail.  C must be 3.  masks_dev: uint32[B*16] scratch
+ * (zeroed by the call).  vals_out_dev (fp32[B*2]: colour, gray; may be NULL)
+ * and lambda_*_dev (may be NULL) export the deterministic half for parity
+ * tests.  counts_*_dev (may be NULL) inject pre-drawn Poisson counts; otherwise
+ * counts are drawn with Philox (seed, offset). */
+int otf_poisson_noise_f32(const float* img, int B, int C, int H, int W,
+                          const float* scale_dev, const float* gray_dev,
+                          const float* counts_color_dev, const float* counts_gray_dev,
+                          uint64_t seed, uint64_t offset, int flags,
+                          uint32_t* masks_dev, float* vals_out_dev,
+                          float* lambda_color_dev, float* lambda_gray_dev,
+                          float* out, void* stream);
+/* out[i] ~ Poisson(lambda[i]) with the library's sampler (distribution tests). */
+int otf_philox_poisson_f32(const float* lambda_dev, float* out, int64_t n,
+                           uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- a6: DiffJPEG.forward — traiNNer/utils/diffjpeg.py:503-527 ----------------
+ * One fused kernel: x255, RGB->YCbCr, 4:2:0, 8x8 DCT, quantise by table*factor[b]
+ * with round-half-even (differentiable=0) or round(x)+(x-round(x))^3, dequantise,
+ * IDCT, chroma x2, YCbCr->RGB, clamp, /255, crop of the x16 zero padding.
+ * factor_dev fp32[B] (already quality_to_factor'ed) or NULL to use factor_scalar.
+ * clamp_in != 0 first clamps the input to [0,1] (the call form used by the chain).
+ * round8_out != 0 additionally applies clamp(round(x*255),0,255)/255 (a7). */
+int otf_quality_to_factor_f32(float* quality_dev, int B, void* stream); /* diffjpeg.py:48-61, in place */
+int otf_diffjpeg_f32(const float* img, int B, int H, int W,
+                     const float* factor_dev, float factor_scalar, int differentiable,
+                     int clamp_in, int round8_out, float* out, void* stream);
+
+/* ---- a7: clamp/round — traiNNer/models/realesrgan_model.py:616 ----------------
+ * out = clamp(round(x*255),0,255)/255, round half to even. In place allowed. */
+int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* stream);
+
+/* ---- a8: paired crop — traiNNer/data/transforms.py:124-135 + .contiguous() ----
+ * Copies the LQ window (top,left,p,p) and the GT window (top*scale,left*scale,
+ * p*scale...) into dense outputs in one launch. */
+int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
+                      const float* lq, int Hl, int Wl,
+                      int top, int left, int lq_patch, int scale,
+                      float* gt_out, float* lq_out, void* stream);
+
+/* Strided (e.g. channels_last) -> dense NCHW copy; strides in elements. */
+int otf_copy_strided_f32(const float* src, const int64_t strides[4],
+                         int B, int C, int H, int W, float* dst, void* stream);
+
+/* ---- a9: pair pool without bulk copies ----------------------
+ * Gathers `n` slots: dst[i] = src[idx_host[i]] for slot_elems floats each, and
+ * scatters likewise (dst[idx_host[i]] = src[i]).  n <= 512. */
+int otf_gather_slots_f32(const float* src, const int32_t* idx_host, int n,
+                         int64_t slot_elems, float* dst, void* stream);
+int otf_scatter_slots_f32(const float* src, const int32_t* idx_host, int n,
+                          int64_t slot_elems, float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTF_B200_H_ */

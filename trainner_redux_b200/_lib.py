@@ -1,0 +1,147 @@
+"""ctypes binding of libotf_b200.so (the C ABI declared in include/otf_b200.h).
+
+PyTorch is used only as the owner of device memory and streams: every call below
+passes raw device pointers, extents and the current CUDA stream handle.  There is
+no CPU fallback — a missing library or a non-CUDA tensor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Any
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libotf_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
+
+OTF_OK = 0
+RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC = range(5)
+NOISE_CLIP, NOISE_ROUNDS, NOISE_FIELD_ONLY = 1, 2, 4
+
+_p, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/otf_b200.h one to one
+SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
+    "otf_abi_version": (_i, []),
+    "otf_last_error": (C.c_char_p, []),
+    "otf_device_cc": (_i, []),
+    "otf_filter2d_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "otf_sepconv_reflect_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p]),
+    "otf_usm_workspace_bytes": (_i64, [_i, _i, _i]),
+    "otf_usm_sharp_f32": (_i, [_p, _i, _i, _i, _p, _i, _f, _f, _p, _i64, _p, _p]),
+    "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
+    "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p]),
+    "otf_philox_normal_f32": (_i, [_p, _i64, _u64, _u64, _p]),
+    "otf_philox_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
+    "otf_poisson_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p]),
+    "otf_philox_poisson_f32": (_i, [_p, _p, _i64, _u64, _u64, _p]),
+    "otf_quality_to_factor_f32": (_i, [_p, _i, _p]),
+    "otf_diffjpeg_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _p, _p]),
+    "otf_clamp_round_f32": (_i, [_p, _i64, _p, _p]),
+    "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "otf_copy_strided_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "otf_gather_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
+    "otf_scatter_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
+}
+
+_lib: C.CDLL | None = None
+_lock = threading.Lock()
+launch_count = 0  # kernels enqueued through this binding (bench.py reports it)
+
+# launches behind each entry point (see the .cu files)
+_LAUNCHES = {
+    "otf_filter2d_f32": 2,  # support scan + blocked kernel
+    "otf_sepconv_reflect_f32": 1,
+    "otf_usm_sharp_f32": 4,
+    "otf_resize_f32": 1,
+    "otf_gaussian_noise_f32": 1,
+    "otf_philox_normal_f32": 1,
+    "otf_philox_uniform_f32": 1,
+    "otf_poisson_noise_f32": 2,
+    "otf_philox_poisson_f32": 1,
+    "otf_quality_to_factor_f32": 1,
+    "otf_diffjpeg_f32": 1,
+    "otf_clamp_round_f32": 1,
+    "otf_crop_pair_f32": 1,
+    "otf_copy_strided_f32": 1,
+    "otf_gather_slots_f32": 1,
+    "otf_scatter_slots_f32": 1,
+}
+
+
+class OtfError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "or `make -C trainner_redux_b200/csrc` (nvcc, sm_100a). There is no CPU fallback."
+                )
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            if lib.otf_abi_version() != 1:
+                raise ImportError("libotf_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().otf_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args: Any) -> None:
+    """Invoke an int-returning entry point; raise OtfError with the library's message."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    if rc != OTF_OK:
+        raise OtfError(f"{name} failed ({rc}): {last_error()}")
+    launch_count += _LAUNCHES.get(name, 0)
+
+
+def require_cuda(*tensors: torch.Tensor | None) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "trainner_redux_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                f"got a tensor on {t.device}"
+            )
+
+
+def ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dense_f32(t: torch.Tensor) -> torch.Tensor:
+    """Dense NCHW fp32 view of a 4-D CUDA tensor; strided inputs (channels_last, slices)
+    are normalised by the library's own copy kernel, not by ATen."""
+    require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"fp32 only, got {t.dtype}")
+    if t.is_contiguous():
+        return t
+    if t.dim() != 4:
+        return t.contiguous()
+    b, c, h, w = t.shape
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=t.device)
+    strides = (C.c_int64 * 4)(*t.stride())
+    call("otf_copy_strided_f32", ptr(t), strides, b, c, h, w, ptr(out), stream())
+    return out

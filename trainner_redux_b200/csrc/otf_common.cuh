@@ -1,0 +1,113 @@
+// Shared device/host helpers for libotf_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/otf_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libotf_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace otf {
+
+// ---------------------------------------------------------------- errors ----
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define OTF_REQUIRE(cond, code, ...)          \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::otf::set_error(__VA_ARGS__);    \
+            return (code);                    \
+        }                                     \
+    } while (0)
+
+#define OTF_LAUNCH_CHECK(what)                                        \
+    do {                                                              \
+        cudaError_t e__ = cudaGetLastError();                         \
+        if (e__ != cudaSuccess) return ::otf::cuda_fail(e__, what);   \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized against this
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// --------------------------------------------------------------- indexing ---
+// torch F.pad(mode="reflect"): mirror without repeating the edge sample.
+__host__ __device__ __forceinline__ int reflect_idx(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+__host__ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------- exact fp32 pieces --
+// The reference evaluates these as separate ATen ops (no FMA contraction), and a
+// rounding cliff follows them, so they are written with non-contractable
+// intrinsics to stay bit-identical.
+__device__ __forceinline__ float quantise8(float x) {
+    // clamp(round(x*255),0,255)/255 — realesrgan_model.py:616, degradations.py:789
+    float v = rintf(__fmul_rn(x, 255.0f));
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    return __fdiv_rn(v, 255.0f);
+}
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+__device__ __forceinline__ float noise_tail(float v, int flags) {
+    // degradations.py:626-632
+    const bool clip = flags & OTF_NOISE_CLIP, rounds = flags & OTF_NOISE_ROUNDS;
+    if (clip && rounds) return quantise8(v);
+    if (clip) return clamp01(v);
+    if (rounds) return __fdiv_rn(rintf(__fmul_rn(v, 255.0f)), 255.0f);
+    return v;
+}
+
+// ------------------------------------------------------------ Philox4x32-10 -
+struct Philox {
+    uint32_t key[2];
+    __device__ __forceinline__ Philox(uint64_t seed) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+    }
+    // counter = (lo64 = index, hi64 = stream/offset)
+    __device__ __forceinline__ uint4 operator()(uint64_t index, uint64_t stream) const {
+        uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32);
+        uint32_t c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+        uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+// (0,1] uniform from 32 random bits (never 0, so log() is finite)
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+
+// Box-Muller: two standard normals from two 32-bit words
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = u01(a), u2 = u01(b);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+// four standard normals for element-quad `quad` of a stream
+__device__ __forceinline__ float4 normal4(const Philox& ph, uint64_t quad, uint64_t stream) {
+    const uint4 r = ph(quad, stream);
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// streams used by the noise kernels (hi 64 bits of the Philox counter = offset*8 + id)
+enum { STREAM_COLOR = 0, STREAM_GRAY = 1, STREAM_POIS_COLOR = 2, STREAM_POIS_GRAY = 3 };
+
+}  // namespace otf

@@ -1,0 +1,166 @@
+// Small streaming kernels of the path: 8-bit lattice clamp/round, paired crop, layout
+// normalisation, pair-pool slot gather/scatter; plus the library's error plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "otf_common.cuh"
+
+namespace otf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return OTF_ERR_CUDA;
+}
+
+// ---- a7: traiNNer/models/realesrgan_model.py:616 ------------------------------------------
+__global__ void __launch_bounds__(256) clamp_round_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+    const int64_t nq = n >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[q];
+        reinterpret_cast<float4*>(out)[q] = make_float4(quantise8(v.x), quantise8(v.y), quantise8(v.z), quantise8(v.w));
+    }
+    const int64_t tail = (nq << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tail < n) out[tail] = quantise8(x[tail]);
+}
+
+// ---- a8: traiNNer/data/transforms.py:124-135 followed by .contiguous() --------------------
+// One launch copies both windows. blockIdx.z = plane; rows of the GT window first, then LQ rows.
+__global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict__ gt, int Hg, int Wg,
+                                                        const float* __restrict__ lq, int Hl, int Wl, int top, int left,
+                                                        int p, int scale, float* __restrict__ gt_out, float* __restrict__ lq_out) {
+    const int plane = blockIdx.z;
+    const int G = p * scale;
+    const int row = blockIdx.y;  // 0..G-1 -> GT rows, G..G+p-1 -> LQ rows
+    if (row < G) {
+        const float* src = gt + ((size_t)plane * Hg + (size_t)(top * scale + row)) * Wg + left * scale;
+        float* dst = gt_out + ((size_t)plane * G + row) * G;
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < G; x += gridDim.x * blockDim.x) dst[x] = __ldg(src + x);
+    } else {
+        const int r = row - G;
+        const float* src = lq + ((size_t)plane * Hl + (size_t)(top + r)) * Wl + left;
+        float* dst = lq_out + ((size_t)plane * p + r) * p;
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p; x += gridDim.x * blockDim.x) dst[x] = __ldg(src + x);
+    }
+}
+
+// ---- strided (channels_last, sliced views...) -> dense NCHW -------------------------------
+__global__ void __launch_bounds__(256) copy_strided_kernel(const float* __restrict__ src, int64_t sb, int64_t sc, int64_t sh,
+                                                           int64_t sw, int C, int H, int W, float* __restrict__ dst,
+                                                           int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        int64_t t = i / W;
+        const int y = (int)(t % H);
+        t /= H;
+        const int c = (int)(t % C);
+        const int64_t b = t / C;
+        dst[i] = __ldg(src + b * sb + c * sc + y * sh + x * sw);
+    }
+}
+
+// ---- pair-pool slot movement ---------------------------------------------
+struct SlotIdx {
+    int32_t idx[512];
+};
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) move_slots_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         int64_t slot_elems, const __grid_constant__ SlotIdx map) {
+    const int s = blockIdx.y;
+    const float* sp = src + (SCATTER ? (int64_t)s : (int64_t)map.idx[s]) * slot_elems;
+    float* dp = dst + (SCATTER ? (int64_t)map.idx[s] : (int64_t)s) * slot_elems;
+    const bool vec = (slot_elems % 4 == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0);
+    if (vec) {
+        const int64_t nq = slot_elems >> 2;
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<float4*>(dp)[q] = __ldg(reinterpret_cast<const float4*>(sp) + q);
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slot_elems; i += (int64_t)gridDim.x * blockDim.x)
+            dp[i] = __ldg(sp + i);
+    }
+}
+
+template <bool SCATTER>
+static int move_slots(const float* src, const int32_t* idx_host, int n, int64_t slot_elems, float* dst, void* stream) {
+    OTF_REQUIRE(src && dst && idx_host, OTF_ERR_BAD_ARG, "move_slots: null pointer");
+    OTF_REQUIRE(n > 0 && n <= 512 && slot_elems > 0, OTF_ERR_BAD_ARG, "move_slots: need 0 < n <= 512 (got %d)", n);
+    SlotIdx m;
+    memset(&m, 0, sizeof(m));
+    for (int i = 0; i < n; ++i) {
+        OTF_REQUIRE(idx_host[i] >= 0, OTF_ERR_BAD_ARG, "move_slots: negative slot index");
+        m.idx[i] = idx_host[i];
+    }
+    int bx = ceil_div(slot_elems / 4 + 1, 256 * 4);
+    if (bx > 64) bx = 64;
+    move_slots_kernel<SCATTER><<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(src, dst, slot_elems, m);
+    OTF_LAUNCH_CHECK("move_slots_kernel");
+    return OTF_OK;
+}
+
+}  // namespace otf
+
+extern "C" int otf_abi_version(void) { return OTF_ABI_VERSION; }
+extern "C" const char* otf_last_error(void) { return otf::g_err; }
+extern "C" int otf_device_cc(void) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return otf::cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return major * 10 + minor;
+}
+
+extern "C" int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(x && out && n > 0, OTF_ERR_BAD_ARG, "clamp_round: bad args");
+    OTF_REQUIRE(((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0, OTF_ERR_BAD_ARG, "clamp_round: pointers must be 16-byte aligned");
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (blocks < 1) blocks = 1;
+    clamp_round_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    OTF_LAUNCH_CHECK("clamp_round_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, const float* lq, int Hl, int Wl, int top,
+                                 int left, int lq_patch, int scale, float* gt_out, float* lq_out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(gt && lq && gt_out && lq_out, OTF_ERR_BAD_ARG, "crop_pair: null pointer");
+    OTF_REQUIRE(planes > 0 && planes <= 65535 && scale > 0 && lq_patch > 0, OTF_ERR_BAD_ARG, "crop_pair: bad extents");
+    OTF_REQUIRE(Hg == Hl * scale && Wg == Wl * scale, OTF_ERR_BAD_ARG, "crop_pair: GT (%d, %d) is not %dx LQ (%d, %d)", Hg, Wg, scale, Hl, Wl);
+    OTF_REQUIRE(top >= 0 && left >= 0 && top + lq_patch <= Hl && left + lq_patch <= Wl, OTF_ERR_BAD_ARG, "crop_pair: window outside LQ");
+    const int G = lq_patch * scale;
+    OTF_REQUIRE(G + lq_patch <= 65535, OTF_ERR_UNSUPPORTED, "crop_pair: patch too large");
+    const dim3 grid(ceil_div(G, 256), G + lq_patch, planes);
+    crop_pair_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, gt_out, lq_out);
+    OTF_LAUNCH_CHECK("crop_pair_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_copy_strided_f32(const float* src, const int64_t strides[4], int B, int C, int H, int W, float* dst,
+                                    void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(src && dst && strides, OTF_ERR_BAD_ARG, "copy_strided: null pointer");
+    OTF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "copy_strided: bad extents");
+    const int64_t n = (int64_t)B * C * H * W;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    copy_strided_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, strides[0], strides[1], strides[2], strides[3], C, H, W, dst, n);
+    OTF_LAUNCH_CHECK("copy_strided_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_gather_slots_f32(const float* src, const int32_t* idx_host, int n, int64_t slot_elems, float* dst,
+                                    void* stream) {
+    return otf::move_slots<false>(src, idx_host, n, slot_elems, dst, stream);
+}
+extern "C" int otf_scatter_slots_f32(const float* src, const int32_t* idx_host, int n, int64_t slot_elems, float* dst,
+                                     void* stream) {
+    return otf::move_slots<true>(src, idx_host, n, slot_elems, dst, stream);
+}

@@ -1,0 +1,353 @@
+"""Drop-in for the OTF half of traiNNer/models/realesrgan_model.py: ``feed_data`` (:455-650) and
+the training-pair pool ``_dequeue_and_enqueue`` (:403-453).
+
+``RealESRGANFeed`` owns what ``RealESRGANModel`` owns for this path — ``self.gt`` / ``self.lq``, the
+``jpeger``, the ``usm_sharpener``, the pool — and nothing else (networks, losses and optimisers are
+out of scope).  A maintainer swaps it in by making ``RealESRGANModel.feed_data`` delegate to it
+(INTEGRATION.md).
+
+Two stage orders are implemented:
+  * ``order="classic"`` — the second-order Real-ESRGAN chain the option schema still describes
+    (traiNNer/utils/redux_options.py:720-851): [USM] blur1, resize1, noise1, jpeg1, blur2, resize2,
+    noise2, {resize3+sinc, jpeg2} in random order, clamp/round, crop, pool.
+  * ``order="fork"`` — the as-shipped order of this fork (realesrgan_model.py:525-526, :564-574,
+    :616-627) minus the probability-0 extras and the PIL codec round trip: [blur1], resize3, sinc,
+    clamp/round, crop, pool.
+
+All host-side decisions are drawn in Python in the reference's order by
+``draw_plan``; the bulk random fields come from the kernels' Philox streams.  Nothing between the
+H2D copies and the finished pair synchronises with the host.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import random
+from dataclasses import dataclass, field
+from typing import Any, Callable, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from . import degradations as D
+from .diffjpeg import DiffJPEG
+from .img_process_util import USMSharp, filter2d
+from .transforms import crop_pair
+
+
+# --------------------------------------------------------------------------- options ----
+@dataclass
+class OTFOptions:
+    """The fields of ``ReduxOptions`` that govern the path, with the reference's names and
+    defaults (traiNNer/utils/redux_options.py:720-901).  Any object exposing these attributes
+    (e.g. a real ``ReduxOptions``) can be passed instead."""
+
+    scale: int = 4
+    gt_size: int = 256  # opt.datasets["train"].gt_size (realesrgan_model.py:619)
+    lq_usm: bool = False
+    lq_usm_radius_range: tuple[int, int] = (1, 25)
+    blur_prob: float = 0
+    resize_prob: Sequence[float] = (0.2, 0.7, 0.1)
+    resize_mode_list: Sequence[str] = ("bilinear", "bicubic", "nearest-exact", "lanczos")
+    resize_mode_prob: Sequence[float] = (0.25, 0.25, 0.25, 0.25)
+    resize_range: tuple[float, float] = (0.4, 1.5)
+    gaussian_noise_prob: float = 0
+    noise_range: tuple[float, float] = (0, 0)
+    poisson_scale_range: tuple[float, float] = (0, 0)
+    gray_noise_prob: float = 0
+    jpeg_prob: float = 1
+    jpeg_range: tuple[float, float] = (75, 95)
+    blur_prob2: float = 0
+    resize_prob2: Sequence[float] = (0.3, 0.4, 0.3)
+    resize_mode_list2: Sequence[str] = ("bilinear", "bicubic", "nearest-exact", "lanczos")
+    resize_mode_prob2: Sequence[float] = (0.25, 0.25, 0.25, 0.25)
+    resize_range2: tuple[float, float] = (0.6, 1.2)
+    gaussian_noise_prob2: float = 0
+    noise_range2: tuple[float, float] = (0, 0)
+    poisson_scale_range2: tuple[float, float] = (0, 0)
+    gray_noise_prob2: float = 0
+    jpeg_prob2: float = 1
+    jpeg_range2: Sequence[float] = (75, 95)
+    resize_mode_list3: Sequence[str] = ("bilinear", "bicubic", "nearest-exact", "lanczos")
+    resize_mode_prob3: Sequence[float] = (0.25, 0.25, 0.25, 0.25)
+    queue_size: int = 120
+    p_clean: float = 0
+    # not in the reference schema: which composition to run, and the upstream 50/50 final-order coin
+    order: str = "classic"
+    final_jpeg_first_prob: float = 0.5
+    noise_enabled: bool = True  # classic order draws a noise stage (Gaussian else Poisson) as upstream does
+
+
+class HostRNG:
+    """The reference's three host generators: a numpy ``Generator`` seeded WITHOUT the rank offset
+    (traiNNer/utils/rng.py:19-25), and Python ``random`` + the torch CPU generator seeded with
+    ``manual_seed + rank`` (train.py:283 -> utils/misc.py:19-22)."""
+
+    def __init__(self, manual_seed: int = 0, rank: int = 0) -> None:
+        self.np = np.random.default_rng(manual_seed)
+        self.py = random.Random(manual_seed + rank)
+        self.torch = torch.Generator().manual_seed(manual_seed + rank)
+        self.philox = D.PhiloxState(seed=(manual_seed + rank) * 0x9E3779B97F4A7C15 + 0xB200)
+
+
+def _opt(o: Any, name: str, default: Any = None) -> Any:
+    return getattr(o, name, default)
+
+
+def _draw_resize(rng: HostRNG, probs, rrange, modes, mode_probs) -> dict:
+    kind = rng.py.choices(["up", "down", "keep"], probs)[0]
+    if kind == "up":
+        s = rng.np.uniform(1, rrange[1])
+    elif kind == "down":
+        s = rng.np.uniform(rrange[0], 1)
+    else:
+        s = 1.0
+    mode = rng.py.choices(list(modes), weights=list(mode_probs))[0]
+    return {"scale": float(s), "mode": mode}
+
+
+def _draw_noise(rng: HostRNG, b: int, gaussian_prob, noise_range, poisson_range, gray_prob) -> dict:
+    # gate first, then the primitive's own draws: rand(B) value, rand(B) gray (degradations.py:673-679)
+    gaussian = rng.np.uniform() < gaussian_prob
+    rr = noise_range if gaussian else poisson_range
+    val = torch.rand(b, generator=rng.torch) * (rr[1] - rr[0]) + rr[0]
+    gray = (torch.rand(b, generator=rng.torch) < gray_prob).float()
+    if gaussian:
+        return {"kind": "gaussian", "sigma": val, "gray": gray}
+    return {"kind": "poisson", "scale": val, "gray": gray}
+
+
+def _draw_quality(rng: HostRNG, b: int, qrange) -> Tensor:
+    # out.new_zeros(B).uniform_(*jpeg_range)
+    return torch.empty(b).uniform_(float(qrange[0]), float(qrange[1]), generator=rng.torch)
+
+
+def draw_plan(opt: Any, b: int, ori_h: int, ori_w: int, rng: HostRNG) -> dict:
+    """Host-side decisions for one ``feed_data`` call, in the order of SURVEY.md appendix A.
+    The result is a plain dict (the format ``oracle.otf_oracle.run_chain_b`` consumes)."""
+    scale = _opt(opt, "scale", 4)
+    plan: dict[str, Any] = {"scale": scale, "gt_size": _opt(opt, "gt_size", ori_h), "order": _opt(opt, "order", "classic")}
+    if _opt(opt, "p_clean", 0) and rng.np.uniform() < opt.p_clean:  # realesrgan_model.py:487-503
+        plan["clean"] = True
+    elif plan["order"] == "fork":
+        plan["blur1"] = bool(rng.np.uniform() < _opt(opt, "blur_prob", 0))  # :525
+        plan["resize3_mode"] = rng.py.choices(list(opt.resize_mode_list3), weights=list(opt.resize_mode_prob3))[0]  # :564
+    else:
+        if _opt(opt, "lq_usm", False):
+            lo, hi = opt.lq_usm_radius_range
+            plan["usm"] = {"radius": rng.py.randint(lo, hi), "weight": 0.5, "threshold": 10}
+        plan["blur1"] = bool(rng.np.uniform() < _opt(opt, "blur_prob", 0))
+        plan["resize1"] = _draw_resize(rng, opt.resize_prob, opt.resize_range, opt.resize_mode_list, opt.resize_mode_prob)
+        if _opt(opt, "noise_enabled", True):
+            plan["noise1"] = _draw_noise(rng, b, opt.gaussian_noise_prob, opt.noise_range, opt.poisson_scale_range, opt.gray_noise_prob)
+        plan["jpeg1"] = _draw_quality(rng, b, opt.jpeg_range) if rng.np.uniform() < opt.jpeg_prob else None
+        plan["blur2"] = bool(rng.np.uniform() < _opt(opt, "blur_prob2", 0))
+        plan["resize2"] = _draw_resize(rng, opt.resize_prob2, opt.resize_range2, opt.resize_mode_list2, opt.resize_mode_prob2)
+        if _opt(opt, "noise_enabled", True):
+            plan["noise2"] = _draw_noise(rng, b, opt.gaussian_noise_prob2, opt.noise_range2, opt.poisson_scale_range2, opt.gray_noise_prob2)
+        plan["final_order"] = "resize_first" if rng.np.uniform() >= _opt(opt, "final_jpeg_first_prob", 0.5) else "jpeg_first"
+        plan["resize3_mode"] = rng.py.choices(list(opt.resize_mode_list3), weights=list(opt.resize_mode_prob3))[0]
+        plan["jpeg2"] = _draw_quality(rng, b, opt.jpeg_range2) if rng.np.uniform() < opt.jpeg_prob2 else None
+    # paired_random_crop: two random.randint draws (transforms.py:119-120)
+    p = plan["gt_size"] // scale
+    h_lq, w_lq = ori_h // scale, ori_w // scale
+    if h_lq < p or w_lq < p:
+        raise ValueError(f"LQ ({h_lq}, {w_lq}) is smaller than patch size ({p}, {p}). Please remove None.")
+    plan["crop"] = (rng.py.randint(0, h_lq - p), rng.py.randint(0, w_lq - p))
+    return plan
+
+
+# --------------------------------------------------------------------- small kernels ----
+def clamp_round(x: Tensor) -> Tensor:
+    """``clamp(round(x*255),0,255)/255`` — realesrgan_model.py:616."""
+    x = _lib.dense_f32(x)
+    out = torch.empty_like(x)
+    _lib.call("otf_clamp_round_f32", _lib.ptr(x), x.numel(), _lib.ptr(out), _lib.stream())
+    return out
+
+
+# ------------------------------------------------------------------------- pair pool ----
+class SlotMover:
+    """Moves pool slots with the library's gather/scatter kernels."""
+
+    def gather(self, src: Tensor, idx: Sequence[int]) -> Tensor:
+        n = len(idx)
+        out = torch.empty((n, *src.shape[1:]), dtype=src.dtype, device=src.device)
+        arr = (C.c_int32 * n)(*idx)
+        _lib.call("otf_gather_slots_f32", _lib.ptr(src), arr, n, src[0].numel(), _lib.ptr(out), _lib.stream())
+        return out
+
+    def scatter(self, dst: Tensor, idx: Sequence[int], src: Tensor) -> None:
+        n = len(idx)
+        arr = (C.c_int32 * n)(*idx)
+        _lib.call("otf_scatter_slots_f32", _lib.ptr(_lib.dense_f32(src)), arr, n, dst[0].numel(), _lib.ptr(dst), _lib.stream())
+
+
+class PairPool:
+    """Training pair pool (realesrgan_model.py:403-453) without the full-queue gather.
+
+    The reference shuffles by materialising ``queue[idx]`` for both queues every iteration
+    (~100 MB of traffic at queue_size 120).  Here the queues never move: a host-side table maps
+    logical positions to physical slots, ``randperm`` permutes the table, and only the ``b``
+    dequeued / enqueued slots are touched.  Given the same ``randperm`` results the returned
+    batches are bit-identical to the reference's (tests/test_pool_cpu.py)."""
+
+    def __init__(self, queue_size: int, mover: Any | None = None, randperm: Callable[[int], Tensor] | None = None) -> None:
+        self.queue_size = queue_size
+        self.mover = mover or SlotMover()
+        self.randperm = randperm or (lambda n: torch.randperm(n))
+        self.queue_lr: Tensor | None = None
+        self.queue_gt: Tensor | None = None
+        self.queue_ptr = 0
+        self.slot_of = list(range(queue_size))  # logical position -> physical slot
+
+    def step(self, lq: Tensor, gt: Tensor) -> tuple[Tensor, Tensor]:
+        b = lq.size(0)
+        if self.queue_lr is None:
+            assert self.queue_size % b == 0, f"queue size {self.queue_size} should be divisible by batch size {b}"
+            self.queue_lr = torch.zeros((self.queue_size, *lq.shape[1:]), dtype=lq.dtype, device=lq.device)
+            self.queue_gt = torch.zeros((self.queue_size, *gt.shape[1:]), dtype=gt.dtype, device=gt.device)
+            self.queue_ptr = 0
+        assert self.queue_gt is not None
+        if self.queue_ptr == self.queue_size:  # the pool is full: shuffle, dequeue b, enqueue b
+            idx = self.randperm(self.queue_size).tolist()
+            self.slot_of = [self.slot_of[i] for i in idx]
+            slots = self.slot_of[:b]
+            lq_out = self.mover.gather(self.queue_lr, slots)
+            gt_out = self.mover.gather(self.queue_gt, slots)
+            self.mover.scatter(self.queue_lr, slots, lq)
+            self.mover.scatter(self.queue_gt, slots, gt)
+            return lq_out, gt_out
+        slots = self.slot_of[self.queue_ptr : self.queue_ptr + b]
+        self.mover.scatter(self.queue_lr, slots, lq)
+        self.mover.scatter(self.queue_gt, slots, gt)
+        self.queue_ptr += b
+        return lq, gt
+
+
+# ------------------------------------------------------------------------------ feed ----
+class RealESRGANFeed:
+    """``feed_data`` for OTF training: turns ``{gt, kernel1, kernel2, sinc_kernel}`` into
+    ``self.gt`` / ``self.lq`` on the device."""
+
+    def __init__(self, opt: Any, device: torch.device | str = "cuda", manual_seed: int = 0, rank: int = 0,
+                 use_pool: bool = True) -> None:
+        self.opt = opt
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RealESRGANFeed runs on a CUDA device only (no CPU fallback)")
+        _lib.load()
+        self.is_train = True
+        self.rng = HostRNG(manual_seed, rank)
+        self.jpeger = DiffJPEG(differentiable=False)  # realesrgan_model.py:81-83
+        self._usm: dict[int, USMSharp] = {}
+        self.queue_size = _opt(opt, "queue_size", 120)
+        self.pool = PairPool(self.queue_size, randperm=lambda n: torch.randperm(n, generator=self.rng.torch)) if use_pool else None
+        self.gt: Tensor | None = None
+        self.lq: Tensor | None = None
+        self.last_plan: dict | None = None
+
+    # -- stages ---------------------------------------------------------------------------
+    def _noise(self, out: Tensor, st: dict, inject: dict | None, key: str) -> Tensor:
+        inject = inject or {}
+        if st["kind"] == "gaussian":
+            return D.add_gaussian_noise_pt(
+                out, st["sigma"].to(self.device, non_blocking=True), st["gray"].to(self.device, non_blocking=True),
+                clip=True, rounds=False, noise=inject.get(f"{key}_color"), noise_gray=inject.get(f"{key}_gray"),
+                generator=self.rng.philox,
+            )
+        return D.add_poisson_noise_pt(
+            out, st["scale"].to(self.device, non_blocking=True), True, False, st["gray"].to(self.device, non_blocking=True),
+            poisson_counts=inject.get(f"{key}_counts_color"), poisson_counts_gray=inject.get(f"{key}_counts_gray"),
+            generator=self.rng.philox,
+        )
+
+    def _jpeg(self, out: Tensor, quality: Tensor, round8: bool) -> Tensor:
+        q = quality.clone().to(self.device, non_blocking=True)
+        return self.jpeger(out, quality=q, _clamp_in=True, _round8=round8)
+
+    def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
+                inject: dict | None = None) -> Tensor:
+        """Run the chain described by ``plan`` on device tensors; returns the full-size LQ on the
+        8-bit lattice (before the crop)."""
+        ori_h, ori_w = gt.shape[2:4]
+        sc = plan["scale"]
+        out = gt
+        if plan.get("clean"):
+            return clamp_round(out)
+        if plan.get("order") == "fork":
+            if plan.get("blur1"):
+                out = filter2d(out, kernel1)
+            out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
+            out = filter2d(out, sinc_kernel)
+            if plan.get("jpeg") is not None:
+                return self._jpeg(out, plan["jpeg"], round8=True)
+            return clamp_round(out)
+        if plan.get("usm"):
+            r = plan["usm"]["radius"]
+            if r not in self._usm:
+                self._usm[r] = USMSharp(radius=r)
+            out = self._usm[r](out, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10))
+        if plan.get("blur1"):
+            out = filter2d(out, kernel1)
+        if plan.get("resize1"):
+            out = D.resize_pt(out, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"])
+        if plan.get("noise1"):
+            out = self._noise(out, plan["noise1"], inject, "noise1")
+        if plan.get("jpeg1") is not None:
+            out = self._jpeg(out, plan["jpeg1"], round8=False)
+        if plan.get("blur2"):
+            out = filter2d(out, kernel2)
+        if plan.get("resize2"):
+            s2 = plan["resize2"]["scale"]
+            out = D.resize_pt(out, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"])
+        if plan.get("noise2"):
+            out = self._noise(out, plan["noise2"], inject, "noise2")
+        jpeg2 = plan.get("jpeg2")
+        if plan.get("final_order", "resize_first") == "resize_first":
+            out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
+            out = filter2d(out, sinc_kernel)
+            if jpeg2 is not None:
+                return self._jpeg(out, jpeg2, round8=True)  # clamp/round fused into the last kernel
+            return clamp_round(out)
+        if jpeg2 is not None:
+            out = self._jpeg(out, jpeg2, round8=False)
+        out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
+        out = filter2d(out, sinc_kernel)
+        return clamp_round(out)
+
+    # -- the reference entry point --------------------------------------------------------
+    @torch.no_grad()
+    def feed_data(self, data: dict, plan: dict | None = None, inject: dict | None = None) -> None:
+        """Accept data from the dataloader and synthesise the LQ batch (realesrgan_model.py:455-650)."""
+        if self.is_train:
+            assert "gt" in data and "kernel1" in data and "kernel2" in data and "sinc_kernel" in data
+            gt = data["gt"].to(self.device, non_blocking=True)
+            kernel1 = data["kernel1"].to(self.device, non_blocking=True)
+            kernel2 = data["kernel2"].to(self.device, non_blocking=True)
+            sinc_kernel = data["sinc_kernel"].to(self.device, non_blocking=True)
+            gt = _lib.dense_f32(gt)
+            ori_h, ori_w = gt.shape[2:4]
+            if plan is None:
+                plan = draw_plan(self.opt, gt.size(0), ori_h, ori_w, self.rng)
+            self.last_plan = plan
+            lq_full = self.degrade(gt, kernel1, kernel2, sinc_kernel, plan, inject)
+            top, left = plan["crop"]
+            self.gt, self.lq = crop_pair(gt, lq_full, plan["gt_size"], plan["scale"], top, left)
+            if self.pool is not None:
+                self.lq, self.gt = self.pool.step(self.lq, self.gt)
+        else:
+            assert "lq" in data
+            self.lq = data["lq"].to(self.device, non_blocking=True)
+            if "gt" in data:
+                self.gt = data["gt"].to(self.device, non_blocking=True)
+
+
+def shard_range(n: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous per-rank slice of a global batch of ``n`` samples: the path has
+    no exchange step, so every rank degrades its own samples and keeps its own pool."""
+    base, rem = divmod(n, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
