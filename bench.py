@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — degraded LR/HR pairs/sec of the OTF second-order degradation path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "Config 2"): batch 64 of synthetic 256x256 RGB
+GT per GPU, scale 4, the classical second-order chain with every stage on:
+  blur1 (21x21 per-sample kernels, true sizes 7..21) -> bicubic resize x0.75 (192^2) ->
+  Gaussian noise sigma~U[1,30], gray 40 % -> DiffJPEG q~U[30,95] -> blur2 -> bilinear resize to 64^2 ->
+  Gaussian noise -> area resize to 64^2 -> sinc filter -> DiffJPEG q~U[30,95] -> clamp/round -> paired crop 224/56.
+A "step" is one pass of that chain over one batch.  The batch shards per sample, so every rank
+runs its own batch with no collective on the data path ("scaling": "weak").
+
+One JSON line on stdout (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
+metric through RealESRGANFeed.feed_data() from pinned HOST buffers with the LQ/GT pair read back;
+`roofline` describes the dominant kernel (blur1 filter2d) from CUDA-event timings taken inside the
+timed region; `cpu_baseline` is the oracle port of the reference pipeline on this box's host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "degraded LR/HR pairs/sec at 256^2 GT x4"
+UNIT = "pairs/s"
+GT, SCALE, BATCH, GT_CROP = 256, 4, 64, 224
+S1, S2 = 0.75, 1.0
+N_ROTATE = 4  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
+
+
+def peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)", "sm_max_mhz": d.get("sm_max_mhz", 1965.0)}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "sm_max_mhz": 1965.0}
+
+
+def make_inputs(seed: int, batch: int):
+    """Synthetic GT + kernels from the shared generators in oracle/otf_oracle.py (data only)."""
+    from oracle import otf_oracle as O
+
+    gt = O.synth_gt(batch, GT, GT, "uniform", seed=1234 + seed)
+    return {
+        "gt": gt,
+        "kernel1": O.synth_blur_kernels(batch, seed=10 + seed),
+        "kernel2": O.synth_blur_kernels(batch, seed=20 + seed),
+        "sinc_kernel": O.synth_sinc_or_pulse(batch, seed=30 + seed),
+    }
+
+
+def make_plan(batch: int, seed: int) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "scale": SCALE, "gt_size": GT_CROP, "order": "classic", "blur1": True,
+        "resize1": {"scale": S1, "mode": "bicubic"},
+        "noise1": {"kind": "gaussian", "sigma": torch.rand(batch, generator=g) * 29 + 1, "gray": (torch.rand(batch, generator=g) < 0.4).float()},
+        "jpeg1": torch.rand(batch, generator=g) * 65 + 30, "blur2": True,
+        "resize2": {"scale": S2, "mode": "bilinear"},
+        "noise2": {"kind": "gaussian", "sigma": torch.rand(batch, generator=g) * 24 + 1, "gray": (torch.rand(batch, generator=g) < 0.4).float()},
+        "final_order": "resize_first", "resize3_mode": "area", "jpeg2": torch.rand(batch, generator=g) * 65 + 30,
+        "crop": (4, 4),
+    }
+
+
+def algorithmic_bytes_per_pair() -> int:
+    """Stage-sum model of SURVEY.md §8d (noise counted with its own read+write here because it is a
+    separate kernel in this round)."""
+    a = 3 * GT * GT * 4
+    b1 = int(round(GT * S1)) ** 2 * 3 * 4
+    c = (GT // SCALE) ** 2 * 3 * 4
+    b2 = int(GT / SCALE * S2) ** 2 * 3 * 4
+    return 2 * a + (a + b1) + 2 * b1 + 2 * b1 + (b1 + b2) + (b2 + c) + 2 * c + 2 * c
+
+
+# ------------------------------------------------------------------ CPU reference arm ----
+def cpu_chain_pairs_per_s(batch: int, steps: int, warmup: int, threads: int) -> tuple[float, float]:
+    """Times the oracle port of the reference pipeline (same plan, same inputs) on host cores."""
+    from oracle import otf_oracle as O
+
+    torch.set_num_threads(threads)
+    data = make_inputs(0, batch)
+    plan = make_plan(batch, 0)
+    g = torch.Generator().manual_seed(0)
+    h1 = int(round(GT * S1))
+    h2 = int(GT / SCALE * S2)
+
+    def one():
+        noise = {"noise1_color": torch.randn(batch, 3, h1, h1, generator=g), "noise1_gray": torch.randn(h1, h1, generator=g),
+                 "noise2_color": torch.randn(batch, 3, h2, h2, generator=g), "noise2_gray": torch.randn(h2, h2, generator=g)}
+        return O.run_chain_b(data["gt"], data["kernel1"], data["kernel2"], data["sinc_kernel"], plan, noise)
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = BATCH if args.steps + args.warmup <= 120 else 16
+    val, ms = cpu_chain_pairs_per_s(batch, args.steps, args.warmup, threads)
+    sample = f"each step = one batch of {batch} x 256^2 GT through the oracle port of the reference chain (torch CPU, {threads} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "batch_per_step": batch, "gt": GT, "scale": SCALE},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name() -> str:
+    return ("Real-ESRGAN OTF second-order chain incl. DiffJPEG + sinc, batch 64 synthetic 256^2 GT x4 per GPU "
+            "(blur1, bicubic x0.75, gaussian, jpeg, blur2, bilinear, gaussian, area->64^2, sinc, jpeg, clamp/round, crop 224/56)")
+
+
+# ------------------------------------------------------------------------- clocks ----
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------- main ----
+def run_b200(args) -> None:
+    import torch.distributed as dist
+
+    from trainner_redux_b200 import _lib
+    from trainner_redux_b200.realesrgan_feed import OTFOptions, RealESRGANFeed
+    from trainner_redux_b200.transforms import crop_pair
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    feed = RealESRGANFeed(OTFOptions(scale=SCALE, gt_size=GT_CROP, queue_size=BATCH * 2), device=dev, manual_seed=0, rank=rank,
+                          use_pool=False)
+    feed.stage_times = {}
+    host = [make_inputs(rank * N_ROTATE + i, BATCH) for i in range(N_ROTATE)]
+    for d in host:
+        for k in d:
+            d[k] = d[k].pin_memory()
+    devd = [{k: v.to(dev) for k, v in d.items()} for d in host]
+    plans = []
+    for i in range(N_ROTATE):
+        p = make_plan(BATCH, rank * N_ROTATE + i)
+        for key in ("noise1", "noise2"):
+            for kk in ("sigma", "gray"):
+                p[key][kk] = p[key][kk].to(dev)
+        plans.append(p)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i: int):
+        d, p = devd[i % N_ROTATE], plans[i % N_ROTATE]
+        lq_full = feed.degrade(d["gt"], d["kernel1"], d["kernel2"], d["sinc_kernel"], p)
+        return crop_pair(d["gt"], lq_full, GT_CROP, SCALE, *p["crop"])
+
+    # ---- value: device-resident inputs, CUDA events, max over ranks ----
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    feed.stage_times = {}
+    feed.time_stages = True
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - l0
+    feed.time_stages = False
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+    stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in feed.stage_times.items()}
+
+    # ---- e2e: feed_data() from pinned host buffers + D2H of the pair, wall clock, max over ranks ----
+    lq_host = torch.empty((BATCH, 3, GT_CROP // SCALE, GT_CROP // SCALE), dtype=torch.float32).pin_memory()
+    gt_host = torch.empty((BATCH, 3, GT_CROP, GT_CROP), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i: int):
+        feed.feed_data(host[i % N_ROTATE], plan=plans[i % N_ROTATE])
+        lq_host.copy_(feed.lq, non_blocking=True)
+        gt_host.copy_(feed.gt, non_blocking=True)
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * args.steps / t.item()
+    h2d = sum(v.numel() * 4 for v in host[0].values()) + 2 * BATCH * 4
+    d2h = (lq_host.numel() + gt_host.numel()) * 4
+
+    if rank == 0:
+        pk = peaks()
+        k_ms = stage_ms.get("blur1", float("nan"))
+        blur_bytes = BATCH * (2 * 3 * GT * GT * 4 + 21 * 21 * 4)
+        achieved = blur_bytes / (k_ms * 1e-3) / 1e9
+        true_k2 = float((devd[0]["kernel1"] != 0).flatten(1).sum(1).float().mean().item())
+        flops = 2.0 * 21 * 21 * 3 * GT * GT * BATCH
+        fma_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        chain_bytes = algorithmic_bytes_per_pair()
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cval, cms = cpu_chain_pairs_per_s(BATCH, 8, 1, threads)
+            cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"8 batches of {BATCH} x 256^2 GT (+1 warm-up) through the oracle port of the reference chain, torch CPU {threads} threads, {cms:.0f} ms/batch"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "batch_per_gpu": BATCH, "gt": GT, "scale": SCALE,
+                       "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * BATCH * 3 * GT * GT * 4 / 1e6:.0f} MB > 126 MB L2)",
+                       "parallelism": f"per-sample shards x{world}, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "filter2d_kernel (blur1, 64x3x256x256, 21x21 zero-padded kernels)", "bound": "hbm",
+                         "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                         "traffic": None, "peak_source": pk["source"], "ms_per_launch": k_ms,
+                         "fma": {"achieved_tflops_full_support": flops / (k_ms * 1e-3) / 1e12, "peak_tflops": fma_peak,
+                                 "mean_nonzero_taps": true_k2,
+                                 "note": "filter2d is FP32-FMA bound above K~9 (SURVEY.md H1); both roofs reported"}},
+            "chain": {"algorithmic_bytes_per_pair": chain_bytes, "achieved_gbs": chain_bytes * value / world / 1e9,
+                      "frac_of_hbm_peak": chain_bytes * value / world / 1e9 / pk["hbm_gbs"], "stage_ms": stage_ms},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

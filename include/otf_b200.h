@@ -74,7 +74,7 @@ int otf_filter2d_f32(const float* img, int B, int C, int H, int W,
 /* ---- 1-D correlation with reflect padding along one axis ----------------------
  * Building block of USMSharp (exactly separable 51x51 Gaussian) and of the
  * Lanczos prefilter in degradations.py:982-998.  `taps_host` is a HOST array of
- * `ntaps` (odd, <= 127) fp32 taps; axis 0 = vertical (H), 1 = horizontal (W). */
+ * `ntaps` (odd, <= 1023) fp32 taps; axis 0 = vertical (H), 1 = horizontal (W). */
 int otf_sepconv_reflect_f32(const float* img, int planes, int H, int W,
                             const float* taps_host, int ntaps, int axis,
                             float* out, void* stream);

@@ -105,12 +105,12 @@ def test_diffjpeg_tables_and_separable_dct():
     y, c = O.jpeg_tables()
     assert y[0, :4].tolist() == [16, 12, 14, 14] and torch.equal(c, c.T) and c[4, 4] == 99
     # the 4-D tensordot DCT of the reference equals the orthonormal separable DCT-II the kernel uses
-    blk = torch.rand(5, 8, 8) * 255 - 128
+    blk = torch.rand(5, 8, 8, generator=torch.Generator().manual_seed(0)) * 255 - 128
     ref = O._DCT_SCALE * torch.tensordot(blk, O._DCT_T, dims=2)
     n = torch.arange(8).float()
     cm = 0.5 * torch.cos((2 * n[None, :] + 1) * n[:, None] * torch.pi / 16)
     cm[0] *= 2 ** -0.5
-    assert (cm @ blk @ cm.T - ref).abs().max() < 2e-4
+    assert (cm @ blk @ cm.T - ref).abs().max() < 5e-4  # coefficients reach ~1e3: a few fp32 ulp
     assert O.quality_to_factor(30) == pytest.approx(5000 / 30 / 100) and O.quality_to_factor(80) == pytest.approx(0.4)
 
 

@@ -23,11 +23,22 @@ struct AxisSpec {
     int max_taps;
 };
 
-__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f; }
-__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A; }
+// Keys cubic pieces, evaluated op by op in fp32 exactly as ATen's cubic_convolution1/2 (no FMA
+// contraction: the CPU reference rounds after every operation, and at coordinates ~300 a fused
+// evaluation moves weights by 1e-5).
+__device__ __forceinline__ float cubic1(float x, float A) {
+    // ((A + 2) * x - (A + 3)) * x * x + 1
+    const float t = __fsub_rn(__fmul_rn(A + 2.0f, x), A + 3.0f);
+    return __fadd_rn(__fmul_rn(__fmul_rn(t, x), x), 1.0f);
+}
+__device__ __forceinline__ float cubic2(float x, float A) {
+    // ((A * x - 5 * A) * x + 8 * A) * x - 4 * A
+    const float t = __fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x), 5.0f * A), x), 8.0f * A);
+    return __fsub_rn(__fmul_rn(t, x), 4.0f * A);
+}
 __device__ __forceinline__ float aa_filter(int mode, float x) {
     x = fabsf(x);
-    if (mode == OTF_RESIZE_BILINEAR_AA) return x < 1.0f ? 1.0f - x : 0.0f;
+    if (mode == OTF_RESIZE_BILINEAR_AA) return x < 1.0f ? __fsub_rn(1.0f, x) : 0.0f;
     if (x < 1.0f) return cubic1(x, -0.5f);
     if (x < 2.0f) return cubic2(x, -0.5f);
     return 0.0f;
@@ -38,16 +49,19 @@ __device__ __forceinline__ float aa_filter(int mode, float x) {
 __device__ void axis_weights(int mode, const AxisSpec& ax, int o, int* lo_out, int* n_out, float* w) {
     int lo = 0, n = 0;
     if (mode == OTF_RESIZE_BILINEAR_AA || mode == OTF_RESIZE_BICUBIC_AA) {
-        const float center = ax.scale * ((float)o + 0.5f);
-        const float invscale = ax.scale >= 1.0f ? 1.0f / ax.scale : 1.0f;
-        lo = max((int)(center - ax.support + 0.5f), 0);
-        n = min((int)(center + ax.support + 0.5f), ax.in_n) - lo;
+        // ATen `_compute_indices_min_size_weights_aa` with scalar_t = float. The C++ mixes in double
+        // through its 0.5 / 1.0 literals; the promotions are reproduced literally.
+        const float center = (float)((double)ax.scale * ((double)o + 0.5));
+        const float invscale = ax.scale >= 1.0f ? (float)(1.0 / (double)ax.scale) : 1.0f;
+        lo = max((int)((double)__fsub_rn(center, ax.support) + 0.5), 0);
+        n = min((int)((double)__fadd_rn(center, ax.support) + 0.5), ax.in_n) - lo;
         n = clampi(n, 0, ax.max_taps);
         float total = 0.0f;
         for (int j = 0; j < n; ++j) {
-            const float v = aa_filter(mode, ((float)(j + lo) - center + 0.5f) * invscale);
+            const float arg = (float)(((double)__fsub_rn((float)(j + lo), center) + 0.5) * (double)invscale);
+            const float v = aa_filter(mode, arg);
             w[j] = v;
-            total += v;
+            total = __fadd_rn(total, v);
         }
         if (total != 0.0f)
             for (int j = 0; j < n; ++j) w[j] = __fdiv_rn(w[j], total);
@@ -59,21 +73,25 @@ __device__ void axis_weights(int mode, const AxisSpec& ax, int o, int* lo_out, i
         const float inv = __fdiv_rn(1.0f, (float)n);
         for (int j = 0; j < n; ++j) w[j] = inv;
     } else if (mode == OTF_RESIZE_NEAREST_EXACT) {
-        lo = min((int)floorf(((float)o + 0.5f) * ax.scale), ax.in_n - 1);
+        lo = min((int)floorf(__fmul_rn((float)o + 0.5f, ax.scale)), ax.in_n - 1);
         n = 1;
         w[0] = 1.0f;
     } else {  // OTF_RESIZE_BICUBIC: src = scale*(o+0.5)-0.5, 4 taps, A=-0.75, indices clamped
-        const float src = ax.scale * ((float)o + 0.5f) - 0.5f;
+        const float src = __fsub_rn(__fmul_rn(ax.scale, (float)o + 0.5f), 0.5f);
         const float fl = floorf(src);
-        const float t = src - fl;
+        const float t = __fsub_rn(src, fl);
         const int i0 = (int)fl - 1;
         const float A = -0.75f;
-        const float c[4] = {cubic2(t + 1.0f, A), cubic1(t, A), cubic1(1.0f - t, A), cubic2(2.0f - t, A)};
+        const float c[4] = {cubic2(__fadd_rn(t, 1.0f), A), cubic1(t, A), cubic1(__fsub_rn(1.0f, t), A),
+                            cubic2(__fadd_rn(__fsub_rn(1.0f, t), 1.0f), A)};
         lo = clampi(i0, 0, ax.in_n - 1);
         const int hi = clampi(i0 + 3, 0, ax.in_n - 1);
         n = hi - lo + 1;
         for (int j = 0; j < n; ++j) w[j] = 0.0f;
-        for (int k = 0; k < 4; ++k) w[clampi(i0 + k, 0, ax.in_n - 1) - lo] += c[k];
+        for (int k = 0; k < 4; ++k) {
+            float* wk = &w[clampi(i0 + k, 0, ax.in_n - 1) - lo];
+            *wk = __fadd_rn(*wk, c[k]);
+        }
     }
     for (int j = n; j < ax.max_taps; ++j) w[j] = 0.0f;
     *lo_out = lo;

@@ -9,7 +9,7 @@
 
 namespace otf {
 
-constexpr int kMaxTaps = 127;
+constexpr int kMaxTaps = 1023;  // 4 KB of the kernel parameter bank
 struct Taps {
     float w[kMaxTaps + 1];
     int n;
@@ -102,6 +102,10 @@ static int fill_taps(Taps& t, const float* taps_host, int ntaps) {
 static int launch_h(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st) {
     const dim3 grid(ceil_div(W, H_TW), ceil_div(H, H_ROWS), planes);
     const size_t smem = (size_t)H_ROWS * (H_TW + 2 * (t.n / 2)) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sepconv_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "sepconv_h smem attribute");
+    }
     sepconv_h_kernel<<<grid, 256, smem, st>>>(img, out, H, W, t);
     OTF_LAUNCH_CHECK("sepconv_h_kernel");
     return OTF_OK;
@@ -112,6 +116,10 @@ static int launch_v(const float* tmp, int planes, int H, int W, const Taps& t, f
                     float weight, float threshold, cudaStream_t st) {
     const dim3 grid(ceil_div(W, V_TW), ceil_div(H, V_TH), planes);
     const size_t smem = (size_t)(V_TH + 2 * (t.n / 2)) * V_TW * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sepconv_v_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "sepconv_v smem attribute");
+    }
     sepconv_v_kernel<EPI><<<grid, 256, smem, st>>>(tmp, out, H, W, t, img, aux, weight, threshold);
     OTF_LAUNCH_CHECK("sepconv_v_kernel");
     return OTF_OK;

@@ -90,8 +90,8 @@ class USMSharp(nn.Module):
                 f"Padding size should be less than the corresponding input dimension, but got: padding ({n // 2}, {n // 2}) "
                 f"at dimension 3 of input {list(img.shape)}"
             )
-        if n > 127:
-            raise _lib.OtfError("USMSharp: radius above 127 is not supported by the sm_100a kernel")
+        if n > 1023:
+            raise _lib.OtfError("USMSharp: radius above 1023 is not supported by the sm_100a kernel")
         lib = _lib.load()
         ws_bytes = lib.otf_usm_workspace_bytes(b * c, h, w)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=x.device)
