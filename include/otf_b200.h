@@ -63,9 +63,10 @@ int otf_device_cc(void);
 /* ---- a1: filter2d — traiNNer/utils/img_process_util.py:8-32 -------------------
  * out[b,c,y,x] = sum_{i,j<K} reflect_pad(img)[b,c,y+i,x+j] * kernel[kb,i,j],
  * kb = b (kernel_batch == B) or 0 (kernel_batch == 1).  K odd, K//2 < min(H,W).
- * `support_dev` (int32[kernel_batch], written by the call; may be NULL) receives
- * the true half-width of each kernel (largest |offset| with a non-zero tap); the
- * kernel only iterates over that support. K <= 21 runs the register-blocked
+ * `support_dev` (int32[2*kernel_batch] scratch written by the call; may be NULL) receives
+ * the true half-width of each kernel (largest |offset| with a non-zero tap) in
+ * [0,kb) and the launch order of the samples (largest support first) in [kb,2kb);
+ * the kernel only iterates over the true support. K <= 21 runs the register-blocked
  * path; larger odd K runs the generic path.  `img` and `out` must not alias. */
 int otf_filter2d_f32(const float* img, int B, int C, int H, int W,
                      const float* kernel, int kernel_batch, int K,

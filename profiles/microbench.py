@@ -1,0 +1,116 @@
+"""Per-stage CUDA-event timings at the bench shapes (B=64): BASELINE.json configs[3] microbench.
+    python profiles/microbench.py [--reps 20] [--json out.json]
+Each row: kernel time (median of reps, L2 flushed between reps), algorithmic bytes,
+achieved GB/s and fraction of the measured HBM peak; filter2d rows also report TFLOP/s at the true
+(zero-trimmed) tap count against the FP32 FMA roof."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import trainner_redux_b200 as T  # noqa: E402
+from oracle import otf_oracle as O  # noqa: E402  (synthetic inputs only)
+from trainner_redux_b200 import degradations as D  # noqa: E402
+from trainner_redux_b200.realesrgan_feed import clamp_round  # noqa: E402
+from trainner_redux_b200.transforms import crop_pair  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--json", default=None)
+ap.add_argument("--only", default=None)
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+peak = 6464.0
+pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    peak = float(json.load(open(pk))["hbm_gbs"])
+FMA_PEAK = 148 * 128 * 2 * 1.965e9 / 1e12
+B = 64
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(args.reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def img(h, w, seed=1):
+    return O.synth_gt(B, h, w, "uniform", seed=seed).to(dev)
+
+
+rows = []
+
+
+def add(name, fn, nbytes, flops=None):
+    if args.only and args.only not in name:
+        return
+    ms = timeit(fn)
+    gbs = nbytes / ms / 1e6
+    r = {"kernel": name, "ms": round(ms, 4), "alg_MB": round(nbytes / 1e6, 2), "GBps": round(gbs, 1), "frac_hbm": round(gbs / peak, 3)}
+    if flops:
+        r["TFLOPs"] = round(flops / ms / 1e9, 2)
+        r["frac_fma"] = round(flops / ms / 1e9 / FMA_PEAK, 3)
+    rows.append(r)
+    print(r, flush=True)
+
+
+x256, x192, x64 = img(256, 256), img(192, 192, 2), img(64, 64, 3)
+N = lambda t: t.numel() * 4
+sigma = (torch.rand(B) * 29 + 1).to(dev)
+gray = (torch.rand(B) < 0.4).float().to(dev)
+nogray = torch.zeros(B, device=dev)
+q = (torch.rand(B) * 65 + 30).to(dev)
+jp = T.DiffJPEG(differentiable=False)
+
+
+def taps(k):
+    return float((k != 0).flatten(1).sum(1).float().mean())
+
+
+for kinds in (("iso", "aniso", "sinc"), ("iso",), ("aniso",), ("sinc",)):
+    k = O.synth_blur_kernels(B, seed=10, kinds=kinds).to(dev)
+    add(f"filter2d 256^2 mixed-size {'/'.join(kinds)}", lambda: T.filter2d(x256, k), 2 * N(x256), 2 * taps(k) * x256.numel())
+for ks in (7, 9, 13, 17, 21):
+    k = torch.rand(B, ks, ks, device=dev)
+    k = k / k.sum((1, 2), keepdim=True)
+    add(f"filter2d 256^2 dense K={ks}", lambda: T.filter2d(x256, k), 2 * N(x256), 2 * ks * ks * x256.numel())
+k2 = O.synth_blur_kernels(B, seed=20).to(dev)
+add("filter2d 192^2 mixed", lambda: T.filter2d(x192, k2), 2 * N(x192), 2 * taps(k2) * x192.numel())
+sk = O.synth_sinc_or_pulse(B, seed=30).to(dev)
+add("filter2d 64^2 final sinc", lambda: T.filter2d(x64, sk), 2 * N(x64), 2 * taps(sk) * x64.numel())
+for mode in ("bilinear", "bicubic", "area", "nearest-exact", "lanczos"):
+    for s in (0.4, 0.75, 1.25, 1.5):
+        oh = round(256 * s)
+        add(f"resize {mode} 256->{oh}", lambda: T.resize_pt(x256, mode, scale_factor=s), N(x256) + B * 3 * oh * oh * 4)
+add("resize bilinear 192->64", lambda: T.resize_pt(x192, "bilinear", size=(64, 64)), N(x192) + N(x64))
+add("resize area 64->64", lambda: T.resize_pt(x64, "area", size=(64, 64)), 2 * N(x64))
+add("gaussian colour 192^2", lambda: D.add_gaussian_noise_pt(x192, sigma, nogray), 2 * N(x192))
+add("gaussian 40% gray 192^2", lambda: D.add_gaussian_noise_pt(x192, sigma, gray), 2 * N(x192))
+add("gaussian 40% gray 64^2", lambda: D.add_gaussian_noise_pt(x64, sigma, gray), 2 * N(x64))
+add("poisson colour 192^2", lambda: D.add_poisson_noise_pt(x192, sigma / 10, True, False, nogray), 3 * N(x192))
+add("poisson 40% gray 192^2", lambda: D.add_poisson_noise_pt(x192, sigma / 10, True, False, gray), 3 * N(x192))
+for qq in (30, 50, 75, 95):
+    add(f"diffjpeg q={qq} 192^2", lambda: jp(x192, quality=float(qq)), 2 * N(x192))
+add("diffjpeg per-sample q 192^2 (+factor kernel)", lambda: jp(x192, quality=q.clone(), _clamp_in=True), 2 * N(x192))
+add("diffjpeg per-sample q 64^2 +round8", lambda: jp(x64, quality=q.clone(), _clamp_in=True, _round8=True), 2 * N(x64))
+usm = T.USMSharp().to(dev)
+add("usm 256^2 (4 launches)", lambda: usm(x256), 2 * N(x256))
+add("clamp_round 64^2", lambda: clamp_round(x64), 2 * N(x64))
+add("crop_pair 256/64 -> 224/56", lambda: crop_pair(x256, x64, 224, 4, 4, 4), 2 * B * 3 * (224 * 224 + 56 * 56) * 4)
+if args.json:
+    json.dump({"hbm_peak_gbs": peak, "fma_peak_tflops": FMA_PEAK, "rows": rows}, open(args.json, "w"), indent=1)

@@ -1,0 +1,50 @@
+"""Launch each kernel of the path a few times on the bench shapes (B=64) — the command ncu wraps.
+    python profiles/prof_kernels.py [stage ...]     stages: blur1 resize1 noise1 jpeg1 blur2 sinc poisson usm all
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import trainner_redux_b200 as T  # noqa: E402
+from oracle import otf_oracle as O  # noqa: E402  (synthetic inputs only)
+from trainner_redux_b200 import degradations as D  # noqa: E402
+
+stages = sys.argv[1:] or ["all"]
+want = lambda s: "all" in stages or s in stages
+dev = torch.device("cuda:0")
+B = 64
+gt = O.synth_gt(B, 256, 256, "uniform", seed=1).to(dev)
+k1 = O.synth_blur_kernels(B, seed=10).to(dev)
+k2 = O.synth_blur_kernels(B, seed=20).to(dev)
+sk = O.synth_sinc_or_pulse(B, seed=30).to(dev)
+x192 = O.synth_gt(B, 192, 192, "uniform", seed=2).to(dev)
+x64 = O.synth_gt(B, 64, 64, "uniform", seed=3).to(dev)
+sigma = (torch.rand(B) * 29 + 1).to(dev)
+gray = (torch.rand(B) < 0.4).float().to(dev)
+q = (torch.rand(B) * 65 + 30).to(dev)
+jp = T.DiffJPEG(differentiable=False)
+for it in range(3):
+    if want("blur1"):
+        T.filter2d(gt, k1)
+    if want("resize1"):
+        T.resize_pt(gt, "bicubic", scale_factor=0.75)
+        T.resize_pt(x192, "bilinear", size=(64, 64))
+        T.resize_pt(x64, "area", size=(64, 64))
+    if want("noise1"):
+        D.add_gaussian_noise_pt(x192, sigma, gray)
+    if want("jpeg1"):
+        jp(x192, quality=q.clone(), _clamp_in=True)
+        jp(x64, quality=q.clone(), _clamp_in=True, _round8=True)
+    if want("blur2"):
+        T.filter2d(x192, k2)
+    if want("sinc"):
+        T.filter2d(x64, sk)
+    if want("poisson"):
+        D.add_poisson_noise_pt(x192, sigma / 10, True, False, gray)
+    if want("usm"):
+        T.USMSharp().to(dev)(gt)
+torch.cuda.synchronize()
+print("ok")

@@ -12,37 +12,64 @@
 //     kernels of true size 7..21 are the norm: realesrgan_dataset.py:171-172), found
 //     on the device so the host never synchronises.
 // Summation order per output: kernel rows ascending, taps left to right, one FFMA each.
+#include <stdlib.h>
+#include <string.h>
+
 #include "otf_common.cuh"
 
 namespace otf {
 
-// ---- true support of each kernel -----------------------------------------------------
-__global__ void kernel_support_kernel(const float* __restrict__ kern, int K, int32_t* __restrict__ support) {
-    const int kb = blockIdx.x, c = K / 2;
-    int r = 0;
-    for (int idx = threadIdx.x; idx < K * K; idx += blockDim.x) {
-        if (kern[(size_t)kb * K * K + idx] != 0.0f) {
-            const int i = idx / K, j = idx - i * K;
-            r = max(r, max(abs(i - c), abs(j - c)));
+// ---- true support of each kernel + processing order -----------------------------------
+// One CTA.  support[kb] = largest |offset| with a non-zero tap.  order[0..kb) = sample indices
+// sorted by support, largest first: CTAs are launched in that order, so (a) the CTAs resident on
+// an SM at any time run the same specialisation (instruction-cache locality) and (b) the expensive
+// tiles go first and the cheap ones fill the tail (LPT scheduling).
+__global__ void __launch_bounds__(1024) kernel_support_kernel(const float* __restrict__ kern, int K, int kernel_batch,
+                                                              int32_t* __restrict__ support, int32_t* __restrict__ order) {
+    extern __shared__ int s_sup[];
+    const int c = K / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int kb = warp; kb < kernel_batch; kb += 32) {
+        int r = 0;
+        for (int idx = lane; idx < K * K; idx += 32) {
+            if (kern[(size_t)kb * K * K + idx] != 0.0f) {
+                const int i = idx / K, j = idx - i * K;
+                r = max(r, max(abs(i - c), abs(j - c)));
+            }
         }
+        r = __reduce_max_sync(0xffffffffu, r);
+        if (lane == 0) { s_sup[kb] = r; support[kb] = r; }
     }
-    r = __reduce_max_sync(0xffffffffu, r);
-    __shared__ int smax;
-    if (threadIdx.x == 0) smax = 0;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) atomicMax(&smax, r);
-    __syncthreads();
-    if (threadIdx.x == 0) support[kb] = smax;
+    for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
+        const int mine = s_sup[t];
+        int rank = 0;
+        for (int u = 0; u < kernel_batch; ++u) rank += (s_sup[u] > mine) || (s_sup[u] == mine && u < t);
+        order[rank] = t;
+    }
 }
 
-constexpr int kMaxRT = 10;  // register-blocked path covers radius <= 10 (K <= 21)
-constexpr int kWPitch = 24; // taps row pitch in smem (float4 broadcast loads)
+constexpr int kMaxRT = 10;   // register-blocked path covers radius <= 10 (K <= 21)
+constexpr int kMaxRA = 12;   // halo rounded up to a float4 boundary
+constexpr int kWPitch = 24;  // taps row pitch in smem (float4 broadcast loads)
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Accumulate a TY x TX register block.  The tile's column 0 sits RA = roundup4(R) pixels left of the
+// block's first output column, so every row window starts on a 16-byte boundary (LDS.128) and tap j
+// of output ox reads row[(RA - R) + ox + j].
 template <int TX, int TY, int KT>
 __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_thread, int pitch,
                                                 const float* __restrict__ wsm, float (&acc)[TY][TX]) {
-    constexpr int NROW = TX + KT - 1;  // multiple of 4 for TX in {4,8}, KT in {5,9,13,17,21}
-    static_assert(NROW % 4 == 0, "row window must be float4 sized");
+    constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
+    constexpr int NROW = TX + 2 * RA;
 #pragma unroll 1
     for (int r = 0; r < TY + KT - 1; ++r) {
         float row[NROW];
@@ -66,7 +93,7 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_t
                         const int j = 4 * q + t;
                         if (j < KT) {
 #pragma unroll
-                            for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(w[t], row[ox + j], acc[oy][ox]);
+                            for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(w[t], row[OFF + ox + j], acc[oy][ox]);
                         }
                     }
                 }
@@ -77,46 +104,60 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_t
 
 template <int TX, int TY, int BX, int BY>
 __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restrict__ img, const float* __restrict__ kern,
-                                                          const int32_t* __restrict__ support, float* __restrict__ out,
-                                                          int C, int H, int W, int K, int kernel_batch, int vec_ok) {
+                                                          const int32_t* __restrict__ support, const int32_t* __restrict__ order,
+                                                          float* __restrict__ out, int C, int H, int W, int K,
+                                                          int kernel_batch, int vec_ok) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY, NT = BX * BY;
-    constexpr int P = TILE_W + 2 * kMaxRT;  // smem row pitch (multiple of 4)
-    static_assert(P % 4 == 0, "pitch");
+    constexpr int P = TILE_W + 2 * kMaxRA;  // smem row pitch (multiple of 4)
+    static_assert(P % 4 == 0 && (TILE_W + 2 * kMaxRA) / 4 <= 32, "a warp fills one tile row with one float4 per lane");
     extern __shared__ __align__(16) float smem[];
-    float* tile = smem;                                  // (TILE_H + 2*RT) x P
-    float* wsm = smem + (TILE_H + 2 * kMaxRT) * P;       // 21 x kWPitch
+    float* tile = smem;                             // (TILE_H + 2*R) rows x P
+    float* wsm = smem + (TILE_H + 2 * kMaxRT) * P;  // 21 x kWPitch
 
-    const int plane = blockIdx.z;
-    const int b = plane / C;
+    const int zb = blockIdx.z / C, zc = blockIdx.z - zb * C;
+    const int b = order ? order[zb] : zb;
+    const int plane = b * C + zc;
     const int kb = kernel_batch == 1 ? 0 : b;
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.x;
-    const int rs = support ? min(support[kb], K / 2) : K / 2;  // true radius (block-uniform)
-    // radius variant: 0 (pulse), 2, 4, 6, 8, 10
-    const int RT = rs == 0 ? 0 : ((rs + 1) & ~1);
-    const int KT = 2 * RT + 1;
+    const int R = support ? min(support[kb], K / 2) : K / 2;  // true radius (block-uniform)
+    const int KT = 2 * R + 1, RA = (R + 3) & ~3;
     const int c = K / 2;
 
-    // taps -> smem, cropped/padded to the KT x KT centre
+    // halo tile -> smem with cp.async (no register staging, every copy in flight at once): one warp
+    // per row, one float4 per lane; 16-byte copies where the four pixels are inside the plane and
+    // aligned, else four 4-byte copies with the reflect index resolved here.
+    const float* ip = img + (size_t)plane * H * W;
+    const int th = TILE_H + 2 * R, nq = (TILE_W + 2 * RA) / 4;
+    const int lane = tid & 31;
+    if (lane < nq) {
+        const int gx0 = x0 - RA + 4 * lane;
+        const bool fast = vec_ok && gx0 >= 0 && gx0 + 3 < W;
+        int gxs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gxs[k] = clampi(reflect_idx(gx0 + k, W), 0, W - 1);
+        for (int yy = tid >> 5; yy < th; yy += NT / 32) {
+            const int gy = clampi(reflect_idx(y0 - R + yy, H), 0, H - 1);
+            const float* rowp = ip + (size_t)gy * W;
+            float* dst = tile + yy * P + 4 * lane;
+            if (fast) {
+                cp_async16(dst, rowp + gx0);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cp_async4(dst + k, rowp + gxs[k]);
+            }
+        }
+    }
+    // taps -> smem, cropped/padded to the KT x KT centre (overlaps with the copies in flight)
     const float* kp = kern + (size_t)kb * K * K;
     for (int idx = tid; idx < 21 * kWPitch; idx += NT) {
         const int i = idx / kWPitch, j = idx - i * kWPitch;
-        const int si = c - RT + i, sj = c - RT + j;
+        const int si = c - R + i, sj = c - R + j;
         float v = 0.0f;
         if (i < KT && j < KT && si >= 0 && si < K && sj >= 0 && sj < K) v = kp[si * K + sj];
         wsm[idx] = v;
     }
-    // halo tile -> smem, reflect resolved here (one warp per row, lanes along x)
-    const float* ip = img + (size_t)plane * H * W;
-    const int th = TILE_H + 2 * RT, tw = TILE_W + 2 * RT;
-    for (int yy = tid >> 5; yy < th; yy += NT / 32) {
-        const int gy = clampi(reflect_idx(y0 - RT + yy, H), 0, H - 1);
-        const float* rowp = ip + (size_t)gy * W;
-        for (int xx = tid & 31; xx < tw; xx += 32) {
-            const int gx = clampi(reflect_idx(x0 - RT + xx, W), 0, W - 1);
-            tile[yy * P + xx] = __ldg(rowp + gx);
-        }
-    }
+    cp_async_wait_all();
     __syncthreads();
 
     const int tx = tid % BX, ty = tid / BX;
@@ -127,7 +168,7 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
         for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = 0.0f;
 
     const float* tt = tile + (ty * TY) * P + tx * TX;
-    switch (RT) {
+    switch (R) {
         case 0: {
             const float w = wsm[0];
 #pragma unroll
@@ -135,10 +176,15 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
 #pragma unroll
                 for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = w * tt[oy * P + ox];
         } break;
+        case 1: accumulate_rows<TX, TY, 3>(tt, P, wsm, acc); break;
         case 2: accumulate_rows<TX, TY, 5>(tt, P, wsm, acc); break;
+        case 3: accumulate_rows<TX, TY, 7>(tt, P, wsm, acc); break;
         case 4: accumulate_rows<TX, TY, 9>(tt, P, wsm, acc); break;
+        case 5: accumulate_rows<TX, TY, 11>(tt, P, wsm, acc); break;
         case 6: accumulate_rows<TX, TY, 13>(tt, P, wsm, acc); break;
+        case 7: accumulate_rows<TX, TY, 15>(tt, P, wsm, acc); break;
         case 8: accumulate_rows<TX, TY, 17>(tt, P, wsm, acc); break;
+        case 9: accumulate_rows<TX, TY, 19>(tt, P, wsm, acc); break;
         default: accumulate_rows<TX, TY, 21>(tt, P, wsm, acc); break;
     }
 
@@ -188,9 +234,9 @@ __global__ void filter2d_generic_kernel(const float* __restrict__ img, const flo
 
 template <int TX, int TY, int BX, int BY>
 static int launch_blocked(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch, int K,
-                          const int32_t* support, float* out, cudaStream_t st) {
+                          const int32_t* support, const int32_t* order, float* out, cudaStream_t st) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY;
-    constexpr int P = TILE_W + 2 * kMaxRT;
+    constexpr int P = TILE_W + 2 * kMaxRA;
     const size_t smem = ((size_t)(TILE_H + 2 * kMaxRT) * P + 21 * kWPitch) * sizeof(float);
     auto kfn = filter2d_kernel<TX, TY, BX, BY>;
     if (smem > 48 * 1024) {
@@ -198,8 +244,8 @@ static int launch_blocked(const float* img, int B, int C, int H, int W, const fl
         if (e != cudaSuccess) return cuda_fail(e, "filter2d smem attribute");
     }
     const dim3 grid(ceil_div(W, TILE_W), ceil_div(H, TILE_H), B * C);
-    const int vec_ok = (W % 4 == 0) && (((uintptr_t)out & 15) == 0);
-    kfn<<<grid, BX * BY, smem, st>>>(img, kernel, support, out, C, H, W, K, kernel_batch, vec_ok);
+    const int vec_ok = (W % 4 == 0) && (((uintptr_t)out & 15) == 0) && (((uintptr_t)img & 15) == 0);
+    kfn<<<grid, BX * BY, smem, st>>>(img, kernel, support, order, out, C, H, W, K, kernel_batch, vec_ok);
     OTF_LAUNCH_CHECK("filter2d_kernel");
     return OTF_OK;
 }
@@ -223,12 +269,16 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
         OTF_LAUNCH_CHECK("filter2d_generic_kernel");
         return OTF_OK;
     }
+    const int32_t* order = nullptr;
     if (support_dev) {
-        kernel_support_kernel<<<kernel_batch, 128, 0, st>>>(kernel, K, support_dev);
+        // scratch layout: [0,kb) true radius per kernel, [kb,2kb) sample order (largest radius first)
+        OTF_REQUIRE(kernel_batch <= 8192, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch > 8192");
+        kernel_support_kernel<<<1, 1024, kernel_batch * sizeof(int), st>>>(kernel, K, kernel_batch, support_dev, support_dev + kernel_batch);
         OTF_LAUNCH_CHECK("kernel_support_kernel");
+        if (kernel_batch == B && B > 1) order = support_dev + kernel_batch;
     }
-    // big planes: 64x64 tiles, 8x8 outputs per thread (64 threads); small planes: 32x32 tiles, 4x4 per thread
+    // big planes: 64x64 tiles, 8x4 outputs per thread (128 threads); small planes: 32x32 tiles, 4x4 per thread
     const int64_t big_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 64) * B * C;
-    if (big_tiles >= 2 * kNumSMs) return launch_blocked<8, 8, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, out, st);
-    return launch_blocked<4, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, out, st);
+    if (big_tiles >= 2 * kNumSMs) return launch_blocked<8, 4, 8, 16>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, order, out, st);
+    return launch_blocked<4, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, order, out, st);
 }

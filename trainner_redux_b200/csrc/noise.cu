@@ -8,62 +8,76 @@
 namespace otf {
 
 // ------------------------------------------------------------------ Gaussian ----
-// One thread = 4 consecutive elements of the flat (B,C,H,W) tensor.
+// grid = (chunks, B): a CTA works inside one sample, so sigma/gray are block-uniform and all index
+// math is 32-bit.  One thread = 4 consecutive elements of the sample's flat (C,H,W) block.
+// Philox use per quad: one call for the colour field; one more for the batch-shared gray field,
+// and only for samples whose gray flag is set (flag 0 -> noise*1 + ng*0 == noise exactly, flag 1 ->
+// noise*0 + ng*1 == ng exactly, so the unused field is never generated).
+template <bool VEC>
 __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __restrict__ img, float* __restrict__ out,
-                                                             int64_t n, int chw, int hw,
+                                                             int chw, int hw,
                                                              const float* __restrict__ sigma, const float* __restrict__ gray,
                                                              const float* __restrict__ ncol, const float* __restrict__ ngray,
                                                              uint64_t seed, uint64_t offset, int flags) {
     const Philox ph(seed);
-    const int64_t nq = (n + 3) >> 2;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e0 = q << 2;
-        float v[4], nc[4];
-        const bool full = e0 + 3 < n;
-        if (full) {
-            const float4 t = *reinterpret_cast<const float4*>(img + e0);
+    const int b = blockIdx.y;
+    const float sg = sigma[b];
+    const float g = gray ? gray[b] : 0.0f;
+    const bool use_gray = gray != nullptr;
+    const float one_minus_g = __fsub_rn(1.0f, g);
+    const int nq = (chw + 3) >> 2;
+    const size_t base = (size_t)b * chw;
+    const float* ip = img + base;
+    float* op = out + base;
+    const bool inject = ncol != nullptr;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int e0 = q << 2;
+        const int cnt = min(4, chw - e0);
+        float v[4] = {0.f, 0.f, 0.f, 0.f}, nc[4] = {0.f, 0.f, 0.f, 0.f}, ng[4] = {0.f, 0.f, 0.f, 0.f};
+        if (VEC) {  // chw % 4 == 0 and 16-byte aligned base: whole quads only
+            const float4 t = *reinterpret_cast<const float4*>(ip + e0);
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         } else {
-            for (int k = 0; k < 4; ++k) v[k] = e0 + k < n ? img[e0 + k] : 0.0f;
+            for (int k = 0; k < cnt; ++k) v[k] = ip[e0 + k];
         }
-        if (ncol) {
-            for (int k = 0; k < 4; ++k) nc[k] = e0 + k < n ? ncol[e0 + k] : 0.0f;
-        } else {
-            const float4 t = normal4(ph, (uint64_t)q, offset * 8 + STREAM_COLOR);
+        if (inject) {
+            for (int k = 0; k < cnt; ++k) nc[k] = ncol[base + e0 + k];
+        } else if (!(use_gray && g == 1.0f)) {
+            const float4 t = normal4(ph, (uint64_t)b * nq + q, offset * 8 + STREAM_COLOR);
             nc[0] = t.x; nc[1] = t.y; nc[2] = t.z; nc[3] = t.w;
+        }
+        if (use_gray && (inject || g != 0.0f)) {
+            const int p0 = e0 % hw;  // pixel index of the first element inside its channel plane
+            if (ngray) {
+                for (int k = 0; k < cnt; ++k) { int p = p0 + k; if (p >= hw) p -= hw; ng[k] = ngray[p]; }
+            } else if ((p0 & 3) == 0 && p0 + 3 < hw) {
+                // ONE (h,w) field shared by the whole batch and all channels (degradations.py:593-596)
+                const float4 t = normal4(ph, (uint64_t)(p0 >> 2), offset * 8 + STREAM_GRAY);
+                ng[0] = t.x; ng[1] = t.y; ng[2] = t.z; ng[3] = t.w;
+            } else {
+                for (int k = 0; k < cnt; ++k) {
+                    int p = p0 + k; if (p >= hw) p -= hw;
+                    const float4 t = normal4(ph, (uint64_t)(p >> 2), offset * 8 + STREAM_GRAY);
+                    const float tt[4] = {t.x, t.y, t.z, t.w};
+                    ng[k] = tt[p & 3];
+                }
+            }
         }
         float r[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int64_t e = e0 + k;
-            if (e >= n) { r[k] = 0.0f; continue; }
-            const int b = (int)(e / chw);
-            const int p = (int)(e % hw);
-            const float sg = sigma[b];
-            // degradations.py:598: noise = randn * sigma / 255
+            // degradations.py:598: noise = randn * sigma / 255 ; :603: noise*(1-gray) + noise_gray*gray
             float noise = __fdiv_rn(__fmul_rn(nc[k], sg), 255.0f);
-            if (gray) {
-                const float g = gray[b];
-                float ng;
-                if (ngray) {
-                    ng = ngray[p];
-                } else {
-                    // ONE (h,w) field shared by the whole batch (degradations.py:593-596)
-                    const float4 t = normal4(ph, (uint64_t)(p >> 2), offset * 8 + STREAM_GRAY);
-                    const float tt[4] = {t.x, t.y, t.z, t.w};
-                    ng = tt[p & 3];
-                }
-                ng = __fdiv_rn(__fmul_rn(ng, sg), 255.0f);
-                // :603: noise*(1-gray) + noise_gray*gray
-                noise = __fadd_rn(__fmul_rn(noise, __fsub_rn(1.0f, g)), __fmul_rn(ng, g));
+            if (use_gray) {
+                const float ngv = __fdiv_rn(__fmul_rn(ng[k], sg), 255.0f);
+                noise = __fadd_rn(__fmul_rn(noise, one_minus_g), __fmul_rn(ngv, g));
             }
             r[k] = (flags & OTF_NOISE_FIELD_ONLY) ? noise : noise_tail(__fadd_rn(v[k], noise), flags);
         }
-        if (full) {
-            *reinterpret_cast<float4*>(out + e0) = make_float4(r[0], r[1], r[2], r[3]);
+        if (VEC) {
+            *reinterpret_cast<float4*>(op + e0) = make_float4(r[0], r[1], r[2], r[3]);
         } else {
-            for (int k = 0; k < 4; ++k)
-                if (e0 + k < n) out[e0 + k] = r[k];
+            for (int k = 0; k < cnt; ++k) op[e0 + k] = r[k];
         }
     }
 }
@@ -290,13 +304,23 @@ extern "C" int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int
     OTF_REQUIRE(img && out && sigma_dev, OTF_ERR_BAD_ARG, "gaussian_noise: null pointer");
     OTF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "gaussian_noise: bad extents");
     OTF_REQUIRE(!(noise_gray_dev && !noise_color_dev), OTF_ERR_BAD_ARG, "gaussian_noise: inject both fields or neither");
-    const int64_t n = (int64_t)B * C * H * W;
-    OTF_REQUIRE((int64_t)C * H * W < (1ll << 31), OTF_ERR_UNSUPPORTED, "gaussian_noise: sample too large");
+    OTF_REQUIRE((int64_t)C * H * W < (1ll << 30), OTF_ERR_UNSUPPORTED, "gaussian_noise: sample too large");
+    OTF_REQUIRE(B <= 65535, OTF_ERR_UNSUPPORTED, "gaussian_noise: B > 65535");
     const float* ng = gray_dev ? noise_gray_dev : nullptr;
     OTF_REQUIRE(!(gray_dev && noise_color_dev && !noise_gray_dev), OTF_ERR_BAD_ARG,
                 "gaussian_noise: gray flags with an injected colour field need the injected gray field too");
-    gaussian_noise_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-        img, out, n, C * H * W, H * W, sigma_dev, gray_dev, noise_color_dev, ng, seed, offset, flags);
+    const int chw = C * H * W;
+    const bool vec = (chw % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
+    int chunks = ceil_div((chw + 3) / 4, 256);
+    const int cap = ceil_div(kNumSMs * 16, B);
+    if (chunks > cap) chunks = cap;
+    const dim3 grid(chunks, B);
+    if (vec)
+        gaussian_noise_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(img, out, chw, H * W, sigma_dev, gray_dev,
+                                                                            noise_color_dev, ng, seed, offset, flags);
+    else
+        gaussian_noise_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(img, out, chw, H * W, sigma_dev, gray_dev,
+                                                                             noise_color_dev, ng, seed, offset, flags);
     OTF_LAUNCH_CHECK("gaussian_noise_kernel");
     return OTF_OK;
 }

@@ -77,7 +77,9 @@ __device__ void axis_weights(int mode, const AxisSpec& ax, int o, int* lo_out, i
         n = 1;
         w[0] = 1.0f;
     } else {  // OTF_RESIZE_BICUBIC: src = scale*(o+0.5)-0.5, 4 taps, A=-0.75, indices clamped
-        const float src = __fsub_rn(__fmul_rn(ax.scale, (float)o + 0.5f), 0.5f);
+        // ATen's CPU build contracts `scale * (o + 0.5) - 0.5` into one fused multiply-add (checked against
+        // the installed torch at 288->431: the unfused form is 1.4e-5 off, the fused one matches)
+        const float src = fmaf(ax.scale, (float)o + 0.5f, -0.5f);
         const float fl = floorf(src);
         const float t = __fsub_rn(src, fl);
         const int i0 = (int)fl - 1;

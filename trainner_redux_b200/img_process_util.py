@@ -59,7 +59,7 @@ def filter2d(img: Tensor, kernel: Tensor) -> Tensor:
             f"at dimension 3 of input {list(img.shape)}"
         )
     out = torch.empty_like(x)
-    support = torch.empty(kb, dtype=torch.int32, device=x.device)
+    support = torch.empty(2 * kb, dtype=torch.int32, device=x.device)  # true radii + launch order
     _lib.call("otf_filter2d_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(kern), kb, k, _lib.ptr(support), _lib.ptr(out), _lib.stream())
     return out
 

@@ -248,6 +248,19 @@ class RealESRGANFeed:
         self.gt: Tensor | None = None
         self.lq: Tensor | None = None
         self.last_plan: dict | None = None
+        # optional per-stage CUDA-event timing (bench.py): name -> [(start, stop), ...]
+        self.time_stages = False
+        self.stage_times: dict[str, list] = {}
+
+    def _timed(self, name: str, fn: Callable[[], Tensor]) -> Tensor:
+        if not self.time_stages:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.stage_times.setdefault(name, []).append((e0, e1))
+        return out
 
     # -- stages ---------------------------------------------------------------------------
     def _noise(self, out: Tensor, st: dict, inject: dict | None, key: str) -> Tensor:
@@ -289,34 +302,34 @@ class RealESRGANFeed:
             r = plan["usm"]["radius"]
             if r not in self._usm:
                 self._usm[r] = USMSharp(radius=r)
-            out = self._usm[r](out, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10))
+            out = self._timed("usm", lambda: self._usm[r](out, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10)))
         if plan.get("blur1"):
-            out = filter2d(out, kernel1)
+            out = self._timed("blur1", lambda: filter2d(out, kernel1))
         if plan.get("resize1"):
-            out = D.resize_pt(out, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"])
+            out = self._timed("resize1", lambda: D.resize_pt(out, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"]))
         if plan.get("noise1"):
-            out = self._noise(out, plan["noise1"], inject, "noise1")
+            out = self._timed("noise1", lambda: self._noise(out, plan["noise1"], inject, "noise1"))
         if plan.get("jpeg1") is not None:
-            out = self._jpeg(out, plan["jpeg1"], round8=False)
+            out = self._timed("jpeg1", lambda: self._jpeg(out, plan["jpeg1"], round8=False))
         if plan.get("blur2"):
-            out = filter2d(out, kernel2)
+            out = self._timed("blur2", lambda: filter2d(out, kernel2))
         if plan.get("resize2"):
             s2 = plan["resize2"]["scale"]
-            out = D.resize_pt(out, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"])
+            out = self._timed("resize2", lambda: D.resize_pt(out, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"]))
         if plan.get("noise2"):
-            out = self._noise(out, plan["noise2"], inject, "noise2")
+            out = self._timed("noise2", lambda: self._noise(out, plan["noise2"], inject, "noise2"))
         jpeg2 = plan.get("jpeg2")
         if plan.get("final_order", "resize_first") == "resize_first":
-            out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
-            out = filter2d(out, sinc_kernel)
-            if jpeg2 is not None:
-                return self._jpeg(out, jpeg2, round8=True)  # clamp/round fused into the last kernel
-            return clamp_round(out)
+            out = self._timed("resize3", lambda: D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
+            out = self._timed("sinc", lambda: filter2d(out, sinc_kernel))
+            if jpeg2 is not None:  # clamp/round fused into the last kernel
+                return self._timed("jpeg2+round", lambda: self._jpeg(out, jpeg2, round8=True))
+            return self._timed("round", lambda: clamp_round(out))
         if jpeg2 is not None:
-            out = self._jpeg(out, jpeg2, round8=False)
-        out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
-        out = filter2d(out, sinc_kernel)
-        return clamp_round(out)
+            out = self._timed("jpeg2", lambda: self._jpeg(out, jpeg2, round8=False))
+        out = self._timed("resize3", lambda: D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
+        out = self._timed("sinc", lambda: filter2d(out, sinc_kernel))
+        return self._timed("round", lambda: clamp_round(out))
 
     # -- the reference entry point --------------------------------------------------------
     @torch.no_grad()
