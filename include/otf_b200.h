@@ -63,14 +63,17 @@ int otf_device_cc(void);
 /* ---- a1: filter2d — traiNNer/utils/img_process_util.py:8-32 -------------------
  * out[b,c,y,x] = sum_{i,j<K} reflect_pad(img)[b,c,y+i,x+j] * kernel[kb,i,j],
  * kb = b (kernel_batch == B) or 0 (kernel_batch == 1).  K odd, K//2 < min(H,W).
- * `support_dev` (int32[2*kernel_batch] scratch written by the call; may be NULL) receives
- * the true half-width of each kernel (largest |offset| with a non-zero tap) in
- * [0,kb) and the launch order of the samples (largest support first) in [kb,2kb);
- * the kernel only iterates over the true support. K <= 21 runs the register-blocked
- * path; larger odd K runs the generic path.  `img` and `out` must not alias. */
+ * `scratch_dev` (otf_filter2d_scratch_words(kernel_batch) 4-byte words, written by
+ * the call; may be NULL = analyse nothing, run every kernel at full K) receives the
+ * per-kernel analysis the main kernel consumes without any host round trip: true
+ * half-width (largest |offset| with a non-zero tap), launch order of the samples
+ * (largest support first), a rank-1 flag and the two rank-1 factors. K <= 21 runs
+ * the register-blocked path specialised on the true support (rank-1 kernels as
+ * K + K taps); larger odd K runs the generic path.  `img` and `out` must not alias. */
+int64_t otf_filter2d_scratch_words(int kernel_batch);
 int otf_filter2d_f32(const float* img, int B, int C, int H, int W,
                      const float* kernel, int kernel_batch, int K,
-                     int32_t* support_dev, float* out, void* stream);
+                     int32_t* scratch_dev, float* out, void* stream);
 
 /* ---- 1-D correlation with reflect padding along one axis ----------------------
  * Building block of USMSharp (exactly separable 51x51 Gaussian) and of the
@@ -91,9 +94,13 @@ int otf_usm_sharp_f32(const float* img, int planes, int H, int W,
 
 /* ---- a3: resize_pt — traiNNer/data/degradations.py:1004-1021 ------------------
  * Separable resampling with ATen's index/weight rules (SURVEY.md §8a "R"),
- * followed by clamp(0,1) when `clamp01` != 0 (resize_pt always clamps). */
+ * followed by clamp(0,1) when `clamp01` != 0 (resize_pt always clamps).  Two
+ * launches: the per-axis (first index, count, weights) tables into workspace_dev
+ * (otf_resize_workspace_bytes bytes, a few KB), then the tiled resampler. */
+int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode);
 int otf_resize_f32(const float* img, int planes, int H, int W,
-                   float* out, int OH, int OW, int mode, int clamp01, void* stream);
+                   float* out, int OH, int OW, int mode, int clamp01,
+                   void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* ---- a4: Gaussian noise — degradations.py:569-633 -----------------------------
  * out = tail(img + mix(N*sigma[b]/255, G*sigma[b]/255, gray[b])).

@@ -29,11 +29,13 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_abi_version": (_i, []),
     "otf_last_error": (C.c_char_p, []),
     "otf_device_cc": (_i, []),
+    "otf_filter2d_scratch_words": (_i64, [_i]),
     "otf_filter2d_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "otf_sepconv_reflect_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p]),
     "otf_usm_workspace_bytes": (_i64, [_i, _i, _i]),
     "otf_usm_sharp_f32": (_i, [_p, _i, _i, _i, _p, _i, _f, _f, _p, _i64, _p, _p]),
-    "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
+    "otf_resize_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i64, _p]),
     "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p]),
     "otf_philox_normal_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_philox_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
@@ -54,10 +56,10 @@ launch_count = 0  # kernels enqueued through this binding (bench.py reports it)
 
 # launches behind each entry point (see the .cu files)
 _LAUNCHES = {
-    "otf_filter2d_f32": 2,  # support scan + blocked kernel
+    "otf_filter2d_f32": 3,  # kernel analysis + launch order + blocked kernel
     "otf_sepconv_reflect_f32": 1,
     "otf_usm_sharp_f32": 4,
-    "otf_resize_f32": 1,
+    "otf_resize_f32": 2,  # weight tables + resampler
     "otf_gaussian_noise_f32": 1,
     "otf_philox_normal_f32": 1,
     "otf_philox_uniform_f32": 1,

@@ -19,32 +19,81 @@
 
 namespace otf {
 
-// ---- true support of each kernel + processing order -----------------------------------
-// One CTA.  support[kb] = largest |offset| with a non-zero tap.  order[0..kb) = sample indices
-// sorted by support, largest first: CTAs are launched in that order, so (a) the CTAs resident on
-// an SM at any time run the same specialisation (instruction-cache locality) and (b) the expensive
-// tiles go first and the cheap ones fill the tail (LPT scheduling).
-__global__ void __launch_bounds__(1024) kernel_support_kernel(const float* __restrict__ kern, int K, int kernel_batch,
-                                                              int32_t* __restrict__ support, int32_t* __restrict__ order) {
-    extern __shared__ int s_sup[];
-    const int c = K / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int kb = warp; kb < kernel_batch; kb += 32) {
-        int r = 0;
-        for (int idx = lane; idx < K * K; idx += 32) {
-            if (kern[(size_t)kb * K * K + idx] != 0.0f) {
-                const int i = idx / K, j = idx - i * K;
-                r = max(r, max(abs(i - c), abs(j - c)));
-            }
+// ---- per-kernel analysis: true support, rank-1 factors, processing order --------------
+// One CTA, one warp per kernel.
+//   support[kb]  largest |offset| with a non-zero tap (kernels arrive zero-padded to 21x21);
+//   rank1[kb]    1 when the kernel is an outer product u v^T to within fp32 rounding of its own
+//                taps (isotropic Gaussians — 45 % of the reference's default kernel_prob — and the
+//                USM kernel are), with the factors in uv[kb][0][*] (rows) and uv[kb][1][*] (columns),
+//                stored centred in 21 slots; the blur is then evaluated as K + K taps instead of K*K.
+//                Acceptance: |K_ij - u_i v_j| <= 4e-7 |K_ij| + 1e-9 max|K|, i.e. the separable result
+//                differs from the full sum by <= ~4e-7 * sum|K_ij| * max|img| — far inside the 1e-5 bar;
+//   order[0..kb) sample indices sorted by support, largest first: CTAs are launched in that order,
+//                so the CTAs resident on an SM at any time run the same specialisation (instruction-
+//                cache locality) and the expensive tiles go first (LPT scheduling).
+constexpr int kUVPitch = 24;
+__host__ __device__ inline size_t scratch_words(int kb) { return (size_t)kb * (3 + 2 * kUVPitch); }
+
+__global__ void __launch_bounds__(128) kernel_support_kernel(const float* __restrict__ kern, int K, int kernel_batch,
+                                                             int32_t* __restrict__ scratch) {
+    int32_t* support = scratch;
+    int32_t* rank1 = scratch + 2 * kernel_batch;
+    float* uv = reinterpret_cast<float*>(scratch + 3 * kernel_batch);
+    const int c = K / 2, lane = threadIdx.x & 31;
+    const int kb = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (kb >= kernel_batch) return;
+    const float* kp = kern + (size_t)kb * K * K;
+    int r = 0;
+    float amax = 0.0f;
+    int imax = 0;
+    for (int idx = lane; idx < K * K; idx += 32) {
+        const float v = kp[idx];
+        if (v != 0.0f) {
+            const int i = idx / K, j = idx - i * K;
+            r = max(r, max(abs(i - c), abs(j - c)));
         }
-        r = __reduce_max_sync(0xffffffffu, r);
-        if (lane == 0) { s_sup[kb] = r; support[kb] = r; }
+        if (fabsf(v) > amax) { amax = fabsf(v); imax = idx; }
     }
+    r = __reduce_max_sync(0xffffffffu, r);
+    // pivot = the largest |tap| (ties -> lowest index)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
+        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
+    }
+    const int pi = imax / K, pj = imax - pi * K;
+    const float piv = kp[imax];
+    bool ok = amax > 0.0f && K <= 21;
+    if (ok) {
+        for (int idx = lane; idx < K * K; idx += 32) {
+            const int i = idx / K, j = idx - i * K;
+            const float kij = kp[idx];
+            const float sep = kp[i * K + pj] * __fdiv_rn(kp[pi * K + j], piv);
+            ok = ok && (fabsf(kij - sep) <= 4e-7f * fabsf(kij) + 1e-9f * amax);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane < kUVPitch) {
+        // centred in 21 slots: slot s <-> offset s - 10
+        const int t = lane - 10 + c;  // tap index for this slot
+        const bool in = lane < 21 && t >= 0 && t < K;
+        uv[((size_t)kb * 2 + 0) * kUVPitch + lane] = (ok && in) ? kp[t * K + pj] : 0.0f;
+        uv[((size_t)kb * 2 + 1) * kUVPitch + lane] = (ok && in) ? __fdiv_rn(kp[pi * K + t], piv) : 0.0f;
+    }
+    if (lane == 0) { support[kb] = r; rank1[kb] = ok ? 1 : 0; }
+}
+
+// order[0..kb): sample indices sorted by support, largest first (stable).  One small CTA.
+__global__ void __launch_bounds__(1024) kernel_order_kernel(int kernel_batch, int32_t* __restrict__ scratch) {
+    extern __shared__ int s_sup[];
+    for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) s_sup[t] = scratch[t];
     __syncthreads();
     for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
         const int mine = s_sup[t];
         int rank = 0;
         for (int u = 0; u < kernel_batch; ++u) rank += (s_sup[u] > mine) || (s_sup[u] == mine && u < t);
-        order[rank] = t;
+        scratch[kernel_batch + rank] = t;
     }
 }
 
@@ -102,9 +151,50 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_t
     }
 }
 
+// Rank-1 kernels: out = u (x) v correlated with the tile, evaluated per thread as a horizontal
+// K-tap pass over each row of its window (kept in registers) followed by the vertical accumulation.
+// u and v sit centred in 21 slots (tap t of a KT-tap kernel is slot 10 - R + t).
+template <int TX, int TY, int KT>
+__device__ __forceinline__ void accumulate_rank1(const float* __restrict__ tile_thread, int pitch,
+                                                 const float* __restrict__ u, const float* __restrict__ v,
+                                                 float (&acc)[TY][TX]) {
+    constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
+    constexpr int NROW = TX + 2 * RA;
+    float vr[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) vr[j] = v[10 - R + j];
+#pragma unroll 1
+    for (int r = 0; r < TY + KT - 1; ++r) {
+        float row[NROW];
+        const float4* rp = reinterpret_cast<const float4*>(tile_thread + r * pitch);
+#pragma unroll
+        for (int q = 0; q < NROW / 4; ++q) {
+            const float4 t4 = rp[q];
+            row[4 * q + 0] = t4.x; row[4 * q + 1] = t4.y; row[4 * q + 2] = t4.z; row[4 * q + 3] = t4.w;
+        }
+        float h[TX];
+#pragma unroll
+        for (int ox = 0; ox < TX; ++ox) {
+            float a = vr[0] * row[OFF + ox];
+#pragma unroll
+            for (int j = 1; j < KT; ++j) a = fmaf(vr[j], row[OFF + ox + j], a);
+            h[ox] = a;
+        }
+#pragma unroll
+        for (int oy = 0; oy < TY; ++oy) {
+            const int i = r - oy;
+            if (i >= 0 && i < KT) {
+                const float ui = u[10 - R + i];
+#pragma unroll
+                for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(ui, h[ox], acc[oy][ox]);
+            }
+        }
+    }
+}
+
 template <int TX, int TY, int BX, int BY>
 __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restrict__ img, const float* __restrict__ kern,
-                                                          const int32_t* __restrict__ support, const int32_t* __restrict__ order,
+                                                          const int32_t* __restrict__ scratch, int use_order,
                                                           float* __restrict__ out, int C, int H, int W, int K,
                                                           int kernel_batch, int vec_ok) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY, NT = BX * BY;
@@ -115,9 +205,12 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
     float* wsm = smem + (TILE_H + 2 * kMaxRT) * P;  // 21 x kWPitch
 
     const int zb = blockIdx.z / C, zc = blockIdx.z - zb * C;
-    const int b = order ? order[zb] : zb;
+    const int b = (scratch && use_order) ? scratch[kernel_batch + zb] : zb;
     const int plane = b * C + zc;
     const int kb = kernel_batch == 1 ? 0 : b;
+    const int32_t* support = scratch;
+    const int R_ = scratch ? min(scratch[kb], K / 2) : K / 2;
+    const bool rank1 = scratch && R_ >= 2 && scratch[2 * kernel_batch + kb] != 0;
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.x;
     const int R = support ? min(support[kb], K / 2) : K / 2;  // true radius (block-uniform)
@@ -148,8 +241,12 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
             }
         }
     }
-    // taps -> smem, cropped/padded to the KT x KT centre (overlaps with the copies in flight)
+    // taps -> smem (overlaps with the copies in flight): the two rank-1 factors, or the KT x KT centre
     const float* kp = kern + (size_t)kb * K * K;
+    if (rank1) {
+        const float* uv = reinterpret_cast<const float*>(scratch + 3 * kernel_batch) + (size_t)kb * 2 * kUVPitch;
+        for (int idx = tid; idx < 2 * kUVPitch; idx += NT) wsm[idx] = uv[idx];
+    } else
     for (int idx = tid; idx < 21 * kWPitch; idx += NT) {
         const int i = idx / kWPitch, j = idx - i * kWPitch;
         const int si = c - R + i, sj = c - R + j;
@@ -168,6 +265,20 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
         for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = 0.0f;
 
     const float* tt = tile + (ty * TY) * P + tx * TX;
+    if (rank1) {
+        const float* u = wsm, *v = wsm + kUVPitch;
+        switch (R) {
+            case 2: accumulate_rank1<TX, TY, 5>(tt, P, u, v, acc); break;
+            case 3: accumulate_rank1<TX, TY, 7>(tt, P, u, v, acc); break;
+            case 4: accumulate_rank1<TX, TY, 9>(tt, P, u, v, acc); break;
+            case 5: accumulate_rank1<TX, TY, 11>(tt, P, u, v, acc); break;
+            case 6: accumulate_rank1<TX, TY, 13>(tt, P, u, v, acc); break;
+            case 7: accumulate_rank1<TX, TY, 15>(tt, P, u, v, acc); break;
+            case 8: accumulate_rank1<TX, TY, 17>(tt, P, u, v, acc); break;
+            case 9: accumulate_rank1<TX, TY, 19>(tt, P, u, v, acc); break;
+            default: accumulate_rank1<TX, TY, 21>(tt, P, u, v, acc); break;
+        }
+    } else
     switch (R) {
         case 0: {
             const float w = wsm[0];
@@ -234,7 +345,7 @@ __global__ void filter2d_generic_kernel(const float* __restrict__ img, const flo
 
 template <int TX, int TY, int BX, int BY>
 static int launch_blocked(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch, int K,
-                          const int32_t* support, const int32_t* order, float* out, cudaStream_t st) {
+                          const int32_t* scratch, int use_order, float* out, cudaStream_t st) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY;
     constexpr int P = TILE_W + 2 * kMaxRA;
     const size_t smem = ((size_t)(TILE_H + 2 * kMaxRT) * P + 21 * kWPitch) * sizeof(float);
@@ -245,12 +356,14 @@ static int launch_blocked(const float* img, int B, int C, int H, int W, const fl
     }
     const dim3 grid(ceil_div(W, TILE_W), ceil_div(H, TILE_H), B * C);
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)out & 15) == 0) && (((uintptr_t)img & 15) == 0);
-    kfn<<<grid, BX * BY, smem, st>>>(img, kernel, support, order, out, C, H, W, K, kernel_batch, vec_ok);
+    kfn<<<grid, BX * BY, smem, st>>>(img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok);
     OTF_LAUNCH_CHECK("filter2d_kernel");
     return OTF_OK;
 }
 
 }  // namespace otf
+
+extern "C" int64_t otf_filter2d_scratch_words(int kernel_batch) { return (int64_t)otf::scratch_words(kernel_batch); }
 
 extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch,
                                 int K, int32_t* support_dev, float* out, void* stream) {
@@ -269,16 +382,24 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
         OTF_LAUNCH_CHECK("filter2d_generic_kernel");
         return OTF_OK;
     }
-    const int32_t* order = nullptr;
+    int use_order = 0;
     if (support_dev) {
-        // scratch layout: [0,kb) true radius per kernel, [kb,2kb) sample order (largest radius first)
+        // scratch layout (4-byte words): [0,kb) true radius, [kb,2kb) sample order (largest radius first),
+        // [2kb,3kb) rank-1 flag, then float uv[kb][2][24] rank-1 factors  (otf_filter2d_scratch_words)
         OTF_REQUIRE(kernel_batch <= 8192, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch > 8192");
-        kernel_support_kernel<<<1, 1024, kernel_batch * sizeof(int), st>>>(kernel, K, kernel_batch, support_dev, support_dev + kernel_batch);
+        kernel_support_kernel<<<ceil_div(kernel_batch, 4), 128, 0, st>>>(kernel, K, kernel_batch, support_dev);
         OTF_LAUNCH_CHECK("kernel_support_kernel");
-        if (kernel_batch == B && B > 1) order = support_dev + kernel_batch;
+        use_order = (kernel_batch == B && B > 1);
+        if (use_order) {
+            kernel_order_kernel<<<1, 1024, kernel_batch * sizeof(int), st>>>(kernel_batch, support_dev);
+            OTF_LAUNCH_CHECK("kernel_order_kernel");
+        }
     }
-    // big planes: 64x64 tiles, 8x4 outputs per thread (128 threads); small planes: 32x32 tiles, 4x4 per thread
+    // big planes: 64x64 tiles, 8x4 outputs per thread (128 threads); tiny planes: 32x32 tiles, 4x4 per thread
     const int64_t big_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 64) * B * C;
-    if (big_tiles >= 2 * kNumSMs) return launch_blocked<8, 4, 8, 16>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, order, out, st);
-    return launch_blocked<4, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, order, out, st);
+    if (big_tiles >= 2 * kNumSMs) return launch_blocked<8, 4, 8, 16>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    // small planes: 64x32 tiles (64 threads) keep the 8x4 register block and halve the tile
+    const int64_t mid_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 32) * B * C;
+    if (mid_tiles >= 2 * kNumSMs && W >= 48) return launch_blocked<8, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    return launch_blocked<4, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
 }

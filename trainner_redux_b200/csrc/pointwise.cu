@@ -32,22 +32,65 @@ __global__ void __launch_bounds__(256) clamp_round_kernel(const float* __restric
 }
 
 // ---- a8: traiNNer/data/transforms.py:124-135 followed by .contiguous() --------------------
-// One launch copies both windows. blockIdx.z = plane; rows of the GT window first, then LQ rows.
+// One launch copies both windows.  A thread moves one quad (4 consecutive output pixels) per
+// iteration and keeps UNR of them in flight; 16-byte loads when the window start is aligned.
+template <bool VEC>
+__device__ __forceinline__ void copy_window(const float* __restrict__ src, int Hs, int Ws, int top, int left, int n,
+                                            float* __restrict__ dst, int planes, int64_t q0, int64_t qstride) {
+    const int qrow = n >> 2;                          // quads per output row (n % 4 == 0 on this path)
+    const int64_t nq = (int64_t)planes * n * qrow;
+    constexpr int UNR = 4;
+    for (int64_t qb = q0; qb < nq; qb += qstride * UNR) {
+        float4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t q = qb + u * qstride;
+            if (q < nq) {
+                const int xq = (int)(q % qrow);
+                const int64_t t = q / qrow;
+                const int y = (int)(t % n);
+                const int64_t pl = t / n;
+                const float* sp = src + ((size_t)pl * Hs + (top + y)) * Ws + left + 4 * xq;
+                if (VEC) v[u] = __ldg(reinterpret_cast<const float4*>(sp));
+                else v[u] = make_float4(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2), __ldg(sp + 3));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t q = qb + u * qstride;
+            if (q < nq) reinterpret_cast<float4*>(dst)[q] = v[u];
+        }
+    }
+}
+
+template <bool VEC_GT, bool VEC_LQ>
 __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict__ gt, int Hg, int Wg,
                                                         const float* __restrict__ lq, int Hl, int Wl, int top, int left,
-                                                        int p, int scale, float* __restrict__ gt_out, float* __restrict__ lq_out) {
-    const int plane = blockIdx.z;
+                                                        int p, int scale, int planes, float* __restrict__ gt_out,
+                                                        float* __restrict__ lq_out) {
+    const int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, qs = (int64_t)gridDim.x * blockDim.x;
+    copy_window<VEC_GT>(gt, Hg, Wg, top * scale, left * scale, p * scale, gt_out, planes, q0, qs);
+    copy_window<VEC_LQ>(lq, Hl, Wl, top, left, p, lq_out, planes, q0, qs);
+}
+
+// any patch size (p % 4 != 0): one element per thread
+__global__ void __launch_bounds__(256) crop_pair_scalar_kernel(const float* __restrict__ gt, int Hg, int Wg,
+                                                               const float* __restrict__ lq, int Hl, int Wl, int top,
+                                                               int left, int p, int scale, int planes,
+                                                               float* __restrict__ gt_out, float* __restrict__ lq_out) {
     const int G = p * scale;
-    const int row = blockIdx.y;  // 0..G-1 -> GT rows, G..G+p-1 -> LQ rows
-    if (row < G) {
-        const float* src = gt + ((size_t)plane * Hg + (size_t)(top * scale + row)) * Wg + left * scale;
-        float* dst = gt_out + ((size_t)plane * G + row) * G;
-        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < G; x += gridDim.x * blockDim.x) dst[x] = __ldg(src + x);
-    } else {
-        const int r = row - G;
-        const float* src = lq + ((size_t)plane * Hl + (size_t)(top + r)) * Wl + left;
-        float* dst = lq_out + ((size_t)plane * p + r) * p;
-        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < p; x += gridDim.x * blockDim.x) dst[x] = __ldg(src + x);
+    const int64_t ng = (int64_t)planes * G * G, nl = (int64_t)planes * p * p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ng + nl; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < ng) {
+            const int x = (int)(i % G), y = (int)((i / G) % G);
+            const int64_t pl = i / ((int64_t)G * G);
+            gt_out[i] = __ldg(gt + ((size_t)pl * Hg + top * scale + y) * Wg + left * scale + x);
+        } else {
+            const int64_t j = i - ng;
+            const int x = (int)(j % p), y = (int)((j / p) % p);
+            const int64_t pl = j / ((int64_t)p * p);
+            lq_out[j] = __ldg(lq + ((size_t)pl * Hl + top + y) * Wl + left + x);
+        }
     }
 }
 
@@ -136,9 +179,23 @@ extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, co
     OTF_REQUIRE(Hg == Hl * scale && Wg == Wl * scale, OTF_ERR_BAD_ARG, "crop_pair: GT (%d, %d) is not %dx LQ (%d, %d)", Hg, Wg, scale, Hl, Wl);
     OTF_REQUIRE(top >= 0 && left >= 0 && top + lq_patch <= Hl && left + lq_patch <= Wl, OTF_ERR_BAD_ARG, "crop_pair: window outside LQ");
     const int G = lq_patch * scale;
-    OTF_REQUIRE(G + lq_patch <= 65535, OTF_ERR_UNSUPPORTED, "crop_pair: patch too large");
-    const dim3 grid(ceil_div(G, 256), G + lq_patch, planes);
-    crop_pair_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, gt_out, lq_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t work = ((int64_t)planes * G * G + (int64_t)planes * lq_patch * lq_patch) / 4;
+    int blocks = (int)((work / 4 + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    const bool quads = (lq_patch % 4 == 0) && ((((uintptr_t)gt_out | (uintptr_t)lq_out) & 15) == 0);
+    if (!quads) {
+        crop_pair_scalar_kernel<<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
+        OTF_LAUNCH_CHECK("crop_pair_scalar_kernel");
+        return OTF_OK;
+    }
+    const bool vg = (Wg % 4 == 0) && ((left * scale) % 4 == 0) && (((uintptr_t)gt & 15) == 0);
+    const bool vl = (Wl % 4 == 0) && (left % 4 == 0) && (((uintptr_t)lq & 15) == 0);
+    if (vg && vl) crop_pair_kernel<true, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
+    else if (vg) crop_pair_kernel<true, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
+    else if (vl) crop_pair_kernel<false, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
+    else crop_pair_kernel<false, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
     OTF_LAUNCH_CHECK("crop_pair_kernel");
     return OTF_OK;
 }

@@ -5,16 +5,15 @@
 //
 // Every mode is expressed as, per output index o on an axis, a contiguous source window
 // [lo, lo+n) with n normalised fp32 weights (ATen: aten/src/ATen/native/cpu/UpSampleKernel.cpp
-// `_compute_indices_min_size_weights_aa`; restated in SURVEY.md §8a row a3 "R").  A CTA owns an
-// output tile; it builds the tile's column/row weight tables in shared memory, runs the
-// horizontal pass over just the source rows the tile needs (result kept in smem), then the
-// vertical pass — the same order ATen uses (W first, then H).  HBM-bound: source rows are read
-// once per tile (+ vertical halo), output written once.
+// `_compute_indices_min_size_weights_aa`; restated in SURVEY.md §8a row a3 "R").  A tiny first
+// launch writes the per-axis tables once; then a CTA owns an output tile: it stages its slice of
+// the tables and the source rectangle it needs in shared memory with cp.async, runs the horizontal
+// pass (result kept in smem), then the vertical pass — the same order ATen uses (W first, then H).
+// HBM-bound: the source is read once per tile (+ halo, served by L2), the output written once.
 #include "otf_common.cuh"
 
 namespace otf {
 
-constexpr int RT_W = 32;  // output tile width  (one lane per column)
 
 struct AxisSpec {
     int in_n, out_n;
@@ -100,64 +99,162 @@ __device__ void axis_weights(int mode, const AxisSpec& ax, int o, int* lo_out, i
     *n_out = n;
 }
 
-// smem layout: wx[RT_W][tx] | wy[tile_h][ty] | xlo[RT_W] xn[RT_W] ylo[tile_h] yn[tile_h] | tmp[rows_cap][RT_W]
-__global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ img, float* __restrict__ out, int mode,
-                                                     AxisSpec ay, AxisSpec ax, int tile_h, int rows_cap, int clamp_out) {
+// ---- pass 0: per-launch weight tables ------------------------------------------------------
+// table layout for an axis with out_n outputs and T = max_taps: int lo[out_n], int n[out_n],
+// float w[out_n][T].  One thread per output index; the tables are a few KB and stay in L2.
+__global__ void __launch_bounds__(128) resize_tables_kernel(int mode, AxisSpec ay, AxisSpec ax, int* __restrict__ ty_lo,
+                                                            int* __restrict__ tx_lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ay.out_n) {
+        float* w = reinterpret_cast<float*>(ty_lo + 2 * ay.out_n) + (size_t)i * ay.max_taps;
+        axis_weights(mode, ay, i, ty_lo + i, ty_lo + ay.out_n + i, w);
+    } else if (i - ay.out_n < ax.out_n) {
+        const int o = i - ay.out_n;
+        float* w = reinterpret_cast<float*>(tx_lo + 2 * ax.out_n) + (size_t)o * ax.max_taps;
+        axis_weights(mode, ax, o, tx_lo + o, tx_lo + ax.out_n + o, w);
+    }
+}
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_f32x4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// ---- pass 1: a CTA produces a (32*CW) x tile_h output tile ----------------------------------
+// (1) its slice of the tables and the source rectangle it needs go to shared memory (cp.async:
+// every byte in flight at once, no register staging); (2) horizontal pass smem -> smem: a thread owns
+// one output column, keeps that column's NT taps in registers and walks down the rows (1 LDS + 1 FFMA
+// per tap); (3) vertical pass smem -> global: a warp owns an output row, keeps the row's NT taps in
+// registers (broadcast) and each lane produces CW columns; clamp fused.  Taps beyond a window's true
+// length are zero and read zero-filled padding, so the unrolled loops need no predicates.
+// smem: wx[TW][NT] wy[tile_h][NT] xlo[TW] ylo[tile_h] | src[rows_cap][SP] | tmp[rows_cap + NT][TW]
+template <int NT, int CW>
+__global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                     AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
+                                                     const int* __restrict__ tx_lo, int tile_h, int rows_cap,
+                                                     int cols_cap, int clamp_out, int vec_ok) {
+    constexpr int TW = 32 * CW;
     extern __shared__ __align__(16) float sm[];
+    const int SP = (cols_cap + NT + 3) & ~3;  // src row pitch: >= NT zero columns behind every row, 16-byte rows
     float* wx = sm;
-    float* wy = wx + RT_W * ax.max_taps;
-    int* xlo = reinterpret_cast<int*>(wy + tile_h * ay.max_taps);
-    int* xn = xlo + RT_W;
-    int* ylo = xn + RT_W;
-    int* yn = ylo + tile_h;
-    float* tmp = reinterpret_cast<float*>(yn + tile_h);
+    float* wy = wx + TW * NT;
+    int* xlo = reinterpret_cast<int*>(wy + tile_h * NT);
+    int* ylo = xlo + TW;
+    float* src = reinterpret_cast<float*>(ylo + tile_h);
+    float* tmp = src + rows_cap * SP;
 
     const int plane = blockIdx.z;
-    const int ox0 = blockIdx.x * RT_W, oy0 = blockIdx.y * tile_h;
-    const int tid = threadIdx.x;
-    if (tid < RT_W) {
-        const int o = min(ox0 + tid, ax.out_n - 1);
-        axis_weights(mode, ax, o, &xlo[tid], &xn[tid], wx + tid * ax.max_taps);
-    } else if (tid - RT_W < tile_h) {
-        const int t = tid - RT_W;
-        const int o = min(oy0 + t, ay.out_n - 1);
-        axis_weights(mode, ay, o, &ylo[t], &yn[t], wy + t * ay.max_taps);
-    }
-    __syncthreads();
-    // source rows this tile needs
-    const int th = min(tile_h, ay.out_n - oy0);
-    int row_lo = ylo[0], row_hi = ylo[0] + yn[0];
-    for (int t = 1; t < th; ++t) {
-        row_lo = min(row_lo, ylo[t]);
-        row_hi = max(row_hi, ylo[t] + yn[t]);
-    }
-    const int nrows = min(row_hi - row_lo, rows_cap);
-    const float* ip = img + (size_t)plane * ay.in_n * ax.in_n;
-    const int lane = tid & 31, wid = tid >> 5;
-    // horizontal pass: tmp[r][lane] = sum_j wx[lane][j] * in[row_lo + r][xlo[lane] + j]
-    {
-        const int lo = xlo[lane], n = xn[lane];
-        const float* wl = wx + lane * ax.max_taps;
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * tile_h;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tw = min(TW, ax.out_n - ox0), th = min(tile_h, ay.out_n - oy0);
+    // windows are monotone in the output index: the rectangle is [first.lo, last.lo + last.n)
+    const int row_lo = ty_lo[oy0], row_hi = ty_lo[oy0 + th - 1] + ty_lo[ay.out_n + oy0 + th - 1];
+    int col_lo = tx_lo[ox0];
+    const int col_hi = tx_lo[ox0 + tw - 1] + tx_lo[ax.out_n + ox0 + tw - 1];
+    if (vec_ok) col_lo &= ~3;  // start the rectangle on a 16-byte boundary so whole quads move with one cp.async
+    const int nrows = min(row_hi - row_lo, rows_cap), ncols = min(col_hi - col_lo, cols_cap);
+    const float* ip = img + (size_t)plane * ay.in_n * ax.in_n + (size_t)row_lo * ax.in_n + col_lo;
+    if (vec_ok) {
+        const int nquad = (ncols + 3) >> 2;
         for (int r = wid; r < nrows; r += 8) {
-            const float* rp = ip + (size_t)(row_lo + r) * ax.in_n + lo;
+            float* srow = src + r * SP;
+            const float* grow = ip + (size_t)r * ax.in_n;
+            for (int qd = lane; qd < nquad; qd += 32) {
+                if (col_lo + 4 * qd + 3 < ax.in_n) {
+                    cp_async_f32x4(srow + 4 * qd, grow + 4 * qd);
+                } else {
+                    for (int k = 0; k < 4; ++k) {
+                        if (col_lo + 4 * qd + k < ax.in_n) cp_async_f32(srow + 4 * qd + k, grow + 4 * qd + k);
+                        else srow[4 * qd + k] = 0.0f;
+                    }
+                }
+            }
+            for (int cidx = 4 * nquad + lane; cidx < SP; cidx += 32) srow[cidx] = 0.0f;
+        }
+    } else {
+        for (int r = wid; r < nrows; r += 8) {
+            float* srow = src + r * SP;
+            for (int cidx = lane; cidx < ncols; cidx += 32) cp_async_f32(srow + cidx, ip + (size_t)r * ax.in_n + cidx);
+            for (int cidx = ncols + lane; cidx < SP; cidx += 32) srow[cidx] = 0.0f;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // table slices, zero-padded to NT taps (plain loads: tiny, L2 resident; overlap the copies)
+    const float* gwx = reinterpret_cast<const float*>(tx_lo + 2 * ax.out_n);
+    const float* gwy = reinterpret_cast<const float*>(ty_lo + 2 * ay.out_n);
+    for (int i = tid; i < TW * NT; i += 256) {
+        const int o = i / NT, j = i - o * NT;
+        wx[i] = (o < tw && j < ax.max_taps) ? gwx[(size_t)(ox0 + o) * ax.max_taps + j] : 0.0f;
+    }
+    for (int i = tid; i < tile_h * NT; i += 256) {
+        const int o = i / NT, j = i - o * NT;
+        wy[i] = (o < th && j < ay.max_taps) ? gwy[(size_t)(oy0 + o) * ay.max_taps + j] : 0.0f;
+    }
+    for (int i = tid; i < TW; i += 256) xlo[i] = tx_lo[ox0 + min(i, tw - 1)] - col_lo;
+    for (int i = tid; i < tile_h; i += 256) ylo[i] = ty_lo[oy0 + min(i, th - 1)] - row_lo;
+    for (int i = tid; i < NT * TW; i += 256) tmp[nrows * TW + i] = 0.0f;  // zero rows behind the last one
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // horizontal pass: thread = (column, row phase)
+    {
+        constexpr int PH = 256 / TW;  // row phases: 8, 4 or 2
+        const int col = tid % TW, ph = tid / TW;
+        float w[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) w[j] = wx[col * NT + j];
+        const float* sp = src + xlo[col];
+        for (int r = ph; r < nrows; r += PH) {
+            const float* rp = sp + r * SP;
             float acc = 0.0f;
-            for (int j = 0; j < n; ++j) acc = fmaf(wl[j], __ldg(rp + j), acc);
-            tmp[r * RT_W + lane] = acc;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc = fmaf(w[j], rp[j], acc);
+            tmp[r * TW + col] = acc;
         }
     }
     __syncthreads();
-    // vertical pass
-    const int x = ox0 + lane;
-    if (x >= ax.out_n) return;
+    // vertical pass: warp = output row, lane = CW columns
+    float* op = out + (size_t)plane * ay.out_n * ax.out_n;
     for (int t = wid; t < th; t += 8) {
-        const float* wl = wy + t * ay.max_taps;
-        const float* tp = tmp + (ylo[t] - row_lo) * RT_W + lane;
-        const int n = yn[t];
-        float acc = 0.0f;
-        for (int i = 0; i < n; ++i) acc = fmaf(wl[i], tp[i * RT_W], acc);
-        if (clamp_out) acc = clamp01(acc);
-        out[(size_t)plane * ay.out_n * ax.out_n + (size_t)(oy0 + t) * ax.out_n + x] = acc;
+        float w[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) w[i] = wy[t * NT + i];
+        const float* tp = tmp + ylo[t] * TW + lane;
+        float acc[CW];
+#pragma unroll
+        for (int k = 0; k < CW; ++k) acc[k] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int k = 0; k < CW; ++k) acc[k] = fmaf(w[i], tp[i * TW + 32 * k], acc[k]);
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+            const int x = ox0 + lane + 32 * k;
+            if (x < ax.out_n) op[(size_t)(oy0 + t) * ax.out_n + x] = clamp_out ? clamp01(acc[k]) : acc[k];
+        }
     }
+}
+
+// Fallback for extreme down-scales (> 64 taps per output on an axis): one thread per output pixel,
+// horizontal sums nested inside the vertical sum, everything straight from L1/L2.  Correct, not fast.
+__global__ void __launch_bounds__(256) resize_generic_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                             AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
+                                                             const int* __restrict__ tx_lo, int clamp_out) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= ax.out_n || y >= ay.out_n) return;
+    const float* wx = reinterpret_cast<const float*>(tx_lo + 2 * ax.out_n) + (size_t)x * ax.max_taps;
+    const float* wy = reinterpret_cast<const float*>(ty_lo + 2 * ay.out_n) + (size_t)y * ay.max_taps;
+    const int xl = tx_lo[x], xn = tx_lo[ax.out_n + x], yl = ty_lo[y], yn = ty_lo[ay.out_n + y];
+    const float* ip = img + (size_t)blockIdx.z * ay.in_n * ax.in_n;
+    float acc = 0.0f;
+    for (int i = 0; i < yn; ++i) {
+        const float* rp = ip + (size_t)(yl + i) * ax.in_n + xl;
+        float h = 0.0f;
+        for (int j = 0; j < xn; ++j) h = fmaf(wx[j], __ldg(rp + j), h);
+        acc = fmaf(wy[i], h, acc);
+    }
+    out[(size_t)blockIdx.z * ay.out_n * ax.out_n + (size_t)y * ax.out_n + x] = clamp_out ? clamp01(acc) : acc;
 }
 
 static AxisSpec make_axis(int mode, int in_n, int out_n) {
@@ -180,33 +277,92 @@ static AxisSpec make_axis(int mode, int in_n, int out_n) {
     return a;
 }
 
+static size_t table_ints(const AxisSpec& a) { return (size_t)a.out_n * (2 + a.max_taps); }
+
 }  // namespace otf
 
-extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
-                              int clamp_out, void* stream) {
+extern "C" int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode) {
     using namespace otf;
-    OTF_REQUIRE(img && out && img != out, OTF_ERR_BAD_ARG, "resize: bad pointers");
+    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || mode < OTF_RESIZE_BILINEAR_AA || mode > OTF_RESIZE_BICUBIC) return -1;
+    return (int64_t)(table_ints(make_axis(mode, H, OH)) + table_ints(make_axis(mode, W, OW))) * 4;
+}
+
+extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
+                              int clamp_out, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out && img != out && workspace_dev, OTF_ERR_BAD_ARG, "resize: bad pointers");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && OH > 0 && OW > 0, OTF_ERR_BAD_ARG, "resize: bad extents");
     OTF_REQUIRE(mode >= OTF_RESIZE_BILINEAR_AA && mode <= OTF_RESIZE_BICUBIC, OTF_ERR_BAD_ARG, "resize: unknown mode %d", mode);
+    OTF_REQUIRE(workspace_bytes >= otf_resize_workspace_bytes(H, W, OH, OW, mode), OTF_ERR_WORKSPACE, "resize: workspace too small");
     const AxisSpec ay = make_axis(mode, H, OH), ax = make_axis(mode, W, OW);
-    // pick the tallest tile (<= 32 rows) whose tables + row buffer fit in shared memory
-    const size_t cap = 200 * 1024;
-    int tile_h = 32, rows_cap = 0;
+    int* ty_lo = (int*)workspace_dev;
+    int* tx_lo = ty_lo + table_ints(ay);
+    cudaStream_t st = (cudaStream_t)stream;
+    resize_tables_kernel<<<ceil_div(OH + OW, 128), 128, 0, st>>>(mode, ay, ax, ty_lo, tx_lo);
+    OTF_LAUNCH_CHECK("resize_tables_kernel");
+    auto span = [](const AxisSpec& a, int nout) {  // source extent covered by nout consecutive outputs
+        int v = (int)ceilf(a.scale * (float)(nout - 1)) + a.max_taps + 2;
+        return v > a.in_n ? a.in_n : v;
+    };
+    const int mt = ay.max_taps > ax.max_taps ? ay.max_taps : ax.max_taps;
+    if (mt > 64) {
+        resize_generic_kernel<<<dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes), 256, 0, st>>>(img, out, ay, ax, ty_lo, tx_lo, clamp_out);
+        OTF_LAUNCH_CHECK("resize_generic_kernel");
+        return OTF_OK;
+    }
+    const int NT = mt <= 1 ? 1 : mt <= 2 ? 2 : mt <= 4 ? 4 : mt <= 6 ? 6 : mt <= 8 ? 8 : mt <= 12 ? 12 : mt <= 16 ? 16
+                   : mt <= 24 ? 24 : mt <= 32 ? 32 : 64;
+    // tile width 32*CW: as wide as the output allows — per-CTA prologue latency (tables, fill, two barriers)
+    // dominates small tiles, so a few padded columns cost less than more, smaller CTAs (measured: 2x at 256->320)
+    int CW = OW >= 96 ? 4 : OW >= 48 ? 2 : 1;
+    const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
+    // pick (CW, tile_h): prefer wide tiles, keep shared memory modest so several CTAs share an SM
+    const size_t cap = 200 * 1024, want = 56 * 1024;
+    int tile_h = 0, rows_cap = 0, cols_cap = 0;
     size_t smem = 0;
-    for (; tile_h >= 1; tile_h /= 2) {
-        // rows spanned by tile_h consecutive outputs: windows advance by `scale` per output
-        rows_cap = (int)ceilf(ay.scale * (float)(tile_h - 1)) + ay.max_taps + 2;
-        if (rows_cap > H) rows_cap = H;
-        smem = ((size_t)RT_W * ax.max_taps + (size_t)tile_h * ay.max_taps + 2 * RT_W + 2 * tile_h + (size_t)rows_cap * RT_W) * 4;
-        if (smem <= cap) break;
+    for (;; CW /= 2) {
+        const int TW = 32 * CW;
+        cols_cap = span(ax, TW) + (vec_ok ? 6 : 0);  // slack for the 16-byte aligned rectangle start/end
+        bool ok = false;
+        for (tile_h = 32; tile_h >= 4; tile_h /= 2) {
+            rows_cap = span(ay, tile_h);
+            smem = ((size_t)TW * NT + (size_t)tile_h * NT + TW + tile_h + (size_t)rows_cap * ((cols_cap + NT + 3) & ~3) +
+                    (size_t)(rows_cap + NT) * TW) * 4;
+            if (smem <= want || (tile_h == 4 && CW == 1 && smem <= cap)) { ok = true; break; }
+        }
+        if (ok || CW == 1) break;
     }
-    OTF_REQUIRE(tile_h >= 1, OTF_ERR_UNSUPPORTED, "resize: scale %f too extreme for shared memory", (double)ay.scale);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "resize smem attribute");
+    OTF_REQUIRE(smem <= cap, OTF_ERR_UNSUPPORTED, "resize: scale %f x %f too extreme for shared memory", (double)ay.scale,
+                (double)ax.scale);
+    if (tile_h < 4) tile_h = 4;
+    const dim3 grid(ceil_div(OW, 32 * CW), ceil_div(OH, tile_h), planes);
+#define OTF_RESIZE_LAUNCH(NT_, CW_)                                                                                       \
+    do {                                                                                                                  \
+        auto kfn = resize_kernel<NT_, CW_>;                                                                               \
+        if (smem > 48 * 1024) {                                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+            if (e != cudaSuccess) return cuda_fail(e, "resize smem attribute");                                           \
+        }                                                                                                                 \
+        kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, tile_h, rows_cap, cols_cap, clamp_out, vec_ok);            \
+    } while (0)
+#define OTF_RESIZE_CW(NT_)                                  \
+    do {                                                    \
+        if (CW == 4) OTF_RESIZE_LAUNCH(NT_, 4);             \
+        else if (CW == 2) OTF_RESIZE_LAUNCH(NT_, 2);        \
+        else OTF_RESIZE_LAUNCH(NT_, 1);                     \
+    } while (0)
+    switch (NT) {
+        case 1: OTF_RESIZE_CW(1); break;
+        case 2: OTF_RESIZE_CW(2); break;
+        case 4: OTF_RESIZE_CW(4); break;
+        case 6: OTF_RESIZE_CW(6); break;
+        case 8: OTF_RESIZE_CW(8); break;
+        case 12: OTF_RESIZE_CW(12); break;
+        case 16: OTF_RESIZE_CW(16); break;
+        case 24: OTF_RESIZE_CW(24); break;
+        case 32: OTF_RESIZE_CW(32); break;
+        default: OTF_RESIZE_CW(64); break;
     }
-    const dim3 grid(ceil_div(OW, RT_W), ceil_div(OH, tile_h), planes);
-    resize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(img, out, mode, ay, ax, tile_h, rows_cap, clamp_out);
     OTF_LAUNCH_CHECK("resize_kernel");
     return OTF_OK;
 }

@@ -227,7 +227,10 @@ def _lanczos_taps(ratio: float, a: int = 3) -> np.ndarray:
 def _resize_call(x: Tensor, oh: int, ow: int, mode_id: int, clamp: bool) -> Tensor:
     b, c, h, w = x.shape
     out = torch.empty((b, c, oh, ow), dtype=torch.float32, device=x.device)
-    _lib.call("otf_resize_f32", _lib.ptr(x), b * c, h, w, _lib.ptr(out), oh, ow, mode_id, int(clamp), _lib.stream())
+    ws_bytes = _lib.load().otf_resize_workspace_bytes(h, w, oh, ow, mode_id)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=x.device)
+    _lib.call("otf_resize_f32", _lib.ptr(x), b * c, h, w, _lib.ptr(out), oh, ow, mode_id, int(clamp), _lib.ptr(ws), ws_bytes,
+              _lib.stream())
     return out
 
 

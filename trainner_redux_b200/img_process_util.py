@@ -59,8 +59,11 @@ def filter2d(img: Tensor, kernel: Tensor) -> Tensor:
             f"at dimension 3 of input {list(img.shape)}"
         )
     out = torch.empty_like(x)
-    support = torch.empty(2 * kb, dtype=torch.int32, device=x.device)  # true radii + launch order
+    # per-kernel analysis scratch: true radii, launch order, rank-1 flags and factors
+    support = torch.empty(_lib.load().otf_filter2d_scratch_words(kb), dtype=torch.int32, device=x.device)
     _lib.call("otf_filter2d_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(kern), kb, k, _lib.ptr(support), _lib.ptr(out), _lib.stream())
+    if kb == 1 or b == 1 or k > 21:
+        _lib.launch_count -= 1 if k <= 21 else 2  # no launch-order kernel for a shared kernel; generic path is one launch
     return out
 
 
