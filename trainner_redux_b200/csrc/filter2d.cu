@@ -12,6 +12,7 @@
 //     kernels of true size 7..21 are the norm: realesrgan_dataset.py:171-172), found
 //     on the device so the host never synchronises.
 // Summation order per output: kernel rows ascending, taps left to right, one FFMA each.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -192,17 +193,51 @@ __device__ __forceinline__ void accumulate_rank1(const float* __restrict__ tile_
     }
 }
 
+// ---- TMA / mbarrier plumbing (sm_100a) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a descriptor mistake must fault the launch, not hang the GPU
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// 3-D tiled bulk tensor copy global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
 template <int TX, int TY, int BX, int BY>
-__global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restrict__ img, const float* __restrict__ kern,
+__global__ void __launch_bounds__(BX* BY) filter2d_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                          const float* __restrict__ img, const float* __restrict__ kern,
                                                           const int32_t* __restrict__ scratch, int use_order,
                                                           float* __restrict__ out, int C, int H, int W, int K,
-                                                          int kernel_batch, int vec_ok) {
+                                                          int kernel_batch, int vec_ok, int use_tma) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY, NT = BX * BY;
-    constexpr int P = TILE_W + 2 * kMaxRA;  // smem row pitch (multiple of 4)
-    static_assert(P % 4 == 0 && (TILE_W + 2 * kMaxRA) / 4 <= 32, "a warp fills one tile row with one float4 per lane");
-    extern __shared__ __align__(16) float smem[];
-    float* tile = smem;                             // (TILE_H + 2*R) rows x P
-    float* wsm = smem + (TILE_H + 2 * kMaxRT) * P;  // 21 x kWPitch
+    constexpr int P = TILE_W + 2 * kMaxRA;     // smem row pitch = TMA box width (multiple of 4)
+    constexpr int ROWS = TILE_H + 2 * kMaxRT;  // TMA box height
+    static_assert(P % 4 == 0 && P / 4 <= 32, "a warp fills one tile row with one float4 per lane");
+    extern __shared__ __align__(128) float smem[];
+    float* tile = smem;              // ROWS x P (rows [0, TILE_H + 2R) are used)
+    float* wsm = smem + ROWS * P;    // 21 x kWPitch
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + 21 * kWPitch);
 
     const int zb = blockIdx.z / C, zc = blockIdx.z - zb * C;
     const int b = (scratch && use_order) ? scratch[kernel_batch + zb] : zb;
@@ -217,13 +252,25 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
     const int KT = 2 * R + 1, RA = (R + 3) & ~3;
     const int c = K / 2;
 
-    // halo tile -> smem with cp.async (no register staging, every copy in flight at once): one warp
-    // per row, one float4 per lane; 16-byte copies where the four pixels are inside the plane and
-    // aligned, else four 4-byte copies with the reflect index resolved here.
+    // halo tile -> smem.
+    //  * aligned planes (W % 4 == 0): ONE elected thread issues a 3-D TMA box load (cp.async.bulk.tensor,
+    //    out-of-bounds zero filled) that completes on an mbarrier; border tiles then mirror the
+    //    out-of-plane columns/rows inside shared memory (torch "reflect": the source pixels are in the box);
+    //  * any other plane: per-thread cp.async (16 bytes where the four pixels are inside the plane and
+    //    aligned, else four 4-byte copies) with the reflect index resolved at issue.
+    // Either way nothing is staged through registers and every byte of the tile is in flight at once;
+    // the other CTAs resident on the SM (7 at 64x64) compute meanwhile.
     const float* ip = img + (size_t)plane * H * W;
     const int th = TILE_H + 2 * R, nq = (TILE_W + 2 * RA) / 4;
     const int lane = tid & 31;
-    if (lane < nq) {
+    if (use_tma) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, ROWS * P * 4);
+            tma_load_3d(tile, &tmap, x0 - RA, y0 - R, plane, bar);
+        }
+    } else if (lane < nq) {
         const int gx0 = x0 - RA + 4 * lane;
         const bool fast = vec_ok && gx0 >= 0 && gx0 + 3 < W;
         int gxs[4];
@@ -255,7 +302,37 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const float* __restric
         wsm[idx] = v;
     }
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();  // taps + cp.async pixels visible; mbarrier initialised
+    if (use_tma) {
+        mbar_wait(bar, 0);
+        // mirror what the box load zero-filled: columns first (rows inside the plane), then whole rows
+        const bool fix_x = (x0 - R < 0) || (x0 + TILE_W + R > W);
+        const bool fix_y = (y0 - R < 0) || (y0 + TILE_H + R > H);
+        if (fix_x) {
+            // out-of-plane columns a stored output can reach: R on the left of x = 0, R on the right of x = W-1
+            for (int idx = tid; idx < th * 2 * R; idx += NT) {
+                const int yy = idx / (2 * R), k = idx - yy * (2 * R);
+                const int gx = k < R ? -1 - k : W + (k - R);
+                const int sc = gx - (x0 - RA), gy = y0 - R + yy;
+                if (sc >= 0 && sc < P && gy >= 0 && gy < H) {
+                    const int src = reflect_idx(gx, W) - (x0 - RA);
+                    if (src >= 0 && src < P) tile[yy * P + sc] = tile[yy * P + src];
+                }
+            }
+            __syncthreads();
+        }
+        if (fix_y) {
+            for (int idx = tid; idx < th * (P / 4); idx += NT) {
+                const int yy = idx / (P / 4), q = idx - yy * (P / 4);
+                const int gy = y0 - R + yy;
+                if (gy < 0 || gy >= H) {
+                    const int src = clampi(clampi(reflect_idx(gy, H), 0, H - 1) - (y0 - R), 0, ROWS - 1);
+                    reinterpret_cast<float4*>(tile + yy * P)[q] = reinterpret_cast<const float4*>(tile + src * P)[q];
+                }
+            }
+            __syncthreads();
+        }
+    }
 
     const int tx = tid % BX, ty = tid / BX;
     float acc[TY][TX];
@@ -343,12 +420,31 @@ __global__ void filter2d_generic_kernel(const float* __restrict__ img, const flo
     out[(size_t)plane * H * W + (size_t)y * W + x] = acc;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 template <int TX, int TY, int BX, int BY>
 static int launch_blocked(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch, int K,
                           const int32_t* scratch, int use_order, float* out, cudaStream_t st) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY;
-    constexpr int P = TILE_W + 2 * kMaxRA;
-    const size_t smem = ((size_t)(TILE_H + 2 * kMaxRT) * P + 21 * kWPitch) * sizeof(float);
+    constexpr int P = TILE_W + 2 * kMaxRA, ROWS = TILE_H + 2 * kMaxRT;
+    const size_t smem = ((size_t)ROWS * P + 21 * kWPitch) * sizeof(float) + sizeof(uint64_t);
     auto kfn = filter2d_kernel<TX, TY, BX, BY>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -356,7 +452,22 @@ static int launch_blocked(const float* img, int B, int C, int H, int W, const fl
     }
     const dim3 grid(ceil_div(W, TILE_W), ceil_div(H, TILE_H), B * C);
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)out & 15) == 0) && (((uintptr_t)img & 15) == 0);
-    kfn<<<grid, BX * BY, smem, st>>>(img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok);
+    // TMA needs 16-byte global strides/base; OTF_F2D_NO_TMA=1 forces the cp.async fill for A/B runs
+    static const bool no_tma = getenv("OTF_F2D_NO_TMA") != nullptr;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tma = 0;
+    if (vec_ok && !no_tma && encode_tiled_fn()) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * C};
+        const cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)P, (cuuint32_t)ROWS, 1};
+        const cuuint32_t estride[3] = {1, 1, 1};
+        const CUresult r = encode_tiled_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)img, gdim, gstride, box, estride,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        use_tma = (r == CUDA_SUCCESS);
+    }
+    kfn<<<grid, BX * BY, smem, st>>>(tmap, img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok, use_tma);
     OTF_LAUNCH_CHECK("filter2d_kernel");
     return OTF_OK;
 }

@@ -251,8 +251,12 @@ class RealESRGANFeed:
         # optional per-stage CUDA-event timing (bench.py): name -> [(start, stop), ...]
         self.time_stages = False
         self.stage_times: dict[str, list] = {}
+        self.record_stage_fns = False
+        self.stage_fns: dict[str, Callable[[], Tensor]] = {}
 
     def _timed(self, name: str, fn: Callable[[], Tensor]) -> Tensor:
+        if self.record_stage_fns:
+            self.stage_fns[name] = fn  # closure over this call's inputs: bench.py re-launches it in a graph
         if not self.time_stages:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -302,34 +306,34 @@ class RealESRGANFeed:
             r = plan["usm"]["radius"]
             if r not in self._usm:
                 self._usm[r] = USMSharp(radius=r)
-            out = self._timed("usm", lambda: self._usm[r](out, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10)))
+            out = self._timed("usm", lambda o=out: self._usm[r](o, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10)))
         if plan.get("blur1"):
-            out = self._timed("blur1", lambda: filter2d(out, kernel1))
+            out = self._timed("blur1", lambda o=out: filter2d(o, kernel1))
         if plan.get("resize1"):
-            out = self._timed("resize1", lambda: D.resize_pt(out, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"]))
+            out = self._timed("resize1", lambda o=out: D.resize_pt(o, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"]))
         if plan.get("noise1"):
-            out = self._timed("noise1", lambda: self._noise(out, plan["noise1"], inject, "noise1"))
+            out = self._timed("noise1", lambda o=out: self._noise(o, plan["noise1"], inject, "noise1"))
         if plan.get("jpeg1") is not None:
-            out = self._timed("jpeg1", lambda: self._jpeg(out, plan["jpeg1"], round8=False))
+            out = self._timed("jpeg1", lambda o=out: self._jpeg(o, plan["jpeg1"], round8=False))
         if plan.get("blur2"):
-            out = self._timed("blur2", lambda: filter2d(out, kernel2))
+            out = self._timed("blur2", lambda o=out: filter2d(o, kernel2))
         if plan.get("resize2"):
             s2 = plan["resize2"]["scale"]
-            out = self._timed("resize2", lambda: D.resize_pt(out, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"]))
+            out = self._timed("resize2", lambda o=out: D.resize_pt(o, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"]))
         if plan.get("noise2"):
-            out = self._timed("noise2", lambda: self._noise(out, plan["noise2"], inject, "noise2"))
+            out = self._timed("noise2", lambda o=out: self._noise(o, plan["noise2"], inject, "noise2"))
         jpeg2 = plan.get("jpeg2")
         if plan.get("final_order", "resize_first") == "resize_first":
-            out = self._timed("resize3", lambda: D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-            out = self._timed("sinc", lambda: filter2d(out, sinc_kernel))
+            out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
+            out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel))
             if jpeg2 is not None:  # clamp/round fused into the last kernel
-                return self._timed("jpeg2+round", lambda: self._jpeg(out, jpeg2, round8=True))
-            return self._timed("round", lambda: clamp_round(out))
+                return self._timed("jpeg2+round", lambda o=out: self._jpeg(o, jpeg2, round8=True))
+            return self._timed("round", lambda o=out: clamp_round(o))
         if jpeg2 is not None:
-            out = self._timed("jpeg2", lambda: self._jpeg(out, jpeg2, round8=False))
-        out = self._timed("resize3", lambda: D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-        out = self._timed("sinc", lambda: filter2d(out, sinc_kernel))
-        return self._timed("round", lambda: clamp_round(out))
+            out = self._timed("jpeg2", lambda o=out: self._jpeg(o, jpeg2, round8=False))
+        out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
+        out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel))
+        return self._timed("round", lambda o=out: clamp_round(o))
 
     # -- the reference entry point --------------------------------------------------------
     @torch.no_grad()
