@@ -236,6 +236,9 @@ def run_b200(args) -> None:
     barrier()
     graphs, graph_out, kernels_per_step = [], [], None
     if not args.no_graph:
+        from trainner_redux_b200.degradations import pin_resize_tables
+
+        pin_resize_tables()  # the warm-up steps filled the weight-table cache; captured graphs may read it
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -63,17 +63,23 @@ int otf_device_cc(void);
 /* ---- a1: filter2d — traiNNer/utils/img_process_util.py:8-32 -------------------
  * out[b,c,y,x] = sum_{i,j<K} reflect_pad(img)[b,c,y+i,x+j] * kernel[kb,i,j],
  * kb = b (kernel_batch == B) or 0 (kernel_batch == 1).  K odd, K//2 < min(H,W).
- * `scratch_dev` (otf_filter2d_scratch_words(kernel_batch) 4-byte words, written by
- * the call; may be NULL = analyse nothing, run every kernel at full K) receives the
- * per-kernel analysis the main kernel consumes without any host round trip: true
- * half-width (largest |offset| with a non-zero tap), launch order of the samples
- * (largest support first), a rank-1 flag and the two rank-1 factors. K <= 21 runs
- * the register-blocked path specialised on the true support (rank-1 kernels as
- * K + K taps); larger odd K runs the generic path.  `img` and `out` must not alias. */
+ * `scratch_dev` (otf_filter2d_scratch_words(kernel_batch) 4-byte words; may be NULL =
+ * analyse nothing, run every kernel at full K) holds the per-kernel analysis the main
+ * kernel consumes without any host round trip: true half-width (largest |offset| with
+ * a non-zero tap), launch order of the samples (largest support first), a rank-1 flag
+ * and the two rank-1 factors.  With scratch_ready == 0 the call runs the analysis
+ * itself (2 small launches); otf_filter2d_analyse_f32 fills the scratch of up to 4
+ * kernel tensors (kernel1, kernel2, sinc_kernel) with ONE pair of launches, laid out
+ * back to back (set i at scratch_dev + i * otf_filter2d_scratch_words(kb)), after which
+ * the filter calls pass scratch_ready == 1.  K <= 21 runs the register-blocked path
+ * specialised on the true support (rank-1 kernels as K + K taps, halo tiles staged by
+ * TMA); larger odd K runs the generic path.  `img` and `out` must not alias. */
 int64_t otf_filter2d_scratch_words(int kernel_batch);
+int otf_filter2d_analyse_f32(const float* const* kernels_host_array, int nsets, int kernel_batch, int K,
+                             int32_t* scratch_dev, void* stream);
 int otf_filter2d_f32(const float* img, int B, int C, int H, int W,
                      const float* kernel, int kernel_batch, int K,
-                     int32_t* scratch_dev, float* out, void* stream);
+                     int32_t* scratch_dev, int scratch_ready, float* out, void* stream);
 
 /* ---- 1-D correlation with reflect padding along one axis ----------------------
  * Building block of USMSharp (exactly separable 51x51 Gaussian) and of the
@@ -96,11 +102,13 @@ int otf_usm_sharp_f32(const float* img, int planes, int H, int W,
  * Separable resampling with ATen's index/weight rules (SURVEY.md §8a "R"),
  * followed by clamp(0,1) when `clamp01` != 0 (resize_pt always clamps).  Two
  * launches: the per-axis (first index, count, weights) tables into workspace_dev
- * (otf_resize_workspace_bytes bytes, a few KB), then the tiled resampler. */
+ * (otf_resize_workspace_bytes bytes, a few KB), then the tiled resampler.  The tables
+ * depend on (H, W, OH, OW, mode) only; a caller that kept a workspace filled by an earlier
+ * call with the same five values passes tables_ready != 0 and skips the first launch. */
 int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode);
 int otf_resize_f32(const float* img, int planes, int H, int W,
                    float* out, int OH, int OW, int mode, int clamp01,
-                   void* workspace_dev, int64_t workspace_bytes, void* stream);
+                   void* workspace_dev, int64_t workspace_bytes, int tables_ready, void* stream);
 
 /* ---- a4: Gaussian noise — degradations.py:569-633 -----------------------------
  * out = tail(img + mix(N*sigma[b]/255, G*sigma[b]/255, gray[b])).
@@ -140,13 +148,15 @@ int otf_philox_poisson_f32(const float* lambda_dev, float* out, int64_t n,
  * One fused kernel: x255, RGB->YCbCr, 4:2:0, 8x8 DCT, quantise by table*factor[b]
  * with round-half-even (differentiable=0) or round(x)+(x-round(x))^3, dequantise,
  * IDCT, chroma x2, YCbCr->RGB, clamp, /255, crop of the x16 zero padding.
- * factor_dev fp32[B] (already quality_to_factor'ed) or NULL to use factor_scalar.
+ * factor_dev fp32[B] or NULL to use factor_scalar; the value is a compression factor
+ * (already quality_to_factor'ed) or, with factor_is_quality != 0, a raw JPEG quality that the
+ * kernel converts itself (saves the separate launch when the caller's tensor need not be mutated).
  * clamp_in != 0 first clamps the input to [0,1] (the call form used by the chain).
  * round8_out != 0 additionally applies clamp(round(x*255),0,255)/255 (a7). */
 int otf_quality_to_factor_f32(float* quality_dev, int B, void* stream); /* diffjpeg.py:48-61, in place */
 int otf_diffjpeg_f32(const float* img, int B, int H, int W,
-                     const float* factor_dev, float factor_scalar, int differentiable,
-                     int clamp_in, int round8_out, float* out, void* stream);
+                     const float* factor_dev, float factor_scalar, int factor_is_quality,
+                     int differentiable, int clamp_in, int round8_out, float* out, void* stream);
 
 /* ---- a7: clamp/round — traiNNer/models/realesrgan_model.py:616 ----------------
  * out = clamp(round(x*255),0,255)/255, round half to even. In place allowed. */

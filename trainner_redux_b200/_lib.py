@@ -30,19 +30,20 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_last_error": (C.c_char_p, []),
     "otf_device_cc": (_i, []),
     "otf_filter2d_scratch_words": (_i64, [_i]),
-    "otf_filter2d_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "otf_filter2d_analyse_f32": (_i, [_p, _i, _i, _i, _p, _p]),
+    "otf_filter2d_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p]),
     "otf_sepconv_reflect_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p]),
     "otf_usm_workspace_bytes": (_i64, [_i, _i, _i]),
     "otf_usm_sharp_f32": (_i, [_p, _i, _i, _i, _p, _i, _f, _f, _p, _i64, _p, _p]),
     "otf_resize_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
-    "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i64, _p]),
+    "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i64, _i, _p]),
     "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p]),
     "otf_philox_normal_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_philox_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_poisson_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p]),
     "otf_philox_poisson_f32": (_i, [_p, _p, _i64, _u64, _u64, _p]),
     "otf_quality_to_factor_f32": (_i, [_p, _i, _p]),
-    "otf_diffjpeg_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _p, _p]),
+    "otf_diffjpeg_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _i, _p, _p]),
     "otf_clamp_round_f32": (_i, [_p, _i64, _p, _p]),
     "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "otf_copy_strided_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
@@ -56,7 +57,8 @@ launch_count = 0  # kernels enqueued through this binding (bench.py reports it)
 
 # launches behind each entry point (see the .cu files)
 _LAUNCHES = {
-    "otf_filter2d_f32": 3,  # kernel analysis + launch order + blocked kernel
+    "otf_filter2d_analyse_f32": 2,  # analysis + launch order
+    "otf_filter2d_f32": 3,  # kernel analysis + launch order + blocked kernel (callers pass the exact count)
     "otf_sepconv_reflect_f32": 1,
     "otf_usm_sharp_f32": 4,
     "otf_resize_f32": 2,  # weight tables + resampler
@@ -106,13 +108,14 @@ def last_error() -> str:
     return load().otf_last_error().decode("utf-8", "replace")
 
 
-def call(name: str, *args: Any) -> None:
-    """Invoke an int-returning entry point; raise OtfError with the library's message."""
+def call(name: str, *args: Any, launches: int | None = None) -> None:
+    """Invoke an int-returning entry point; raise OtfError with the library's message.
+    `launches` overrides the table above when the number of kernels depends on the arguments."""
     global launch_count
     rc = getattr(load(), name)(*args)
     if rc != OTF_OK:
         raise OtfError(f"{name} failed ({rc}): {last_error()}")
-    launch_count += _LAUNCHES.get(name, 0)
+    launch_count += _LAUNCHES.get(name, 0) if launches is None else launches
 
 
 def require_cuda(*tensors: torch.Tensor | None) -> None:

@@ -114,10 +114,16 @@ __device__ __forceinline__ void block_codec(float (&f)[8], int lane, float facto
     for (int k = 0; k < 8; ++k) f[k] += 128.0f;
 }
 
+// diffjpeg.py:57-61 evaluated on fp32 0-d tensors
+__device__ __forceinline__ float quality_to_factor_dev(float v) {
+    const float f = v < 50.0f ? __fdiv_rn(5000.0f, v) : __fsub_rn(200.0f, __fmul_rn(v, 2.0f));
+    return __fdiv_rn(f, 100.0f);
+}
+
 __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
                                                        float factor_scalar, int differentiable, int clamp_in,
-                                                       int round8_out, int vec_ok) {
+                                                       int round8_out, int vec_ok, int factor_is_quality) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t total = (int64_t)B * mcu_x * mcu_y;
@@ -125,7 +131,8 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
     const int b = (int)(warp / ((int64_t)mcu_x * mcu_y));
     const int m = (int)(warp - (int64_t)b * mcu_x * mcu_y);
     const int my = m / mcu_x, mx = m - my * mcu_x;
-    const float factor = factor_dev ? factor_dev[b] : factor_scalar;
+    float factor = factor_dev ? factor_dev[b] : factor_scalar;
+    if (factor_is_quality) factor = quality_to_factor_dev(factor);  // diffjpeg.py:57-61 fused (no extra launch)
 
     const int yb = lane >> 3, r = lane & 7;
     const int by = yb >> 1, bx = yb & 1;
@@ -233,11 +240,7 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
 
 __global__ void quality_to_factor_kernel(float* q, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    const float v = q[i];
-    // diffjpeg.py:57-61 evaluated on fp32 0-d tensors
-    const float f = v < 50.0f ? __fdiv_rn(5000.0f, v) : __fsub_rn(200.0f, __fmul_rn(v, 2.0f));
-    q[i] = __fdiv_rn(f, 100.0f);
+    if (i < B) q[i] = quality_to_factor_dev(q[i]);
 }
 
 }  // namespace otf
@@ -251,7 +254,8 @@ extern "C" int otf_quality_to_factor_f32(float* quality_dev, int B, void* stream
 }
 
 extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const float* factor_dev, float factor_scalar,
-                                int differentiable, int clamp_in, int round8_out, float* out, void* stream) {
+                                int factor_is_quality, int differentiable, int clamp_in, int round8_out, float* out,
+                                void* stream) {
     using namespace otf;
     OTF_REQUIRE(img && out, OTF_ERR_BAD_ARG, "diffjpeg: null pointer");
     OTF_REQUIRE(B > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "diffjpeg: bad extents");
@@ -260,7 +264,7 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
     diffjpeg_kernel<<<ceil_div(warps, 4), 128, 0, (cudaStream_t)stream>>>(img, out, B, H, W, mcu_x, mcu_y, factor_dev,
                                                                           factor_scalar, differentiable, clamp_in,
-                                                                          round8_out, vec_ok);
+                                                                          round8_out, vec_ok, factor_is_quality);
     OTF_LAUNCH_CHECK("diffjpeg_kernel");
     return OTF_OK;
 }

@@ -35,8 +35,14 @@ namespace otf {
 constexpr int kUVPitch = 24;
 __host__ __device__ inline size_t scratch_words(int kb) { return (size_t)kb * (3 + 2 * kUVPitch); }
 
-__global__ void __launch_bounds__(128) kernel_support_kernel(const float* __restrict__ kern, int K, int kernel_batch,
-                                                             int32_t* __restrict__ scratch) {
+struct KernelSets {
+    const float* ptr[4];  // up to 4 kernel tensors (kernel1, kernel2, sinc_kernel, ...) analysed by one launch
+};
+
+__global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch,
+                                                             int32_t* __restrict__ scratch_base) {
+    const float* kern = sets.ptr[blockIdx.y];
+    int32_t* scratch = scratch_base + (size_t)blockIdx.y * scratch_words(kernel_batch);
     int32_t* support = scratch;
     int32_t* rank1 = scratch + 2 * kernel_batch;
     float* uv = reinterpret_cast<float*>(scratch + 3 * kernel_batch);
@@ -85,9 +91,10 @@ __global__ void __launch_bounds__(128) kernel_support_kernel(const float* __rest
     if (lane == 0) { support[kb] = r; rank1[kb] = ok ? 1 : 0; }
 }
 
-// order[0..kb): sample indices sorted by support, largest first (stable).  One small CTA.
-__global__ void __launch_bounds__(1024) kernel_order_kernel(int kernel_batch, int32_t* __restrict__ scratch) {
+// order[0..kb): sample indices sorted by support, largest first (stable).  One small CTA per kernel set.
+__global__ void __launch_bounds__(1024) kernel_order_kernel(int kernel_batch, int32_t* __restrict__ scratch_base) {
     extern __shared__ int s_sup[];
+    int32_t* scratch = scratch_base + (size_t)blockIdx.x * scratch_words(kernel_batch);
     for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) s_sup[t] = scratch[t];
     __syncthreads();
     for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
@@ -96,6 +103,20 @@ __global__ void __launch_bounds__(1024) kernel_order_kernel(int kernel_batch, in
         for (int u = 0; u < kernel_batch; ++u) rank += (s_sup[u] > mine) || (s_sup[u] == mine && u < t);
         scratch[kernel_batch + rank] = t;
     }
+}
+
+static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch, int K, int32_t* scratch, cudaStream_t st) {
+    OTF_REQUIRE(nsets >= 1 && nsets <= 4, OTF_ERR_BAD_ARG, "filter2d_analyse: 1..4 kernel sets per call");
+    OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 8192, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..8192");
+    KernelSets sets;
+    for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
+    kernel_support_kernel<<<dim3(ceil_div(kernel_batch, 4), nsets), 128, 0, st>>>(sets, K, kernel_batch, scratch);
+    OTF_LAUNCH_CHECK("kernel_support_kernel");
+    if (kernel_batch > 1) {
+        kernel_order_kernel<<<nsets, 1024, kernel_batch * sizeof(int), st>>>(kernel_batch, scratch);
+        OTF_LAUNCH_CHECK("kernel_order_kernel");
+    }
+    return OTF_OK;
 }
 
 constexpr int kMaxRT = 10;   // register-blocked path covers radius <= 10 (K <= 21)
@@ -476,8 +497,17 @@ static int launch_blocked(const float* img, int B, int C, int H, int W, const fl
 
 extern "C" int64_t otf_filter2d_scratch_words(int kernel_batch) { return (int64_t)otf::scratch_words(kernel_batch); }
 
+extern "C" int otf_filter2d_analyse_f32(const float* const* kernels_host_array, int nsets, int kernel_batch, int K,
+                                        int32_t* scratch_dev, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(kernels_host_array && scratch_dev, OTF_ERR_BAD_ARG, "filter2d_analyse: null pointer");
+    OTF_REQUIRE(K > 0 && (K % 2) == 1 && K <= 2 * kMaxRT + 1, OTF_ERR_BAD_ARG, "filter2d_analyse: K must be odd and <= 21");
+    for (int i = 0; i < nsets && i < 4; ++i) OTF_REQUIRE(kernels_host_array[i], OTF_ERR_BAD_ARG, "filter2d_analyse: null kernel set");
+    return analyse_sets(kernels_host_array, nsets, kernel_batch, K, scratch_dev, (cudaStream_t)stream);
+}
+
 extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch,
-                                int K, int32_t* support_dev, float* out, void* stream) {
+                                int K, int32_t* support_dev, int scratch_ready, float* out, void* stream) {
     using namespace otf;
     OTF_REQUIRE(img && kernel && out, OTF_ERR_BAD_ARG, "filter2d: null pointer");
     OTF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "filter2d: bad extents %d %d %d %d", B, C, H, W);
@@ -497,14 +527,10 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
     if (support_dev) {
         // scratch layout (4-byte words): [0,kb) true radius, [kb,2kb) sample order (largest radius first),
         // [2kb,3kb) rank-1 flag, then float uv[kb][2][24] rank-1 factors  (otf_filter2d_scratch_words)
-        OTF_REQUIRE(kernel_batch <= 8192, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch > 8192");
-        kernel_support_kernel<<<ceil_div(kernel_batch, 4), 128, 0, st>>>(kernel, K, kernel_batch, support_dev);
-        OTF_LAUNCH_CHECK("kernel_support_kernel");
-        use_order = (kernel_batch == B && B > 1);
-        if (use_order) {
-            kernel_order_kernel<<<1, 1024, kernel_batch * sizeof(int), st>>>(kernel_batch, support_dev);
-            OTF_LAUNCH_CHECK("kernel_order_kernel");
+        if (!scratch_ready) {
+            if (int rc = analyse_sets(&kernel, 1, kernel_batch, K, support_dev, st)) return rc;
         }
+        use_order = (kernel_batch == B && B > 1);
     }
     // big planes: 64x64 tiles, 8x4 outputs per thread (128 threads); tiny planes: 32x32 tiles, 4x4 per thread
     const int64_t big_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 64) * B * C;

@@ -288,7 +288,8 @@ extern "C" int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int 
 }
 
 extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
-                              int clamp_out, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+                              int clamp_out, void* workspace_dev, int64_t workspace_bytes, int tables_ready,
+                              void* stream) {
     using namespace otf;
     OTF_REQUIRE(img && out && img != out && workspace_dev, OTF_ERR_BAD_ARG, "resize: bad pointers");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && OH > 0 && OW > 0, OTF_ERR_BAD_ARG, "resize: bad extents");
@@ -298,8 +299,10 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
     int* ty_lo = (int*)workspace_dev;
     int* tx_lo = ty_lo + table_ints(ay);
     cudaStream_t st = (cudaStream_t)stream;
-    resize_tables_kernel<<<ceil_div(OH + OW, 128), 128, 0, st>>>(mode, ay, ax, ty_lo, tx_lo);
-    OTF_LAUNCH_CHECK("resize_tables_kernel");
+    if (!tables_ready) {  // the tables depend on (H, W, OH, OW, mode) only: a caller may keep and reuse them
+        resize_tables_kernel<<<ceil_div(OH + OW, 128), 128, 0, st>>>(mode, ay, ax, ty_lo, tx_lo);
+        OTF_LAUNCH_CHECK("resize_tables_kernel");
+    }
     auto span = [](const AxisSpec& a, int nout) {  // source extent covered by nout consecutive outputs
         int v = (int)ceilf(a.scale * (float)(nout - 1)) + a.max_taps + 2;
         return v > a.in_n ? a.in_n : v;

@@ -224,13 +224,51 @@ def _lanczos_taps(ratio: float, a: int = 3) -> np.ndarray:
     return np.ascontiguousarray((w / w.sum(dtype=np.float32)).astype(np.float32))
 
 
+# Resize weight tables depend on (H, W, OH, OW, mode) only: keep the last few per device.  An entry
+# remembers the event that follows the launch which filled it; another stream waits on that event, and
+# a capturing stream only takes entries pinned beforehand with pin_resize_tables() (a captured graph
+# keeps reading the same memory, so pinned tables live for the life of the process).
+_TABLE_CACHE: dict[tuple, tuple[Tensor, "torch.cuda.Event", int]] = {}
+_TABLE_PINNED: dict[tuple, Tensor] = {}
+_TABLE_CACHE_MAX = 64
+
+
+def pin_resize_tables() -> int:
+    """Wait for every cached table to be complete and pin it, so that a CUDA-graph capture that follows
+    can read it (captured graphs keep reading the same memory, so pinned tables are never evicted)."""
+    for key, (tab, ev, _) in list(_TABLE_CACHE.items()):
+        ev.synchronize()
+        _TABLE_PINNED[key] = tab
+    return len(_TABLE_PINNED)
+
+
 def _resize_call(x: Tensor, oh: int, ow: int, mode_id: int, clamp: bool) -> Tensor:
     b, c, h, w = x.shape
     out = torch.empty((b, c, oh, ow), dtype=torch.float32, device=x.device)
-    ws_bytes = _lib.load().otf_resize_workspace_bytes(h, w, oh, ow, mode_id)
-    ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=x.device)
-    _lib.call("otf_resize_f32", _lib.ptr(x), b * c, h, w, _lib.ptr(out), oh, ow, mode_id, int(clamp), _lib.ptr(ws), ws_bytes,
-              _lib.stream())
+    key = (x.device.index, h, w, oh, ow, mode_id)
+    cur = torch.cuda.current_stream()
+    capturing = torch.cuda.is_current_stream_capturing()
+    ws = _TABLE_PINNED.get(key)
+    if ws is None:
+        hit = _TABLE_CACHE.get(key)
+        if hit is not None:
+            tab, ev, sid = hit
+            if not capturing:  # (event queries are illegal under capture: only pinned tables are used there)
+                if sid != cur.cuda_stream:
+                    cur.wait_event(ev)
+                ws = tab
+    ready = ws is not None
+    if ws is None:
+        ws_bytes = _lib.load().otf_resize_workspace_bytes(h, w, oh, ow, mode_id)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=x.device)
+    _lib.call("otf_resize_f32", _lib.ptr(x), b * c, h, w, _lib.ptr(out), oh, ow, mode_id, int(clamp), _lib.ptr(ws),
+              ws.numel() * 4, int(ready), _lib.stream(), launches=1 if ready else 2)
+    if not ready and not capturing:
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        if len(_TABLE_CACHE) >= _TABLE_CACHE_MAX:
+            _TABLE_CACHE.pop(next(iter(_TABLE_CACHE)))
+        _TABLE_CACHE[key] = (ws, ev, cur.cuda_stream)
     return out
 
 

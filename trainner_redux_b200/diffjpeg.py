@@ -26,7 +26,8 @@ class DiffJPEG(nn.Module):
         super().__init__()
         self.differentiable = bool(differentiable)
 
-    def forward(self, x: Tensor, quality: float | Tensor, *, _clamp_in: bool = False, _round8: bool = False) -> Tensor:
+    def forward(self, x: Tensor, quality: float | Tensor, *, _clamp_in: bool = False, _round8: bool = False,
+                _keep_quality: bool = False) -> Tensor:
         """
         Args:
             x (Tensor): Input image, bchw, rgb, [0, 1]
@@ -39,16 +40,20 @@ class DiffJPEG(nn.Module):
         if c != 3:
             raise RuntimeError(f"DiffJPEG expects 3 channels, got {c}")
         out = torch.empty_like(img)
+        raw = 0
         if isinstance(quality, (int, float)):
             fac_t, fac_s = None, float(quality_to_factor(quality))
         else:
             _lib.require_cuda(quality)
             if quality.dtype != torch.float32 or not quality.is_contiguous() or quality.numel() != b:
                 raise RuntimeError("quality must be a contiguous fp32 tensor of shape (b,)")
-            _lib.call("otf_quality_to_factor_f32", _lib.ptr(quality), b, _lib.stream())
+            if _keep_quality:
+                raw = 1  # the kernel converts quality -> factor itself; the caller's tensor is left alone
+            else:
+                _lib.call("otf_quality_to_factor_f32", _lib.ptr(quality), b, _lib.stream())  # quirk Q1: in place
             fac_t, fac_s = quality, 0.0
         _lib.call(
-            "otf_diffjpeg_f32", _lib.ptr(img), b, h, w, _lib.ptr(fac_t), fac_s, int(self.differentiable),
+            "otf_diffjpeg_f32", _lib.ptr(img), b, h, w, _lib.ptr(fac_t), fac_s, raw, int(self.differentiable),
             int(_clamp_in), int(_round8), _lib.ptr(out), _lib.stream(),
         )
         return out

@@ -35,7 +35,27 @@ def gaussian_kernel_1d(ksize: int, sigma: float = 0.0) -> np.ndarray:
     return k / k.sum()
 
 
-def filter2d(img: Tensor, kernel: Tensor) -> Tensor:
+class KernelAnalysis:
+    """Device-side analysis (true support, launch order, rank-1 factors) of up to four kernel
+    tensors, produced by ONE pair of launches; ``filter2d(..., _analysis=(ka, i))`` then skips its own."""
+
+    def __init__(self, kernels: list[Tensor]) -> None:
+        assert 1 <= len(kernels) <= 4
+        kb, k = kernels[0].size(0), kernels[0].size(-1)
+        assert all(t.size(0) == kb and t.size(-1) == k for t in kernels), "kernel sets must share batch and size"
+        self.kernels = [t.to(torch.float32).contiguous() for t in kernels]
+        _lib.require_cuda(*self.kernels)
+        self.words = _lib.load().otf_filter2d_scratch_words(kb)
+        self.scratch = torch.empty(len(kernels) * self.words, dtype=torch.int32, device=kernels[0].device)
+        ptrs = (C.c_void_p * len(kernels))(*[t.data_ptr() for t in self.kernels])
+        _lib.call("otf_filter2d_analyse_f32", ptrs, len(kernels), kb, k, _lib.ptr(self.scratch), _lib.stream(),
+                  launches=2 if kb > 1 else 1)
+
+    def scratch_ptr(self, i: int) -> C.c_void_p:
+        return C.c_void_p(self.scratch.data_ptr() + 4 * i * self.words)
+
+
+def filter2d(img: Tensor, kernel: Tensor, *, _analysis: tuple[KernelAnalysis, int] | None = None) -> Tensor:
     """PyTorch version of cv2.filter2D (img_process_util.py:8-32).
 
     Args:
@@ -47,7 +67,6 @@ def filter2d(img: Tensor, kernel: Tensor) -> Tensor:
         raise ValueError("Wrong kernel size")
     _lib.require_cuda(img, kernel)
     x = _lib.dense_f32(img)
-    kern = kernel.to(torch.float32).contiguous()
     b, c, h, w = x.shape
     kb = kernel.size(0)
     if kb not in (1, b):
@@ -59,11 +78,16 @@ def filter2d(img: Tensor, kernel: Tensor) -> Tensor:
             f"at dimension 3 of input {list(img.shape)}"
         )
     out = torch.empty_like(x)
+    if _analysis is not None and k <= 21:
+        ka, i = _analysis
+        _lib.call("otf_filter2d_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(ka.kernels[i]), kb, k, ka.scratch_ptr(i), 1, _lib.ptr(out),
+                  _lib.stream(), launches=1)
+        return out
+    kern = kernel.to(torch.float32).contiguous()
     # per-kernel analysis scratch: true radii, launch order, rank-1 flags and factors
-    support = torch.empty(_lib.load().otf_filter2d_scratch_words(kb), dtype=torch.int32, device=x.device)
-    _lib.call("otf_filter2d_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(kern), kb, k, _lib.ptr(support), _lib.ptr(out), _lib.stream())
-    if kb == 1 or b == 1 or k > 21:
-        _lib.launch_count -= 1 if k <= 21 else 2  # no launch-order kernel for a shared kernel; generic path is one launch
+    scratch = torch.empty(_lib.load().otf_filter2d_scratch_words(kb), dtype=torch.int32, device=x.device)
+    _lib.call("otf_filter2d_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(kern), kb, k, _lib.ptr(scratch), 0, _lib.ptr(out), _lib.stream(),
+              launches=1 if k > 21 else (3 if kb > 1 else 2))
     return out
 
 

@@ -33,7 +33,7 @@ from torch import Tensor
 from . import _lib
 from . import degradations as D
 from .diffjpeg import DiffJPEG
-from .img_process_util import USMSharp, filter2d
+from .img_process_util import KernelAnalysis, USMSharp, filter2d
 from .transforms import crop_pair
 
 
@@ -282,8 +282,8 @@ class RealESRGANFeed:
         )
 
     def _jpeg(self, out: Tensor, quality: Tensor, round8: bool) -> Tensor:
-        q = quality.clone().to(self.device, non_blocking=True)
-        return self.jpeger(out, quality=q, _clamp_in=True, _round8=round8)
+        q = quality.to(self.device, non_blocking=True)  # raw qualities: the kernel converts them, nothing is mutated
+        return self.jpeger(out, quality=q, _clamp_in=True, _round8=round8, _keep_quality=True)
 
     def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
                 inject: dict | None = None) -> Tensor:
@@ -294,11 +294,16 @@ class RealESRGANFeed:
         out = gt
         if plan.get("clean"):
             return clamp_round(out)
+        # one pair of launches analyses all three kernel tensors (support, launch order, rank-1 factors)
+        ka = None
+        if kernel1.shape == kernel2.shape == sinc_kernel.shape and kernel1.size(-1) <= 21 and kernel1.size(0) == gt.size(0):
+            ka = KernelAnalysis([kernel1, kernel2, sinc_kernel])
+        an = (lambda i: (ka, i)) if ka is not None else (lambda i: None)
         if plan.get("order") == "fork":
             if plan.get("blur1"):
-                out = filter2d(out, kernel1)
+                out = filter2d(out, kernel1, _analysis=an(0))
             out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
-            out = filter2d(out, sinc_kernel)
+            out = filter2d(out, sinc_kernel, _analysis=an(2))
             if plan.get("jpeg") is not None:
                 return self._jpeg(out, plan["jpeg"], round8=True)
             return clamp_round(out)
@@ -308,7 +313,7 @@ class RealESRGANFeed:
                 self._usm[r] = USMSharp(radius=r)
             out = self._timed("usm", lambda o=out: self._usm[r](o, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10)))
         if plan.get("blur1"):
-            out = self._timed("blur1", lambda o=out: filter2d(o, kernel1))
+            out = self._timed("blur1", lambda o=out: filter2d(o, kernel1, _analysis=an(0)))
         if plan.get("resize1"):
             out = self._timed("resize1", lambda o=out: D.resize_pt(o, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"]))
         if plan.get("noise1"):
@@ -316,7 +321,7 @@ class RealESRGANFeed:
         if plan.get("jpeg1") is not None:
             out = self._timed("jpeg1", lambda o=out: self._jpeg(o, plan["jpeg1"], round8=False))
         if plan.get("blur2"):
-            out = self._timed("blur2", lambda o=out: filter2d(o, kernel2))
+            out = self._timed("blur2", lambda o=out: filter2d(o, kernel2, _analysis=an(1)))
         if plan.get("resize2"):
             s2 = plan["resize2"]["scale"]
             out = self._timed("resize2", lambda o=out: D.resize_pt(o, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"]))
@@ -325,14 +330,14 @@ class RealESRGANFeed:
         jpeg2 = plan.get("jpeg2")
         if plan.get("final_order", "resize_first") == "resize_first":
             out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-            out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel))
+            out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel, _analysis=an(2)))
             if jpeg2 is not None:  # clamp/round fused into the last kernel
                 return self._timed("jpeg2+round", lambda o=out: self._jpeg(o, jpeg2, round8=True))
             return self._timed("round", lambda o=out: clamp_round(o))
         if jpeg2 is not None:
             out = self._timed("jpeg2", lambda o=out: self._jpeg(o, jpeg2, round8=False))
         out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-        out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel))
+        out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel, _analysis=an(2)))
         return self._timed("round", lambda o=out: clamp_round(o))
 
     # -- the reference entry point --------------------------------------------------------
