@@ -15,7 +15,7 @@ from typing import Any
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libotf_b200.so")
+LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so")  # override: A/B builds in profiles/experiments
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0

@@ -173,6 +173,78 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_t
     }
 }
 
+// Packed variant of accumulate_rows for sm_100a: FFMA2 (fma.rn.f32x2) performs two fp32 FMAs per
+// issued instruction.  The FMA pipe has the same peak either way (measured 73 TFLOP/s with both,
+// profiles/experiments/ffma2_rate.cu) but the packed form needs half the issue slots, which leaves
+// room for the LDS / address work that kept the scalar loop at ~2/3 of the FMA peak.
+// Pairing is over two vertically adjacent outputs: they read the SAME pixel with the taps of two
+// consecutive kernel rows, so operand a = (pixel, pixel), operand b = (w[i][j], w[i-1][j]) comes
+// pre-paired from shared memory (rows i = 0..KT, out-of-range taps zero) and the accumulator pair is
+// (acc[2p][ox], acc[2p+1][ox]).  Each lane is an ordinary IEEE fp32 FMA: results are bit-identical
+// to the scalar loop.
+#ifndef OTF_F2D_MINB
+#define OTF_F2D_MINB 4
+#endif
+constexpr int kW2Pitch = 24;  // float2 per paired tap row
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+    const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+    const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+
+template <int TX, int TY, int KT>
+__device__ __forceinline__ void accumulate_rows_packed(const float* __restrict__ tile_thread, int pitch,
+                                                       const float2* __restrict__ wsm2, float (&acc)[TY][TX]) {
+    static_assert(TY % 2 == 0, "pairs of output rows");
+    constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
+    constexpr int NROW = TX + 2 * RA;
+    float2 acc2[TY / 2][TX];
+#pragma unroll
+    for (int p = 0; p < TY / 2; ++p)
+#pragma unroll
+        for (int ox = 0; ox < TX; ++ox) acc2[p][ox] = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int r = 0; r < TY + KT - 1; ++r) {
+        float2 rd[NROW];  // every pixel of the row window duplicated into a register pair
+        const float4* rp = reinterpret_cast<const float4*>(tile_thread + r * pitch);
+#pragma unroll
+        for (int q = 0; q < NROW / 4; ++q) {
+            const float4 v = rp[q];
+            rd[4 * q + 0] = make_float2(v.x, v.x); rd[4 * q + 1] = make_float2(v.y, v.y);
+            rd[4 * q + 2] = make_float2(v.z, v.z); rd[4 * q + 3] = make_float2(v.w, v.w);
+        }
+#pragma unroll
+        for (int p = 0; p < TY / 2; ++p) {
+            const int i = r - 2 * p;  // output row 2p uses kernel row i, output row 2p+1 uses kernel row i-1
+            if (i >= 0 && i <= KT) {
+                const float4* wp = reinterpret_cast<const float4*>(wsm2 + i * kW2Pitch);
+#pragma unroll
+                for (int q = 0; q < (KT + 1) / 2; ++q) {
+                    const float4 w4 = wp[q];  // taps j = 2q, 2q+1 as (lo, hi) pairs
+                    const float2 w[2] = {make_float2(w4.x, w4.y), make_float2(w4.z, w4.w)};
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int j = 2 * q + t;
+                        if (j < KT) {
+#pragma unroll
+                            for (int ox = 0; ox < TX; ++ox) ffma2(acc2[p][ox], rd[OFF + ox + j], w[t]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < TY / 2; ++p)
+#pragma unroll
+        for (int ox = 0; ox < TX; ++ox) {
+            acc[2 * p][ox] = acc2[p][ox].x;
+            acc[2 * p + 1][ox] = acc2[p][ox].y;
+        }
+}
+
 // Rank-1 kernels: out = u (x) v correlated with the tile, evaluated per thread as a horizontal
 // K-tap pass over each row of its window (kept in registers) followed by the vertical accumulation.
 // u and v sit centred in 21 slots (tap t of a KT-tap kernel is slot 10 - R + t).
@@ -245,8 +317,8 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
-template <int TX, int TY, int BX, int BY>
-__global__ void __launch_bounds__(BX* BY) filter2d_kernel(const __grid_constant__ CUtensorMap tmap,
+template <int TX, int TY, int BX, int BY, bool PACKED>
+__global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_kernel(const __grid_constant__ CUtensorMap tmap,
                                                           const float* __restrict__ img, const float* __restrict__ kern,
                                                           const int32_t* __restrict__ scratch, int use_order,
                                                           float* __restrict__ out, int C, int H, int W, int K,
@@ -257,8 +329,9 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const __grid_constant_
     static_assert(P % 4 == 0 && P / 4 <= 32, "a warp fills one tile row with one float4 per lane");
     extern __shared__ __align__(128) float smem[];
     float* tile = smem;              // ROWS x P (rows [0, TILE_H + 2R) are used)
-    float* wsm = smem + ROWS * P;    // 21 x kWPitch
-    uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + 21 * kWPitch);
+    constexpr int WSM_FLOATS = PACKED ? 22 * kW2Pitch * 2 : 21 * kWPitch;
+    float* wsm = smem + ROWS * P;    // 21 x kWPitch taps, or 22 x kW2Pitch paired taps
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + WSM_FLOATS);
 
     const int zb = blockIdx.z / C, zc = blockIdx.z - zb * C;
     const int b = (scratch && use_order) ? scratch[kernel_batch + zb] : zb;
@@ -314,6 +387,17 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const __grid_constant_
     if (rank1) {
         const float* uv = reinterpret_cast<const float*>(scratch + 3 * kernel_batch) + (size_t)kb * 2 * kUVPitch;
         for (int idx = tid; idx < 2 * kUVPitch; idx += NT) wsm[idx] = uv[idx];
+    } else if (PACKED && R >= 1) {
+        // paired taps: row i holds (w[i][j], w[i-1][j]) for i = 0..KT, zeros outside the KT x KT centre
+        float2* w2 = reinterpret_cast<float2*>(wsm);
+        auto tap = [&](int i, int j) {
+            const int si = c - R + i, sj = c - R + j;
+            return (i >= 0 && i < KT && j < KT && si >= 0 && si < K && sj >= 0 && sj < K) ? kp[si * K + sj] : 0.0f;
+        };
+        for (int idx = tid; idx < 22 * kW2Pitch; idx += NT) {
+            const int i = idx / kW2Pitch, j = idx - i * kW2Pitch;
+            w2[idx] = make_float2(tap(i, j), tap(i - 1, j));
+        }
     } else
     for (int idx = tid; idx < 21 * kWPitch; idx += NT) {
         const int i = idx / kWPitch, j = idx - i * kWPitch;
@@ -375,6 +459,20 @@ __global__ void __launch_bounds__(BX* BY) filter2d_kernel(const __grid_constant_
             case 8: accumulate_rank1<TX, TY, 17>(tt, P, u, v, acc); break;
             case 9: accumulate_rank1<TX, TY, 19>(tt, P, u, v, acc); break;
             default: accumulate_rank1<TX, TY, 21>(tt, P, u, v, acc); break;
+        }
+    } else if (PACKED && R >= 1) {
+        const float2* w2 = reinterpret_cast<const float2*>(wsm);
+        switch (R) {
+            case 1: accumulate_rows_packed<TX, TY, 3>(tt, P, w2, acc); break;
+            case 2: accumulate_rows_packed<TX, TY, 5>(tt, P, w2, acc); break;
+            case 3: accumulate_rows_packed<TX, TY, 7>(tt, P, w2, acc); break;
+            case 4: accumulate_rows_packed<TX, TY, 9>(tt, P, w2, acc); break;
+            case 5: accumulate_rows_packed<TX, TY, 11>(tt, P, w2, acc); break;
+            case 6: accumulate_rows_packed<TX, TY, 13>(tt, P, w2, acc); break;
+            case 7: accumulate_rows_packed<TX, TY, 15>(tt, P, w2, acc); break;
+            case 8: accumulate_rows_packed<TX, TY, 17>(tt, P, w2, acc); break;
+            case 9: accumulate_rows_packed<TX, TY, 19>(tt, P, w2, acc); break;
+            default: accumulate_rows_packed<TX, TY, 21>(tt, P, w2, acc); break;
         }
     } else
     switch (R) {
@@ -460,13 +558,13 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-template <int TX, int TY, int BX, int BY>
+template <int TX, int TY, int BX, int BY, bool PACKED>
 static int launch_blocked(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch, int K,
                           const int32_t* scratch, int use_order, float* out, cudaStream_t st) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY;
     constexpr int P = TILE_W + 2 * kMaxRA, ROWS = TILE_H + 2 * kMaxRT;
-    const size_t smem = ((size_t)ROWS * P + 21 * kWPitch) * sizeof(float) + sizeof(uint64_t);
-    auto kfn = filter2d_kernel<TX, TY, BX, BY>;
+    const size_t smem = ((size_t)ROWS * P + (PACKED ? 22 * kW2Pitch * 2 : 21 * kWPitch)) * sizeof(float) + sizeof(uint64_t);
+    auto kfn = filter2d_kernel<TX, TY, BX, BY, PACKED>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "filter2d smem attribute");
@@ -534,9 +632,16 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
     }
     // big planes: 64x64 tiles, 8x4 outputs per thread (128 threads); tiny planes: 32x32 tiles, 4x4 per thread
     const int64_t big_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 64) * B * C;
-    if (big_tiles >= 2 * kNumSMs) return launch_blocked<8, 4, 8, 16>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    static const bool scalar = getenv("OTF_F2D_SCALAR") != nullptr;  // A/B switch: scalar FFMA instead of packed FFMA2
+    if (big_tiles >= 2 * kNumSMs) {
+        if (scalar) return launch_blocked<8, 4, 8, 16, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+        return launch_blocked<8, 4, 8, 16, true>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    }
     // small planes: 64x32 tiles (64 threads) keep the 8x4 register block and halve the tile
     const int64_t mid_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 32) * B * C;
-    if (mid_tiles >= 2 * kNumSMs && W >= 48) return launch_blocked<8, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
-    return launch_blocked<4, 4, 8, 8>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    if (mid_tiles >= 2 * kNumSMs && W >= 48) {
+        if (scalar) return launch_blocked<8, 4, 8, 8, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+        return launch_blocked<8, 4, 8, 8, true>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    }
+    return launch_blocked<4, 4, 8, 8, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
 }
