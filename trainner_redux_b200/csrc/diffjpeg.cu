@@ -83,30 +83,31 @@ __device__ __forceinline__ void transpose8(float (&a)[8], int lane) {
 }
 
 // Quantise + dequantise an 8x8 block held as: lane v (within its group of 8) owns coefficients
-// D[u][v], u = register index.  tab is [u][v].
-template <bool LUMA>
-__device__ __forceinline__ void quant_dequant(float (&d)[8], int v, float factor, bool differentiable) {
+// D[u][v], u = register index.  tab is [u][v]: luma or chroma table, selected at run time so that the
+// codec below is ONE loop body for both planes (half the code: the fully unrolled kernel overflowed
+// the instruction cache — "no_instruction" was its second largest stall in profiles/).
+__device__ __forceinline__ void quant_dequant(float (&d)[8], int v, bool luma, float factor, bool differentiable) {
+    const float(*tab)[8] = luma ? c_ytab : c_ctab;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        const float t = __fmul_rn(LUMA ? c_ytab[u][v] : c_ctab[u][v], factor);  // table * factor
-        const float x = __fdiv_rn(d[u], t);                                      // diffjpeg.py:207-212
-        float q = rintf(x);                                                      // torch.round
+        const float t = __fmul_rn(tab[u][v], factor);  // table * factor
+        const float x = __fdiv_rn(d[u], t);            // diffjpeg.py:207-212
+        float q = rintf(x);                            // torch.round
         if (differentiable) {
             const float e = __fsub_rn(x, q);
-            q = __fadd_rn(q, __fmul_rn(__fmul_rn(e, e), e));                     // :40-42
+            q = __fadd_rn(q, __fmul_rn(__fmul_rn(e, e), e));  // :40-42
         }
-        d[u] = __fmul_rn(q, t);                                                  // :300-306
+        d[u] = __fmul_rn(q, t);  // :300-306
     }
 }
 
 // Full 2-D DCT -> quantise -> dequantise -> 2-D IDCT on the block whose row `lane&7` is in f[].
 // Input is level-shifted (f-128); output has +128 restored.
-template <bool LUMA>
-__device__ __forceinline__ void block_codec(float (&f)[8], int lane, float factor, bool differentiable) {
+__device__ __forceinline__ void block_codec(float (&f)[8], int lane, bool luma, float factor, bool differentiable) {
     dct8(f);             // along the row (y index -> v)
     transpose8(f, lane); // lane now = v, registers = x (row index)
     dct8(f);             // along x -> u
-    quant_dequant<LUMA>(f, lane & 7, factor, differentiable);
+    quant_dequant(f, lane & 7, luma, factor, differentiable);
     idct8(f);            // u -> x
     transpose8(f, lane); // lane = x, registers = v
     idct8(f);            // v -> y
@@ -194,9 +195,18 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
             ch[4 + k] = is_cr ? rr : rb;
         }
     }
-    // ---- codec ----
-    block_codec<true>(yv, lane, factor, differentiable);
-    block_codec<false>(ch, lane, factor, differentiable);   // lanes 16-31 redo lanes 0-15 (harmless)
+    // ---- codec: one loop body, pass 0 = the four luma blocks, pass 1 = Cb | Cr (lanes 16-31 redo 0-15) ----
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        float blk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) blk[k] = pass ? ch[k] : yv[k];
+        block_codec(blk, lane, pass == 0, factor, differentiable);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (pass) ch[k] = blk[k]; else yv[k] = blk[k];
+        }
+    }
     // ---- chroma back to pixel lanes: nearest x2 (diffjpeg.py:397-402) ----
     {
         const int mrow = by * 4 + (r >> 1);
@@ -262,9 +272,11 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
     const int64_t warps = (int64_t)B * mcu_x * mcu_y;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
-    diffjpeg_kernel<<<ceil_div(warps, 4), 128, 0, (cudaStream_t)stream>>>(img, out, B, H, W, mcu_x, mcu_y, factor_dev,
-                                                                          factor_scalar, differentiable, clamp_in,
-                                                                          round8_out, vec_ok, factor_is_quality);
+    // one warp per MCU; few MCUs (64^2 LQ stage) -> one-warp CTAs so they spread over all 148 SMs
+    const int wpc = warps >= (int64_t)kNumSMs * 32 ? 4 : 1;
+    diffjpeg_kernel<<<ceil_div(warps, wpc), 32 * wpc, 0, (cudaStream_t)stream>>>(img, out, B, H, W, mcu_x, mcu_y, factor_dev,
+                                                                             factor_scalar, differentiable, clamp_in,
+                                                                             round8_out, vec_ok, factor_is_quality);
     OTF_LAUNCH_CHECK("diffjpeg_kernel");
     return OTF_OK;
 }

@@ -97,7 +97,8 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     // MUFU-based log/sin/cos: abs error ~1e-6 on the normal deviates, far below what the
     // distribution tests (KS at 4M samples) or an 8-bit image can resolve
     const float u1 = u01(a), u2 = u01(b);
-    const float r = sqrtf(-2.0f * __logf(u1));
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
     return make_float2(r * c, r * s);
