@@ -276,7 +276,7 @@ def run_b200(args) -> None:
     # graph, and around eager launches they would include the Python launch gap, so every stage of the
     # chain (on the tensors of one real pass) is re-captured into its own graph of REP launches and that
     # graph's replay is timed with an event pair: kernel time only, measured live in this run.
-    feed.record_stage_fns = True
+    feed.record_stage_fns = not args.no_stage_timing
     step_resident(0)
     feed.record_stage_fns = False
     torch.cuda.synchronize()
@@ -348,6 +348,11 @@ def run_b200(args) -> None:
     if rank == 0:
         pk = peaks()
         k_ms = stage_ms.get("blur1", float("nan"))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read+write of this kernel from the committed ncu --set full capture
+            with open(tpath) as f:
+                traffic = json.load(f).get("filter2d_blur1_dram_bytes_per_launch")
         blur_bytes = BATCH * (2 * 3 * GT * GT * 4 + 21 * 21 * 4)
         achieved = blur_bytes / (k_ms * 1e-3) / 1e9
         true_k2 = float((devd[0]["kernel1"] != 0).flatten(1).sum(1).float().mean().item())
@@ -373,7 +378,7 @@ def run_b200(args) -> None:
             "clocks": clocks,
             "roofline": {"kernel": "filter2d_kernel (blur1, 64x3x256x256, 21x21 zero-padded kernels)", "bound": "hbm",
                          "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": None, "peak_source": pk["source"], "ms_per_launch": k_ms,
+                         "traffic": traffic, "peak_source": pk["source"], "ms_per_launch": k_ms,
                          "fma": {"achieved_tflops_true_taps": flops * (true_k2 / 441.0) / (k_ms * 1e-3) / 1e12,
                                  "frac_of_fma_peak": flops * (true_k2 / 441.0) / (k_ms * 1e-3) / 1e12 / fma_peak,
                                  "peak_tflops": fma_peak, "mean_nonzero_taps": true_k2,
@@ -395,6 +400,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-capture pass (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
