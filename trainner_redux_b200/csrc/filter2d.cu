@@ -41,20 +41,26 @@ struct KernelSets {
 
 __global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch,
                                                              int32_t* __restrict__ scratch_base) {
+    // one CTA per kernel: the K*K taps go to shared memory with one coalesced pass, then 128 threads
+    // scan them (support, pivot, rank-1 residual) — three short passes instead of a 14-deep serial loop per lane
+    __shared__ float sk[32 * 32];
+    __shared__ float s_red[4];
+    __shared__ int s_idx[4], s_r[4], s_ok[4];
     const float* kern = sets.ptr[blockIdx.y];
     int32_t* scratch = scratch_base + (size_t)blockIdx.y * scratch_words(kernel_batch);
     int32_t* support = scratch;
     int32_t* rank1 = scratch + 2 * kernel_batch;
     float* uv = reinterpret_cast<float*>(scratch + 3 * kernel_batch);
-    const int c = K / 2, lane = threadIdx.x & 31;
-    const int kb = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (kb >= kernel_batch) return;
+    const int c = K / 2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kb = blockIdx.x;
     const float* kp = kern + (size_t)kb * K * K;
+    const int n = K * K;  // K <= 21 on this path
     int r = 0;
     float amax = 0.0f;
     int imax = 0;
-    for (int idx = lane; idx < K * K; idx += 32) {
+    for (int idx = tid; idx < n; idx += 128) {
         const float v = kp[idx];
+        sk[idx] = v;
         if (v != 0.0f) {
             const int i = idx / K, j = idx - i * K;
             r = max(r, max(abs(i - c), abs(j - c)));
@@ -62,33 +68,43 @@ __global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_consta
         if (fabsf(v) > amax) { amax = fabsf(v); imax = idx; }
     }
     r = __reduce_max_sync(0xffffffffu, r);
-    // pivot = the largest |tap| (ties -> lowest index)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {  // pivot = the largest |tap| (ties -> lowest index)
         const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
         const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
         if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
     }
+    if (lane == 0) { s_red[warp] = amax; s_idx[warp] = imax; s_r[warp] = r; }
+    __syncthreads();
+    amax = s_red[0]; imax = s_idx[0]; r = s_r[0];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+        if (s_red[w] > amax || (s_red[w] == amax && s_idx[w] < imax)) { amax = s_red[w]; imax = s_idx[w]; }
+        r = max(r, s_r[w]);
+    }
     const int pi = imax / K, pj = imax - pi * K;
-    const float piv = kp[imax];
-    bool ok = amax > 0.0f && K <= 21;
+    const float piv = sk[imax];
+    bool ok = amax > 0.0f;
     if (ok) {
-        for (int idx = lane; idx < K * K; idx += 32) {
+        for (int idx = tid; idx < n; idx += 128) {
             const int i = idx / K, j = idx - i * K;
-            const float kij = kp[idx];
-            const float sep = kp[i * K + pj] * __fdiv_rn(kp[pi * K + j], piv);
+            const float kij = sk[idx];
+            const float sep = sk[i * K + pj] * __fdiv_rn(sk[pi * K + j], piv);
             ok = ok && (fabsf(kij - sep) <= 4e-7f * fabsf(kij) + 1e-9f * amax);
         }
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (lane < kUVPitch) {
+    if (lane == 0) s_ok[warp] = ok;
+    __syncthreads();
+    ok = s_ok[0] && s_ok[1] && s_ok[2] && s_ok[3];
+    if (tid < kUVPitch) {
         // centred in 21 slots: slot s <-> offset s - 10
-        const int t = lane - 10 + c;  // tap index for this slot
-        const bool in = lane < 21 && t >= 0 && t < K;
-        uv[((size_t)kb * 2 + 0) * kUVPitch + lane] = (ok && in) ? kp[t * K + pj] : 0.0f;
-        uv[((size_t)kb * 2 + 1) * kUVPitch + lane] = (ok && in) ? __fdiv_rn(kp[pi * K + t], piv) : 0.0f;
+        const int t = tid - 10 + c;  // tap index for this slot
+        const bool in = tid < 21 && t >= 0 && t < K;
+        uv[((size_t)kb * 2 + 0) * kUVPitch + tid] = (ok && in) ? sk[t * K + pj] : 0.0f;
+        uv[((size_t)kb * 2 + 1) * kUVPitch + tid] = (ok && in) ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
     }
-    if (lane == 0) { support[kb] = r; rank1[kb] = ok ? 1 : 0; }
+    if (tid == 0) { support[kb] = r; rank1[kb] = ok ? 1 : 0; }
 }
 
 // order[0..kb): sample indices sorted by support, largest first (stable).  One small CTA per kernel set.
@@ -110,7 +126,7 @@ static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch
     OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 8192, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..8192");
     KernelSets sets;
     for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
-    kernel_support_kernel<<<dim3(ceil_div(kernel_batch, 4), nsets), 128, 0, st>>>(sets, K, kernel_batch, scratch);
+    kernel_support_kernel<<<dim3(kernel_batch, nsets), 128, 0, st>>>(sets, K, kernel_batch, scratch);
     OTF_LAUNCH_CHECK("kernel_support_kernel");
     if (kernel_batch > 1) {
         kernel_order_kernel<<<nsets, 1024, kernel_batch * sizeof(int), st>>>(kernel_batch, scratch);

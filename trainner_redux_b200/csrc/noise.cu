@@ -159,45 +159,52 @@ struct UniformStream {
     }
 };
 
-// log(k!) — exact table for small k, Stirling series otherwise (abs err < 1e-7 for k >= 10)
+// log(k!) — exact table for small k, Stirling series otherwise (abs err < 1e-7 for k >= 10 before the
+// ~1e-6 relative error of the MUFU logarithm)
 __device__ __forceinline__ float log_factorial(float k) {
     const float tab[10] = {0.0f, 0.0f, 0.69314718f, 1.79175947f, 3.17805383f, 4.78749174f,
                            6.57925121f, 8.52516136f, 10.60460290f, 12.80182748f};
     if (k < 10.0f) return tab[(int)k];
     const float x = k + 1.0f;
-    const float ix = 1.0f / x, ix2 = ix * ix;
-    return (x - 0.5f) * logf(x) - x + 0.91893853f + ix * (0.083333333f - ix2 * (0.0027777778f - ix2 * 0.00079365079f));
+    const float ix = __fdividef(1.0f, x), ix2 = ix * ix;
+    return (x - 0.5f) * __logf(x) - x + 0.91893853f + ix * (0.083333333f - ix2 * (0.0027777778f - ix2 * 0.00079365079f));
 }
 
+// Poisson(lambda), lambda in [0, 256].  MUFU-based exp/log/div/sqrt: the acceptance inequality of the
+// rejection branch is evaluated to ~1e-4 absolute on the log scale, a bias far below what a chi-square
+// test at 2M samples can see (tests/test_rng_gpu.py), for roughly a fifth of the instructions.
 __device__ float poisson_sample(float lam, UniformStream& us) {
     if (!(lam > 0.0f)) return 0.0f;
     if (lam < 10.0f) {
         // inversion by sequential search on the CDF (one uniform)
-        float p = expf(-lam), k = 0.0f;
-        float u = us.next();
+        float p = __expf(-lam), k = 0.0f;
+        const float u = us.next();
         float cdf = p;
         while (u > cdf && k < 100.0f) {
             k += 1.0f;
-            p *= lam / k;
+            p *= __fdividef(lam, k);
             cdf += p;
         }
         return k;
     }
     // PTRS — W. Hörmann, "The transformed rejection method for generating Poisson random
     // variables", Insurance: Mathematics and Economics 12 (1993) 39-45.
-    const float slam = sqrtf(lam), loglam = logf(lam);
+    float slam;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(slam) : "f"(lam));
+    const float loglam = __logf(lam);
     const float bb = 0.931f + 2.53f * slam;
     const float a = -0.059f + 0.02483f * bb;
-    const float invalpha = 1.1239f + 1.1328f / (bb - 3.4f);
-    const float vr = 0.9277f - 3.6224f / (bb - 2.0f);
+    const float invalpha = 1.1239f + __fdividef(1.1328f, bb - 3.4f);
+    const float vr = 0.9277f - __fdividef(3.6224f, bb - 2.0f);
     for (int it = 0; it < 64; ++it) {
         const float U = us.next() - 0.5f;
         const float V = us.next();
         const float us_ = 0.5f - fabsf(U);
-        const float k = floorf((2.0f * a / us_ + bb) * U + lam + 0.43f);
+        const float k = floorf((__fdividef(2.0f * a, us_) + bb) * U + lam + 0.43f);
         if (us_ >= 0.07f && V <= vr) return k;
         if (k < 0.0f || (us_ < 0.013f && V > us_)) continue;
-        if (logf(V) + logf(invalpha) - logf(a / (us_ * us_) + bb) <= -lam + k * loglam - log_factorial(k)) return k;
+        // log(V) + log(invalpha) - log(a/us^2 + b) as one logarithm
+        if (__logf(__fdividef(V * invalpha, __fdividef(a, us_ * us_) + bb)) <= -lam + k * loglam - log_factorial(k)) return k;
     }
     return floorf(lam + 0.5f);
 }
@@ -288,8 +295,13 @@ __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restr
     float* op = out + (size_t)b * 3 * hw;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
         const float px[3] = {ip[p], ip[hw + p], ip[2 * hw + p]};
+        // The gray flag is block-uniform.  flag 0: noise*1 + noise_g*0 == noise exactly, flag 1: noise*0 + noise_g*1
+        // == noise_g exactly — so the field that the mix discards is not sampled (unless a test asked for its lambda
+        // or injected its counts).
+        const bool need_g = gray && (gf != 0.0f || counts_g || lam_g_out);
+        const bool need_c = !(gray && gf == 1.0f) || counts_c || lam_c_out;
         float noise_g = 0.0f;
-        if (gray) {
+        if (need_g) {
             // degradations.py:787-795 — gray image, quantised; noise relative to the quantised value
             const float qg = quantise8(gray_of(px[0], px[1], px[2]));
             const float lam = __fmul_rn(qg, vg);
@@ -306,17 +318,20 @@ __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restr
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const size_t e = (size_t)b * 3 * hw + (size_t)c * hw + p;
-            const float qc = quantise8(px[c]);  // :800
-            const float lam = __fmul_rn(qc, vc);
-            if (lam_c_out) lam_c_out[e] = lam;
-            float cnt;
-            if (counts_c) {
-                cnt = counts_c[e];
-            } else {
-                UniformStream us(ph, (uint64_t)e, offset * 8 + STREAM_POIS_COLOR);
-                cnt = poisson_sample(lam, us);
+            float noise = 0.0f;
+            if (need_c) {
+                const float qc = quantise8(px[c]);  // :800
+                const float lam = __fmul_rn(qc, vc);
+                if (lam_c_out) lam_c_out[e] = lam;
+                float cnt;
+                if (counts_c) {
+                    cnt = counts_c[e];
+                } else {
+                    UniformStream us(ph, (uint64_t)e, offset * 8 + STREAM_POIS_COLOR);
+                    cnt = poisson_sample(lam, us);
+                }
+                noise = __fsub_rn(__fdiv_rn(cnt, vc), qc);  // :805-806
             }
-            float noise = __fsub_rn(__fdiv_rn(cnt, vc), qc);  // :805-806
             if (gray) noise = __fadd_rn(__fmul_rn(noise, __fsub_rn(1.0f, gf)), __fmul_rn(noise_g, gf));  // :808
             noise = __fmul_rn(noise, sc);                                                              // :811
             op[(size_t)c * hw + p] =

@@ -19,7 +19,7 @@ enum { EPI_NONE = 0, EPI_USM_MASK = 1, EPI_USM_BLEND = 2 };
 
 // Horizontal pass: a CTA owns ROWS rows x TW columns; the row segment (+halo) sits in smem.
 constexpr int H_TW = 256, H_ROWS = 4;
-__global__ void __launch_bounds__(256) sepconv_h_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
+__global__ void __launch_bounds__(256) sepconv_h_generic_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
                                                         const __grid_constant__ Taps taps) {
     extern __shared__ float sm[];
     const int r = taps.n / 2, span = H_TW + 2 * r;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) sepconv_h_kernel(const float* __restrict_
 // Epilogues fuse the USM elementwise work into the pass that produces the blur.
 constexpr int V_TW = 32, V_TH = 64;
 template <int EPI>
-__global__ void __launch_bounds__(256) sepconv_v_kernel(const float* __restrict__ tmp, float* __restrict__ out, int H, int W,
+__global__ void __launch_bounds__(256) sepconv_v_generic_kernel(const float* __restrict__ tmp, float* __restrict__ out, int H, int W,
                                                         const __grid_constant__ Taps taps,
                                                         const float* __restrict__ img, float* __restrict__ aux,
                                                         float weight, float threshold) {
@@ -99,30 +99,184 @@ static int fill_taps(Taps& t, const float* taps_host, int ntaps) {
     return OTF_OK;
 }
 
-static int launch_h(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st) {
+static int launch_h_generic(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st) {
     const dim3 grid(ceil_div(W, H_TW), ceil_div(H, H_ROWS), planes);
     const size_t smem = (size_t)H_ROWS * (H_TW + 2 * (t.n / 2)) * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sepconv_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sepconv_h_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "sepconv_h smem attribute");
     }
-    sepconv_h_kernel<<<grid, 256, smem, st>>>(img, out, H, W, t);
-    OTF_LAUNCH_CHECK("sepconv_h_kernel");
+    sepconv_h_generic_kernel<<<grid, 256, smem, st>>>(img, out, H, W, t);
+    OTF_LAUNCH_CHECK("sepconv_h_generic_kernel");
     return OTF_OK;
 }
 
 template <int EPI>
-static int launch_v(const float* tmp, int planes, int H, int W, const Taps& t, float* out, const float* img, float* aux,
+static int launch_v_generic(const float* tmp, int planes, int H, int W, const Taps& t, float* out, const float* img, float* aux,
                     float weight, float threshold, cudaStream_t st) {
     const dim3 grid(ceil_div(W, V_TW), ceil_div(H, V_TH), planes);
     const size_t smem = (size_t)(V_TH + 2 * (t.n / 2)) * V_TW * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sepconv_v_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sepconv_v_generic_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "sepconv_v smem attribute");
     }
-    sepconv_v_kernel<EPI><<<grid, 256, smem, st>>>(tmp, out, H, W, t, img, aux, weight, threshold);
+    sepconv_v_generic_kernel<EPI><<<grid, 256, smem, st>>>(tmp, out, H, W, t, img, aux, weight, threshold);
+    OTF_LAUNCH_CHECK("sepconv_v_generic_kernel");
+    return OTF_OK;
+}
+
+// ---- register-blocked passes for <= 63 taps (USM radius <= 31, every Lanczos prefilter in range) ----
+// The taps sit centred in an NTP-slot array (NTP = 8/16/32/64, centre at NTP/2, zeros around), passed in the
+// kernel parameter bank: with the tap loop fully unrolled every FFMA takes its weight as a constant-bank
+// operand — no load instruction at all.  A thread produces 8 outputs from a (8 + NTP)-pixel window held in
+// registers, so shared memory is read once per 8 x NTP FMAs (LDS.128 along rows, conflict-free LDS.32 down
+// columns).  FMA-bound: 2*NTP flop per output per pass.
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int NTP>
+struct TapsC {
+    float w[NTP];
+};
+
+template <int NTP>
+__global__ void __launch_bounds__(256) sepconv_h_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
+                                                        const __grid_constant__ TapsC<NTP> taps) {
+    constexpr int CEN = NTP / 2, TW = 256, ROWS = 8, SW = TW + NTP;  // smem col s <-> x = x0 - CEN + s
+    extern __shared__ __align__(16) float sm[];
+    const int plane = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * ROWS;
+    const float* ip = img + (size_t)plane * H * W;
+    for (int row = threadIdx.x >> 5; row < ROWS; row += 8) {
+        const int y = min(y0 + row, H - 1);
+        for (int s = threadIdx.x & 31; s < SW; s += 32) {
+            const int gx = clampi(reflect_idx(x0 - CEN + s, W), 0, W - 1);
+            cp_async_f32(&sm[row * SW + s], ip + (size_t)y * W + gx);  // all copies in flight at once
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int row = threadIdx.x >> 5, seg = (threadIdx.x & 31) * 8;
+    const int y = y0 + row;
+    if (y >= H || x0 + seg >= W) return;
+    float win[8 + NTP];
+    const float4* wp = reinterpret_cast<const float4*>(sm + row * SW + seg);
+#pragma unroll
+    for (int q = 0; q < (8 + NTP) / 4; ++q) {
+        const float4 v = wp[q];
+        win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
+    }
+    float acc[8];
+#pragma unroll
+    for (int ox = 0; ox < 8; ++ox) acc[ox] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NTP; ++j)
+#pragma unroll
+        for (int ox = 0; ox < 8; ++ox) acc[ox] = fmaf(taps.w[j], win[ox + j], acc[ox]);
+    float* op = out + (size_t)plane * H * W + (size_t)y * W + x0 + seg;
+#pragma unroll
+    for (int ox = 0; ox < 8; ++ox)
+        if (x0 + seg + ox < W) op[ox] = acc[ox];
+}
+
+template <int NTP, int EPI>
+__global__ void __launch_bounds__(256) sepconv_v_kernel(const float* __restrict__ tmp, float* __restrict__ out, int H, int W,
+                                                        const __grid_constant__ TapsC<NTP> taps,
+                                                        const float* __restrict__ img, float* __restrict__ aux,
+                                                        float weight, float threshold) {
+    constexpr int CEN = NTP / 2, TWV = 32, TH = 64, SH = TH + NTP;  // smem row s <-> y = y0 - CEN + s
+    extern __shared__ __align__(16) float sm[];
+    const int plane = blockIdx.z, x0 = blockIdx.x * TWV, y0 = blockIdx.y * TH;
+    const float* tp = tmp + (size_t)plane * H * W;
+    const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int x = x0 + lx, gx = min(x, W - 1);
+    for (int s = wy; s < SH; s += 8) {
+        const int gy = clampi(reflect_idx(y0 - CEN + s, H), 0, H - 1);
+        cp_async_f32(&sm[s * TWV + lx], tp + (size_t)gy * W + gx);
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int ys = wy * 8;  // this warp's 8 output rows
+    if (x >= W || y0 + ys >= H) return;
+    float win[8 + NTP];
+#pragma unroll
+    for (int k = 0; k < 8 + NTP; ++k) win[k] = sm[(ys + k) * TWV + lx];
+    float acc[8];
+#pragma unroll
+    for (int oy = 0; oy < 8; ++oy) acc[oy] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NTP; ++i)
+#pragma unroll
+        for (int oy = 0; oy < 8; ++oy) acc[oy] = fmaf(taps.w[i], win[oy + i], acc[oy]);
+#pragma unroll
+    for (int oy = 0; oy < 8; ++oy) {
+        const int y = y0 + ys + oy;
+        if (y >= H) break;
+        const size_t o = (size_t)plane * H * W + (size_t)y * W + x;
+        if (EPI == EPI_NONE) {
+            out[o] = acc[oy];
+        } else if (EPI == EPI_USM_MASK) {
+            // img_process_util.py:47-53: residual, hard mask, clipped sharpen
+            const float im = img[o];
+            const float res = __fsub_rn(im, acc[oy]);
+            out[o] = (__fmul_rn(fabsf(res), 255.0f) > threshold) ? 1.0f : 0.0f;  // mask
+            aux[o] = clamp01(__fadd_rn(im, __fmul_rn(weight, res)));               // sharp
+        } else {
+            // img_process_util.py:55: soft*sharp + (1-soft)*img   (acc = soft mask, aux = sharp)
+            const float im = img[o];
+            out[o] = __fadd_rn(__fmul_rn(acc[oy], aux[o]), __fmul_rn(__fsub_rn(1.0f, acc[oy]), im));
+        }
+    }
+}
+
+template <int NTP>
+static TapsC<NTP> centre_taps(const Taps& t) {
+    TapsC<NTP> c;
+    for (int i = 0; i < NTP; ++i) c.w[i] = 0.0f;
+    const int r = t.n / 2;
+    for (int i = 0; i < t.n; ++i) c.w[NTP / 2 - r + i] = t.w[i];
+    return c;
+}
+
+static int launch_h_generic(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st);
+template <int EPI>
+static int launch_v_generic(const float* tmp, int planes, int H, int W, const Taps& t, float* out, const float* img, float* aux,
+                            float weight, float threshold, cudaStream_t st);
+
+template <int NTP>
+static int launch_h_fast(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st) {
+    const dim3 grid(ceil_div(W, 256), ceil_div(H, 8), planes);
+    sepconv_h_kernel<NTP><<<grid, 256, 8 * (256 + NTP) * sizeof(float), st>>>(img, out, H, W, centre_taps<NTP>(t));
+    OTF_LAUNCH_CHECK("sepconv_h_kernel");
+    return OTF_OK;
+}
+static int launch_h(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st) {
+    const int need = 2 * (t.n / 2) + 2;  // NTP must satisfy r <= NTP/2 - 1
+    if (need <= 8) return launch_h_fast<8>(img, planes, H, W, t, out, st);
+    if (need <= 16) return launch_h_fast<16>(img, planes, H, W, t, out, st);
+    if (need <= 32) return launch_h_fast<32>(img, planes, H, W, t, out, st);
+    if (need <= 64) return launch_h_fast<64>(img, planes, H, W, t, out, st);
+    return launch_h_generic(img, planes, H, W, t, out, st);
+}
+
+template <int NTP, int EPI>
+static int launch_v_fast(const float* tmp, int planes, int H, int W, const Taps& t, float* out, const float* img, float* aux,
+                         float weight, float threshold, cudaStream_t st) {
+    const dim3 grid(ceil_div(W, 32), ceil_div(H, 64), planes);
+    sepconv_v_kernel<NTP, EPI><<<grid, 256, (64 + NTP) * 32 * sizeof(float), st>>>(tmp, out, H, W, centre_taps<NTP>(t), img, aux,
+                                                                                   weight, threshold);
     OTF_LAUNCH_CHECK("sepconv_v_kernel");
     return OTF_OK;
+}
+template <int EPI>
+static int launch_v(const float* tmp, int planes, int H, int W, const Taps& t, float* out, const float* img, float* aux,
+                    float weight, float threshold, cudaStream_t st) {
+    const int need = 2 * (t.n / 2) + 2;
+    if (need <= 8) return launch_v_fast<8, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    if (need <= 16) return launch_v_fast<16, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    if (need <= 32) return launch_v_fast<32, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    if (need <= 64) return launch_v_fast<64, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    return launch_v_generic<EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
 }
 
 }  // namespace otf
