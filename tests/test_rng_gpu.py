@@ -116,3 +116,4 @@ def test_poisson_noise_statistics_on_flat_image(dev):
     assert export["vals"][:, 0].tolist() == [1.0, 1.0]
     noise = (out - img) / 0.1
     assert abs(noise.mean().item()) < 0.01 and abs(noise.var().item() - q) < 0.02
+
