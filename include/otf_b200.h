@@ -170,6 +170,10 @@ int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
                       int top, int left, int lq_patch, int scale,
                       float* gt_out, float* lq_out, void* stream);
 
+/* uint8 image -> fp32 / 255 (the host-side normalisation of traiNNer/utils/img_util.py:65-109 `img2tensor`,
+ * moved behind a 4x smaller upload). */
+int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* stream);
+
 /* Strided (e.g. channels_last) -> dense NCHW copy; strides in elements. */
 int otf_copy_strided_f32(const float* src, const int64_t strides[4],
                          int B, int C, int H, int W, float* dst, void* stream);

@@ -366,3 +366,23 @@ def test_feed_pool_and_philox_reproducibility(dev):
         assert torch.equal(l0, l1) and torch.equal(g0, g1), "same (seed, rank) must reproduce the run bit for bit"
     lat = runs[0][-1][0] * 255
     assert torch.equal(lat, lat.round()), "LQ must sit on the 8-bit lattice"
+
+
+def test_uint8_gt_upload_equals_host_normalisation(dev):
+    """Extension: a uint8 GT batch normalised on the device gives exactly the pair that the
+    reference's host-side img2tensor (float32(img) / 255) gives."""
+    from trainner_redux_b200.realesrgan_feed import HostRNG, OTFOptions, RealESRGANFeed, draw_plan
+
+    b, h = 4, 96
+    g = torch.Generator().manual_seed(5)
+    gt8 = torch.randint(0, 256, (b, 3, h, h), generator=g, dtype=torch.uint8)
+    gtf = gt8.float() / 255.0
+    opt = OTFOptions(scale=4, gt_size=64, blur_prob=1, blur_prob2=1, gaussian_noise_prob=1, noise_range=(1, 30),
+                     gaussian_noise_prob2=1, noise_range2=(1, 25), jpeg_range=(30, 95), jpeg_range2=(30, 95))
+    data = {"kernel1": O.synth_blur_kernels(b, seed=1), "kernel2": O.synth_blur_kernels(b, seed=2), "sinc_kernel": O.synth_sinc_or_pulse(b, seed=3)}
+    outs = []
+    for gt in (gt8, gtf):
+        feed = RealESRGANFeed(opt, device=dev, manual_seed=9, use_pool=False)
+        feed.feed_data({"gt": gt, **data})
+        outs.append((feed.gt.clone(), feed.lq.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

@@ -31,6 +31,20 @@ __global__ void __launch_bounds__(256) clamp_round_kernel(const float* __restric
     if (tail < n) out[tail] = quantise8(x[tail]);
 }
 
+// ---- uint8 GT upload: x / 255 on the device ------------------------------
+// The reference normalises on the host (traiNNer/utils/img_util.py:65-109 `img2tensor`: float32(img) / 255) and
+// ships fp32 over PCIe; uploading the 8-bit image and dividing here moves 4x fewer bytes.  Same IEEE division.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t nq = n >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        const uchar4 u = reinterpret_cast<const uchar4*>(src)[q];
+        reinterpret_cast<float4*>(dst)[q] = make_float4(__fdiv_rn((float)u.x, 255.0f), __fdiv_rn((float)u.y, 255.0f),
+                                                        __fdiv_rn((float)u.z, 255.0f), __fdiv_rn((float)u.w, 255.0f));
+    }
+    const int64_t tail = (nq << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tail < n) dst[tail] = __fdiv_rn((float)src[tail], 255.0f);
+}
+
 // ---- a8: traiNNer/data/transforms.py:124-135 followed by .contiguous() --------------------
 // One launch copies both windows.  A thread moves one quad (4 consecutive output pixels) per
 // iteration and keeps UNR of them in flight; 16-byte loads when the window start is aligned.
@@ -168,6 +182,18 @@ extern "C" int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* 
     if (blocks < 1) blocks = 1;
     clamp_round_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n);
     OTF_LAUNCH_CHECK("clamp_round_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(src && dst && n > 0, OTF_ERR_BAD_ARG, "u8_to_f32: bad args");
+    OTF_REQUIRE((((uintptr_t)src) & 3) == 0 && (((uintptr_t)dst) & 15) == 0, OTF_ERR_BAD_ARG, "u8_to_f32: misaligned pointers");
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (blocks < 1) blocks = 1;
+    u8_to_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    OTF_LAUNCH_CHECK("u8_to_f32_kernel");
     return OTF_OK;
 }
 

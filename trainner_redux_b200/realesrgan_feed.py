@@ -350,6 +350,12 @@ class RealESRGANFeed:
             kernel1 = data["kernel1"].to(self.device, non_blocking=True)
             kernel2 = data["kernel2"].to(self.device, non_blocking=True)
             sinc_kernel = data["sinc_kernel"].to(self.device, non_blocking=True)
+            if gt.dtype == torch.uint8:
+                # extension: an 8-bit GT batch is normalised on the device (x / 255, the division
+                # img2tensor does on the host) — a quarter of the PCIe bytes of the reference's fp32 upload
+                gt8 = gt.contiguous()
+                gt = torch.empty(gt8.shape, dtype=torch.float32, device=self.device)
+                _lib.call("otf_u8_to_f32", _lib.ptr(gt8), gt8.numel(), _lib.ptr(gt), _lib.stream())
             gt = _lib.dense_f32(gt)
             ori_h, ori_w = gt.shape[2:4]
             if plan is None:
