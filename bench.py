@@ -180,6 +180,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA
+    node the GPU hangs off, so that N ranks do not all pull their H2D traffic through one socket."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001  (topology files missing in a container: stay unbound)
+        return None
+    return None
+
+
 # ---------------------------------------------------------------------------- main ----
 def run_b200(args) -> None:
     import torch.distributed as dist
@@ -195,6 +219,7 @@ def run_b200(args) -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -381,7 +406,7 @@ def run_b200(args) -> None:
             "config": {"workload": workload_name(), "batch_per_gpu": BATCH, "gt": GT, "scale": SCALE,
                        "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * BATCH * 3 * GT * GT * 4 / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "eager" if args.no_graph else f"CUDA graph replay ({kernels_per_step} kernels/step); stage_ms: each stage re-captured alone (x20) and replayed",
-                       "parallelism": f"per-sample shards x{world}, no collective"},
+                       "parallelism": f"per-sample shards x{world}, no collective", "numa_node_rank0": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
                        "note": "extension: uint8 GT upload + on-device /255 (not the reference's fp32 host format)"},

@@ -178,6 +178,13 @@ int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* stream);
 int otf_copy_strided_f32(const float* src, const int64_t strides[4],
                          int B, int C, int H, int W, float* dst, void* stream);
 
+/* ---- f2: blur / sinc kernel synthesis — traiNNer/data/degradations.py:22-212, :472-507 ----------
+ * params_dev: double[B][8] = [type, ksize, sig_x, sig_y, theta, beta, omega_c, pad_to], type 0 iso,
+ * 1 aniso, 2 generalized_iso, 3 generalized_aniso, 4 plateau_iso, 5 plateau_aniso, 6 sinc, 7 pulse
+ * (the host draws them in the order of traiNNer/data/realesrgan_dataset.py:149-206).  out: fp32[B][21][21],
+ * normalised, zero-padded to 21x21 as the dataset does. */
+int otf_synth_kernels_f32(const double* params_dev, int B, float* out, void* stream);
+
 /* ---- a9: pair pool without bulk copies ----------------------
  * Gathers `n` slots: dst[i] = src[idx_host[i]] for slot_elems floats each, and
  * scatters likewise (dst[idx_host[i]] = src[i]).  n <= 512. */

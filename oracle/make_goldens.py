@@ -243,6 +243,80 @@ def main() -> None:
     ):
         put(f"chain_{name}", t)
 
+
+    # ---- f2 kernel synthesis: reference generators with explicit parameters + a seeded dataset-style draw ----
+    from oracle import kernel_synth_oracle as KS
+
+    prm = []
+    g2 = np.random.default_rng(51)
+    for kind in range(6):
+        for k in (5, 7, 13, 21):
+            prm.append([kind, k, g2.uniform(0.2, 3), g2.uniform(0.2, 3), g2.uniform(-np.pi, np.pi), g2.uniform(0.5, 4), 0.0, 21])
+    for k in (5, 7, 11, 13, 21):
+        prm.append([6, k, 0, 0, 0, 0, g2.uniform(np.pi / 5, np.pi), 21])
+    prm.append([7, 21, 0, 0, 0, 0, 0, 21])
+    prm = np.asarray(prm, np.float64)
+    ref_k = np.zeros((len(prm), 21, 21), np.float32)
+    for i, (kind, k, sx, sy, th, beta, wc, _pad) in enumerate(prm):
+        kind, k = int(kind), int(k)
+        iso = kind in (0, 2, 4)
+        if kind == 7:
+            ref_k[i, 10, 10] = 1
+            continue
+        if kind == 6:
+            ker = R.deg.circular_lowpass_kernel(wc, k, pad_to=False)
+        else:
+            if kind < 2:
+                ker = R.deg.bivariate_gaussian(k, sx, sy, th, isotropic=iso)
+            elif kind < 4:
+                ker = R.deg.bivariate_generalized_gaussian(k, sx, sy, th, beta, isotropic=iso)
+            else:
+                ker = R.deg.bivariate_plateau(k, sx, sy, th, beta, isotropic=iso)
+            ker = ker / np.sum(ker)  # the random_* wrappers normalise once more (degradations.py:258/313/369)
+        pd = (21 - k) // 2
+        ref_k[i] = np.pad(ker, ((pd, pd), (pd, pd))).astype(np.float32)
+    assert np.array_equal(KS.synthesize(prm), ref_k), "kernel_synth oracle != reference"
+    put("ks_params", prm)
+    put("ks_ref", ref_k)
+    # dataset-style draws (realesrgan_dataset.py:149-206) through the reference's own random_* functions
+    import math as _math
+    import random as _random
+
+    from trainner_redux_b200.kernels import KernelOptions, draw_kernel_params
+
+    kopt = KernelOptions(sinc_prob=0.1, sinc_prob2=0.1, final_sinc_prob=0.8, kernel_range=(7, 21), kernel_range2=(7, 21),
+                         final_kernel_range=(7, 21))
+    R.RNG._rng = np.random.default_rng(77)
+    _random.seed(78)
+    ds_k1, ds_k2, ds_sk = [], [], []
+
+    def ref_blur(sizes, sinc_prob, klist, kprob, sigma, betag, betap):
+        ksz = _random.choice(sizes)
+        if R.RNG.get_rng().uniform() < sinc_prob:
+            wc = R.RNG.get_rng().uniform(np.pi / 3, np.pi) if ksz < 13 else R.RNG.get_rng().uniform(np.pi / 5, np.pi)
+            ker = R.deg.circular_lowpass_kernel(wc, ksz, pad_to=False)
+        else:
+            ker = R.deg.random_mixed_kernels(klist, kprob, ksz, sigma, sigma, (-_math.pi, _math.pi), betag, betap, noise_range=None)
+        pd = (21 - ksz) // 2
+        return np.pad(ker, ((pd, pd), (pd, pd)))
+
+    for _ in range(12):
+        ds_k1.append(ref_blur(list(range(7, 22, 2)), kopt.sinc_prob, kopt.kernel_list, kopt.kernel_prob, kopt.blur_sigma, kopt.betag_range, kopt.betap_range))
+        ds_k2.append(ref_blur(list(range(7, 22, 2)), kopt.sinc_prob2, kopt.kernel_list2, kopt.kernel_prob2, kopt.blur_sigma2, kopt.betag_range2, kopt.betap_range2))
+        if R.RNG.get_rng().uniform() < kopt.final_sinc_prob:
+            ksz = _random.choice(list(range(7, 22, 2)))
+            wc = R.RNG.get_rng().uniform(np.pi / 3, np.pi)
+            ds_sk.append(R.deg.circular_lowpass_kernel(wc, ksz, pad_to=21))
+        else:
+            pulse = np.zeros((21, 21))
+            pulse[10, 10] = 1
+            ds_sk.append(pulse)
+    ds = [np.stack(x).astype(np.float32) for x in (ds_k1, ds_k2, ds_sk)]
+    mine = draw_kernel_params(kopt, 12, _random.Random(78), np.random.default_rng(77))
+    for name, want, prm_i in zip(("k1", "k2", "sinc"), ds, mine):
+        assert np.array_equal(KS.synthesize(prm_i), want), f"dataset-order draw mismatch for {name}"
+        put(f"ks_ds_{name}", want)
+
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     np.savez_compressed(OUT, **G)
     print(f"wrote {OUT}: {len(G)} arrays, {os.path.getsize(OUT)/1e6:.2f} MB; oracle == reference on every case")

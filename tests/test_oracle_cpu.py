@@ -148,3 +148,23 @@ def test_pool_semantics():
             assert out_lq.flatten().tolist() != lq.flatten().tolist()
     with pytest.raises(AssertionError):
         O.PairPool(5).step(torch.zeros(2, 1, 1, 1), torch.zeros(2, 1, 1, 1))
+
+
+def test_kernel_synthesis_oracle_and_draw_order(golden):
+    """Row f2: the numpy restatement reproduces the reference generators bit for bit, and the host-side draw
+    order of trainner_redux_b200.kernels equals the dataset's (realesrgan_dataset.py:149-206)."""
+    import random
+
+    from oracle import kernel_synth_oracle as KS
+    from trainner_redux_b200.kernels import KernelOptions, draw_kernel_params
+
+    g = golden
+    got = KS.synthesize(g["ks_params"].numpy())
+    assert np.abs(got - g["ks_ref"].numpy()).max() < 1e-9  # bit-identical where the numpy/scipy builds match
+    assert np.allclose(got.sum((1, 2)), 1.0, atol=1e-6)
+    kopt = KernelOptions(sinc_prob=0.1, sinc_prob2=0.1, final_sinc_prob=0.8, kernel_range=(7, 21), kernel_range2=(7, 21),
+                         final_kernel_range=(7, 21))
+    p1, p2, p3 = draw_kernel_params(kopt, 12, random.Random(78), np.random.default_rng(77))
+    for name, prm in (("k1", p1), ("k2", p2), ("sinc", p3)):
+        assert np.abs(KS.synthesize(prm) - g[f"ks_ds_{name}"].numpy()).max() < 1e-9, name
+    assert set(p1[:, 0].astype(int)) <= set(range(7)) and (p3[:, 0] >= 6).all()

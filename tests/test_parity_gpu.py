@@ -386,3 +386,32 @@ def test_uint8_gt_upload_equals_host_normalisation(dev):
         feed.feed_data({"gt": gt, **data})
         outs.append((feed.gt.clone(), feed.lq.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_kernel_synthesis_on_gpu(golden, dev):
+    """Row f2: kernels synthesised on the device vs the reference's numpy/scipy generators."""
+    import random
+
+    import numpy as np
+
+    from trainner_redux_b200.kernels import KernelOptions, draw_kernel_params, synthesize_kernels
+    from trainner_redux_b200.realesrgan_feed import OTFOptions, RealESRGANFeed
+
+    g = golden
+    got = synthesize_kernels(g["ks_params"].numpy(), dev).cpu()
+    d = (got - g["ks_ref"]).abs().max().item()
+    assert d <= 1e-7, f"max-abs {d:.2e}"
+    kopt = KernelOptions(sinc_prob=0.1, sinc_prob2=0.1, final_sinc_prob=0.8, kernel_range=(7, 21), kernel_range2=(7, 21),
+                         final_kernel_range=(7, 21))
+    prm = draw_kernel_params(kopt, 12, random.Random(78), np.random.default_rng(77))
+    for name, p in zip(("k1", "k2", "sinc"), prm):
+        assert (synthesize_kernels(p, dev).cpu() - g[f"ks_ds_{name}"]).abs().max().item() <= 1e-7, name
+    # feed_data accepts the parameter tables in place of the three kernel tensors
+    opt = OTFOptions(scale=4, gt_size=64, blur_prob=1, blur_prob2=1, gaussian_noise_prob=1, noise_range=(1, 30),
+                     gaussian_noise_prob2=1, noise_range2=(1, 25), jpeg_range=(30, 95), jpeg_range2=(30, 95))
+    gt = O.synth_gt(12, 96, 96, "natural", seed=4)
+    a = RealESRGANFeed(opt, device=dev, manual_seed=1, use_pool=False)
+    a.feed_data({"gt": gt, "kernel_params": prm})
+    b = RealESRGANFeed(opt, device=dev, manual_seed=1, use_pool=False)
+    b.feed_data({"gt": gt, "kernel1": g["ks_ds_k1"], "kernel2": g["ks_ds_k2"], "sinc_kernel": g["ks_ds_sinc"]})
+    assert (a.lq - b.lq).abs().max().item() <= 1 / 255 + 1e-6

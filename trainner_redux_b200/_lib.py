@@ -48,6 +48,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "otf_u8_to_f32": (_i, [_p, _i64, _p, _p]),
     "otf_copy_strided_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "otf_synth_kernels_f32": (_i, [_p, _i, _p, _p]),
     "otf_gather_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
     "otf_scatter_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
 }
@@ -74,6 +75,7 @@ _LAUNCHES = {
     "otf_crop_pair_f32": 1,
     "otf_u8_to_f32": 1,
     "otf_copy_strided_f32": 1,
+    "otf_synth_kernels_f32": 1,
     "otf_gather_slots_f32": 1,
     "otf_scatter_slots_f32": 1,
 }

@@ -345,6 +345,14 @@ class RealESRGANFeed:
     def feed_data(self, data: dict, plan: dict | None = None, inject: dict | None = None) -> None:
         """Accept data from the dataloader and synthesise the LQ batch (realesrgan_model.py:455-650)."""
         if self.is_train:
+            if "kernel_params" in data and "kernel1" not in data:
+                # extension (SURVEY.md §8 f2): the dataset ships 3 x (B,8) parameter tables instead of three
+                # (B,21,21) kernels; the kernels are synthesised on the device (kernels.py)
+                from .kernels import synthesize_kernels
+
+                p1, p2, p3 = data["kernel_params"]
+                data = dict(data, kernel1=synthesize_kernels(p1, self.device), kernel2=synthesize_kernels(p2, self.device),
+                            sinc_kernel=synthesize_kernels(p3, self.device))
             assert "gt" in data and "kernel1" in data and "kernel2" in data and "sinc_kernel" in data
             gt = data["gt"].to(self.device, non_blocking=True)
             kernel1 = data["kernel1"].to(self.device, non_blocking=True)
