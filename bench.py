@@ -278,25 +278,43 @@ def run_b200(args) -> None:
         for i in range(args.warmup):
             graphs[i % N_ROTATE].replay()
     barrier()
+    def timed_region(n_streams: int) -> float:
+        """K steps, one batch each.  With 2 streams consecutive batches overlap (step i on stream i % 2): every
+        batch runs the identical chain, but the tail of one step's small kernels fills with the next step's work —
+        what a prefetching loader gets when it degrades batch i+1 while batch i is being consumed."""
+        main = torch.cuda.current_stream()
+        lanes = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else [main]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for ln in lanes:
+            if ln is not main:
+                ln.wait_stream(main)
+        for i in range(args.steps):
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                if graphs:
+                    graphs[i % N_ROTATE].replay()  # N_ROTATE is even: a graph always replays on the same lane
+                else:
+                    step_resident(i)
+        for ln in lanes:
+            if ln is not main:
+                main.wait_stream(ln)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        if graphs:
-            graphs[i % N_ROTATE].replay()
-        else:
-            step_resident(i)
-    e1.record()
-    barrier()
+    n_streams = 1 if args.no_graph else max(1, args.streams)
+    ms_total = timed_region(n_streams)
     launches = kernels_per_step * args.steps if graphs else _lib.launch_count - l0
     clocks = sampler.stop() if sampler else None
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
     value = world * BATCH * args.steps / (ms_total / 1e3)
+    ms_single = timed_region(1) if n_streams > 1 else ms_total
+    value_single = world * BATCH * args.steps / (ms_single / 1e3)
     # per-stage GPU durations for the roofline.  CUDA events cannot be read back from inside a replayed
     # graph, and around eager launches they would include the Python launch gap, so every stage of the
     # chain (on the tensors of one real pass) is re-captured into its own graph of REP launches and that
@@ -405,8 +423,9 @@ def run_b200(args) -> None:
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(), "batch_per_gpu": BATCH, "gt": GT, "scale": SCALE,
                        "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * BATCH * 3 * GT * GT * 4 / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "eager" if args.no_graph else f"CUDA graph replay ({kernels_per_step} kernels/step); stage_ms: each stage re-captured alone (x20) and replayed",
+                       "launch": "eager" if args.no_graph else f"CUDA graph replay ({kernels_per_step} kernels/step), {n_streams} batches in flight on {n_streams} streams; stage_ms: each stage re-captured alone (x20) and replayed",
                        "parallelism": f"per-sample shards x{world}, no collective", "numa_node_rank0": numa},
+            "value_one_batch_in_flight": value_single, "ms_per_step_one_batch_in_flight": ms_single / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
                        "note": "extension: uint8 GT upload + on-device /255 (not the reference's fp32 host format)"},
@@ -436,6 +455,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--streams", type=int, default=2, help="batches in flight during the timed region (graph mode)")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-capture pass (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
