@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json configs[1], SURVEY.md §8d "Config 2"): batch 64 of synthetic 256x256 RGB
 GT per GPU, scale 4, the classical second-order chain with every stage on:
-  blur1 (21x21 per-sample kernels, true sizes 7..21) -> bicubic resize x0.75 (192^2) ->
+  blur1 (per-sample 21x21 kernels from the reference's random_mixed_kernels mix, true sizes 7..21) ->
+  bicubic resize x0.75 (192^2) ->
   Gaussian noise sigma~U[1,30], gray 40 % -> DiffJPEG q~U[30,95] -> blur2 -> bilinear resize to 64^2 ->
   Gaussian noise -> area resize to 64^2 -> sinc filter -> DiffJPEG q~U[30,95] -> clamp/round -> paired crop 224/56.
 A "step" is one pass of that chain over one batch.  The batch shards per sample, so every rank
@@ -51,15 +52,28 @@ def peaks() -> dict:
 
 
 def make_inputs(seed: int, batch: int):
-    """Synthetic GT + kernels from the shared generators in oracle/otf_oracle.py (data only)."""
-    from oracle import otf_oracle as O
+    """Synthetic GT + kernels as SURVEY.md §8d specifies: U[0,1) GT; blur kernels from the reference's
+    `random_mixed_kernels` distribution (default kernel_list / kernel_prob of redux_options.py:102-119, odd sizes
+    7..21 zero-padded to 21, sinc_prob 0.1), final sinc w.p. 0.8 else the pulse.  Parameters are drawn in the
+    dataset's order by trainner_redux_b200.kernels.draw_kernel_params and evaluated by the CPU oracle of those
+    generators, so the GPU arm and the CPU reference arm see the same tensors."""
+    import random
 
-    gt = O.synth_gt(batch, GT, GT, "uniform", seed=1234 + seed)
+    import numpy as np
+
+    from oracle import kernel_synth_oracle as KS
+    from oracle import otf_oracle as O
+    from trainner_redux_b200.kernels import KernelOptions, draw_kernel_params
+
+    kopt = KernelOptions(kernel_range=(7, 21), kernel_range2=(7, 21), final_kernel_range=(7, 21), sinc_prob=0.1, sinc_prob2=0.1,
+                         final_sinc_prob=0.8, blur_sigma=(0.2, 3), blur_sigma2=(0.2, 1.5), betag_range=(0.5, 4),
+                         betag_range2=(0.5, 4), betap_range=(1, 2), betap_range2=(1, 2))
+    p1, p2, p3 = draw_kernel_params(kopt, batch, random.Random(100 + seed), np.random.default_rng(200 + seed))
     return {
-        "gt": gt,
-        "kernel1": O.synth_blur_kernels(batch, seed=10 + seed),
-        "kernel2": O.synth_blur_kernels(batch, seed=20 + seed),
-        "sinc_kernel": O.synth_sinc_or_pulse(batch, seed=30 + seed),
+        "gt": O.synth_gt(batch, GT, GT, "uniform", seed=1234 + seed),
+        "kernel1": torch.from_numpy(KS.synthesize(p1)),
+        "kernel2": torch.from_numpy(KS.synthesize(p2)),
+        "sinc_kernel": torch.from_numpy(KS.synthesize(p3)),
     }
 
 
@@ -431,7 +445,7 @@ def run_b200(args) -> None:
                        "note": "extension: uint8 GT upload + on-device /255 (not the reference's fp32 host format)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "filter2d_kernel (blur1, 64x3x256x256, 21x21 zero-padded kernels)", "bound": "hbm",
+            "roofline": {"kernel": "filter2d_kernel (blur1, 64x3x256x256, per-sample kernels zero-padded to 21x21: default kernel_list mix, sizes 7..21)", "bound": "hbm",
                          "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": traffic, "peak_source": pk["source"], "ms_per_launch": k_ms,
                          "fma": {"achieved_tflops_true_taps": flops * (true_k2 / 441.0) / (k_ms * 1e-3) / 1e12,
