@@ -14,6 +14,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "otf_goldens.npz")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the shared library is a build artefact (git-ignored): build it once if this checkout has none
+    lib = os.path.join(ROOT, "trainner_redux_b200", "libotf_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(ROOT, "trainner_redux_b200", "csrc"), "-j8"], check=True)
 
 
 def pytest_collection_modifyitems(config, items):
