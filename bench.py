@@ -307,7 +307,7 @@ def run_b200(args) -> None:
         for i in range(args.steps):
             with torch.cuda.stream(lanes[i % len(lanes)]):
                 if graphs:
-                    graphs[i % N_ROTATE].replay()  # N_ROTATE is even: a graph always replays on the same lane
+                    graphs[i % N_ROTATE].replay()  # lanes divides N_ROTATE: a graph always replays on the same lane
                 else:
                     step_resident(i)
         for ln in lanes:
@@ -322,7 +322,9 @@ def run_b200(args) -> None:
 
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count
-    n_streams = 1 if args.no_graph else max(1, args.streams)
+    n_streams = 1 if args.no_graph else max(1, min(args.streams, N_ROTATE))
+    while N_ROTATE % n_streams:
+        n_streams -= 1
     ms_total = timed_region(n_streams)
     launches = kernels_per_step * args.steps if graphs else _lib.launch_count - l0
     clocks = sampler.stop() if sampler else None
@@ -469,7 +471,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--streams", type=int, default=2, help="batches in flight during the timed region (graph mode)")
+    ap.add_argument("--streams", type=int, default=4, help="batches in flight during the timed region (graph mode)")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-capture pass (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
