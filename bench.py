@@ -51,30 +51,24 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "sm_max_mhz": 1965.0}
 
 
-def make_inputs(seed: int, batch: int):
+def make_inputs(seed: int, batch: int, device=None):
     """Synthetic GT + kernels as SURVEY.md §8d specifies: U[0,1) GT; blur kernels from the reference's
-    `random_mixed_kernels` distribution (default kernel_list / kernel_prob of redux_options.py:102-119, odd sizes
-    7..21 zero-padded to 21, sinc_prob 0.1), final sinc w.p. 0.8 else the pulse.  Parameters are drawn in the
-    dataset's order by trainner_redux_b200.kernels.draw_kernel_params and evaluated by the CPU oracle of those
-    generators, so the GPU arm and the CPU reference arm see the same tensors."""
-    import random
+    `random_mixed_kernels` distribution (default kernel_list / kernel_prob, odd sizes 7..21 zero-padded to 21,
+    sinc_prob 0.1), final sinc w.p. 0.8 else the pulse.  The parameter tables are drawn once (dataset order);
+    the GPU arm evaluates them with the product's own synthesis kernel (device given), the CPU reference arm with
+    the oracle of those generators (device None) — the two agree to 1e-7 (tests/test_parity_gpu.py)."""
+    from trainner_redux_b200.synthetic import synth_gt, synth_kernel_params
 
-    import numpy as np
+    p1, p2, p3 = synth_kernel_params(batch, seed)
+    if device is None:
+        from oracle import kernel_synth_oracle as KS  # CPU reference arm only
 
-    from oracle import kernel_synth_oracle as KS
-    from oracle import otf_oracle as O
-    from trainner_redux_b200.kernels import KernelOptions, draw_kernel_params
+        k1, k2, k3 = (torch.from_numpy(KS.synthesize(p)) for p in (p1, p2, p3))
+    else:
+        from trainner_redux_b200.kernels import synthesize_kernels
 
-    kopt = KernelOptions(kernel_range=(7, 21), kernel_range2=(7, 21), final_kernel_range=(7, 21), sinc_prob=0.1, sinc_prob2=0.1,
-                         final_sinc_prob=0.8, blur_sigma=(0.2, 3), blur_sigma2=(0.2, 1.5), betag_range=(0.5, 4),
-                         betag_range2=(0.5, 4), betap_range=(1, 2), betap_range2=(1, 2))
-    p1, p2, p3 = draw_kernel_params(kopt, batch, random.Random(100 + seed), np.random.default_rng(200 + seed))
-    return {
-        "gt": O.synth_gt(batch, GT, GT, "uniform", seed=1234 + seed),
-        "kernel1": torch.from_numpy(KS.synthesize(p1)),
-        "kernel2": torch.from_numpy(KS.synthesize(p2)),
-        "sinc_kernel": torch.from_numpy(KS.synthesize(p3)),
-    }
+        k1, k2, k3 = (synthesize_kernels(p, device).cpu() for p in (p1, p2, p3))
+    return {"gt": synth_gt(batch, GT, GT, "uniform", seed=1234 + seed), "kernel1": k1, "kernel2": k2, "sinc_kernel": k3}
 
 
 def make_plan(batch: int, seed: int) -> dict:
@@ -241,7 +235,7 @@ def run_b200(args) -> None:
     feed = RealESRGANFeed(OTFOptions(scale=SCALE, gt_size=GT_CROP, queue_size=BATCH * 2), device=dev, manual_seed=0, rank=rank,
                           use_pool=False)
     feed.stage_times = {}
-    host = [make_inputs(rank * N_ROTATE + i, BATCH) for i in range(N_ROTATE)]
+    host = [make_inputs(rank * N_ROTATE + i, BATCH, dev) for i in range(N_ROTATE)]
     for d in host:
         for k in d:
             d[k] = d[k].pin_memory()

@@ -14,7 +14,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import trainner_redux_b200 as T  # noqa: E402
-from oracle import otf_oracle as O  # noqa: E402  (synthetic inputs only)
+from trainner_redux_b200 import synthetic as S  # noqa: E402
+from trainner_redux_b200.kernels import synthesize_kernels  # noqa: E402
 from trainner_redux_b200 import degradations as D  # noqa: E402
 from trainner_redux_b200.realesrgan_feed import clamp_round  # noqa: E402
 from trainner_redux_b200.transforms import crop_pair  # noqa: E402
@@ -68,7 +69,7 @@ def timeit(make_fn, in_bytes):
 
 
 def img(h, w, seed=1):
-    return O.synth_gt(B, h, w, "uniform", seed=seed).to(dev)
+    return S.synth_gt(B, h, w, "uniform", seed=seed).to(dev)
 
 
 rows = []
@@ -109,16 +110,22 @@ def taps(k):
     return float((k != 0).flatten(1).sum(1).float().mean())
 
 
-for kinds in (("iso", "aniso", "sinc"), ("iso",), ("aniso",), ("sinc",)):
-    k = O.synth_blur_kernels(B, seed=10, kinds=kinds).to(dev)
-    add(f"filter2d 256^2 mixed-size {'/'.join(kinds)}", lambda t, k=k: T.filter2d(t, k), 2 * N(x256), 2 * taps(k) * x256.numel(), x=x256)
+def kernels(seed, kernel_list=None, sinc_prob=0.1, which=0):
+    """(B,21,21) kernels synthesised on the device from the reference's parameter distributions (sizes 7..21)."""
+    return synthesize_kernels(S.synth_kernel_params(B, seed, S.bench_kernel_options(kernel_list, sinc_prob))[which], dev)
+
+
+for kinds, sp in ((None, 0.1), (("iso",), 0.0), (("aniso",), 0.0), (("generalized_iso", "plateau_iso"), 0.0), (("iso",), 1.0)):
+    k = kernels(10, kinds, sp)
+    label = "default mix" if kinds is None else ("sinc" if sp == 1.0 else "/".join(kinds))
+    add(f"filter2d 256^2 sizes 7..21 {label}", lambda t, k=k: T.filter2d(t, k), 2 * N(x256), 2 * taps(k) * x256.numel(), x=x256)
 for ks in (7, 9, 13, 17, 21):
     k = torch.rand(B, ks, ks, device=dev)
     k = k / k.sum((1, 2), keepdim=True)
     add(f"filter2d 256^2 dense K={ks}", lambda t, k=k: T.filter2d(t, k), 2 * N(x256), 2 * ks * ks * x256.numel(), x=x256)
-k2 = O.synth_blur_kernels(B, seed=20).to(dev)
+k2 = kernels(20, which=1)
 add("filter2d 192^2 mixed", lambda t: T.filter2d(t, k2), 2 * N(x192), 2 * taps(k2) * x192.numel(), x=x192)
-sk = O.synth_sinc_or_pulse(B, seed=30).to(dev)
+sk = kernels(30, which=2)
 add("filter2d 64^2 final sinc", lambda t: T.filter2d(t, sk), 2 * N(x64), 2 * taps(sk) * x64.numel(), x=x64)
 for mode in ("bilinear", "bicubic", "area", "nearest-exact", "lanczos"):
     for s in (0.4, 0.75, 1.25, 1.5):

@@ -9,19 +9,18 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import trainner_redux_b200 as T  # noqa: E402
-from oracle import otf_oracle as O  # noqa: E402  (synthetic inputs only)
+from trainner_redux_b200 import synthetic as S  # noqa: E402
+from trainner_redux_b200.kernels import synthesize_kernels  # noqa: E402
 from trainner_redux_b200 import degradations as D  # noqa: E402
 
 stages = sys.argv[1:] or ["all"]
 want = lambda s: "all" in stages or s in stages
 dev = torch.device("cuda:0")
 B = 64
-gt = O.synth_gt(B, 256, 256, "uniform", seed=1).to(dev)
-k1 = O.synth_blur_kernels(B, seed=10).to(dev)
-k2 = O.synth_blur_kernels(B, seed=20).to(dev)
-sk = O.synth_sinc_or_pulse(B, seed=30).to(dev)
-x192 = O.synth_gt(B, 192, 192, "uniform", seed=2).to(dev)
-x64 = O.synth_gt(B, 64, 64, "uniform", seed=3).to(dev)
+gt = S.synth_gt(B, 256, 256, "uniform", seed=1).to(dev)
+k1, k2, sk = (synthesize_kernels(p, dev) for p in S.synth_kernel_params(B, 10))
+x192 = S.synth_gt(B, 192, 192, "uniform", seed=2).to(dev)
+x64 = S.synth_gt(B, 64, 64, "uniform", seed=3).to(dev)
 sigma = (torch.rand(B) * 29 + 1).to(dev)
 gray = (torch.rand(B) < 0.4).float().to(dev)
 q = (torch.rand(B) * 65 + 30).to(dev)
