@@ -13,10 +13,13 @@ GT per GPU, scale 4, the classical second-order chain with every stage on:
 A "step" is one pass of that chain over one batch.  The batch shards per sample, so every rank
 runs its own batch with no collective on the data path ("scaling": "weak").
 
-One JSON line on stdout (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
-metric through RealESRGANFeed.feed_data() from pinned HOST buffers with the LQ/GT pair read back;
-`roofline` describes the dominant kernel (blur1 filter2d) from CUDA-event timings taken inside the
-timed region; `cpu_baseline` is the oracle port of the reference pipeline on this box's host cores.
+One JSON line on stdout (rank 0).  `value` = pairs/s with inputs resident in HBM, `--streams` (default 4)
+batches in flight as CUDA-graph replays on as many streams (`value_one_batch_in_flight` = one stream);
+`e2e` = the same metric through RealESRGANFeed.feed_data() from pinned HOST fp32 buffers (H2D of the batch
+and its kernels prefetched on a copy stream) with the finished LQ read back every step; `e2e_u8` = the
+uint8-GT upload extension; `roofline` describes the dominant kernel (blur1 filter2d) from CUDA-event
+timings of graph replays; `cpu_baseline` is the oracle port of the reference pipeline on this box's host
+cores (`--impl reference` runs only that).
 """
 
 from __future__ import annotations
