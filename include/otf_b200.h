@@ -193,6 +193,23 @@ int otf_gather_slots_f32(const float* src, const int32_t* idx_host, int n,
 int otf_scatter_slots_f32(const float* src, const int32_t* idx_host, int n,
                           int64_t slot_elems, float* dst, void* stream);
 
+/* ---- f4: MoA batch augment on the finished pair — traiNNer/ops/batchaug.py:21-509 ----------------
+ * The host draws the augmentation, ratio, permutation and box exactly as the reference does; the
+ * resizes inside resizemix / cutblur / downup / up go through otf_resize_f32.
+ *
+ * otf_mixup_f32 (batchaug.py:150-158): out[b] = lam * img[b] + one_minus_lam * img[perm_host[b]], each
+ * product and the sum rounded to fp32 separately as torch does. Not in place. B <= 512.
+ *
+ * otf_copy_box_f32: dst[b, :, dy:dy+bh, dx:dx+bw] = src[perm_host ? perm_host[b] : b, :, sy:sy+bh, sx:sx+bw]
+ * for dense (B, planes_per_sample, Hs, Ws) / (B, planes_per_sample, Hd, Wd) tensors: the box paste of
+ * cutmix (:222-227), resizemix (:318-319) and cutblur (:394-401), and the crops of `up` (:476-477).
+ * A permuted copy must not be in place (stage the boxes in a workspace first); empty boxes are a no-op. */
+int otf_mixup_f32(const float* img, const int32_t* perm_host, int B, int64_t sample_elems,
+                  float lam, float one_minus_lam, float* out, void* stream);
+int otf_copy_box_f32(const float* src, int Hs, int Ws, int sy, int sx,
+                     float* dst, int Hd, int Wd, int dy, int dx, int bh, int bw,
+                     int B, int planes_per_sample, const int32_t* perm_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

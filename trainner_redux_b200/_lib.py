@@ -51,6 +51,8 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_synth_kernels_f32": (_i, [_p, _i, _p, _p]),
     "otf_gather_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
     "otf_scatter_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
+    "otf_mixup_f32": (_i, [_p, _p, _i, _i64, _f, _f, _p, _p]),
+    "otf_copy_box_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
 
 _lib: C.CDLL | None = None
@@ -78,6 +80,8 @@ _LAUNCHES = {
     "otf_synth_kernels_f32": 1,
     "otf_gather_slots_f32": 1,
     "otf_scatter_slots_f32": 1,
+    "otf_mixup_f32": 1,
+    "otf_copy_box_f32": 1,
 }
 
 

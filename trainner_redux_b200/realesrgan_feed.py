@@ -74,6 +74,11 @@ class OTFOptions:
     resize_mode_prob3: Sequence[float] = (0.25, 0.25, 0.25, 0.25)
     queue_size: int = 120
     p_clean: float = 0
+    # MoA batch augment on the finished pair (redux_options.py:295-322 `train.use_moa` ...; realesrgan_model.py:649-650)
+    use_moa: bool = False
+    # the schema's own defaults (4 names, 5 weights) fail batch_aug's length check in the reference too: set both
+    moa_augs: Sequence[str] = ("none", "mixup", "cutmix", "resizemix")
+    moa_probs: Sequence[float] = (0.4, 0.084, 0.084, 0.084, 0.348)
     # not in the reference schema: which composition to run, and the upstream 50/50 final-order coin
     order: str = "classic"
     final_jpeg_first_prob: float = 0.5
@@ -245,6 +250,11 @@ class RealESRGANFeed:
         self._usm: dict[int, USMSharp] = {}
         self.queue_size = _opt(opt, "queue_size", 120)
         self.pool = PairPool(self.queue_size, randperm=lambda n: torch.randperm(n, generator=self.rng.torch)) if use_pool else None
+        self.batch_augment = None  # base_model.py:875-876
+        if _opt(opt, "use_moa", False):
+            from .batchaug import BatchAugment
+
+            self.batch_augment = BatchAugment(_opt(opt, "scale", 4), opt, rng=self.rng)
         self.gt: Tensor | None = None
         self.lq: Tensor | None = None
         self.last_plan: dict | None = None
@@ -374,6 +384,8 @@ class RealESRGANFeed:
             self.gt, self.lq = crop_pair(gt, lq_full, plan["gt_size"], plan["scale"], top, left)
             if self.pool is not None:
                 self.lq, self.gt = self.pool.step(self.lq, self.gt)
+            if self.batch_augment:  # realesrgan_model.py:649-650 (is_train holds on this branch)
+                self.gt, self.lq = self.batch_augment(self.gt, self.lq)
         else:
             assert "lq" in data
             self.lq = data["lq"].to(self.device, non_blocking=True)
