@@ -210,6 +210,48 @@ int otf_copy_box_f32(const float* src, int Hs, int Ws, int sy, int sx,
                      float* dst, int Hd, int Wd, int dy, int dx, int bh, int bw,
                      int B, int planes_per_sample, const int32_t* perm_host, void* stream);
 
+/* ---- native stage executor: one call launches a whole degradation chain ---------------------------
+ * feed_data (traiNNer/models/realesrgan_model.py:455-650) issues its stages one Python call at a time;
+ * with a freshly drawn plan per iteration that is ~20 launches of interpreter + binding overhead, more
+ * than the GPU time of the chain at the reference's usual batch sizes.  The host side still decides
+ * WHAT runs (it mirrors the reference's branches and random draws) and describes it as an array of
+ * stages; this entry point launches them back to back on `stream`, threading the image through two
+ * ping-pong buffers inside `workspace_dev`.  Every stage is the entry point documented above with the
+ * same arithmetic, so a chain run here is bit-identical to the same stages called one by one.
+ *
+ * Stage i reads the previous stage's output (stage 0 reads `img`, which is never written) and writes
+ * either `dst` (caller-owned, dense) or an executor-owned buffer.  Ops and the fields they read:
+ *   OTF_OP_ANALYSE      p0..p3 kernel tensors (n = number of them), kb, K     -> shared analysis scratch
+ *   OTF_OP_FILTER2D     p0 kernel, kb, K, n = set index in the shared analysis or -1 (analyse alone)
+ *   OTF_OP_USM          p0 HOST taps, n = ntaps, f0 weight, f1 threshold
+ *   OTF_OP_SEPCONV      p0 HOST taps, n = ntaps, mode = axis (0 vertical, 1 horizontal)
+ *   OTF_OP_RESIZE       mode, oh, ow, flags&1 = clamp01, p0 = prebuilt tables or NULL (flags&2 = ready)
+ *   OTF_OP_GAUSS        p0 sigma, p1 gray|NULL, p2/p3 injected fields|NULL, seed, offset, flags = OTF_NOISE_*
+ *   OTF_OP_POISSON      p0 scale, p1 gray|NULL, p2/p3 injected counts|NULL, seed, offset, flags = OTF_NOISE_*
+ *   OTF_OP_JPEG         p0 per-sample factor/quality or NULL (f0 scalar), flags: 1 is_quality, 2 differentiable,
+ *                       4 clamp_in, 8 round8_out
+ *   OTF_OP_CLAMP_ROUND  -
+ *   OTF_OP_CROP_PAIR    terminal: p0 = GT (B,C,H0,W0 of the chain input), oh = top, ow = left, n = lq_patch,
+ *                       mode = scale; writes p1 = gt_out, p2 = lq_out
+ * `final_h/final_w` (host, may be NULL) receive the extent of the last image-producing stage. */
+enum {
+    OTF_OP_ANALYSE = 0, OTF_OP_FILTER2D = 1, OTF_OP_USM = 2, OTF_OP_SEPCONV = 3, OTF_OP_RESIZE = 4,
+    OTF_OP_GAUSS = 5, OTF_OP_POISSON = 6, OTF_OP_JPEG = 7, OTF_OP_CLAMP_ROUND = 8, OTF_OP_CROP_PAIR = 9
+};
+typedef struct OtfStage {
+    int32_t op, mode, oh, ow, n, kb, K, flags;
+    float f0, f1;
+    uint64_t seed, offset;
+    const void* p0;
+    const void* p1;
+    const void* p2;
+    const void* p3;
+    void* dst;
+} OtfStage;
+int64_t otf_run_stages_workspace_bytes(int B, int C, int H, int W, const OtfStage* stages, int nstages);
+int otf_run_stages_f32(const float* img, int B, int C, int H, int W, const OtfStage* stages, int nstages,
+                       void* workspace_dev, int64_t workspace_bytes, int* final_h, int* final_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ def timeit(make_fn, in_bytes):
     for f in fns[:3]:
         f()
     torch.cuda.synchronize()
+    D.pin_resize_tables()  # weight tables built during warm-up are reused by the captured launches
     n = max(nbuf, args.reps)
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
@@ -146,5 +147,40 @@ usm = T.USMSharp().to(dev)
 add("usm 256^2 (4 launches)", lambda t: usm(t), 2 * N(x256), x=x256)
 add("clamp_round 64^2", lambda t: clamp_round(t), 2 * N(x64), x=x64)
 add("crop_pair 256/64 -> 224/56", lambda t: crop_pair(t, x64, 224, 4, 4, 4), 2 * B * 3 * (224 * 224 + 56 * 56) * 4, x=x256)
+
+# ---- "next" rows of SURVEY.md §8f: pair pool (f1), kernel synthesis (f2), uint8 upload + MoA (f4) --------------
+import random  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from trainner_redux_b200 import _lib, batchaug as BA  # noqa: E402
+from trainner_redux_b200.realesrgan_feed import PairPool  # noqa: E402
+
+
+class _Rng:
+    def __init__(self, seed):
+        self.py, self.np, self.torch = random.Random(seed), np.random.default_rng(seed), torch.Generator().manual_seed(seed)
+
+
+gt224, lq56 = img(224, 224, 5), img(56, 56, 6)
+pair_bytes = N(gt224) + N(lq56)
+pool = PairPool(192, randperm=lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(1)))
+for _ in range(3):  # fill the pool: 192 / 64
+    pool.step(lq56, gt224)
+add("pair pool step, queue 192 (2 gathers + 2 scatters of 64 slots)", lambda t: pool.step(lq56, t), 4 * pair_bytes, x=gt224)
+params = S.synth_kernel_params(B, seed=3)[0] if hasattr(S, "synth_kernel_params") else None
+if params is not None:
+    pdev = torch.as_tensor(params, dtype=torch.float64).to(dev)
+    add("kernel synthesis 64 x 21x21 (fp64)", lambda t: synthesize_kernels(pdev, dev), B * (64 + 441 * 4), x=x64)
+u8 = (x256 * 255).round().to(torch.uint8)
+f32 = torch.empty_like(x256)
+add("u8 -> f32 /255 256^2", lambda t: _lib.call("otf_u8_to_f32", _lib.ptr(u8), u8.numel(), _lib.ptr(f32), _lib.stream()),
+    u8.numel() * 5, x=x64)
+for name, fn, nb in (("mixup", BA.mixup, 3 * pair_bytes), ("cutmix", BA.cutmix, None), ("resizemix", BA.resizemix, None),
+                     ("cutblur", BA.cutblur, None)):
+    add(f"moa {name} 224^2/56^2 pair", lambda t, fn=fn: fn(t, lq56, 4, rng=_Rng(11)), nb or 2 * pair_bytes, x=gt224)
+add("moa downup 56^2", lambda t: BA.downup(gt224, t, rng=_Rng(12)), 4 * N(lq56), x=lq56)
+add("moa up 224^2/56^2 pair", lambda t: BA.up(t, lq56, 4, rng=_Rng(13)), 2 * pair_bytes, x=gt224)
+
 if args.json:
     json.dump({"hbm_peak_gbs": peak, "fma_peak_tflops": FMA_PEAK, "rows": rows}, open(args.json, "w"), indent=1)

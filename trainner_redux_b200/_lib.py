@@ -53,7 +53,22 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_scatter_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
     "otf_mixup_f32": (_i, [_p, _p, _i, _i64, _f, _f, _p, _p]),
     "otf_copy_box_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "otf_run_stages_workspace_bytes": (_i64, [_i, _i, _i, _i, _p, _i]),
+    "otf_run_stages_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i64, _p, _p, _p]),
 }
+
+(OP_ANALYSE, OP_FILTER2D, OP_USM, OP_SEPCONV, OP_RESIZE, OP_GAUSS, OP_POISSON, OP_JPEG, OP_CLAMP_ROUND,
+ OP_CROP_PAIR) = range(10)
+
+
+class Stage(C.Structure):
+    """``OtfStage`` of include/otf_b200.h (one step of otf_run_stages_f32)."""
+
+    _fields_ = [("op", C.c_int32), ("mode", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32), ("n", C.c_int32),
+                ("kb", C.c_int32), ("K", C.c_int32), ("flags", C.c_int32), ("f0", C.c_float), ("f1", C.c_float),
+                ("seed", C.c_uint64), ("offset", C.c_uint64), ("p0", C.c_void_p), ("p1", C.c_void_p), ("p2", C.c_void_p),
+                ("p3", C.c_void_p), ("dst", C.c_void_p)]
+
 
 _lib: C.CDLL | None = None
 _lock = threading.Lock()
@@ -139,7 +154,16 @@ def ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+try:  # the raw handle without building a torch.cuda.Stream object (~10x cheaper; this runs once per launch)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _cur_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover - other torch builds
+    _raw_stream = _cur_device = None
+
+
 def stream() -> C.c_void_p:
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(_cur_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

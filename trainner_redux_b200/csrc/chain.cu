@@ -1,0 +1,172 @@
+// Native stage executor (host code): launches a whole degradation chain from one C call.
+// See include/otf_b200.h "native stage executor".  Nothing here touches pixels: every stage is one
+// of the library's own entry points, called in sequence on the caller's stream, with the image
+// threaded through two ping-pong buffers carved out of the caller's workspace.
+#include "otf_common.cuh"
+
+namespace otf {
+
+static inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
+
+// What one pass over the stage list learns: extents after every stage and the scratch each needs.
+struct Layout {
+    int64_t image_bytes = 0;    // each of the two ping-pong buffers
+    int64_t analysis_bytes = 0; // shared filter2d analysis (lives for the whole chain)
+    int64_t scratch_bytes = 0;  // per-stage scratch (stream-ordered, so one region of the largest size)
+    int final_h = 0, final_w = 0;
+};
+
+static int plan_layout(int B, int C, int H, int W, const OtfStage* st, int n, Layout* L) {
+    OTF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "run_stages: bad image extents");
+    OTF_REQUIRE(st && n > 0 && n <= 64, OTF_ERR_BAD_ARG, "run_stages: need 1..64 stages (got %d)", n);
+    int h = H, w = W;
+    for (int i = 0; i < n; ++i) {
+        const OtfStage& s = st[i];
+        int64_t scratch = 0;
+        bool makes_image = true;
+        switch (s.op) {
+            case OTF_OP_ANALYSE:
+                OTF_REQUIRE(s.n >= 1 && s.n <= 4, OTF_ERR_BAD_ARG, "run_stages[%d]: analyse takes 1..4 kernel tensors", i);
+                L->analysis_bytes = align_up((int64_t)s.n * otf_filter2d_scratch_words(s.kb) * 4);
+                makes_image = false;
+                break;
+            case OTF_OP_FILTER2D:
+                if (s.n < 0) scratch = otf_filter2d_scratch_words(s.kb) * 4;
+                break;
+            case OTF_OP_USM:
+                scratch = otf_usm_workspace_bytes(B * C, h, w);
+                break;
+            case OTF_OP_SEPCONV:
+            case OTF_OP_GAUSS:
+            case OTF_OP_JPEG:
+            case OTF_OP_CLAMP_ROUND:
+                break;
+            case OTF_OP_POISSON:
+                scratch = (int64_t)B * 16 * 4;
+                break;
+            case OTF_OP_RESIZE:
+                OTF_REQUIRE(s.oh > 0 && s.ow > 0, OTF_ERR_BAD_ARG, "run_stages[%d]: resize to (%d, %d)", i, s.oh, s.ow);
+                if (!s.p0) scratch = otf_resize_workspace_bytes(h, w, s.oh, s.ow, s.mode);
+                OTF_REQUIRE(scratch >= 0, OTF_ERR_BAD_ARG, "run_stages[%d]: resize mode %d or extents (%d, %d) -> (%d, %d) not supported", i, s.mode, h, w, s.oh, s.ow);
+                h = s.oh;
+                w = s.ow;
+                break;
+            case OTF_OP_CROP_PAIR:
+                OTF_REQUIRE(i == n - 1, OTF_ERR_BAD_ARG, "run_stages[%d]: crop_pair must be the last stage", i);
+                makes_image = false;
+                break;
+            default:
+                OTF_REQUIRE(false, OTF_ERR_BAD_ARG, "run_stages[%d]: unknown op %d", i, s.op);
+        }
+        if (makes_image && !s.dst) {
+            const int64_t bytes = align_up((int64_t)B * C * h * w * 4);
+            if (bytes > L->image_bytes) L->image_bytes = bytes;
+        }
+        scratch = align_up(scratch);
+        if (scratch > L->scratch_bytes) L->scratch_bytes = scratch;
+    }
+    L->final_h = h;
+    L->final_w = w;
+    return OTF_OK;
+}
+
+}  // namespace otf
+
+extern "C" int64_t otf_run_stages_workspace_bytes(int B, int C, int H, int W, const OtfStage* stages, int nstages) {
+    otf::Layout L;
+    if (int rc = otf::plan_layout(B, C, H, W, stages, nstages, &L)) return rc;
+    return 2 * L.image_bytes + L.analysis_bytes + L.scratch_bytes + 256;
+}
+
+extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, const OtfStage* stages, int nstages,
+                                  void* workspace_dev, int64_t workspace_bytes, int* final_h, int* final_w, void* stream) {
+    using namespace otf;
+    Layout L;
+    if (int rc = plan_layout(B, C, H, W, stages, nstages, &L)) return rc;
+    const int64_t need = 2 * L.image_bytes + L.analysis_bytes + L.scratch_bytes;
+    OTF_REQUIRE(img, OTF_ERR_BAD_ARG, "run_stages: null image");
+    OTF_REQUIRE(need == 0 || workspace_dev, OTF_ERR_BAD_ARG, "run_stages: null workspace");
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~(uintptr_t)255);
+    OTF_REQUIRE(need == 0 || (base - reinterpret_cast<char*>(workspace_dev)) + need <= workspace_bytes, OTF_ERR_BAD_ARG,
+                "run_stages: workspace of %lld bytes is too small (need %lld)", (long long)workspace_bytes, (long long)need + 256);
+    float* pong[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + L.image_bytes)};
+    int32_t* analysis = reinterpret_cast<int32_t*>(base + 2 * L.image_bytes);
+    void* scratch = base + 2 * L.image_bytes + L.analysis_bytes;
+    bool analysed = false;
+    int analysed_kb = 0, analysed_sets = 0;
+
+    const float* cur = img;
+    int h = H, w = W, which = 0;
+    for (int i = 0; i < nstages; ++i) {
+        const OtfStage& s = stages[i];
+        float* out = s.dst ? reinterpret_cast<float*>(s.dst) : pong[which];
+        int rc = OTF_OK;
+        bool makes_image = true;
+        switch (s.op) {
+            case OTF_OP_ANALYSE: {
+                const float* sets[4] = {(const float*)s.p0, (const float*)s.p1, (const float*)s.p2, (const float*)s.p3};
+                rc = otf_filter2d_analyse_f32(sets, s.n, s.kb, s.K, analysis, stream);
+                analysed = true;
+                analysed_kb = s.kb;
+                analysed_sets = s.n;
+                makes_image = false;
+                break;
+            }
+            case OTF_OP_FILTER2D:
+                if (s.n >= 0) {
+                    OTF_REQUIRE(analysed && s.n < analysed_sets && s.kb == analysed_kb, OTF_ERR_BAD_ARG,
+                                "run_stages[%d]: filter2d refers to analysis set %d that no earlier analyse stage produced", i, s.n);
+                    rc = otf_filter2d_f32(cur, B, C, h, w, (const float*)s.p0, s.kb, s.K,
+                                          analysis + (int64_t)s.n * otf_filter2d_scratch_words(s.kb), 1, out, stream);
+                } else {
+                    rc = otf_filter2d_f32(cur, B, C, h, w, (const float*)s.p0, s.kb, s.K, (int32_t*)scratch, 0, out, stream);
+                }
+                break;
+            case OTF_OP_USM:
+                rc = otf_usm_sharp_f32(cur, B * C, h, w, (const float*)s.p0, s.n, s.f0, s.f1, scratch,
+                                       otf_usm_workspace_bytes(B * C, h, w), out, stream);
+                break;
+            case OTF_OP_SEPCONV:
+                rc = otf_sepconv_reflect_f32(cur, B * C, h, w, (const float*)s.p0, s.n, s.mode, out, stream);
+                break;
+            case OTF_OP_RESIZE: {
+                void* tables = s.p0 ? const_cast<void*>(s.p0) : scratch;
+                rc = otf_resize_f32(cur, B * C, h, w, out, s.oh, s.ow, s.mode, s.flags & 1, tables,
+                                    otf_resize_workspace_bytes(h, w, s.oh, s.ow, s.mode), (s.p0 && (s.flags & 2)) ? 1 : 0, stream);
+                h = s.oh;
+                w = s.ow;
+                break;
+            }
+            case OTF_OP_GAUSS:
+                rc = otf_gaussian_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1, (const float*)s.p2,
+                                            (const float*)s.p3, s.seed, s.offset, s.flags, out, stream);
+                break;
+            case OTF_OP_POISSON:
+                rc = otf_poisson_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1, (const float*)s.p2,
+                                           (const float*)s.p3, s.seed, s.offset, s.flags, (uint32_t*)scratch, nullptr, nullptr,
+                                           nullptr, out, stream);
+                break;
+            case OTF_OP_JPEG:
+                OTF_REQUIRE(C == 3, OTF_ERR_BAD_ARG, "run_stages[%d]: DiffJPEG needs 3 channels", i);
+                rc = otf_diffjpeg_f32(cur, B, h, w, (const float*)s.p0, s.f0, s.flags & 1, (s.flags >> 1) & 1, (s.flags >> 2) & 1,
+                                      (s.flags >> 3) & 1, out, stream);
+                break;
+            case OTF_OP_CLAMP_ROUND:
+                rc = otf_clamp_round_f32(cur, (int64_t)B * C * h * w, out, stream);
+                break;
+            case OTF_OP_CROP_PAIR:
+                rc = otf_crop_pair_f32((const float*)s.p0, B * C, H, W, cur, h, w, s.oh, s.ow, s.n, s.mode,
+                                       (float*)const_cast<void*>(s.p1), (float*)const_cast<void*>(s.p2), stream);
+                makes_image = false;
+                break;
+        }
+        if (rc != OTF_OK) return rc;  // the entry point has set the message
+        if (makes_image) {
+            cur = out;
+            if (!s.dst) which ^= 1;
+        }
+    }
+    if (final_h) *final_h = h;
+    if (final_w) *final_w = w;
+    return OTF_OK;
+}

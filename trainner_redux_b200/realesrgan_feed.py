@@ -34,6 +34,7 @@ from . import _lib
 from . import degradations as D
 from .diffjpeg import DiffJPEG
 from .img_process_util import KernelAnalysis, USMSharp, filter2d
+from .stages import StageList
 from .transforms import crop_pair
 
 
@@ -263,6 +264,9 @@ class RealESRGANFeed:
         self.stage_times: dict[str, list] = {}
         self.record_stage_fns = False
         self.stage_fns: dict[str, Callable[[], Tensor]] = {}
+        # launch the whole chain from ONE library call (stages.py / otf_run_stages_f32) instead of one Python call
+        # per stage; same kernels, same arguments, bit-identical results.  The per-stage path stays for the stage hooks.
+        self.native_chain = True
 
     def _timed(self, name: str, fn: Callable[[], Tensor]) -> Tensor:
         if self.record_stage_fns:
@@ -295,10 +299,80 @@ class RealESRGANFeed:
         q = quality.to(self.device, non_blocking=True)  # raw qualities: the kernel converts them, nothing is mutated
         return self.jpeger(out, quality=q, _clamp_in=True, _round8=round8, _keep_quality=True)
 
+    def _record(self, sl: StageList, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
+                inject: dict | None = None) -> StageList:
+        """The chain of ``degrade`` written as a stage list for the native executor: same branches, same
+        arguments, same order of Philox offsets."""
+        inject = inject or {}
+        ori_h, ori_w, sc = sl.h, sl.w, plan["scale"]
+        if plan.get("clean"):
+            sl.clamp_round()
+            return sl
+        joint = kernel1.shape == kernel2.shape == sinc_kernel.shape and kernel1.size(-1) <= 21 and kernel1.size(0) == sl.b
+        fork = plan.get("order") == "fork"
+        if joint:  # one pair of launches analyses all three kernel tensors, as KernelAnalysis does in degrade()
+            sl.analyse([kernel1, kernel2, sinc_kernel])
+        an = (lambda i: i) if joint else (lambda i: None)
+
+        def noise(st: dict, key: str) -> None:
+            if st["kind"] == "gaussian":
+                sl.gaussian_noise(st["sigma"], st["gray"], self.rng.philox, noise=inject.get(f"{key}_color"),
+                                  noise_gray=inject.get(f"{key}_gray"))
+            else:
+                sl.poisson_noise(st["scale"], st["gray"], self.rng.philox, counts=inject.get(f"{key}_counts_color"),
+                                 counts_gray=inject.get(f"{key}_counts_gray"))
+
+        def tail(jpeg: Tensor | None) -> None:  # resize3, sinc, then the 8-bit lattice (fused into the last JPEG)
+            sl.resize(plan["resize3_mode"], size=(ori_h // sc, ori_w // sc))
+            sl.filter2d(sinc_kernel, an(2))
+            if jpeg is not None:
+                sl.jpeg(jpeg, round8=True)
+            else:
+                sl.clamp_round()
+
+        if fork:
+            if plan.get("blur1"):
+                sl.filter2d(kernel1, an(0))
+            tail(plan.get("jpeg"))
+            return sl
+        if plan.get("usm"):
+            r = plan["usm"]["radius"]
+            if r not in self._usm:
+                self._usm[r] = USMSharp(radius=r)
+            sl.usm(self._usm[r]._taps, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10))
+        if plan.get("blur1"):
+            sl.filter2d(kernel1, an(0))
+        if plan.get("resize1"):
+            sl.resize(plan["resize1"]["mode"], scale_factor=plan["resize1"]["scale"])
+        if plan.get("noise1"):
+            noise(plan["noise1"], "noise1")
+        if plan.get("jpeg1") is not None:
+            sl.jpeg(plan["jpeg1"])
+        if plan.get("blur2"):
+            sl.filter2d(kernel2, an(1))
+        if plan.get("resize2"):
+            s2 = plan["resize2"]["scale"]
+            sl.resize(plan["resize2"]["mode"], size=(int(ori_h / sc * s2), int(ori_w / sc * s2)))
+        if plan.get("noise2"):
+            noise(plan["noise2"], "noise2")
+        jpeg2 = plan.get("jpeg2")
+        if plan.get("final_order", "resize_first") == "resize_first":
+            tail(jpeg2)
+            return sl
+        if jpeg2 is not None:
+            sl.jpeg(jpeg2)
+        tail(None)
+        return sl
+
+    def _native(self) -> bool:
+        return self.native_chain and not (self.time_stages or self.record_stage_fns)
+
     def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
                 inject: dict | None = None) -> Tensor:
         """Run the chain described by ``plan`` on device tensors; returns the full-size LQ on the
         8-bit lattice (before the crop)."""
+        if self._native():
+            return self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject).run()
         ori_h, ori_w = gt.shape[2:4]
         sc = plan["scale"]
         out = gt
@@ -379,9 +453,20 @@ class RealESRGANFeed:
             if plan is None:
                 plan = draw_plan(self.opt, gt.size(0), ori_h, ori_w, self.rng)
             self.last_plan = plan
-            lq_full = self.degrade(gt, kernel1, kernel2, sinc_kernel, plan, inject)
             top, left = plan["crop"]
-            self.gt, self.lq = crop_pair(gt, lq_full, plan["gt_size"], plan["scale"], top, left)
+            if plan.get("clean") and plan["scale"] != 1:
+                # the clean pass-through keeps LQ at GT size, so the reference's paired_random_crop raises
+                # (realesrgan_model.py:491-499 -> transforms.py:106-110)
+                raise ValueError(f"Scale mismatches. GT ({ori_h}, {ori_w}) is not {plan['scale']}x ",
+                                 f"multiplication of LQ ({ori_h}, {ori_w}). None")
+            if self._native():  # chain + crop from one library call
+                if plan["gt_size"] % plan["scale"]:
+                    raise _lib.OtfError(f"gt_patch_size {plan['gt_size']} must be a multiple of scale {plan['scale']}")
+                sl = self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject)
+                self.gt, self.lq = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left))
+            else:
+                lq_full = self.degrade(gt, kernel1, kernel2, sinc_kernel, plan, inject)
+                self.gt, self.lq = crop_pair(gt, lq_full, plan["gt_size"], plan["scale"], top, left)
             if self.pool is not None:
                 self.lq, self.gt = self.pool.step(self.lq, self.gt)
             if self.batch_augment:  # realesrgan_model.py:649-650 (is_train holds on this branch)
