@@ -1,5 +1,5 @@
 """Launch each kernel of the path a few times on the bench shapes (B=64) — the command ncu wraps.
-    python profiles/prof_kernels.py [stage ...]     stages: blur1 resize1 noise1 jpeg1 blur2 sinc poisson usm all
+    python profiles/prof_kernels.py [stage ...]     stages: blur1 resize1 resize_up noise1 jpeg1 blur2 sinc poisson usm all
 """
 import os
 import sys
@@ -32,6 +32,10 @@ for it in range(3):
         T.resize_pt(gt, "bicubic", scale_factor=0.75)
         T.resize_pt(x192, "bilinear", size=(64, 64))
         T.resize_pt(x64, "area", size=(64, 64))
+    if want("resize_ne"):
+        T.resize_pt(gt, "nearest-exact", scale_factor=0.75)
+    if want("resize_up"):
+        T.resize_pt(gt, "bilinear", scale_factor=1.5)
     if want("noise1"):
         D.add_gaussian_noise_pt(x192, sigma, gray)
     if want("jpeg1"):
