@@ -45,8 +45,18 @@ enum {
     OTF_RESIZE_BICUBIC_AA = 1,  /* F.interpolate(mode="bicubic",  antialias=True), a=-0.5 */
     OTF_RESIZE_AREA = 2,        /* adaptive average pooling                             */
     OTF_RESIZE_NEAREST_EXACT = 3,
-    OTF_RESIZE_BICUBIC = 4      /* non-antialiased bicubic, a=-0.75 (tail of "lanczos") */
+    OTF_RESIZE_BICUBIC = 4,     /* non-antialiased bicubic, a=-0.75 (tail of "lanczos") */
+    OTF_RESIZE_NEAREST = 5      /* legacy F.interpolate(mode="nearest"): floor(o * in/out) — the fork's aliasing stage */
 };
+
+/* fork extras — traiNNer/models/paragon_otf_degradations.py */
+enum {
+    OTF_WARP_LENS = 0,    /* apply_lens_distortion  :297-342  (p0 = strength)               */
+    OTF_WARP_SHUTTER = 1, /* apply_rolling_shutter  :417-455  (p0 = strength*H/W)           */
+    OTF_WARP_CHROMA = 2   /* apply_chromatic_aberration :485-523 (R x1.001, B x0.999, clamp) */
+};
+enum { OTF_TAPS_NONE = 0, OTF_TAPS_OVERSHARPEN = 1 };
+#define OTF_MAX_TAPS 160
 
 /* flags for the noise tails: degradations.py:626-632 */
 enum {
@@ -251,6 +261,29 @@ typedef struct OtfStage {
 int64_t otf_run_stages_workspace_bytes(int B, int C, int H, int W, const OtfStage* stages, int nstages);
 int otf_run_stages_f32(const float* img, int B, int C, int H, int W, const OtfStage* stages, int nstages,
                        void* workspace_dev, int64_t workspace_bytes, int* final_h, int* final_w, void* stream);
+
+/* ---- f3: fork extras — traiNNer/models/paragon_otf_degradations.py:251-572 ----------------
+ * otf_warp_f32: analytic sampling grid + F.grid_sample(bilinear, align_corners=False) in one pass.
+ *   LENS (:297-342, padding reflection), SHUTTER (:417-455, reflection), CHROMA (:485-523 and
+ *   realesrgan_model.py:244-310: per-channel affine scale, zeros padding, clamp(0,1); needs C == 3
+ *   to move anything).  ATen's fp32 arithmetic is reproduced operation by operation.
+ * otf_taps_zero_f32: F.conv2d(img, k.repeat(C,1,1,1), padding=K//2, groups=C) for a small K x K
+ *   kernel given on the HOST (zeros are skipped; at most OTF_MAX_TAPS non-zero taps): motion blur
+ *   (:251-273; an even K grows the image by one row/column exactly as the reference does) and, with
+ *   epilogue OTF_TAPS_OVERSHARPEN, clamp(img + (img - blur) * strength, 0, 1) (:458-482).
+ *   out holds planes x (H + 2*(K/2) - K + 1) x (W + 2*(K/2) - K + 1).
+ * otf_channel_gain_f32: out = img * g[c] (+ clamp(0,1)): exposure (:345-362), colour temperature
+ *   (:365-394), editing exposure (realesrgan_model.py:596-603).
+ * otf_sensor_noise_f32: clamp(img + N * std, 0, 1) (:397-414); N injected (noise_dev) or Philox. */
+int otf_warp_f32(const float* img, int B, int C, int H, int W, int mode, float p0, float* out, void* stream);
+int otf_taps_zero_f32(const float* img, int planes, int H, int W, int K, const float* kernel_host,
+                      int epilogue, float strength, float* out, void* stream);
+int otf_channel_gain_f32(const float* img, int B, int C, int64_t hw, float g0, float g1, float g2,
+                         int clamp01_out, float* out, void* stream);
+int otf_sensor_noise_f32(const float* img, int64_t n, float std, const float* noise_dev,
+                         uint64_t seed, uint64_t offset, float* out, void* stream);
+/* floor(clamp(img,0,1) * 255) / 255: the uint8 truncation in front of every codec round (:114-115). */
+int otf_trunc8_f32(const float* img, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,9 @@ LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0
-RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC = range(5)
+RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST = range(6)
+WARP_LENS, WARP_SHUTTER, WARP_CHROMA = range(3)
+TAPS_NONE, TAPS_OVERSHARPEN = 0, 1
 NOISE_CLIP, NOISE_ROUNDS, NOISE_FIELD_ONLY = 1, 2, 4
 
 _p, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -53,6 +55,11 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_scatter_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
     "otf_mixup_f32": (_i, [_p, _p, _i, _i64, _f, _f, _p, _p]),
     "otf_copy_box_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "otf_warp_f32": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
+    "otf_taps_zero_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _f, _p, _p]),
+    "otf_channel_gain_f32": (_i, [_p, _i, _i, _i64, _f, _f, _f, _i, _p, _p]),
+    "otf_sensor_noise_f32": (_i, [_p, _i64, _f, _p, _u64, _u64, _p, _p]),
+    "otf_trunc8_f32": (_i, [_p, _i64, _p, _p]),
     "otf_run_stages_workspace_bytes": (_i64, [_i, _i, _i, _i, _p, _i]),
     "otf_run_stages_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i64, _p, _p, _p]),
 }
@@ -97,6 +104,11 @@ _LAUNCHES = {
     "otf_scatter_slots_f32": 1,
     "otf_mixup_f32": 1,
     "otf_copy_box_f32": 1,
+    "otf_warp_f32": 1,
+    "otf_taps_zero_f32": 1,
+    "otf_channel_gain_f32": 1,
+    "otf_sensor_noise_f32": 1,
+    "otf_trunc8_f32": 1,
 }
 
 

@@ -1,0 +1,259 @@
+// Fork extras: the tensor-math stages that this fork's feed_data runs around the
+// classical primitives — traiNNer/models/paragon_otf_degradations.py:251-572 and the model's own copies
+// (traiNNer/models/realesrgan_model.py:193-402).  All of them are HBM-bound pointwise / gather work:
+//   warp_kernel          lens distortion, rolling shutter, chromatic aberration  (analytic grid + grid_sample)
+//   taps_zero_kernel     motion blur (line kernel) and the 5x5 box of "oversharpen"   (conv2d, ZERO padding)
+//   channel_gain_kernel  exposure, colour temperature, editing exposure          (x * g[c], clamp)
+//   sensor_noise_kernel  x + N * std, clamp                                       (Philox or injected field)
+// Legacy `nearest` resampling for the aliasing stage lives in resize.cu (OTF_RESIZE_NEAREST).
+//
+// The warp reproduces ATen's fp32 arithmetic operation by operation (checked bit for bit against the CPU
+// build in oracle/paragon_oracle.py): torch.linspace = fma(step, i, -1) below the midpoint and
+// fma(-step, n-1-i, 1) above it; grid_sample's unnormalise = fma(g + 1, size / 2, -0.5); bilinear sum =
+// fma chain nw, ne, sw, se.  One ulp of a source coordinate at x >= 128 is 1.5e-5 of a pixel, so anything
+// looser than that would show up against the 1e-5 bar on noisy images.
+#include "otf_common.cuh"
+
+namespace otf {
+
+__device__ __forceinline__ float linspace_pm1(int i, int n, float step) {
+    // at::linspace(-1, 1, n) on fp32 (aten/src/ATen/native/cpu/RangeFactoriesKernel.cpp)
+    return i < n / 2 ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
+}
+
+// grid_sample source coordinate, align_corners=False (GridSamplerKernel.cpp ComputeLocation)
+__device__ __forceinline__ float gs_unnormalise(float g, int size) {
+    return __fmaf_rn(__fadd_rn(g, 1.0f), __fdiv_rn((float)size, 2.0f), -0.5f);
+}
+__device__ __forceinline__ float gs_reflect_clip(float x, int size) {
+    const float low = -0.5f, twice_span = __fmul_rn((float)size, 2.0f);
+    const float a = fabsf(__fsub_rn(x, low));
+    const float flips = truncf(__fdiv_rn(a, twice_span));
+    const float extra = __fsub_rn(a, __fmul_rn(flips, twice_span));
+    const float r = fminf(__fadd_rn(extra, low), __fadd_rn(__fsub_rn(twice_span, extra), low));
+    return fminf(fmaxf(r, 0.0f), (float)(size - 1));
+}
+
+struct WarpParams {
+    int mode;       // OTF_WARP_*
+    float p0;       // lens strength | shutter slant
+    float step_h, step_w;  // linspace steps 2/(H-1), 2/(W-1) as fp32
+};
+
+__device__ __forceinline__ float bilinear_zero(const float* __restrict__ pl, int H, int W, float x, float y) {
+    const float xw = floorf(x), yn = floorf(y);
+    const float xe = __fadd_rn(xw, 1.0f), ys = __fadd_rn(yn, 1.0f);
+    const float wxe = __fsub_rn(xe, x), wxw = __fsub_rn(x, xw), wys = __fsub_rn(ys, y), wyn = __fsub_rn(y, yn);
+    const float nw = __fmul_rn(wxe, wys), ne = __fmul_rn(wxw, wys), sw = __fmul_rn(wxe, wyn), se = __fmul_rn(wxw, wyn);
+    const int ix = (int)xw, iy = (int)yn;
+    const bool x0 = ix >= 0 && ix < W, x1 = ix + 1 >= 0 && ix + 1 < W, y0 = iy >= 0 && iy < H, y1 = iy + 1 >= 0 && iy + 1 < H;
+    const float a = (x0 && y0) ? __ldg(pl + (size_t)iy * W + ix) : 0.0f;
+    const float b = (x1 && y0) ? __ldg(pl + (size_t)iy * W + ix + 1) : 0.0f;
+    const float c = (x0 && y1) ? __ldg(pl + (size_t)(iy + 1) * W + ix) : 0.0f;
+    const float d = (x1 && y1) ? __ldg(pl + (size_t)(iy + 1) * W + ix + 1) : 0.0f;
+    float r = __fmul_rn(a, nw);
+    r = __fmaf_rn(b, ne, r);
+    r = __fmaf_rn(c, sw, r);
+    return __fmaf_rn(d, se, r);
+}
+
+// thread = output pixel (j fastest); loops over the C channels of its sample
+__global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W,
+                                                   WarpParams p) {
+    const int j = blockIdx.x * 64 + (threadIdx.x & 63), i = blockIdx.y * 4 + (threadIdx.x >> 6), b = blockIdx.z;
+    if (j >= W || i >= H) return;
+    const float lh = linspace_pm1(i, H, p.step_h), lw = linspace_pm1(j, W, p.step_w);
+    const size_t plane = (size_t)H * W;
+    const float* ip = img + (size_t)b * C * plane;
+    float* op = out + (size_t)b * C * plane + (size_t)i * W + j;
+    if (p.mode == OTF_WARP_CHROMA) {
+        // affine_grid(align_corners=False): base = linspace * (n-1) / n, then base * scale (theta is diagonal);
+        // R sampled at scale 1.001, G untouched, B at 0.999; zeros padding; clamp(0,1) on all three
+        const float bx = __fdiv_rn(__fmul_rn(lw, (float)(W - 1)), (float)W), by = __fdiv_rn(__fmul_rn(lh, (float)(H - 1)), (float)H);
+        for (int c = 0; c < C; ++c) {
+            float v;
+            if (C == 3 && c != 1) {
+                const float s = c == 0 ? 1.001f : 0.999f;
+                v = bilinear_zero(ip + c * plane, H, W, gs_unnormalise(__fmul_rn(bx, s), W), gs_unnormalise(__fmul_rn(by, s), H));
+            } else {
+                v = __ldg(ip + c * plane + (size_t)i * W + j);
+            }
+            op[c * plane] = clamp01(v);
+        }
+        return;
+    }
+    float gx, gy;
+    if (p.mode == OTF_WARP_LENS) {
+        // paragon_otf_degradations.py:313-331 — note grid_x runs along the ROWS (meshgrid 'ij' of (H, W)) and is
+        // stacked as the x coordinate: the reference samples the transposed position, reproduced as is
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(lh, lh), __fmul_rn(lw, lw)));
+        float rd = __fmul_rn(r, __fadd_rn(1.0f, __fmul_rn(p.p0, __fmul_rn(r, r))));
+        float rr = r;
+        if (r == 0.0f) { rd = 0.0f; rr = 1e-6f; }
+        const float ratio = __fdiv_rn(rd, rr);
+        gx = __fmul_rn(lh, ratio);
+        gy = __fmul_rn(lw, ratio);
+    } else {  // OTF_WARP_SHUTTER: :440-447 — x + slant * y, y
+        gx = __fadd_rn(lw, __fmul_rn(p.p0, lh));
+        gy = lh;
+    }
+    const float x = gs_reflect_clip(gs_unnormalise(gx, W), W), y = gs_reflect_clip(gs_unnormalise(gy, H), H);
+    for (int c = 0; c < C; ++c) op[c * plane] = bilinear_zero(ip + c * plane, H, W, x, y);
+}
+
+// ---- small correlation with ZERO padding (F.conv2d(padding=K//2, groups=C)) ------------------------
+struct TapList {
+    int n;
+    float w[OTF_MAX_TAPS];
+    int8_t dy[OTF_MAX_TAPS], dx[OTF_MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(256) taps_zero_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
+                                                        int OH, int OW, const __grid_constant__ TapList taps, int epilogue,
+                                                        float strength) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= OW || y >= OH) return;
+    const float* ip = img + (size_t)blockIdx.z * H * W;
+    float acc = 0.0f;
+    for (int k = 0; k < taps.n; ++k) {
+        const int yy = y + taps.dy[k], xx = x + taps.dx[k];
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc = fmaf(taps.w[k], __ldg(ip + (size_t)yy * W + xx), acc);
+    }
+    if (epilogue == OTF_TAPS_OVERSHARPEN) {
+        // img + (img - blurred) * strength, clamp(0,1) — paragon_otf_degradations.py:480-482 (separate ATen ops)
+        const float v = __ldg(ip + (size_t)y * W + x);
+        acc = clamp01(__fadd_rn(v, __fmul_rn(__fsub_rn(v, acc), strength)));
+    }
+    out[(size_t)blockIdx.z * OH * OW + (size_t)y * OW + x] = acc;
+}
+
+// ---- x * gain[c], optional clamp --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) channel_gain_kernel(const float4* __restrict__ img, float4* __restrict__ out, int C,
+                                                           int64_t quads_per_plane, float g0, float g1, float g2, int clamp_out) {
+    const int plane = blockIdx.y, c = plane % C;
+    const float g = c == 0 ? g0 : c == 1 ? g1 : g2;
+    const float4* ip = img + (size_t)plane * quads_per_plane;
+    float4* op = out + (size_t)plane * quads_per_plane;
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < quads_per_plane; q += (int64_t)gridDim.x * 256) {
+        float4 v = __ldg(ip + q);
+        v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g); v.z = __fmul_rn(v.z, g); v.w = __fmul_rn(v.w, g);
+        if (clamp_out) { v.x = clamp01(v.x); v.y = clamp01(v.y); v.z = clamp01(v.z); v.w = clamp01(v.w); }
+        op[q] = v;
+    }
+}
+__global__ void __launch_bounds__(256) channel_gain_scalar_kernel(const float* __restrict__ img, float* __restrict__ out, int C,
+                                                                  int64_t hw, float g0, float g1, float g2, int clamp_out) {
+    const int plane = blockIdx.y, c = plane % C;
+    const float g = c == 0 ? g0 : c == 1 ? g1 : g2;
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < hw; q += (int64_t)gridDim.x * 256) {
+        const float v = __fmul_rn(__ldg(img + (size_t)plane * hw + q), g);
+        out[(size_t)plane * hw + q] = clamp_out ? clamp01(v) : v;
+    }
+}
+
+// ---- clamp(x + N * std, 0, 1) — paragon_otf_degradations.py:411-414 ---------------------------------
+__global__ void __launch_bounds__(256) sensor_noise_kernel(const float* __restrict__ img, const float* __restrict__ noise,
+                                                           float* __restrict__ out, int64_t n, float std, uint64_t seed,
+                                                           uint64_t offset) {
+    const Philox ph(seed);
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; 4 * q < n; q += (int64_t)gridDim.x * 256) {
+        float nv[4];
+        if (noise) {
+            for (int k = 0; k < 4; ++k) nv[k] = 4 * q + k < n ? __ldg(noise + 4 * q + k) : 0.0f;
+        } else {
+            const float4 z = normal4(ph, (uint64_t)q, offset * 8 + STREAM_COLOR);
+            nv[0] = z.x; nv[1] = z.y; nv[2] = z.z; nv[3] = z.w;
+        }
+        for (int k = 0; k < 4; ++k)
+            if (4 * q + k < n) out[4 * q + k] = clamp01(__fadd_rn(__ldg(img + 4 * q + k), __fmul_rn(nv[k], std)));
+    }
+}
+
+// floor(clamp(x,0,1) * 255) / 255 — the `(img * 255).astype("uint8")` in front of every codec round (:114-115)
+__global__ void __launch_bounds__(256) trunc8_kernel(const float* __restrict__ img, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        out[i] = __fdiv_rn(floorf(__fmul_rn(clamp01(__ldg(img + i)), 255.0f)), 255.0f);
+}
+
+}  // namespace otf
+
+extern "C" int otf_trunc8_f32(const float* img, int64_t n, float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out && n > 0, OTF_ERR_BAD_ARG, "trunc8: bad arguments");
+    int grid = ceil_div(n, 256 * 4);
+    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    trunc8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, out, n);
+    OTF_LAUNCH_CHECK("trunc8_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_warp_f32(const float* img, int B, int C, int H, int W, int mode, float p0, float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out && img != out, OTF_ERR_BAD_ARG, "warp: bad pointers");
+    OTF_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 1 && W > 1, OTF_ERR_BAD_ARG, "warp: bad extents");
+    OTF_REQUIRE(mode >= OTF_WARP_LENS && mode <= OTF_WARP_CHROMA, OTF_ERR_BAD_ARG, "warp: unknown mode %d", mode);
+    WarpParams p;
+    p.mode = mode;
+    p.p0 = p0;
+    p.step_h = 2.0f / (float)(H - 1);
+    p.step_w = 2.0f / (float)(W - 1);
+    warp_kernel<<<dim3(ceil_div(W, 64), ceil_div(H, 4), B), 256, 0, (cudaStream_t)stream>>>(img, out, C, H, W, p);
+    OTF_LAUNCH_CHECK("warp_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_taps_zero_f32(const float* img, int planes, int H, int W, int K, const float* kernel_host, int epilogue,
+                                 float strength, float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out && kernel_host && img != out, OTF_ERR_BAD_ARG, "taps_zero: bad pointers");
+    OTF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && K > 0 && K <= 127, OTF_ERR_BAD_ARG, "taps_zero: bad extents");
+    OTF_REQUIRE(epilogue == OTF_TAPS_NONE || (epilogue == OTF_TAPS_OVERSHARPEN && (K & 1)), OTF_ERR_BAD_ARG, "taps_zero: epilogue");
+    TapList t;
+    t.n = 0;
+    const int pad = K / 2;  // F.conv2d(padding=K//2): an even K grows the image by one row and column, as in the reference
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            const float w = kernel_host[i * K + j];
+            if (w == 0.0f) continue;
+            OTF_REQUIRE(t.n < OTF_MAX_TAPS, OTF_ERR_UNSUPPORTED, "taps_zero: more than %d non-zero taps", OTF_MAX_TAPS);
+            t.w[t.n] = w;
+            t.dy[t.n] = (int8_t)(i - pad);
+            t.dx[t.n] = (int8_t)(j - pad);
+            ++t.n;
+        }
+    const int OH = H + 2 * pad - K + 1, OW = W + 2 * pad - K + 1;
+    taps_zero_kernel<<<dim3(ceil_div(OW, 64), ceil_div(OH, 4), planes), 256, 0, (cudaStream_t)stream>>>(img, out, H, W, OH, OW, t,
+                                                                                                     epilogue, strength);
+    OTF_LAUNCH_CHECK("taps_zero_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_channel_gain_f32(const float* img, int B, int C, int64_t hw, float g0, float g1, float g2, int clamp01_out,
+                                    float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out, OTF_ERR_BAD_ARG, "channel_gain: bad pointers");
+    OTF_REQUIRE(B > 0 && C > 0 && hw > 0 && (int64_t)B * C <= 65535, OTF_ERR_BAD_ARG, "channel_gain: bad extents");
+    const bool vec = hw % 4 == 0 && (((uintptr_t)img | (uintptr_t)out) & 15) == 0;
+    const int64_t units = vec ? hw / 4 : hw;
+    int gx = ceil_div(units, 256 * 4);
+    if (gx < 1) gx = 1;
+    if (gx > 4 * kNumSMs) gx = 4 * kNumSMs;
+    if (vec)
+        channel_gain_kernel<<<dim3(gx, B * C), 256, 0, (cudaStream_t)stream>>>((const float4*)img, (float4*)out, C, units, g0, g1, g2,
+                                                                             clamp01_out);
+    else
+        channel_gain_scalar_kernel<<<dim3(gx, B * C), 256, 0, (cudaStream_t)stream>>>(img, out, C, hw, g0, g1, g2, clamp01_out);
+    OTF_LAUNCH_CHECK("channel_gain_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_sensor_noise_f32(const float* img, int64_t n, float std, const float* noise_dev, uint64_t seed, uint64_t offset,
+                                    float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out && n > 0, OTF_ERR_BAD_ARG, "sensor_noise: bad arguments");
+    int grid = ceil_div((n + 3) / 4, 256 * 2);
+    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    sensor_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, noise_dev, out, n, std, seed, offset);
+    OTF_LAUNCH_CHECK("sensor_noise_kernel");
+    return OTF_OK;
+}

@@ -77,6 +77,13 @@ __device__ void axis_weights(int mode, const AxisSpec& ax, int o, int* lo_out, i
         lo = min((int)floorf(__fmul_rn((float)o + 0.5f, ax.scale)), ax.in_n - 1);
         n = 1;
         w[0] = 1.0f;
+    } else if (mode == OTF_RESIZE_NEAREST) {
+        // legacy nearest (UpSample.h nearest_idx): identity / halving shortcuts, else floorf(o * scale)
+        if (ax.out_n == ax.in_n) lo = o;
+        else if (ax.out_n == 2 * ax.in_n) lo = o >> 1;
+        else lo = min((int)floorf(__fmul_rn((float)o, ax.scale)), ax.in_n - 1);
+        n = 1;
+        w[0] = 1.0f;
     } else {  // OTF_RESIZE_BICUBIC: src = scale*(o+0.5)-0.5, 4 taps, A=-0.75, indices clamped
         // ATen's CPU build contracts `scale * (o + 0.5) - 0.5` into one fused multiply-add (checked against
         // the installed torch at 288->431: the unfused form is 1.4e-5 off, the fused one matches)
@@ -418,7 +425,7 @@ static AxisSpec make_axis(int mode, int in_n, int out_n) {
         a.max_taps = (int)ceilf(a.support) * 2 + 1;
     } else if (mode == OTF_RESIZE_AREA) {
         a.max_taps = (in_n + out_n - 1) / out_n + 1;
-    } else if (mode == OTF_RESIZE_NEAREST_EXACT) {
+    } else if (mode == OTF_RESIZE_NEAREST_EXACT || mode == OTF_RESIZE_NEAREST) {
         a.max_taps = 1;
     } else {
         a.max_taps = 4;
@@ -432,7 +439,7 @@ static size_t table_ints(const AxisSpec& a) { return (size_t)a.out_n * (2 + a.ma
 
 extern "C" int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode) {
     using namespace otf;
-    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || mode < OTF_RESIZE_BILINEAR_AA || mode > OTF_RESIZE_BICUBIC) return -1;
+    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || mode < OTF_RESIZE_BILINEAR_AA || mode > OTF_RESIZE_NEAREST) return -1;
     return (int64_t)(table_ints(make_axis(mode, H, OH)) + table_ints(make_axis(mode, W, OW))) * 4;
 }
 
@@ -442,7 +449,7 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
     using namespace otf;
     OTF_REQUIRE(img && out && img != out && workspace_dev, OTF_ERR_BAD_ARG, "resize: bad pointers");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && OH > 0 && OW > 0, OTF_ERR_BAD_ARG, "resize: bad extents");
-    OTF_REQUIRE(mode >= OTF_RESIZE_BILINEAR_AA && mode <= OTF_RESIZE_BICUBIC, OTF_ERR_BAD_ARG, "resize: unknown mode %d", mode);
+    OTF_REQUIRE(mode >= OTF_RESIZE_BILINEAR_AA && mode <= OTF_RESIZE_NEAREST, OTF_ERR_BAD_ARG, "resize: unknown mode %d", mode);
     OTF_REQUIRE(workspace_bytes >= otf_resize_workspace_bytes(H, W, OH, OW, mode), OTF_ERR_WORKSPACE, "resize: workspace too small");
     const AxisSpec ay = make_axis(mode, H, OH), ax = make_axis(mode, W, OW);
     int* ty_lo = (int*)workspace_dev;

@@ -80,6 +80,41 @@ class OTFOptions:
     # the schema's own defaults (4 names, 5 weights) fail batch_aug's length check in the reference too: set both
     moa_augs: Sequence[str] = ("none", "mixup", "cutmix", "resizemix")
     moa_probs: Sequence[float] = (0.4, 0.084, 0.084, 0.084, 0.348)
+    # the fork's extra stages (redux_options.py:525-700, :854-894; all off by default, as in the schema)
+    lens_distort_prob: float = 0
+    lens_distort_strength_range: tuple[float, float] = (-0.3, 0.3)
+    chromatic_aberration_prob: float = 0
+    motion_blur_prob: float = 0
+    motion_blur_kernel_size: tuple[int, int] = (5, 15)
+    motion_blur_angle_range: tuple[float, float] = (0, 360)
+    demosaic_prob: float = 0
+    sensor_noise_prob: float = 0
+    sensor_noise_std_range: tuple[float, float] = (0.01, 0.1)
+    rolling_shutter_prob: float = 0
+    rolling_shutter_strength_range: tuple[float, float] = (-0.1, 0.1)
+    exposure_prob: float = 0
+    exposure_factor_range: tuple[float, float] = (0.5, 2.0)
+    color_temp_prob: float = 0
+    color_temp_shift_range: tuple[float, float] = (-0.2, 0.2)
+    oversharpen_prob: float = 0
+    oversharpen_strength: tuple[float, float] = (1.0, 2.0)
+    aliasing_prob: float = 0
+    aliasing_scale_range: tuple[float, float] = (0.6, 0.9)
+    compression_formats: Sequence[str] = ("jpeg", "webp", "avif", "heif")
+    compression_weights: Sequence[float] = (0.60, 0.25, 0.10, 0.05)
+    compression_jpeg_range: tuple[float, float] = (45, 95)
+    compression_webp_range: tuple[float, float] = (45, 95)
+    compression_avif_range: tuple[float, float] = (35, 90)
+    compression_heif_range: tuple[float, float] = (40, 90)
+    recompression_prob: float = 0
+    recompression_formats: Sequence[str] = ("jpeg", "webp", "avif", "heif")
+    recompression_weights: Sequence[float] = (0.50, 0.35, 0.10, 0.05)
+    editing_prob: float = 0
+    editing_exposure_prob: float = 0
+    editing_exposure_range: tuple[float, float] = (0.9, 1.1)
+    editing_oversharpen_prob: float = 0
+    editing_oversharpen_strength: tuple[float, float] = (1.0, 1.3)
+    fork_compression: bool = True  # order="fork": run the unified compression stage (realesrgan_model.py:581)
     # not in the reference schema: which composition to run, and the upstream 50/50 final-order coin
     order: str = "classic"
     final_jpeg_first_prob: float = 0.5
@@ -130,6 +165,58 @@ def _draw_quality(rng: HostRNG, b: int, qrange) -> Tensor:
     return torch.empty(b).uniform_(float(qrange[0]), float(qrange[1]), generator=rng.torch)
 
 
+EXTRA_KEYS = ("lens", "chroma", "motion", "demosaic", "sensor", "shutter", "exposure", "color_temp", "oversharpen", "aliasing",
+              "compression", "editing_exposure")
+
+
+def _draw_fork(opt: Any, rng: HostRNG) -> dict:
+    """Host draws of the fork's order (A), realesrgan_model.py:512-611 with the `hasattr` guards of
+    paragon_otf_degradations.py: a stage whose option fields exist draws its gate even at probability 0, and its
+    parameters only when the gate passes.  Pinned against the reference by oracle/make_paragon_goldens.py."""
+    u = rng.np.uniform
+    has = lambda *names: all(hasattr(opt, n) for n in names)  # noqa: E731
+    p: dict[str, Any] = {}
+    if has("lens_distort_prob", "lens_distort_strength_range") and u() < opt.lens_distort_prob:
+        p["lens"] = float(u(*opt.lens_distort_strength_range))
+    if has("chromatic_aberration_prob") and u() < opt.chromatic_aberration_prob:
+        p["chroma"] = True
+    if has("motion_blur_prob") and u() < opt.motion_blur_prob:
+        ks = rng.py.randint(opt.motion_blur_kernel_size[0], opt.motion_blur_kernel_size[1])
+        p["motion"] = (ks, float(u(*opt.motion_blur_angle_range)))
+    p["blur1"] = bool(u() < _opt(opt, "blur_prob", 0))  # :525
+    if has("demosaic_prob") and u() < opt.demosaic_prob:
+        p["demosaic"] = True
+    if has("sensor_noise_prob", "sensor_noise_std_range") and u() < opt.sensor_noise_prob:
+        p["sensor"] = float(u(*opt.sensor_noise_std_range))
+    if has("rolling_shutter_prob", "rolling_shutter_strength_range") and u() < opt.rolling_shutter_prob:
+        p["shutter"] = float(u(*opt.rolling_shutter_strength_range))
+    if has("exposure_prob", "exposure_factor_range") and u() < opt.exposure_prob:
+        p["exposure"] = float(u(*opt.exposure_factor_range))
+    if has("color_temp_prob", "color_temp_shift_range") and u() < opt.color_temp_prob:
+        p["color_temp"] = float(u(*opt.color_temp_shift_range))
+    if has("oversharpen_prob", "oversharpen_strength") and u() < opt.oversharpen_prob:
+        p["oversharpen"] = float(u(*opt.oversharpen_strength))
+    if has("aliasing_prob", "aliasing_scale_range") and u() < opt.aliasing_prob:
+        p["aliasing"] = float(u(*opt.aliasing_scale_range))
+    p["resize3_mode"] = rng.py.choices(list(opt.resize_mode_list3), weights=list(opt.resize_mode_prob3))[0]  # :564
+    if _opt(opt, "fork_compression", True) and has("compression_formats"):  # :581 -> paragon :39-87
+        def one(formats, weights):
+            fmt = str(rng.np.choice(list(formats), p=list(weights)))
+            rr = getattr(opt, f"compression_{fmt}_range", None)
+            return fmt, (float(u(rr[0], rr[1])) if rr is not None else None)
+
+        comp = [one(opt.compression_formats, opt.compression_weights)]
+        if u() < opt.recompression_prob:
+            comp.append(one(opt.recompression_formats, opt.recompression_weights))
+        p["compression"] = comp
+    if u() < _opt(opt, "editing_prob", 0):  # :589-611
+        if has("editing_exposure_prob") and u() < opt.editing_exposure_prob:
+            p["editing_exposure"] = float(u(*_opt(opt, "editing_exposure_range", (0.9, 1.1))))
+        if has("editing_oversharpen_prob"):
+            u()  # the gate is drawn; the branch applies nothing (:606-611)
+    return p
+
+
 def draw_plan(opt: Any, b: int, ori_h: int, ori_w: int, rng: HostRNG) -> dict:
     """Host-side decisions for one ``feed_data`` call, in the order of SURVEY.md appendix A.
     The result is a plain dict (the format ``oracle.otf_oracle.run_chain_b`` consumes)."""
@@ -138,8 +225,7 @@ def draw_plan(opt: Any, b: int, ori_h: int, ori_w: int, rng: HostRNG) -> dict:
     if _opt(opt, "p_clean", 0) and rng.np.uniform() < opt.p_clean:  # realesrgan_model.py:487-503
         plan["clean"] = True
     elif plan["order"] == "fork":
-        plan["blur1"] = bool(rng.np.uniform() < _opt(opt, "blur_prob", 0))  # :525
-        plan["resize3_mode"] = rng.py.choices(list(opt.resize_mode_list3), weights=list(opt.resize_mode_prob3))[0]  # :564
+        plan.update(_draw_fork(opt, rng))
     else:
         if _opt(opt, "lq_usm", False):
             lo, hi = opt.lq_usm_radius_range
@@ -364,14 +450,16 @@ class RealESRGANFeed:
         tail(None)
         return sl
 
-    def _native(self) -> bool:
-        return self.native_chain and not (self.time_stages or self.record_stage_fns)
+    def _native(self, plan: dict | None = None) -> bool:
+        # the fork's extra stages are launched per stage from Python (they are not in the native executor's op table)
+        extras = plan is not None and any(k in plan for k in EXTRA_KEYS)
+        return self.native_chain and not (self.time_stages or self.record_stage_fns or extras)
 
     def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
                 inject: dict | None = None) -> Tensor:
         """Run the chain described by ``plan`` on device tensors; returns the full-size LQ on the
         8-bit lattice (before the crop)."""
-        if self._native():
+        if self._native(plan):
             return self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject).run()
         ori_h, ori_w = gt.shape[2:4]
         sc = plan["scale"]
@@ -383,14 +471,42 @@ class RealESRGANFeed:
         if kernel1.shape == kernel2.shape == sinc_kernel.shape and kernel1.size(-1) <= 21 and kernel1.size(0) == gt.size(0):
             ka = KernelAnalysis([kernel1, kernel2, sinc_kernel])
         an = (lambda i: (ka, i)) if ka is not None else (lambda i: None)
-        if plan.get("order") == "fork":
+        if plan.get("order") == "fork":  # realesrgan_model.py:512-616
+            from . import paragon_otf as PO
+
+            inject = inject or {}
+            if "lens" in plan:
+                out = self._timed("lens", lambda o=out: PO.lens_distortion(o, plan["lens"]))
+            if plan.get("chroma"):
+                out = self._timed("chroma", lambda o=out: PO.chromatic_aberration(o))
+            if "motion" in plan:
+                out = self._timed("motion", lambda o=out: PO.motion_blur(o, *plan["motion"]))
             if plan.get("blur1"):
-                out = filter2d(out, kernel1, _analysis=an(0))
-            out = D.resize_pt(out, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"])
-            out = filter2d(out, sinc_kernel, _analysis=an(2))
-            if plan.get("jpeg") is not None:
+                out = self._timed("blur1", lambda o=out: filter2d(o, kernel1, _analysis=an(0) if o.shape == gt.shape else None))
+            if plan.get("demosaic"):
+                raise NotImplementedError("demosaic artifacts run cv2.demosaicing on the host (paragon_otf_degradations.py:526-552): "
+                                          "outside the GPU path; keep demosaic_prob at 0")
+            if "sensor" in plan:
+                out = self._timed("sensor", lambda o=out: PO.sensor_noise(o, plan["sensor"], inject.get("sensor_noise"), self.rng.philox))
+            if "shutter" in plan:
+                out = self._timed("shutter", lambda o=out: PO.rolling_shutter(o, plan["shutter"]))
+            if "exposure" in plan:
+                out = self._timed("exposure", lambda o=out: PO.exposure(o, plan["exposure"]))
+            if "color_temp" in plan:
+                out = self._timed("color_temp", lambda o=out: PO.color_temperature(o, plan["color_temp"]))
+            if "oversharpen" in plan:
+                out = self._timed("oversharpen", lambda o=out: PO.oversharpen(o, plan["oversharpen"]))
+            if "aliasing" in plan:
+                out = self._timed("aliasing", lambda o=out: PO.aliasing(o, plan["aliasing"]))
+            out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
+            out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel, _analysis=an(2)))
+            if plan.get("jpeg") is not None:  # per-sample qualities through DiffJPEG (this repo's earlier routing)
                 return self._jpeg(out, plan["jpeg"], round8=True)
-            return clamp_round(out)
+            for fmt, q in plan.get("compression", []):
+                out = self._timed(f"compress_{fmt}", lambda o=out: PO.compress_with_format(o, fmt, q))
+            if "editing_exposure" in plan:
+                out = self._timed("editing_exposure", lambda o=out: PO.exposure(o, plan["editing_exposure"]))
+            return self._timed("round", lambda o=out: clamp_round(o))
         if plan.get("usm"):
             r = plan["usm"]["radius"]
             if r not in self._usm:
@@ -459,7 +575,7 @@ class RealESRGANFeed:
                 # (realesrgan_model.py:491-499 -> transforms.py:106-110)
                 raise ValueError(f"Scale mismatches. GT ({ori_h}, {ori_w}) is not {plan['scale']}x ",
                                  f"multiplication of LQ ({ori_h}, {ori_w}). None")
-            if self._native():  # chain + crop from one library call
+            if self._native(plan):  # chain + crop from one library call
                 if plan["gt_size"] % plan["scale"]:
                     raise _lib.OtfError(f"gt_patch_size {plan['gt_size']} must be a multiple of scale {plan['scale']}")
                 sl = self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject)
