@@ -132,10 +132,10 @@ def run_reference(args) -> None:
     threads = os.cpu_count() or 1
     batch = BATCH if args.steps + args.warmup <= 120 else 16
     val, ms = cpu_chain_pairs_per_s(batch, args.steps, args.warmup, threads)
-    sample = f"each step = one batch of {batch} x 256^2 GT through the oracle port of the reference chain (torch CPU, {threads} threads)"
+    sample = f"each step = one batch of {batch} x {GT}^2 GT through the oracle port of the reference chain (torch CPU, {threads} threads)"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "batch_per_step": batch, "gt": GT, "scale": SCALE},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -145,9 +145,24 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+SCALING = "weak"
+
+
+def set_workload(name: str, world: int) -> None:
+    """c2 (default, the config the metric is quoted on): B=64 x 256^2 GT x4 per GPU, weak scaling.
+    c3 (BASELINE.json configs[2]): ONE batch of 32 x 512^2 GT x2 sharded per sample over the ranks, strong scaling."""
+    global GT, SCALE, BATCH, GT_CROP, SCALING, METRIC
+    if name == "c3":
+        GT, SCALE, GT_CROP, SCALING = 512, 2, 480, "strong"
+        BATCH = max(1, 32 // world)
+        METRIC = "degraded LR/HR pairs/sec at 512^2 GT x2 (batch 32 sharded over the ranks)"
+
+
 def workload_name() -> str:
-    return ("Real-ESRGAN OTF second-order chain incl. DiffJPEG + sinc, batch 64 synthetic 256^2 GT x4 per GPU "
-            "(blur1, bicubic x0.75, gaussian, jpeg, blur2, bilinear, gaussian, area->64^2, sinc, jpeg, clamp/round, crop 224/56)")
+    lq = GT // SCALE
+    return (f"Real-ESRGAN OTF second-order chain incl. DiffJPEG + sinc, batch {BATCH} synthetic {GT}^2 GT x{SCALE} per GPU "
+            f"(blur1, bicubic x0.75, gaussian, jpeg, blur2, bilinear, gaussian, area->{lq}^2, sinc, jpeg, clamp/round, "
+            f"crop {GT_CROP}/{GT_CROP // SCALE})")
 
 
 # ------------------------------------------------------------------------- clocks ----
@@ -429,10 +444,10 @@ def run_b200(args) -> None:
             threads = os.cpu_count() or 1
             cval, cms = cpu_chain_pairs_per_s(BATCH, 8, 1, threads)
             cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"8 batches of {BATCH} x 256^2 GT (+1 warm-up) through the oracle port of the reference chain, torch CPU {threads} threads, {cms:.0f} ms/batch"}
+                   "sample": f"8 batches of {BATCH} x {GT}^2 GT (+1 warm-up) through the oracle port of the reference chain, torch CPU {threads} threads, {cms:.0f} ms/batch"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(), "batch_per_gpu": BATCH, "gt": GT, "scale": SCALE,
                        "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * BATCH * 3 * GT * GT * 4 / 1e6:.0f} MB > 126 MB L2)",
@@ -444,7 +459,7 @@ def run_b200(args) -> None:
                        "note": "extension: uint8 GT upload + on-device /255 (not the reference's fp32 host format)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "filter2d_kernel (blur1, 64x3x256x256, per-sample kernels zero-padded to 21x21: default kernel_list mix, sizes 7..21)", "bound": "hbm",
+            "roofline": {"kernel": f"filter2d_kernel (blur1, {BATCH}x3x{GT}x{GT}, per-sample kernels zero-padded to 21x21: default kernel_list mix, sizes 7..21)", "bound": "hbm",
                          "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": traffic, "peak_source": pk["source"], "ms_per_launch": k_ms,
                          "fma": {"achieved_tflops_true_taps": flops * (true_k2 / 441.0) / (k_ms * 1e-3) / 1e12,
@@ -466,12 +481,14 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: 64 x 256^2 x4 per GPU (default); c3: 32 x 512^2 x2 sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--streams", type=int, default=4, help="batches in flight during the timed region (graph mode)")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-capture pass (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    set_workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")))
     if args.impl == "reference":
         run_reference(args)
     else:

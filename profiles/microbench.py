@@ -182,5 +182,19 @@ for name, fn, nb in (("mixup", BA.mixup, 3 * pair_bytes), ("cutmix", BA.cutmix, 
 add("moa downup 56^2", lambda t: BA.downup(gt224, t, rng=_Rng(12)), 4 * N(lq56), x=lq56)
 add("moa up 224^2/56^2 pair", lambda t: BA.up(t, lq56, 4, rng=_Rng(13)), 2 * pair_bytes, x=gt224)
 
+# ---- row f3: the fork's extra stages (paragon_otf.py) at 256^2 ---------------------------------------------------
+from trainner_redux_b200 import paragon_otf as PO  # noqa: E402
+
+add("f3 lens distortion 256^2", lambda t: PO.lens_distortion(t, 0.2), 2 * N(x256), x=x256)
+add("f3 rolling shutter 256^2", lambda t: PO.rolling_shutter(t, 0.08), 2 * N(x256), x=x256)
+add("f3 chromatic aberration 256^2", lambda t: PO.chromatic_aberration(t), 2 * N(x256), x=x256)
+add("f3 motion blur K=15 256^2", lambda t: PO.motion_blur(t, 15, 30.0), 2 * N(x256), x=x256)
+add("f3 oversharpen (5x5 box) 256^2", lambda t: PO.oversharpen(t, 1.5), 2 * N(x256), x=x256)
+add("f3 exposure 256^2", lambda t: PO.exposure(t, 1.3), 2 * N(x256), x=x256)
+add("f3 colour temperature 256^2", lambda t: PO.color_temperature(t, 0.1), 2 * N(x256), x=x256)
+add("f3 sensor noise 256^2", lambda t: PO.sensor_noise(t, 0.05), 2 * N(x256), x=x256)
+add("f3 aliasing x0.75 256^2 (2 launches)", lambda t: PO.aliasing(t, 0.75), 2 * N(x256) + 2 * N(x192), x=x256)
+add("f3 jpeg round 64^2 (trunc8 + diffjpeg)", lambda t: PO.compress_with_format(t, "jpeg", 77.0), 4 * N(x64), x=x64)
+
 if args.json:
     json.dump({"hbm_peak_gbs": peak, "fma_peak_tflops": FMA_PEAK, "rows": rows}, open(args.json, "w"), indent=1)

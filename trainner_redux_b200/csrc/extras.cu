@@ -28,7 +28,8 @@ __device__ __forceinline__ float gs_unnormalise(float g, int size) {
 __device__ __forceinline__ float gs_reflect_clip(float x, int size) {
     const float low = -0.5f, twice_span = __fmul_rn((float)size, 2.0f);
     const float a = fabsf(__fsub_rn(x, low));
-    const float flips = truncf(__fdiv_rn(a, twice_span));
+    // a < twice_span => trunc(fl(a / twice_span)) == 0 (the quotient cannot round up to 1): skip the IEEE division
+    const float flips = a < twice_span ? 0.0f : truncf(__fdiv_rn(a, twice_span));
     const float extra = __fsub_rn(a, __fmul_rn(flips, twice_span));
     const float r = fminf(__fadd_rn(extra, low), __fadd_rn(__fsub_rn(twice_span, extra), low));
     return fminf(fmaxf(r, 0.0f), (float)(size - 1));
@@ -60,7 +61,9 @@ __device__ __forceinline__ float bilinear_zero(const float* __restrict__ pl, int
 // thread = output pixel (j fastest); loops over the C channels of its sample
 __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W,
                                                    WarpParams p) {
-    const int j = blockIdx.x * 64 + (threadIdx.x & 63), i = blockIdx.y * 4 + (threadIdx.x >> 6), b = blockIdx.z;
+    // 16 x 16 output tile per CTA: the lens grid samples the TRANSPOSED position (see below), so a flat row of threads
+    // would read one source column (32 sectors per load); a square tile touches a square source patch either way
+    const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4), b = blockIdx.z;
     if (j >= W || i >= H) return;
     const float lh = linspace_pm1(i, H, p.step_h), lw = linspace_pm1(j, W, p.step_w);
     const size_t plane = (size_t)H * W;
@@ -125,6 +128,55 @@ __global__ void __launch_bounds__(256) taps_zero_kernel(const float* __restrict_
         acc = clamp01(__fadd_rn(v, __fmul_rn(__fsub_rn(v, acc), strength)));
     }
     out[(size_t)blockIdx.z * OH * OW + (size_t)y * OW + x] = acc;
+}
+
+// Tiled variant for K <= 31: the (tile + halo) source patch is staged in shared memory with the zero padding written
+// in, so the tap loop carries no bounds checks; a thread owns 4 adjacent columns x 2 rows and every tap costs it
+// 8 LDS + 8 FFMA (tap offsets and weights are warp-uniform reads of the parameter bank).
+constexpr int kTapTW = 64, kTapTH = 32, kTapMaxR = 15;
+__global__ void __launch_bounds__(256) taps_zero_tile_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
+                                                             int OH, int OW, const __grid_constant__ TapList taps, int R,
+                                                             int epilogue, float strength) {
+    extern __shared__ float tile[];
+    const int P = kTapTW + 2 * R + 1;  // odd pitch
+    const int rows = kTapTH + 2 * R;
+    const int ox0 = blockIdx.x * kTapTW, oy0 = blockIdx.y * kTapTH;
+    const float* ip = img + (size_t)blockIdx.z * H * W;
+    for (int idx = threadIdx.x; idx < rows * (kTapTW + 2 * R); idx += 256) {
+        const int r = idx / (kTapTW + 2 * R), c = idx - r * (kTapTW + 2 * R);
+        const int yy = oy0 - R + r, xx = ox0 - R + c;
+        tile[r * P + c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ip + (size_t)yy * W + xx) : 0.0f;
+    }
+    __syncthreads();
+    const int tx = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;  // rows ty and ty + 16
+    float acc[2][4] = {};
+    const float* base = tile + (ty + R) * P + tx + R;
+    for (int k = 0; k < taps.n; ++k) {
+        const float w = taps.w[k];
+        const float* tp = base + taps.dy[k] * P + taps.dx[k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            acc[0][c] = fmaf(w, tp[c], acc[0][c]);
+            acc[1][c] = fmaf(w, tp[16 * P + c], acc[1][c]);
+        }
+    }
+    float* op = out + (size_t)blockIdx.z * OH * OW;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int y = oy0 + ty + 16 * r;
+        if (y >= OH) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int x = ox0 + tx + c;
+            if (x >= OW) continue;
+            float a = acc[r][c];
+            if (epilogue == OTF_TAPS_OVERSHARPEN) {
+                const float v = base[(16 * r) * P + c];  // centre pixel (OH == H, OW == W for odd K)
+                a = clamp01(__fadd_rn(v, __fmul_rn(__fsub_rn(v, a), strength)));
+            }
+            op[(size_t)y * OW + x] = a;
+        }
+    }
 }
 
 // ---- x * gain[c], optional clamp --------------------------------------------------------------------
@@ -197,7 +249,7 @@ extern "C" int otf_warp_f32(const float* img, int B, int C, int H, int W, int mo
     p.p0 = p0;
     p.step_h = 2.0f / (float)(H - 1);
     p.step_w = 2.0f / (float)(W - 1);
-    warp_kernel<<<dim3(ceil_div(W, 64), ceil_div(H, 4), B), 256, 0, (cudaStream_t)stream>>>(img, out, C, H, W, p);
+    warp_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), 256, 0, (cudaStream_t)stream>>>(img, out, C, H, W, p);
     OTF_LAUNCH_CHECK("warp_kernel");
     return OTF_OK;
 }
@@ -222,6 +274,13 @@ extern "C" int otf_taps_zero_f32(const float* img, int planes, int H, int W, int
             ++t.n;
         }
     const int OH = H + 2 * pad - K + 1, OW = W + 2 * pad - K + 1;
+    if (pad <= kTapMaxR) {
+        const size_t smem = (size_t)(kTapTH + 2 * pad) * (kTapTW + 2 * pad + 1) * sizeof(float);
+        taps_zero_tile_kernel<<<dim3(ceil_div(OW, kTapTW), ceil_div(OH, kTapTH), planes), 256, smem, (cudaStream_t)stream>>>(
+            img, out, H, W, OH, OW, t, pad, epilogue, strength);
+        OTF_LAUNCH_CHECK("taps_zero_tile_kernel");
+        return OTF_OK;
+    }
     taps_zero_kernel<<<dim3(ceil_div(OW, 64), ceil_div(OH, 4), planes), 256, 0, (cudaStream_t)stream>>>(img, out, H, W, OH, OW, t,
                                                                                                      epilogue, strength);
     OTF_LAUNCH_CHECK("taps_zero_kernel");

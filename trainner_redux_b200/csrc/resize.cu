@@ -278,36 +278,45 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
     const int col_hi = tx_lo[ox0 + tw - 1] + tx_lo[ax.out_n + ox0 + tw - 1];
     if (VEC) col_lo &= ~3;
     const int ncols = min(col_hi - col_lo, pitch - (NT ? NT : ax.max_taps));  // host sizes pitch from a bound on the span
+    const int nunit = VEC ? (ncols + 3) >> 2 : ncols;   // work items per output row
+    const int ufill = VEC ? 4 * nunit : nunit;
+    // Prologue without per-element divisions (it used to be 40 % of the kernel's instructions): every loop below
+    // maps threads onto a fixed 2-D shape.
     {   // pull the tile's source rectangle towards L1 now: the vertical pass then finds its rows there instead of
         // paying one DRAM round trip per output-row iteration (one 128-byte line per prefetch)
         const int row_lo = ty_lo[oy0], row_hi = min(ty_lo[oy0 + th - 1] + ty_lo[ay.out_n + oy0 + th - 1], ay.in_n);
-        const float* base = img + (size_t)plane * ay.in_n * ax.in_n;
+        const float* base = img + (size_t)plane * ay.in_n * ax.in_n + col_lo;
         const int lpr = (ncols * 4 + 127) / 128 + 1;  // lines per row (unaligned start)
-        for (int i = tid; i < (row_hi - row_lo) * lpr; i += 256) {
-            const int r = i / lpr, l = i - r * lpr;
-            const int c = min(col_lo + 32 * l, col_lo + ncols - 1);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)(row_lo + r) * ax.in_n + c));
-        }
+        for (int r = row_lo + (tid >> 3); r < row_hi; r += 32)
+            for (int l = tid & 7; l < lpr; l += 8)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)r * ax.in_n + min(32 * l, ncols - 1)));
     }
     const float* gwy = reinterpret_cast<const float*>(ty_lo + 2 * ay.out_n);
     const float* gwx = reinterpret_cast<const float*>(tx_lo + 2 * ax.out_n);
-    for (int i = tid; i < th * nty; i += 256) {
-        const int o = i / nty, j = i - o * nty;
-        wy[i] = j < ay.max_taps ? gwy[(size_t)(oy0 + o) * ay.max_taps + j] : 0.0f;
+    if (NT) {
+        // vertical taps: thread = (row o, tap j); horizontal taps: thread = (column o, a run of taps)
+        constexpr int NTc = NT ? NT : 1;
+        for (int i = tid; i < th * NTc; i += 256) {
+            const int o = i / NTc, j = i % NTc;
+            wy[i] = j < ay.max_taps ? __ldg(gwy + (size_t)(oy0 + o) * ay.max_taps + j) : 0.0f;
+        }
+        const int o = tid & (TW - 1), part = tid / TW, parts = 256 / TW;  // TW is a power of two
+        if (o < tw) {
+            const float* gp = gwx + (size_t)(ox0 + o) * ax.max_taps;
+            for (int j = part; j < NTc; j += parts) wxs[o * wxp + j] = j < ax.max_taps ? __ldg(gp + j) : 0.0f;
+        }
+    } else {
+        for (int i = tid; i < th * nty; i += 256) wy[i] = __ldg(gwy + (size_t)oy0 * ay.max_taps + i);  // nty == max_taps: contiguous
+        for (int i = tid; i < tw * ntx; i += 256) {
+            const int o = i / ntx, j = i - o * ntx;
+            wxs[o * wxp + j] = __ldg(gwx + (size_t)ox0 * ax.max_taps + i);
+        }
     }
     for (int i = tid; i < th; i += 256) ylo[i] = ty_lo[oy0 + i];
-    for (int i = tid; i < tw * ntx; i += 256) {
-        const int o = i / ntx, j = i - o * ntx;
-        wxs[o * wxp + j] = j < ax.max_taps ? gwx[(size_t)(ox0 + o) * ax.max_taps + j] : 0.0f;
-    }
     for (int i = tid; i < tw; i += 256) xlo[i] = tx_lo[ox0 + i] - col_lo;
     // columns behind the span: padded taps (weight 0) of the last output columns read them
-    const int nunit = VEC ? (ncols + 3) >> 2 : ncols;   // work items per output row
-    const int ufill = VEC ? 4 * nunit : nunit;
-    for (int i = tid; i < th * (pitch - ufill); i += 256) {
-        const int r = i / (pitch - ufill), c = i - r * (pitch - ufill);
-        vbuf[r * pitch + ufill + c] = 0.0f;
-    }
+    for (int r = tid >> 4; r < th; r += 16)
+        for (int c = ufill + (tid & 15); c < pitch; c += 16) vbuf[r * pitch + c] = 0.0f;
     __syncthreads();
     // ---- vertical pass: global -> vbuf ----
     {
@@ -319,14 +328,21 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
             for (int t = tph; t < th; t += rpar) {
                 const int r0 = ylo[t];
                 const float* wt = wy + t * nty;
+                // rows past the image only carry zero weights: step the row pointer by W while inside, then hold it
+                const bool inside = r0 + nty - 1 <= Hm1;
                 for (int u = u0; u < nunit; u += upar) {
                     if (VEC) {
                         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float* cp = ip + 4 * u;
+                        const float* cp = ip + (size_t)r0 * W + 4 * u;
                         if (NT) {
                             float4 v[NT ? NT : 1];
+                            if (inside) {
 #pragma unroll
-                            for (int i = 0; i < NT; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(cp + (size_t)min(r0 + i, Hm1) * W));
+                                for (int i = 0; i < NT; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(cp + i * W));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < NT; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(cp + (min(r0 + i, Hm1) - r0) * W));
+                            }
 #pragma unroll
                             for (int i = 0; i < NT; ++i) {
                                 const float w = wt[i];
@@ -335,7 +351,7 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
                             }
                         } else {
                             for (int i = 0; i < nty; ++i) {
-                                const float4 v = __ldg(reinterpret_cast<const float4*>(cp + (size_t)min(r0 + i, Hm1) * W));
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(cp + (min(r0 + i, Hm1) - r0) * W));
                                 const float w = wt[i];
                                 acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                                 acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
@@ -344,15 +360,20 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
                         *reinterpret_cast<float4*>(vbuf + t * pitch + 4 * u) = acc;
                     } else {
                         float acc = 0.0f;
-                        const float* cp = ip + u;
+                        const float* cp = ip + (size_t)r0 * W + u;
                         if (NT) {
                             float v[NT ? NT : 1];
+                            if (inside) {
 #pragma unroll
-                            for (int i = 0; i < NT; ++i) v[i] = __ldg(cp + (size_t)min(r0 + i, Hm1) * W);
+                                for (int i = 0; i < NT; ++i) v[i] = __ldg(cp + i * W);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < NT; ++i) v[i] = __ldg(cp + (min(r0 + i, Hm1) - r0) * W);
+                            }
 #pragma unroll
                             for (int i = 0; i < NT; ++i) acc = fmaf(wt[i], v[i], acc);
                         } else {
-                            for (int i = 0; i < nty; ++i) acc = fmaf(wt[i], __ldg(cp + (size_t)min(r0 + i, Hm1) * W), acc);
+                            for (int i = 0; i < nty; ++i) acc = fmaf(wt[i], __ldg(cp + (min(r0 + i, Hm1) - r0) * W), acc);
                         }
                         vbuf[t * pitch + u] = acc;
                     }
