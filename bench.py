@@ -247,6 +247,7 @@ def run_b200(args) -> None:
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
