@@ -139,15 +139,25 @@ int otf_philox_uniform_f32(float* out, int64_t n, uint64_t seed, uint64_t offset
  * Two launches behind one call: (1) per-sample 256-bit presence masks of the
  * 8-bit-quantised colour and gray images -> vals = 2^ceil(log2(#distinct));
  * (2) sampling + mixing + tail.  C must be 3.  masks_dev: uint32[B*16] scratch
- * (zeroed by the call).  vals_out_dev (fp32[B*2]: colour, gray; may be NULL)
- * and lambda_*_dev (may be NULL) export the deterministic half for parity
- * tests.  counts_*_dev (may be NULL) inject pre-drawn Poisson counts; otherwise
- * counts are drawn with Philox (seed, offset). */
+ * (zeroed by the call).
+ * tables_dev (may be NULL): the universal CDF tables filled once per device by
+ * otf_poisson_build_tables (otf_poisson_tables_bytes() bytes, 16-byte aligned, read-only
+ * afterwards).  lambda = (level/255) * vals with vals = 2^v, v <= 8, so only 2304
+ * lambdas can ever occur; with the tables and production arguments (no injected
+ * counts, no exports) every count is drawn by EXACT INVERSION from one Philox
+ * uniform and ~2 table reads.  Without them (or with injected counts, exports,
+ * fractional gray flags) counts come from a rejection sampler (sequential inversion
+ * below lambda 10, PTRS above).
+ * vals_out_dev (fp32[B*2]: colour, gray; may be NULL) and lambda_*_dev (may be
+ * NULL) export the deterministic half for parity tests.  counts_*_dev (may be
+ * NULL) inject pre-drawn Poisson counts. */
+int64_t otf_poisson_tables_bytes(void);
+int otf_poisson_build_tables(void* tables_dev, void* stream);
 int otf_poisson_noise_f32(const float* img, int B, int C, int H, int W,
                           const float* scale_dev, const float* gray_dev,
                           const float* counts_color_dev, const float* counts_gray_dev,
                           uint64_t seed, uint64_t offset, int flags,
-                          uint32_t* masks_dev, float* vals_out_dev,
+                          uint32_t* masks_dev, const void* tables_dev, float* vals_out_dev,
                           float* lambda_color_dev, float* lambda_gray_dev,
                           float* out, void* stream);
 /* out[i] ~ Poisson(lambda[i]) with the library's sampler (distribution tests). */
@@ -237,7 +247,8 @@ int otf_copy_box_f32(const float* src, int Hs, int Ws, int sy, int sx,
  *   OTF_OP_SEPCONV      p0 HOST taps, n = ntaps, mode = axis (0 vertical, 1 horizontal)
  *   OTF_OP_RESIZE       mode, oh, ow, flags&1 = clamp01, p0 = prebuilt tables or NULL (flags&2 = ready)
  *   OTF_OP_GAUSS        p0 sigma, p1 gray|NULL, p2/p3 injected fields|NULL, seed, offset, flags = OTF_NOISE_*
- *   OTF_OP_POISSON      p0 scale, p1 gray|NULL, p2/p3 injected counts|NULL, seed, offset, flags = OTF_NOISE_*
+ *   OTF_OP_POISSON      p0 scale, p1 gray|NULL, p2/p3 injected counts|NULL, seed, offset, flags = OTF_NOISE_*;
+ *                       with flags bit 3 (8) set, p2 is the universal CDF table block of otf_poisson_build_tables instead
  *   OTF_OP_JPEG         p0 per-sample factor/quality or NULL (f0 scalar), flags: 1 is_quality, 2 differentiable,
  *                       4 clamp_in, 8 round8_out
  *   OTF_OP_CLAMP_ROUND  -

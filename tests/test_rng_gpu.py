@@ -117,3 +117,71 @@ def test_poisson_noise_statistics_on_flat_image(dev):
     noise = (out - img) / 0.1
     assert abs(noise.mean().item()) < 0.01 and abs(noise.var().item() - q) < 0.02
 
+
+
+def _counts_through_noise_api(levels_img, dev, gray_flag, seed):
+    """Poisson counts recovered from the production path (generate_poisson_noise_pt: presence masks, CDF tables,
+    table inversion): noise = cnt / vals - q with scale 1."""
+    from trainner_redux_b200 import degradations as D
+
+    gen = D.PhiloxState(seed)
+    b = levels_img.size(0)
+    gray = torch.full((b,), float(gray_flag), device=dev)
+    noise = D.generate_poisson_noise_pt(levels_img, 1.0, gray, generator=gen)
+    return noise
+
+
+@pytest.mark.parametrize("gray_flag", [0, 1])
+def test_poisson_table_inversion_distribution(dev, gray_flag):
+    """The production sampler (exact table inversion, one uniform per sample) through the public noise API: an image
+    that holds all 256 levels (so vals = 256 and lambda_L = L/255*256), chi-square of the counts at several levels."""
+    import math
+
+    n_per = 4096  # pixels per level and channel
+    lv = torch.arange(256, dtype=torch.float32).repeat_interleave(n_per)  # (256 * n_per,)
+    h, w = 1024, 256 * n_per // 1024
+    plane = (lv / 255.0).view(1, 1, h, w)
+    img = plane.repeat(2, 3, 1, 1).to(dev)  # gray of an r=g=b image is the same level (0.2989+0.587+0.114 = 1.0009 -> rounds back)
+    noise = _counts_through_noise_api(img, dev, gray_flag, seed=77)
+    q = torch.round(plane * 255) / 255
+    cnt = torch.round((noise[:, 0:1].cpu() + q) * 256).view(2, 256, n_per)  # vals = 256
+    if gray_flag:  # one field for the three channels
+        assert torch.equal(noise[:, 0], noise[:, 1]) and torch.equal(noise[:, 1], noise[:, 2])
+    else:
+        assert not torch.equal(noise[:, 0], noise[:, 1])
+    for level in (1, 4, 10, 40, 128, 200, 255):
+        lam = float(torch.tensor(level / 255.0, dtype=torch.float32) * 256)
+        x = cnt[:, level].flatten().numpy()
+        n = x.size
+        lo, hi = max(0, int(lam - 5 * math.sqrt(lam) - 2)), int(lam + 5 * math.sqrt(lam) + 3)
+        # chi-square over the integer bins [lo, hi) + two tail bins
+        ks = np.arange(lo, hi)
+        logp = -lam + ks * math.log(lam) - np.array([math.lgamma(k + 1) for k in ks])
+        p = np.exp(logp)
+        obs = np.array([(x == k).sum() for k in ks], dtype=np.float64)
+        p_tail = max(1.0 - p.sum(), 1e-12)
+        obs_tail = n - obs.sum()
+        keep = p * n >= 5
+        chi2 = (((obs[keep] - p[keep] * n) ** 2) / (p[keep] * n)).sum()
+        rest_p, rest_o = p[~keep].sum() + p_tail, obs[~keep].sum() + obs_tail
+        if rest_p * n >= 5:
+            chi2 += (rest_o - rest_p * n) ** 2 / (rest_p * n)
+        dof = int(keep.sum())
+        assert chi2 < dof + 5 * math.sqrt(2 * dof) + 10, (level, lam, chi2, dof)
+        assert abs(x.mean() - lam) < 5 * math.sqrt(lam / n) + 1e-3, (level, x.mean(), lam)
+    assert torch.all(cnt[:, 0] == 0)  # lambda 0
+
+
+def test_poisson_table_and_rejection_paths_agree_in_law(dev, monkeypatch):
+    """Same image through both samplers: different streams, same distribution (mean / variance per level band)."""
+    from trainner_redux_b200 import degradations as D
+
+    img = torch.rand(4, 3, 256, 256, device=dev)
+    a = D.generate_poisson_noise_pt(img, 1.0, 0, generator=D.PhiloxState(5))
+    small = D._poisson(img, 1.0, 0, False, False, False, generator=D.PhiloxState(5), export={})  # export -> rejection sampler
+    for lo in (0.0, 0.25, 0.5, 0.75):
+        m = (img >= lo) & (img < lo + 0.25)
+        assert abs(a[m].mean().item() - small[m].mean().item()) < 2e-3
+        assert abs(a[m].var().item() / small[m].var().item() - 1) < 0.03
+    again = D.generate_poisson_noise_pt(img, 1.0, 0, generator=D.PhiloxState(5))
+    assert torch.equal(a, again)  # reproducible from (seed, offset)

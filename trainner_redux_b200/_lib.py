@@ -42,7 +42,9 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p]),
     "otf_philox_normal_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_philox_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
-    "otf_poisson_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p]),
+    "otf_poisson_tables_bytes": (_i64, []),
+    "otf_poisson_build_tables": (_i, [_p, _p]),
+    "otf_poisson_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p, _p]),
     "otf_philox_poisson_f32": (_i, [_p, _p, _i64, _u64, _u64, _p]),
     "otf_quality_to_factor_f32": (_i, [_p, _i, _p]),
     "otf_diffjpeg_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _i, _p, _p]),
@@ -92,6 +94,7 @@ _LAUNCHES = {
     "otf_philox_normal_f32": 1,
     "otf_philox_uniform_f32": 1,
     "otf_poisson_noise_f32": 2,
+    "otf_poisson_build_tables": 1,
     "otf_philox_poisson_f32": 1,
     "otf_quality_to_factor_f32": 1,
     "otf_diffjpeg_f32": 1,

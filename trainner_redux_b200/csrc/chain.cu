@@ -142,9 +142,11 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
                                             (const float*)s.p3, s.seed, s.offset, s.flags, out, stream);
                 break;
             case OTF_OP_POISSON:
-                rc = otf_poisson_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1, (const float*)s.p2,
-                                           (const float*)s.p3, s.seed, s.offset, s.flags, (uint32_t*)scratch, nullptr, nullptr,
-                                           nullptr, out, stream);
+                // flags bit 3: p2 carries the universal CDF tables (otf_poisson_build_tables) instead of injected counts
+                rc = otf_poisson_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1,
+                                           (s.flags & 8) ? nullptr : (const float*)s.p2, (s.flags & 8) ? nullptr : (const float*)s.p3,
+                                           s.seed, s.offset, s.flags & 7, (uint32_t*)scratch, (s.flags & 8) ? s.p2 : nullptr,
+                                           nullptr, nullptr, nullptr, out, stream);
                 break;
             case OTF_OP_JPEG:
                 OTF_REQUIRE(C == 3, OTF_ERR_BAD_ARG, "run_stages[%d]: DiffJPEG needs 3 channels", i);

@@ -232,37 +232,46 @@ __device__ __forceinline__ int level8(float x) {  // clamp(round(x*255),0,255) a
 // masks[b*16 + 0..7] colour, [b*16 + 8..15] gray.  grid = (chunks, B).
 __global__ void __launch_bounds__(256) poisson_presence_kernel(const float* __restrict__ img, int hw,
                                                                uint32_t* __restrict__ masks) {
+    // One byte flag per level in shared memory: setting it is a plain store (every writer stores the same 1, so the
+    // race is benign) — 4 stores per pixel instead of the ~100 select instructions of per-thread register masks or the
+    // contended atomics of a shared bit mask.  At the end 16 ballots pack the flags into the sample's 2 x 256-bit masks.
     const int b = blockIdx.y;
     const float* ip = img + (size_t)b * 3 * hw;
-    uint32_t mc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
-        const float r = ip[p], g = ip[hw + p], bl = ip[2 * hw + p];
-        const int lv[4] = {level8(r), level8(g), level8(bl), level8(gray_of(r, g, bl))};
+    __shared__ uint8_t flag[512];  // [0,256) colour levels, [256,512) gray levels
+    flag[threadIdx.x] = 0;
+    flag[256 + threadIdx.x] = 0;
+    __syncthreads();
+    if ((hw & 3) == 0 && (((uintptr_t)img) & 15) == 0) {  // three independent 16-byte loads per trip
+        const float4* i4 = reinterpret_cast<const float4*>(ip);
+        const int q4 = hw >> 2;
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < q4; p += gridDim.x * blockDim.x) {
+            const float4 r = __ldg(i4 + p), g = __ldg(i4 + q4 + p), bl = __ldg(i4 + 2 * q4 + p);
+            const float rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {bl.x, bl.y, bl.z, bl.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t bit = 1u << (lv[k] & 31);
-            const int word = lv[k] >> 5;
-#pragma unroll
-            for (int wd = 0; wd < 8; ++wd) {
-                const uint32_t m = word == wd ? bit : 0u;
-                if (k < 3) mc[wd] |= m; else mg[wd] |= m;
+            for (int k = 0; k < 4; ++k) {
+                flag[level8(rr[k])] = 1;
+                flag[level8(gg[k])] = 1;
+                flag[level8(bb[k])] = 1;
+                flag[256 + level8(gray_of(rr[k], gg[k], bb[k]))] = 1;
             }
         }
-    }
-    __shared__ uint32_t sm[16];
-    if (threadIdx.x < 16) sm[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int wd = 0; wd < 8; ++wd) {
-        const uint32_t c = __reduce_or_sync(0xffffffffu, mc[wd]);
-        const uint32_t g = __reduce_or_sync(0xffffffffu, mg[wd]);
-        if ((threadIdx.x & 31) == 0) {
-            if (c) atomicOr(&sm[wd], c);
-            if (g) atomicOr(&sm[8 + wd], g);
+    } else {
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+            const float r = ip[p], g = ip[hw + p], bl = ip[2 * hw + p];
+            flag[level8(r)] = 1;
+            flag[level8(g)] = 1;
+            flag[level8(bl)] = 1;
+            flag[256 + level8(gray_of(r, g, bl))] = 1;
         }
     }
     __syncthreads();
-    if (threadIdx.x < 16 && sm[threadIdx.x]) atomicOr(&masks[b * 16 + threadIdx.x], sm[threadIdx.x]);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;  // warp w packs levels [32w, 32w+32) of both kinds
+    const uint32_t mc = __ballot_sync(0xffffffffu, flag[threadIdx.x] != 0);
+    const uint32_t mg = __ballot_sync(0xffffffffu, flag[256 + threadIdx.x] != 0);
+    if (lane == 0) {
+        if (mc) atomicOr(&masks[b * 16 + wid], mc);
+        if (mg) atomicOr(&masks[b * 16 + 8 + wid], mg);
+    }
 }
 
 __device__ __forceinline__ float vals_from_mask(const uint32_t* m) {
@@ -279,6 +288,57 @@ __device__ __forceinline__ float vals_from_mask(const uint32_t* m) {
 // (Tried and dropped in round 1: a per-thread state machine that runs one PTRS trial per loop iteration so that
 // lanes never wait for the slowest rejection loop — bit-identical output, but 0.23 ms vs 0.165 ms here at
 // 64x3x192^2: the bookkeeping costs more than the ~1.5 extra warp-level trials it saves.)
+// one pixel (all three channels) of the generic path: any gray flag, injected counts, exported lambdas
+__device__ __forceinline__ void poisson_pixel_generic(const float* __restrict__ ip, float* __restrict__ op, int hw, int b, int p,
+                                                      float vc, float vg, float sc, const float* gray, float gf,
+                                                      const float* __restrict__ counts_c, const float* __restrict__ counts_g,
+                                                      const Philox& ph, uint64_t offset, int flags, float* __restrict__ lam_c_out,
+                                                      float* __restrict__ lam_g_out) {
+    const float px[3] = {ip[p], ip[hw + p], ip[2 * hw + p]};
+    // The gray flag is block-uniform.  flag 0: noise*1 + noise_g*0 == noise exactly, flag 1: noise*0 + noise_g*1
+    // == noise_g exactly — so the field that the mix discards is not sampled (unless a test asked for its lambda
+    // or injected its counts).
+    const bool need_g = gray && (gf != 0.0f || counts_g || lam_g_out);
+    const bool need_c = !(gray && gf == 1.0f) || counts_c || lam_c_out;
+    float noise_g = 0.0f;
+    if (need_g) {
+        // degradations.py:787-795 — gray image, quantised; noise relative to the quantised value
+        const float qg = quantise8(gray_of(px[0], px[1], px[2]));
+        const float lam = __fmul_rn(qg, vg);
+        if (lam_g_out) lam_g_out[(size_t)b * hw + p] = lam;
+        float cnt;
+        if (counts_g) {
+            cnt = counts_g[(size_t)b * hw + p];
+        } else {
+            UniformStream us(ph, (uint64_t)b * hw + p, offset * 8 + STREAM_POIS_GRAY);
+            cnt = poisson_sample(lam, us);
+        }
+        noise_g = __fsub_rn(__fdiv_rn(cnt, vg), qg);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t e = (size_t)b * 3 * hw + (size_t)c * hw + p;
+        float noise = 0.0f;
+        if (need_c) {
+            const float qc = quantise8(px[c]);  // :800
+            const float lam = __fmul_rn(qc, vc);
+            if (lam_c_out) lam_c_out[e] = lam;
+            float cnt;
+            if (counts_c) {
+                cnt = counts_c[e];
+            } else {
+                UniformStream us(ph, (uint64_t)e, offset * 8 + STREAM_POIS_COLOR);
+                cnt = poisson_sample(lam, us);
+            }
+            noise = __fsub_rn(__fdiv_rn(cnt, vc), qc);  // :805-806
+        }
+        if (gray) noise = __fadd_rn(__fmul_rn(noise, __fsub_rn(1.0f, gf)), __fmul_rn(noise_g, gf));  // :808
+        noise = __fmul_rn(noise, sc);                                                              // :811
+        op[(size_t)c * hw + p] =
+            (flags & OTF_NOISE_FIELD_ONLY) ? noise : noise_tail(__fadd_rn(px[c], noise), flags);           // :834-841
+    }
+}
+
 __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restrict__ img, float* __restrict__ out, int hw,
                                                             const float* __restrict__ scale, const float* __restrict__ gray,
                                                             const float* __restrict__ counts_c, const float* __restrict__ counts_g,
@@ -298,49 +358,140 @@ __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restr
     const Philox ph(seed);
     const float* ip = img + (size_t)b * 3 * hw;
     float* op = out + (size_t)b * 3 * hw;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x)
+        poisson_pixel_generic(ip, op, hw, b, p, vc, vg, sc, gray, gf, counts_c, counts_g, ph, offset, flags, lam_c_out, lam_g_out);
+}
+
+// ---- table inversion (the production path) ----------------------------------------------------------
+// lambda = q * vals with q = level / 255 and vals = 2^v, v in 0..8 (a sample has at most 256 distinct levels): only
+// 9 x 256 = 2304 different lambdas can ever occur, whatever the image.  Their exact CDFs are tabulated ONCE per
+// device (otf_poisson_build_tables: 2304 rows x a 256-wide window [k_lo, k_lo + 256) around lambda — >= 7.9 sigma at
+// lambda = 256, tail mass < 1e-14 — 2.96 MB, L2 resident, the 320 KB of one vals mostly L1 resident).  A sample then
+// costs ONE uniform, one guide byte (the first k whose CDF can reach the uniform's 1/256 bucket) and ~1.3 CDF reads:
+// no rejection loop, no divergence, one Philox call per pixel.  The rejection kernel above pays ~2.6 warp-level PTRS
+// attempts per element (85 % acceptance per lane, so nearly every warp retries).  Tables are built in fp64
+// (p(k+1) = p(k) * lambda / (k+1) from p(k_lo) = exp(-lambda + k_lo ln lambda - lgamma(k_lo + 1))) and stored as
+// fp32; with 24-bit uniforms every outcome's probability is exact to 2^-24.
+constexpr int kPoisWin = 256, kPoisRows = 9 * 256;
+
+struct PoissonTables {
+    const int* klo;        // [9][256]
+    const uint8_t* guide;  // [9][256][256]
+    const float* cdf;      // [9][256][256]
+};
+static int64_t poisson_tables_bytes() { return (int64_t)kPoisRows * (4 + kPoisWin + (int64_t)kPoisWin * 4); }
+static PoissonTables poisson_tables(const void* dev) {
+    PoissonTables t;
+    const char* p = (const char*)dev;
+    t.klo = (const int*)p;
+    p += (size_t)kPoisRows * 4;
+    t.guide = (const uint8_t*)p;
+    p += (size_t)kPoisRows * kPoisWin;
+    t.cdf = (const float*)p;
+    return t;
+}
+
+// one thread per (vals exponent, level) row — runs once per device
+__global__ void __launch_bounds__(256) poisson_tables_kernel(int* __restrict__ klo_out, uint8_t* __restrict__ guide_out,
+                                                             float* __restrict__ cdf_out) {
+    const int v = blockIdx.x, level = threadIdx.x;
+    const float lamf = __fmul_rn(__fdiv_rn((float)level, 255.0f), (float)(1 << v));  // exactly what the apply kernel forms
+    const double lam = (double)lamf;
+    const size_t row = (size_t)v * 256 + level;
+    int klo = (int)floor(lam - 8.0 * sqrt(lam));
+    if (klo < 0) klo = 0;
+    klo_out[row] = klo;
+    float* cdf = cdf_out + row * kPoisWin;
+    uint8_t* guide = guide_out + row * kPoisWin;
+    double p = lam > 0.0 ? exp(-lam + klo * log(lam) - lgamma((double)klo + 1.0)) : (klo == 0 ? 1.0 : 0.0);
+    double acc = 0.0;
+    int g = 0;  // next guide bucket to fill
+    for (int k = 0; k < kPoisWin; ++k) {
+        acc += p;
+        const float c = k == kPoisWin - 1 ? 1.0f : fminf((float)acc, 1.0f);
+        cdf[k] = c;
+        // bucket j holds the uniforms (j*65536 + 1 .. (j+1)*65536) / 2^24: its first admissible k is the first one
+        // whose CDF reaches the bucket's smallest uniform
+        while (g < 256 && c >= (float)(g * 65536 + 1) * (1.0f / 16777216.0f)) guide[g++] = (uint8_t)k;
+        p = p * lam / (double)(klo + k + 1);
+    }
+}
+
+__device__ __forceinline__ float poisson_by_table(const PoissonTables& tab, int row, uint32_t bits) {
+    const uint32_t u24 = bits >> 8;
+    const float u = ((float)u24 + 1.0f) * (1.0f / 16777216.0f);  // the same (0,1] uniform as u01()
+    const float* cdf = tab.cdf + (size_t)row * kPoisWin;
+    int k = __ldg(tab.guide + (size_t)row * kPoisWin + (u24 >> 16));
+    while (__ldg(cdf + k) < u) ++k;  // cdf[255] == 1 >= u: terminates
+    return (float)(__ldg(tab.klo + row) + k);
+}
+
+// Pass 2, production flags (no injected counts, no exports, per-sample gray flag exactly 0 or 1): one thread per
+// pixel, one Philox call per pixel (3 of its 4 words for the colour channels, 1 for a gray sample).
+__global__ void __launch_bounds__(256) poisson_apply_table_kernel(const float* __restrict__ img, float* __restrict__ out, int hw,
+                                                                  const float* __restrict__ scale, const float* __restrict__ gray,
+                                                                  uint64_t seed, uint64_t offset, int flags,
+                                                                  const uint32_t* __restrict__ masks, PoissonTables tab) {
+    const int b = blockIdx.y;
+    const float gf = gray ? gray[b] : 0.0f;
+    const bool is_gray = gray && gf == 1.0f;
+    __shared__ float s_vals[2];
+    if (threadIdx.x < 2) s_vals[threadIdx.x] = vals_from_mask(masks + b * 16 + threadIdx.x * 8);
+    __syncthreads();
+    const float sc = scale[b];
+    const Philox ph(seed);
+    const float* ip = img + (size_t)b * 3 * hw;
+    float* op = out + (size_t)b * 3 * hw;
+    if (gray && gf != 0.0f && gf != 1.0f) {
+        // a fractional flag mixes both fields (the API allows it; the reference only ever draws 0 or 1): rejection sampler
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x)
+            poisson_pixel_generic(ip, op, hw, b, p, s_vals[0], s_vals[1], sc, gray, gf, nullptr, nullptr, ph, offset, flags, nullptr, nullptr);
+        return;
+    }
+    const float vsel = s_vals[is_gray ? 1 : 0];
+    const float inv_vals = 1.0f / vsel;  // vals is a power of two: the reciprocal and the product are exact
+    const int row0 = (31 - __clz((int)vsel)) * 256;  // table rows of this sample's vals
+    __shared__ float s_q[256];  // level / 255 with the IEEE division the reference performs, once per CTA
+    s_q[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+    __syncthreads();
+    const uint64_t stream = offset * 8 + (is_gray ? STREAM_POIS_GRAY : STREAM_POIS_COLOR);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
         const float px[3] = {ip[p], ip[hw + p], ip[2 * hw + p]};
-        // The gray flag is block-uniform.  flag 0: noise*1 + noise_g*0 == noise exactly, flag 1: noise*0 + noise_g*1
-        // == noise_g exactly — so the field that the mix discards is not sampled (unless a test asked for its lambda
-        // or injected its counts).
-        const bool need_g = gray && (gf != 0.0f || counts_g || lam_g_out);
-        const bool need_c = !(gray && gf == 1.0f) || counts_c || lam_c_out;
-        float noise_g = 0.0f;
-        if (need_g) {
-            // degradations.py:787-795 — gray image, quantised; noise relative to the quantised value
-            const float qg = quantise8(gray_of(px[0], px[1], px[2]));
-            const float lam = __fmul_rn(qg, vg);
-            if (lam_g_out) lam_g_out[(size_t)b * hw + p] = lam;
-            float cnt;
-            if (counts_g) {
-                cnt = counts_g[(size_t)b * hw + p];
-            } else {
-                UniformStream us(ph, (uint64_t)b * hw + p, offset * 8 + STREAM_POIS_GRAY);
-                cnt = poisson_sample(lam, us);
+        const uint4 r = ph((uint64_t)b * hw + p, stream);
+        float noise[3];
+        if (is_gray) {
+            const int lv = level8(gray_of(px[0], px[1], px[2]));
+            const float cnt = poisson_by_table(tab, row0 + lv, r.x);
+            // mix with flag 1: noise * 0 + noise_g * 1 == noise_g exactly (degradations.py:808)
+            noise[0] = noise[1] = noise[2] = __fsub_rn(__fmul_rn(cnt, inv_vals), s_q[lv]);
+        } else {
+            // the three channels' table walks are independent: issue their loads side by side
+            const uint32_t w[3] = {r.x, r.y, r.z};
+            int lv[3], k[3], klo[3];
+            float u[3], c[3];
+            const float* cdf[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                lv[ch] = level8(px[ch]);
+                const uint32_t u24 = w[ch] >> 8;
+                u[ch] = ((float)u24 + 1.0f) * (1.0f / 16777216.0f);
+                const size_t row = (size_t)(row0 + lv[ch]);
+                cdf[ch] = tab.cdf + row * kPoisWin;
+                k[ch] = __ldg(tab.guide + row * kPoisWin + (u24 >> 16));
+                klo[ch] = __ldg(tab.klo + row);
             }
-            noise_g = __fsub_rn(__fdiv_rn(cnt, vg), qg);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) c[ch] = __ldg(cdf[ch] + k[ch]);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                while (c[ch] < u[ch]) c[ch] = __ldg(cdf[ch] + ++k[ch]);  // cdf[255] == 1 >= u: terminates
+                noise[ch] = __fsub_rn(__fmul_rn((float)(klo[ch] + k[ch]), inv_vals), s_q[lv[ch]]);  // :805-806
+            }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const size_t e = (size_t)b * 3 * hw + (size_t)c * hw + p;
-            float noise = 0.0f;
-            if (need_c) {
-                const float qc = quantise8(px[c]);  // :800
-                const float lam = __fmul_rn(qc, vc);
-                if (lam_c_out) lam_c_out[e] = lam;
-                float cnt;
-                if (counts_c) {
-                    cnt = counts_c[e];
-                } else {
-                    UniformStream us(ph, (uint64_t)e, offset * 8 + STREAM_POIS_COLOR);
-                    cnt = poisson_sample(lam, us);
-                }
-                noise = __fsub_rn(__fdiv_rn(cnt, vc), qc);  // :805-806
-            }
-            if (gray) noise = __fadd_rn(__fmul_rn(noise, __fsub_rn(1.0f, gf)), __fmul_rn(noise_g, gf));  // :808
-            noise = __fmul_rn(noise, sc);                                                              // :811
-            op[(size_t)c * hw + p] =
-                (flags & OTF_NOISE_FIELD_ONLY) ? noise : noise_tail(__fadd_rn(px[c], noise), flags);           // :834-841
+            const float nz = __fmul_rn(noise[c], sc);  // :811
+            op[(size_t)c * hw + p] = (flags & OTF_NOISE_FIELD_ONLY) ? nz : noise_tail(__fadd_rn(px[c], nz), flags);
         }
     }
 }
@@ -412,10 +563,23 @@ extern "C" int otf_philox_poisson_f32(const float* lambda_dev, float* out, int64
     return OTF_OK;
 }
 
+extern "C" int64_t otf_poisson_tables_bytes(void) { return otf::poisson_tables_bytes(); }
+
+extern "C" int otf_poisson_build_tables(void* tables_dev, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(tables_dev && (((uintptr_t)tables_dev) & 15) == 0, OTF_ERR_BAD_ARG, "poisson_build_tables: null or unaligned pointer");
+    char* p = (char*)tables_dev;
+    poisson_tables_kernel<<<9, 256, 0, (cudaStream_t)stream>>>((int*)p, (uint8_t*)(p + (size_t)kPoisRows * 4),
+                                                              (float*)(p + (size_t)kPoisRows * (4 + kPoisWin)));
+    OTF_LAUNCH_CHECK("poisson_tables_kernel");
+    return OTF_OK;
+}
+
 extern "C" int otf_poisson_noise_f32(const float* img, int B, int C, int H, int W, const float* scale_dev,
                                      const float* gray_dev, const float* counts_color_dev, const float* counts_gray_dev,
-                                     uint64_t seed, uint64_t offset, int flags, uint32_t* masks_dev, float* vals_out_dev,
-                                     float* lambda_color_dev, float* lambda_gray_dev, float* out, void* stream) {
+                                     uint64_t seed, uint64_t offset, int flags, uint32_t* masks_dev, const void* tables_dev,
+                                     float* vals_out_dev, float* lambda_color_dev, float* lambda_gray_dev, float* out,
+                                     void* stream) {
     using namespace otf;
     OTF_REQUIRE(img && out && scale_dev && masks_dev, OTF_ERR_BAD_ARG, "poisson_noise: null pointer");
     OTF_REQUIRE(C == 3, OTF_ERR_UNSUPPORTED, "poisson_noise: C must be 3 (rgb_to_grayscale), got %d", C);
@@ -434,6 +598,15 @@ extern "C" int otf_poisson_noise_f32(const float* img, int B, int C, int H, int 
     int chunks2 = ceil_div(hw, 256);
     const int max_chunks2 = ceil_div(kNumSMs * 16, B);
     if (chunks2 > max_chunks2) chunks2 = max_chunks2;
+    // production flags + room for the CDF tables: exact table inversion; OTF_POISSON_IMPL=ptrs forces the rejection sampler
+    static const bool force_ptrs = [] { const char* e = getenv("OTF_POISSON_IMPL"); return e && e[0] == 'p'; }();
+    const bool plain = !counts_color_dev && !counts_gray_dev && !vals_out_dev && !lambda_color_dev && !lambda_gray_dev;
+    if (plain && !force_ptrs && tables_dev) {
+        poisson_apply_table_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, seed, offset, flags,
+                                                                     masks_dev, poisson_tables(tables_dev));
+        OTF_LAUNCH_CHECK("poisson_apply_table_kernel");
+        return OTF_OK;
+    }
     poisson_apply_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, counts_color_dev,
                                                            counts_gray_dev, seed, offset, flags, masks_dev, vals_out_dev,
                                                            lambda_color_dev, lambda_gray_dev);

@@ -127,6 +127,42 @@ def random_add_gaussian_noise_pt(img: Tensor, sigma_range: tuple[float, float] =
 # ------------------------------------------------------------------- Poisson ----
 
 
+# Universal Poisson CDF tables (2.96 MB, one per device, read-only once built): lambda = level/255 * 2^v can take only
+# 2304 values, so the table-inversion sampler never rebuilds anything.  Same stream discipline as the resize tables:
+# the entry remembers the event that follows the build; other streams wait on it; a capturing stream only uses tables
+# whose build has completed (poisson_tables() is called eagerly by RealESRGANFeed.__init__).
+_POISSON_TABLES: dict[int, tuple[Tensor, "torch.cuda.Event", int, bool]] = {}
+
+
+def poisson_tables(device: torch.device) -> Tensor | None:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cur = torch.cuda.current_stream(device)
+    capturing = torch.cuda.is_current_stream_capturing()
+    hit = _POISSON_TABLES.get(idx)
+    if hit is None:
+        if capturing:
+            return None  # no build inside a capture: this call falls back to the rejection sampler
+        tab = torch.empty(_lib.load().otf_poisson_tables_bytes() // 4, dtype=torch.int32, device=device)
+        _lib.call("otf_poisson_build_tables", _lib.ptr(tab), _lib.stream())
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        _POISSON_TABLES[idx] = (tab, ev, cur.cuda_stream, False)
+        return tab
+    tab, ev, sid, done = hit
+    if done:
+        return tab
+    if capturing:
+        if not ev.query():
+            ev.synchronize()
+        _POISSON_TABLES[idx] = (tab, ev, sid, True)
+        return tab
+    if sid != cur.cuda_stream:
+        cur.wait_event(ev)
+    if ev.query():
+        _POISSON_TABLES[idx] = (tab, ev, sid, True)
+    return tab
+
+
 def _poisson(img, scale, gray_noise, clip, rounds, add, counts=None, counts_gray=None, generator=None,
              export: dict | None = None) -> Tensor:
     _lib.require_cuda(img)
@@ -144,6 +180,8 @@ def _poisson(img, scale, gray_noise, clip, rounds, add, counts=None, counts_gray
         else:
             gray = None  # reference skips the gray branch when no flag is set (:784-796)
     masks = torch.empty(b * 16, dtype=torch.int32, device=x.device)
+    # counts drawn on the device: exact table inversion (the tables are built once per device)
+    tables = poisson_tables(x.device) if counts is None and counts_gray is None and export is None else None
     vals = lam_c = lam_g = None
     if export is not None:
         vals = torch.empty(b, 2, dtype=torch.float32, device=x.device)
@@ -154,7 +192,7 @@ def _poisson(img, scale, gray_noise, clip, rounds, add, counts=None, counts_gray
     _lib.call(
         "otf_poisson_noise_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(sc), _lib.ptr(gray), _lib.ptr(counts),
         _lib.ptr(counts_gray), gen.seed, gen.next_offset(), _flags(clip, rounds) if add else _lib.NOISE_FIELD_ONLY, _lib.ptr(masks),
-        _lib.ptr(vals), _lib.ptr(lam_c), _lib.ptr(lam_g), _lib.ptr(out), _lib.stream(),
+        _lib.ptr(tables), _lib.ptr(vals), _lib.ptr(lam_c), _lib.ptr(lam_g), _lib.ptr(out), _lib.stream(),
     )
     if export is not None:
         export.update(vals=vals, lambda_color=lam_c, lambda_gray=lam_g)

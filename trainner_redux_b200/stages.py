@@ -184,8 +184,13 @@ class StageList:
             gray = None
         if counts is not None and counts_gray is None:
             gray = None
-        s = self._add(_lib.OP_POISSON, seed=gen.seed, offset=gen.next_offset(), flags=D._flags(clip, rounds),
-                      p2=self._dev_ptr(counts), p3=self._dev_ptr(counts_gray) if counts is not None else None)
+        tables = D.poisson_tables(self.device) if counts is None else None  # exact table inversion when the counts are drawn here
+        if tables is not None:
+            s = self._add(_lib.OP_POISSON, seed=gen.seed, offset=gen.next_offset(), flags=D._flags(clip, rounds) | 8,
+                          p2=tables.data_ptr())  # (raw table block: owned by degradations._POISSON_TABLES for the life of the process)
+        else:
+            s = self._add(_lib.OP_POISSON, seed=gen.seed, offset=gen.next_offset(), flags=D._flags(clip, rounds),
+                          p2=self._dev_ptr(counts), p3=self._dev_ptr(counts_gray) if counts is not None else None)
         self._per_sample(s, "p0", scale)
         self._per_sample(s, "p1", gray)
         self.launches += 2
