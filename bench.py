@@ -74,8 +74,19 @@ def make_inputs(seed: int, batch: int, device=None):
     return {"gt": synth_gt(batch, GT, GT, "uniform", seed=1234 + seed), "kernel1": k1, "kernel2": k2, "sinc_kernel": k3}
 
 
+NOISE = "gaussian"  # --noise poisson: the Poisson variant of SURVEY.md §8d Config 2 (scale ~ U[0.05, 3] / U[0.05, 2.5])
+
+
 def make_plan(batch: int, seed: int) -> dict:
     g = torch.Generator().manual_seed(seed)
+    plan = _make_plan(batch, g)
+    if NOISE == "poisson":
+        for key, hi in (("noise1", 3.0), ("noise2", 2.5)):
+            plan[key] = {"kind": "poisson", "scale": torch.rand(batch, generator=g) * (hi - 0.05) + 0.05, "gray": plan[key]["gray"]}
+    return plan
+
+
+def _make_plan(batch: int, g) -> dict:
     return {
         "scale": SCALE, "gt_size": GT_CROP, "order": "classic", "blur1": True,
         "resize1": {"scale": S1, "mode": "bicubic"},
@@ -161,7 +172,7 @@ def set_workload(name: str, world: int) -> None:
 def workload_name() -> str:
     lq = GT // SCALE
     return (f"Real-ESRGAN OTF second-order chain incl. DiffJPEG + sinc, batch {BATCH} synthetic {GT}^2 GT x{SCALE} per GPU "
-            f"(blur1, bicubic x0.75, gaussian, jpeg, blur2, bilinear, gaussian, area->{lq}^2, sinc, jpeg, clamp/round, "
+            f"(blur1, bicubic x0.75, {NOISE}, jpeg, blur2, bilinear, {NOISE}, area->{lq}^2, sinc, jpeg, clamp/round, "
             f"crop {GT_CROP}/{GT_CROP // SCALE})")
 
 
@@ -263,8 +274,9 @@ def run_b200(args) -> None:
     for i in range(N_ROTATE):
         p = make_plan(BATCH, rank * N_ROTATE + i)
         for key in ("noise1", "noise2"):
-            for kk in ("sigma", "gray"):
-                p[key][kk] = p[key][kk].to(dev)
+            for kk in ("sigma", "scale", "gray"):
+                if kk in p[key]:
+                    p[key][kk] = p[key][kk].to(dev)
         for key in ("jpeg1", "jpeg2"):
             p[key] = p[key].to(dev)
         plans.append(p)
@@ -483,6 +495,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: 64 x 256^2 x4 per GPU (default); c3: 32 x 512^2 x2 sharded")
+    ap.add_argument("--noise", default="gaussian", choices=["gaussian", "poisson"], help="noise kind of both noise stages")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--streams", type=int, default=4, help="batches in flight during the timed region (graph mode)")
@@ -490,6 +503,8 @@ def main() -> None:
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     set_workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")))
+    global NOISE
+    NOISE = args.noise
     if args.impl == "reference":
         run_reference(args)
     else:
