@@ -42,7 +42,7 @@ METRIC = "degraded LR/HR pairs/sec at 256^2 GT x4"
 UNIT = "pairs/s"
 GT, SCALE, BATCH, GT_CROP = 256, 4, 64, 224
 S1, S2 = 0.75, 1.0
-N_ROTATE = 4  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
+N_ROTATE = int(os.environ.get("OTF_BENCH_ROTATE", "4"))  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
 
 
 def peaks() -> dict:

@@ -415,3 +415,35 @@ def test_kernel_synthesis_on_gpu(golden, dev):
     b = RealESRGANFeed(opt, device=dev, manual_seed=1, use_pool=False)
     b.feed_data({"gt": gt, "kernel1": g["ks_ds_k1"], "kernel2": g["ks_ds_k2"], "sinc_kernel": g["ks_ds_sinc"]})
     assert (a.lq - b.lq).abs().max().item() <= 1 / 255 + 1e-6
+
+
+def test_paired_feed_second_caller(dev):
+    """RealESRGANPairedModel.feed_data (realesrgan_paired_model.py:34-67): one numpy coin per call picks the pre-made
+    pair (uploaded untouched) or the OTF path on the `otf_`-prefixed keys."""
+    import numpy as np
+
+    from trainner_redux_b200.realesrgan_feed import OTFOptions, RealESRGANFeed, RealESRGANPairedFeed
+
+    opt = OTFOptions(scale=4, gt_size=64, blur_prob=1, jpeg_range=(30, 95), jpeg_range2=(30, 95))
+    opt.dataroot_lq_prob = 0.5
+    base = {"gt": O.synth_gt(2, 96, 96, "natural", seed=7), "kernel1": O.synth_blur_kernels(2, seed=1),
+            "kernel2": O.synth_blur_kernels(2, seed=2), "sinc_kernel": O.synth_sinc_or_pulse(2, seed=3)}
+    data = {f"otf_{k}": v for k, v in base.items()}
+    data["paired_lq"], data["paired_gt"] = torch.rand(2, 3, 16, 16), torch.rand(2, 3, 64, 64)
+    feed = RealESRGANPairedFeed(opt, device=dev, manual_seed=3, use_pool=False)
+    coins = np.random.default_rng(3)
+    took = set()
+    for _ in range(12):
+        # replay: the paired coin comes first; the OTF branch then consumes its own draws from the same generator
+        state = feed.rng.np.bit_generator.state
+        coins.bit_generator.state = state
+        paired = coins.uniform() < 0.5
+        feed.feed_data(data)
+        took.add(paired)
+        if paired:
+            assert torch.equal(feed.lq.cpu(), data["paired_lq"]) and torch.equal(feed.gt.cpu(), data["paired_gt"])
+        else:
+            assert tuple(feed.lq.shape) == (2, 3, 16, 16) and tuple(feed.gt.shape) == (2, 3, 64, 64) and feed.last_plan is not None
+    assert took == {True, False}
+    with pytest.raises(AssertionError):
+        RealESRGANPairedFeed(OTFOptions(gt_size=64), device=dev, use_pool=False).feed_data({"paired_lq": data["paired_lq"]})  # no otf_ keys

@@ -596,6 +596,30 @@ class RealESRGANFeed:
                 self.gt = data["gt"].to(self.device, non_blocking=True)
 
 
+class RealESRGANPairedFeed(RealESRGANFeed):
+    """The path's second caller, ``RealESRGANPairedModel.feed_data`` (traiNNer/models/realesrgan_paired_model.py:34-67,
+    chosen when ``dataroot_lq_prob > 0``): one numpy-generator coin per call; with probability ``dataroot_lq_prob`` the
+    pre-made ``paired_lq`` / ``paired_gt`` batch is uploaded as is (MoA applied when it is on), otherwise the ``otf_``
+    keys lose their prefix and go through the OTF ``feed_data``."""
+
+    def __init__(self, opt: Any, *args: Any, **kw: Any) -> None:
+        super().__init__(opt, *args, **kw)
+        self.dataroot_lq_prob = _opt(opt, "dataroot_lq_prob", 0)
+
+    @torch.no_grad()
+    def feed_data(self, data: dict, plan: dict | None = None, inject: dict | None = None) -> None:
+        if self.rng.np.uniform() < self.dataroot_lq_prob:
+            new_data = {k.replace("paired_", ""): v for k, v in data.items() if k.startswith("paired_")}
+            assert "lq" in new_data
+            self.lq = new_data["lq"].to(self.device, non_blocking=True)
+            if "gt" in new_data:
+                self.gt = new_data["gt"].to(self.device, non_blocking=True)
+            if self.is_train and self.batch_augment and self.gt is not None:
+                self.gt, self.lq = self.batch_augment(self.gt, self.lq)
+            return
+        super().feed_data({k.replace("otf_", ""): v for k, v in data.items() if k.startswith("otf_")}, plan=plan, inject=inject)
+
+
 def shard_range(n: int, rank: int, world_size: int) -> tuple[int, int]:
     """Contiguous per-rank slice of a global batch of ``n`` samples: the path has
     no exchange step, so every rank degrades its own samples and keeps its own pool."""
