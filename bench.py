@@ -258,8 +258,19 @@ def run_b200(args) -> None:
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line only: NCCL's banner ("NCCL version ...", NCCL_DEBUG output) goes to stderr —
+        # file descriptor 1 points at stderr while the communicator is created
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.load()
 
     feed = RealESRGANFeed(OTFOptions(scale=SCALE, gt_size=GT_CROP, queue_size=BATCH * 2), device=dev, manual_seed=0, rank=rank,
