@@ -293,6 +293,10 @@ int otf_channel_gain_f32(const float* img, int B, int C, int64_t hw, float g0, f
                          int clamp01_out, float* out, void* stream);
 int otf_sensor_noise_f32(const float* img, int64_t n, float std, const float* noise_dev,
                          uint64_t seed, uint64_t offset, float* out, void* stream);
+/* Bayer mosaic + cv2.demosaicing(COLOR_BAYER_BG2BGR) of apply_demosaicing_artifacts (:526-552), bit for bit:
+ * uint8 truncation, one channel per pixel, OpenCV's integer bilinear demosaic with its border rule, / 255.
+ * img / out: B x 3 x H x W. */
+int otf_demosaic_f32(const float* img, int B, int H, int W, float* out, void* stream);
 /* floor(clamp(img,0,1) * 255) / 255: the uint8 truncation in front of every codec round (:114-115). */
 int otf_trunc8_f32(const float* img, int64_t n, float* out, void* stream);
 

@@ -156,6 +156,14 @@ def main() -> None:
             same(P.sensor_noise(img, sd, nz), ref, "sensor noise")
             put(f"sensor_{key}_{s}_p", np.float64(sd)); put(f"sensor_{key}_{s}_noise", nz); put(f"sensor_{key}_{s}", ref)
             n_cases += 9
+        # Bayer demosaic (cv2 on the host in the reference): reference == cv2 restatement == numpy integer restatement
+        opt = base_opt(demosaic_prob=1.0)
+        seed(850)
+        ref = Ref.apply_demosaicing_artifacts(img, opt)
+        same(P.demosaic_cv2(img), ref, "demosaic (cv2)")
+        same(P.demosaic(img), ref, "demosaic (numpy restatement of OpenCV's bilinear Bayer interpolation)")
+        put(f"demosaic_{key}", ref)
+        n_cases += 1
         # chromatic aberration (no parameters) and aliasing at the identity / halving shortcuts of legacy nearest
         opt = base_opt(chromatic_aberration_prob=1.0)
         seed(900)
@@ -164,6 +172,11 @@ def main() -> None:
         put(f"chroma_{key}", ref)
         put(f"alias_{key}_half", P.aliasing(img, 0.5))
         n_cases += 2
+    for hh, ww in ((3, 3), (4, 7), (9, 4), (2, 6), (31, 33)):  # odd sizes, the 3x3 minimum, and the degenerate < 3 case (zeros)
+        small = O.synth_gt(1, hh, ww, "uniform", seed=hh * 10 + ww)
+        ref = Ref.apply_demosaicing_artifacts(small, base_opt(demosaic_prob=1.0)) if seed(851) else None
+        same(P.demosaic(small), ref, f"demosaic {hh}x{ww}")
+        put(f"demosaic_small_{hh}x{ww}_in", small); put(f"demosaic_small_{hh}x{ww}", ref)
     # the PIL JPEG round the product replaces with DiffJPEG: oracle restatement == reference
     opt = base_opt()
     nr, _ = seed(950)
@@ -180,8 +193,7 @@ def main() -> None:
         out = Ref.apply_motion_blur(out, opt)                          # :522
         if R.RNG.get_rng().uniform() < opt.blur_prob:                  # :525
             out = R.ipu.filter2d(out, k1)
-        if R.RNG.get_rng().uniform() < opt.demosaic_prob:              # :534 (cv2 demosaic: never on here)
-            raise SystemExit("demosaic is outside the restated path")
+        out = Ref.apply_demosaicing_artifacts(out, opt)                # :534 (the model's copy, :312-363, is the same code)
         out = Ref.apply_sensor_noise(out, opt)                         # :537
         out = Ref.apply_rolling_shutter(out, opt)                      # :540
         out = Ref.apply_exposure_errors(out, opt)                      # :548
@@ -205,7 +217,7 @@ def main() -> None:
     sk = O.synth_sinc_or_pulse(2, seed=6)
     put("chain_gt", gt); put("chain_k1", k1); put("chain_sk", sk)
     probs = dict(blur_prob=0.6, lens_distort_prob=0.6, chromatic_aberration_prob=0.6, motion_blur_prob=0.6, sensor_noise_prob=0.6,
-                 rolling_shutter_prob=0.6, exposure_prob=0.6, color_temp_prob=0.6, oversharpen_prob=0.6, aliasing_prob=0.6,
+                 rolling_shutter_prob=0.6, demosaic_prob=0.5, exposure_prob=0.6, color_temp_prob=0.6, oversharpen_prob=0.6, aliasing_prob=0.6,
                  recompression_prob=0.5, editing_prob=0.6, editing_exposure_prob=0.6, editing_oversharpen_prob=0.5,
                  motion_blur_kernel_size=(5, 15), compression_formats=["jpeg", "avif"], compression_weights=[0.8, 0.2],
                  recompression_formats=["jpeg", "heif"], recompression_weights=[0.7, 0.3],
@@ -230,7 +242,7 @@ def main() -> None:
         pplan = draw_plan(popt, 2, 64, 48, rng)
         for k, v in plan.items():
             assert pplan.get(k) == v, f"product draw_plan differs at {k!r}: {pplan.get(k)!r} vs {v!r} (seed {s})"
-        n_on = sum(k in plan for k in ("lens", "chroma", "motion", "sensor", "shutter", "exposure", "color_temp", "oversharpen", "aliasing"))
+        n_on = sum(k in plan for k in ("lens", "chroma", "motion", "demosaic", "sensor", "shutter", "exposure", "color_temp", "oversharpen", "aliasing"))
         if stored is None or n_on > stored[0]:
             stored = (n_on, s, plan, inject, taps)
     n_on, s, plan, inject, taps = stored

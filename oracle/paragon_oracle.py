@@ -129,6 +129,53 @@ def aliasing(img: Tensor, scale: float) -> Tensor:
     return F.interpolate(down, size=(h, w), mode="nearest")
 
 
+def demosaic_cv2(img: Tensor) -> Tensor:
+    """:526-552 as the reference runs it: uint8 truncation, Bayer mosaic, cv2.demosaicing on the host."""
+    import cv2
+
+    out = []
+    for i in range(img.size(0)):
+        a = (img[i].clamp(0, 1).numpy() * 255).astype("uint8").transpose(1, 2, 0)
+        h, w, _ = a.shape
+        bayer = np.zeros((h, w), dtype=np.uint8)
+        bayer[0::2, 0::2] = a[0::2, 0::2, 2]
+        bayer[0::2, 1::2] = a[0::2, 1::2, 1]
+        bayer[1::2, 0::2] = a[1::2, 0::2, 1]
+        bayer[1::2, 1::2] = a[1::2, 1::2, 0]
+        d = cv2.demosaicing(bayer, cv2.COLOR_BAYER_BG2BGR)
+        out.append((torch.from_numpy(d).float() / 255.0).permute(2, 0, 1))
+    return torch.stack(out, dim=0)
+
+
+def demosaic(img: Tensor) -> Tensor:
+    """Restatement of OpenCV's bilinear Bayer demosaic (the third-party algorithm behind :546; opencv-python is unpinned
+    in the reference, 4.13.0 here) in numpy integer arithmetic: missing channels are (a+b+1)>>1 / (a+b+c+d+2)>>2 of the
+    nearest mosaic samples, border rows/columns copy their inner neighbours, images under 3x3 come out zero.  Pinned
+    bit for bit against cv2 (oracle/make_paragon_goldens.py) so that tests need no OpenCV on the GPU box."""
+    out = []
+    for i in range(img.size(0)):
+        a = (img[i].clamp(0, 1).numpy() * 255).astype("uint8").astype(np.int32)  # (3, H, W)
+        _c, h, w = a.shape
+        if h < 3 or w < 3:
+            out.append(torch.zeros(3, h, w))
+            continue
+        yy, xx = np.mgrid[0:h, 0:w]
+        ey, ex = yy % 2 == 0, xx % 2 == 0
+        bay = np.where(ey & ex, a[2], np.where(~ey & ~ex, a[0], a[1]))
+        p = np.pad(bay, 1, mode="edge")
+        at = lambda dy, dx: p[1 + dy : 1 + dy + h, 1 + dx : 1 + dx + w]  # noqa: E731
+        cross4 = (at(-1, 0) + at(1, 0) + at(0, -1) + at(0, 1) + 2) >> 2
+        diag4 = (at(-1, -1) + at(-1, 1) + at(1, -1) + at(1, 1) + 2) >> 2
+        hor2, ver2 = (at(0, -1) + at(0, 1) + 1) >> 1, (at(-1, 0) + at(1, 0) + 1) >> 1
+        d = np.stack([np.where(~ey & ~ex, bay, np.where(~ey & ex, hor2, np.where(ey & ~ex, ver2, diag4))),
+                      np.where(ey ^ ex, bay, cross4),
+                      np.where(ey & ex, bay, np.where(ey & ~ex, hor2, np.where(~ey & ex, ver2, diag4)))])
+        cy, cx = np.clip(np.arange(h), 1, h - 2), np.clip(np.arange(w), 1, w - 2)
+        d = d[:, cy][:, :, cx].astype(np.uint8)
+        out.append(torch.from_numpy(d).float() / 255.0)
+    return torch.stack(out, dim=0)
+
+
 def pil_jpeg(img: Tensor, quality: float) -> Tensor:
     """`_compress_with_format(..., "jpeg")` (:95-158): uint8 truncation, libjpeg through PIL, back to [0,1].
     The product routes this codec choice to the fused DiffJPEG kernel instead (a substitution, not parity:
@@ -216,6 +263,8 @@ def apply_extras_a(gt: Tensor, kernel1: Tensor, sinc_kernel: Tensor, plan: dict,
         out = tap("motion", motion_blur(out, *plan["motion"]))
     if plan.get("blur1"):
         out = tap("blur1", O.filter2d(out, kernel1))
+    if plan.get("demosaic"):
+        out = tap("demosaic", demosaic(out))
     if "sensor" in plan:
         out = tap("sensor", sensor_noise(out, plan["sensor"], inject["sensor_noise"]))
     if "shutter" in plan:

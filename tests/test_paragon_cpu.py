@@ -44,6 +44,20 @@ def test_oracle_reproduces_reference_vectors(pg, key):
         got = P.sensor_noise(img, float(pg[f"sensor_{key}_{s}_p"]), _t(pg[f"sensor_{key}_{s}_noise"]))
         assert torch.equal(got, _t(pg[f"sensor_{key}_{s}"]))
     assert torch.equal(P.chromatic_aberration(img), _t(pg[f"chroma_{key}"]))
+    assert torch.equal(P.demosaic(img), _t(pg[f"demosaic_{key}"]))  # numpy restatement of OpenCV's bilinear Bayer demosaic
+
+
+def test_demosaic_restatement_small_and_degenerate_sizes(pg):
+    for hh, ww in ((3, 3), (4, 7), (9, 4), (2, 6), (31, 33)):
+        got = P.demosaic(_t(pg[f"demosaic_small_{hh}x{ww}_in"]))
+        assert torch.equal(got, _t(pg[f"demosaic_small_{hh}x{ww}"])), (hh, ww)
+    assert torch.all(_t(pg["demosaic_small_2x6"]) == 0)  # OpenCV leaves images under 3 rows / columns at zero
+    try:
+        import cv2  # noqa: F401
+    except ImportError:
+        return
+    x = torch.rand(2, 3, 37, 52, generator=torch.Generator().manual_seed(4))
+    assert torch.equal(P.demosaic(x), P.demosaic_cv2(x))
 
 
 def test_ieee_sqrt_variant_is_within_one_coordinate_ulp(pg):

@@ -62,6 +62,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_channel_gain_f32": (_i, [_p, _i, _i, _i64, _f, _f, _f, _i, _p, _p]),
     "otf_sensor_noise_f32": (_i, [_p, _i64, _f, _p, _u64, _u64, _p, _p]),
     "otf_trunc8_f32": (_i, [_p, _i64, _p, _p]),
+    "otf_demosaic_f32": (_i, [_p, _i, _i, _i, _p, _p]),
     "otf_run_stages_workspace_bytes": (_i64, [_i, _i, _i, _i, _p, _i]),
     "otf_run_stages_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i64, _p, _p, _p]),
 }
@@ -112,6 +113,7 @@ _LAUNCHES = {
     "otf_channel_gain_f32": 1,
     "otf_sensor_noise_f32": 1,
     "otf_trunc8_f32": 1,
+    "otf_demosaic_f32": 1,
 }
 
 

@@ -221,6 +221,46 @@ __global__ void __launch_bounds__(256) sensor_noise_kernel(const float* __restri
     }
 }
 
+// ---- Bayer mosaic + bilinear demosaic — paragon_otf_degradations.py:526-552 ---------------------------
+// The reference quantises to uint8 (truncation), keeps ONE channel per pixel (rows/cols even-even: channel 2,
+// odd-odd: channel 0, mixed parity: channel 1) and calls cv2.demosaicing(COLOR_BAYER_BG2BGR) on the host, image by
+// image.  OpenCV's bilinear demosaic is integer arithmetic: the two missing channels of a pixel are the rounded-up
+// mean of their 2 (horizontal / vertical) or 4 (cross / diagonal) nearest mosaic samples, (a+b+1)>>1, (a+b+c+d+2)>>2;
+// the outermost rows and columns copy their inner neighbours; images with fewer than 3 rows or columns come out
+// zero.  Reproduced bit for bit (pinned against cv2 in tests/golden/paragon_goldens.npz).
+__device__ __forceinline__ int bayer_at(const float* __restrict__ ip, size_t plane, int W, int y, int x) {
+    const int c = (y & 1) ? ((x & 1) ? 0 : 1) : ((x & 1) ? 1 : 2);
+    return (int)floorf(__fmul_rn(clamp01(__ldg(ip + c * plane + (size_t)y * W + x)), 255.0f));
+}
+__global__ void __launch_bounds__(256) demosaic_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6), b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)H * W;
+    const float* ip = img + (size_t)b * 3 * plane;
+    float* op = out + (size_t)b * 3 * plane + (size_t)y * W + x;
+    if (H < 3 || W < 3) {
+        op[0] = op[plane] = op[2 * plane] = 0.0f;
+        return;
+    }
+    const int yc = min(max(y, 1), H - 2), xc = min(max(x, 1), W - 2);  // border pixels copy their inner neighbour
+    int v[3][3];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) v[dy][dx] = bayer_at(ip, plane, W, yc + dy - 1, xc + dx - 1);
+    const int ctr = v[1][1];
+    const int hor2 = (v[1][0] + v[1][2] + 1) >> 1, ver2 = (v[0][1] + v[2][1] + 1) >> 1;
+    const int cross4 = (v[0][1] + v[2][1] + v[1][0] + v[1][2] + 2) >> 2;
+    const int diag4 = (v[0][0] + v[0][2] + v[2][0] + v[2][2] + 2) >> 2;
+    const bool ey = !(yc & 1), ex = !(xc & 1);
+    const int c2 = ey ? (ex ? ctr : hor2) : (ex ? ver2 : diag4);   // channel 2 lives on (even, even)
+    const int c0 = !ey ? (!ex ? ctr : hor2) : (!ex ? ver2 : diag4);  // channel 0 on (odd, odd)
+    const int c1 = (ey != ex) ? ctr : cross4;                      // channel 1 on mixed parity
+    op[0] = __fdiv_rn((float)c0, 255.0f);
+    op[plane] = __fdiv_rn((float)c1, 255.0f);
+    op[2 * plane] = __fdiv_rn((float)c2, 255.0f);
+}
+
 // floor(clamp(x,0,1) * 255) / 255 — the `(img * 255).astype("uint8")` in front of every codec round (:114-115)
 __global__ void __launch_bounds__(256) trunc8_kernel(const float* __restrict__ img, float* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
@@ -228,6 +268,15 @@ __global__ void __launch_bounds__(256) trunc8_kernel(const float* __restrict__ i
 }
 
 }  // namespace otf
+
+extern "C" int otf_demosaic_f32(const float* img, int B, int H, int W, float* out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && out && img != out, OTF_ERR_BAD_ARG, "demosaic: bad pointers");
+    OTF_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "demosaic: bad extents");
+    demosaic_kernel<<<dim3(ceil_div(W, 64), ceil_div(H, 4), B), 256, 0, (cudaStream_t)stream>>>(img, out, H, W);
+    OTF_LAUNCH_CHECK("demosaic_kernel");
+    return OTF_OK;
+}
 
 extern "C" int otf_trunc8_f32(const float* img, int64_t n, float* out, void* stream) {
     using namespace otf;

@@ -9,8 +9,8 @@ Two layers:
     the process-wide ones of ``set_rng`` (the reference's ``RNG.get_rng()`` / ``random`` singletons) unless ``rng=``
     is given.
 
-Out of scope (host codecs / cv2): WebP / AVIF / HEIF / ffmpeg video rounds and the cv2 Bayer
-demosaic.  The unified pipeline's "jpeg" choice is routed to the fused DiffJPEG kernel (a substitution for the PIL
+Out of scope (host codecs): WebP / AVIF / HEIF / ffmpeg video rounds.  The cv2 Bayer demosaic IS
+reproduced on the device (bit for bit).  The unified pipeline's "jpeg" choice is routed to the fused DiffJPEG kernel (a substitution for the PIL
 codec, not bit parity: tests bound the distance); other formats pass through, which is what the reference does
 when a codec plugin is missing (paragon_otf_degradations.py:125-134).
 """
@@ -161,6 +161,18 @@ def aliasing(img: Tensor, scale: float) -> Tensor:
     return D._resize_call(down, h, w, _lib.RESIZE_NEAREST, False)
 
 
+def demosaic(img: Tensor) -> Tensor:
+    """:526-552 — Bayer mosaic of the uint8-truncated image + OpenCV's bilinear demosaic, bit for bit, in one launch
+    (the reference does this on the host with cv2, image by image)."""
+    x = _f32(img)
+    b, c, h, w = x.shape
+    if c != 3:
+        raise RuntimeError(f"demosaic expects 3 channels, got {c}")
+    out = torch.empty_like(x)
+    _lib.call("otf_demosaic_f32", _lib.ptr(x), b, h, w, _lib.ptr(out), _lib.stream())
+    return out
+
+
 def trunc8(img: Tensor) -> Tensor:
     """``(img.clamp(0,1) * 255).astype(uint8) / 255`` — the truncation in front of every codec round (:114-115)."""
     x = _f32(img)
@@ -173,17 +185,21 @@ _JPEGER = DiffJPEG(differentiable=False)
 _WARNED: set[str] = set()
 
 
-def compress_with_format(img: Tensor, format_name: str, quality: float | None) -> Tensor:
+def compress_with_format(img: Tensor, format_name: str, quality: float | None, fallback: str = "passthrough") -> Tensor:
     """`_compress_with_format` (:95-158) for one drawn (format, quality).  "jpeg" = uint8 truncation, fused DiffJPEG at
-    ``int(quality)``, back onto the 8-bit lattice (what a decoded file holds); every other format passes through."""
+    ``int(quality)``, back onto the 8-bit lattice (what a decoded file holds).  WebP / AVIF / HEIF are host codecs:
+    ``fallback="passthrough"`` (default) returns the image unchanged with a one-time warning — what the reference does
+    when the codec plugin is missing; ``fallback="jpeg"`` runs the JPEG round at the drawn quality instead, so the
+    share of compressed batches stays what the option file asks for."""
     if quality is None:
         return img
-    if format_name == "jpeg":
+    if format_name == "jpeg" or (fallback == "jpeg" and format_name in ("webp", "avif", "heif")):
         return _JPEGER(trunc8(img), quality=float(int(quality)), _round8=True)
     if format_name not in _WARNED:
         _WARNED.add(format_name)
         warnings.warn(f"paragon_otf: {format_name!r} is a host codec outside the GPU path; the image passes through unchanged "
-                      "(as the reference does when the codec plugin is missing)", stacklevel=2)
+                      "(as the reference does when the codec plugin is missing); set codec_fallback='jpeg' to run a JPEG round "
+                      "at the drawn quality instead", stacklevel=2)
     return img
 
 
@@ -276,8 +292,7 @@ class ParagonOTF:
             return img_tensor
         if _rng(rng).np.uniform() >= opt.demosaic_prob:
             return img_tensor
-        raise NotImplementedError("demosaic artifacts go through cv2.demosaicing on the host (paragon_otf_degradations.py:526-552): "
-                                  "outside the GPU path; keep demosaic_prob at 0")
+        return demosaic(img_tensor)
 
     @staticmethod
     def apply_aliasing_artifacts(img_tensor: Tensor, opt: Any, rng: Any = None) -> Tensor:
@@ -298,7 +313,7 @@ class ParagonOTF:
         if not hasattr(opt, attr):
             return img_tensor
         lo, hi = getattr(opt, attr)
-        return compress_with_format(img_tensor, format_name, _rng(rng).np.uniform(lo, hi))
+        return compress_with_format(img_tensor, format_name, _rng(rng).np.uniform(lo, hi), getattr(opt, "codec_fallback", "passthrough"))
 
     @staticmethod
     def apply_realistic_compression_pipeline(img_tensor: Tensor, opt: Any, rng: Any = None) -> Tensor:

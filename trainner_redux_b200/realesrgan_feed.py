@@ -115,6 +115,7 @@ class OTFOptions:
     editing_oversharpen_prob: float = 0
     editing_oversharpen_strength: tuple[float, float] = (1.0, 1.3)
     fork_compression: bool = True  # order="fork": run the unified compression stage (realesrgan_model.py:581)
+    codec_fallback: str = "passthrough"  # webp/avif/heif rounds: "passthrough" (reference without the plugin) or "jpeg" (DiffJPEG round)
     # not in the reference schema: which composition to run, and the upstream 50/50 final-order coin
     order: str = "classic"
     final_jpeg_first_prob: float = 0.5
@@ -486,8 +487,7 @@ class RealESRGANFeed:
             if plan.get("blur1"):
                 out = self._timed("blur1", lambda o=out: filter2d(o, kernel1, _analysis=an(0) if o.shape == gt.shape else None))
             if plan.get("demosaic"):
-                raise NotImplementedError("demosaic artifacts run cv2.demosaicing on the host (paragon_otf_degradations.py:526-552): "
-                                          "outside the GPU path; keep demosaic_prob at 0")
+                out = self._timed("demosaic", lambda o=out: PO.demosaic(o))
             if "sensor" in plan:
                 out = self._timed("sensor", lambda o=out: PO.sensor_noise(o, plan["sensor"], inject.get("sensor_noise"), self.rng.philox))
             if "shutter" in plan:
@@ -505,7 +505,7 @@ class RealESRGANFeed:
             if plan.get("jpeg") is not None:  # per-sample qualities through DiffJPEG (this repo's earlier routing)
                 return self._jpeg(out, plan["jpeg"], round8=True)
             for fmt, q in plan.get("compression", []):
-                out = self._timed(f"compress_{fmt}", lambda o=out: PO.compress_with_format(o, fmt, q))
+                out = self._timed(f"compress_{fmt}", lambda o=out: PO.compress_with_format(o, fmt, q, _opt(self.opt, "codec_fallback", "passthrough")))
             if "editing_exposure" in plan:
                 out = self._timed("editing_exposure", lambda o=out: PO.exposure(o, plan["editing_exposure"]))
             return self._timed("round", lambda o=out: clamp_round(o))
