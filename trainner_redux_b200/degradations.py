@@ -134,32 +134,32 @@ def random_add_gaussian_noise_pt(img: Tensor, sigma_range: tuple[float, float] =
 _POISSON_TABLES: dict[int, tuple[Tensor, "torch.cuda.Event", int, bool]] = {}
 
 
-def poisson_tables(device: torch.device) -> Tensor | None:
+def poisson_tables(device: torch.device, wait: bool = False) -> Tensor | None:
+    """The device's table block, building it on first use.  ``wait=True`` (RealESRGANFeed.__init__) blocks until the
+    build has finished so that later CUDA-graph captures can use it; inside a capture an unfinished table is never
+    touched (event queries are illegal there): the call returns None and the rejection sampler runs instead."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    cur = torch.cuda.current_stream(device)
-    capturing = torch.cuda.is_current_stream_capturing()
     hit = _POISSON_TABLES.get(idx)
+    if hit is not None and hit[3]:
+        return hit[0]
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing:
+        return None
+    cur = torch.cuda.current_stream(device)
     if hit is None:
-        if capturing:
-            return None  # no build inside a capture: this call falls back to the rejection sampler
         tab = torch.empty(_lib.load().otf_poisson_tables_bytes() // 4, dtype=torch.int32, device=device)
         _lib.call("otf_poisson_build_tables", _lib.ptr(tab), _lib.stream())
         ev = torch.cuda.Event()
         ev.record(cur)
-        _POISSON_TABLES[idx] = (tab, ev, cur.cuda_stream, False)
-        return tab
-    tab, ev, sid, done = hit
-    if done:
-        return tab
-    if capturing:
-        if not ev.query():
-            ev.synchronize()
-        _POISSON_TABLES[idx] = (tab, ev, sid, True)
-        return tab
-    if sid != cur.cuda_stream:
-        cur.wait_event(ev)
+        hit = (tab, ev, cur.cuda_stream, False)
+        _POISSON_TABLES[idx] = hit
+    tab, ev, sid, _ = hit
+    if wait:
+        ev.synchronize()
     if ev.query():
         _POISSON_TABLES[idx] = (tab, ev, sid, True)
+    elif sid != cur.cuda_stream:
+        cur.wait_event(ev)
     return tab
 
 

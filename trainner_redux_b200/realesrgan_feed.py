@@ -336,7 +336,7 @@ class RealESRGANFeed:
         self.rng = HostRNG(manual_seed, rank)
         self.jpeger = DiffJPEG(differentiable=False)  # realesrgan_model.py:81-83
         with torch.cuda.device(self.device):
-            D.poisson_tables(self.device)  # the Poisson sampler's universal CDF tables: built once per device, outside any capture
+            D.poisson_tables(self.device, wait=True)  # the Poisson sampler's universal CDF tables: built once per device, outside any capture
         self._usm: dict[int, USMSharp] = {}
         self.queue_size = _opt(opt, "queue_size", 120)
         self.pool = PairPool(self.queue_size, randperm=lambda n: torch.randperm(n, generator=self.rng.torch)) if use_pool else None
