@@ -254,7 +254,10 @@ static int launch_h(const float* img, int planes, int H, int W, const Taps& t, f
     const int need = 2 * (t.n / 2) + 2;  // NTP must satisfy r <= NTP/2 - 1
     if (need <= 8) return launch_h_fast<8>(img, planes, H, W, t, out, st);
     if (need <= 16) return launch_h_fast<16>(img, planes, H, W, t, out, st);
+    if (need <= 24) return launch_h_fast<24>(img, planes, H, W, t, out, st);
     if (need <= 32) return launch_h_fast<32>(img, planes, H, W, t, out, st);
+    if (need <= 40) return launch_h_fast<40>(img, planes, H, W, t, out, st);
+    if (need <= 52) return launch_h_fast<52>(img, planes, H, W, t, out, st);  // USMSharp's default radius 50 -> 51 taps
     if (need <= 64) return launch_h_fast<64>(img, planes, H, W, t, out, st);
     return launch_h_generic(img, planes, H, W, t, out, st);
 }
@@ -274,7 +277,10 @@ static int launch_v(const float* tmp, int planes, int H, int W, const Taps& t, f
     const int need = 2 * (t.n / 2) + 2;
     if (need <= 8) return launch_v_fast<8, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
     if (need <= 16) return launch_v_fast<16, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    if (need <= 24) return launch_v_fast<24, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
     if (need <= 32) return launch_v_fast<32, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    if (need <= 40) return launch_v_fast<40, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
+    if (need <= 52) return launch_v_fast<52, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
     if (need <= 64) return launch_v_fast<64, EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
     return launch_v_generic<EPI>(tmp, planes, H, W, t, out, img, aux, weight, threshold, st);
 }
