@@ -46,7 +46,9 @@ enum {
     OTF_RESIZE_AREA = 2,        /* adaptive average pooling                             */
     OTF_RESIZE_NEAREST_EXACT = 3,
     OTF_RESIZE_BICUBIC = 4,     /* non-antialiased bicubic, a=-0.75 (tail of "lanczos") */
-    OTF_RESIZE_NEAREST = 5      /* legacy F.interpolate(mode="nearest"): floor(o * in/out) — the fork's aliasing stage */
+    OTF_RESIZE_NEAREST = 5,     /* legacy F.interpolate(mode="nearest"): floor(o * in/out) — the fork's aliasing stage */
+    OTF_RESIZE_LANCZOS = 6      /* the whole "lanczos" mode (:961-1001) as one pass: Lanczos-3 prefilter (reflect padding) on the
+                                   shrinking axes composed with the plain bicubic sample; prefilter radius <= 62 */
 };
 
 /* fork extras — traiNNer/models/paragon_otf_degradations.py */

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0
-RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST = range(6)
+RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST, RESIZE_LANCZOS = range(7)
 WARP_LENS, WARP_SHUTTER, WARP_CHROMA = range(3)
 TAPS_NONE, TAPS_OVERSHARPEN = 0, 1
 NOISE_CLIP, NOISE_ROUNDS, NOISE_FIELD_ONLY = 1, 2, 4

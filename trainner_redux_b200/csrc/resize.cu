@@ -108,6 +108,56 @@ __device__ void axis_weights(int mode, const AxisSpec& ax, int o, int* lo_out, i
     *n_out = n;
 }
 
+// "lanczos" mode of resize_pt (degradations.py:961-1001) as ONE separable resampling: on a shrinking axis the
+// reference convolves with a Lanczos-3 prefilter (reflect padding) and then takes the plain 4-tap bicubic sample;
+// both are linear, so their composition is a single window of 4 + 2r weights per output (r = prefilter radius) —
+// one launch and one pass over the image instead of three.  The prefilter taps follow :961-978 operation by
+// operation: positions accumulated in double and stored as fp32, sinc(t) * sinc(t / 3) in fp32, normalised.
+constexpr int kLanczosMaxR = 62;
+__device__ void lanczos_axis_weights(const AxisSpec& ax, int o, int* lo_out, int* n_out, float* w) {
+    AxisSpec bc = ax;
+    bc.max_taps = 4;
+    int lo4, n4;
+    float c4[4];
+    axis_weights(OTF_RESIZE_BICUBIC, bc, o, &lo4, &n4, c4);
+    if (ax.out_n >= ax.in_n) {  // no prefilter on an axis that does not shrink
+        for (int j = 0; j < ax.max_taps; ++j) w[j] = j < 4 ? c4[j] : 0.0f;
+        *lo_out = lo4;
+        *n_out = n4;
+        return;
+    }
+    const double ratio = (double)ax.out_n / (double)ax.in_n;
+    const int n = (int)ceil(3.0 / ratio + 1.0), r = n - 2, nt = 2 * n - 3;
+    float f[2 * kLanczosMaxR + 1];
+    float total = 0.0f;
+    for (int j = 0; j < nt; ++j) {
+        const int i = j < r ? r - j : j - r;             // |index| into the ramp
+        double cur = 0.0;  // the reference's ramp accumulates (cur += ratio) in double and stores fp32: same running sum
+        for (int t = 0; t < i; ++t) cur += ratio;
+        float pos = (float)cur;
+        if (j < r) pos = -pos;
+        float v = 0.0f;
+        if (-3.0f < pos && pos < 3.0f) {
+            const float px = __fmul_rn(3.14159274101257324f, pos), p3 = __fmul_rn(3.14159274101257324f, __fdiv_rn(pos, 3.0f));
+            const float s1 = pos != 0.0f ? __fdiv_rn(sinf(px), px) : 1.0f;
+            const float s3 = __fdiv_rn(pos, 3.0f) != 0.0f ? __fdiv_rn(sinf(p3), p3) : 1.0f;
+            v = __fmul_rn(s1, s3);
+        }
+        f[j] = v;
+        total = __fadd_rn(total, v);
+    }
+    for (int j = 0; j < nt; ++j) f[j] = __fdiv_rn(f[j], total);
+    const int LO = max(lo4 - r, 0), HI = min(lo4 + n4 - 1 + r, ax.in_n - 1);
+    for (int j = 0; j < ax.max_taps; ++j) w[j] = 0.0f;
+    for (int k = 0; k < n4; ++k)
+        for (int j = 0; j < nt; ++j) {
+            const int src = reflect_idx(lo4 + k + j - r, ax.in_n);
+            w[src - LO] = fmaf(c4[k], f[j], w[src - LO]);
+        }
+    *lo_out = LO;
+    *n_out = HI - LO + 1;
+}
+
 // ---- pass 0: per-launch weight tables ------------------------------------------------------
 // table layout for an axis with out_n outputs and T = max_taps: int lo[out_n], int n[out_n],
 // float w[out_n][T].  One thread per output index; the tables are a few KB and stay in L2.
@@ -116,11 +166,13 @@ __global__ void __launch_bounds__(128) resize_tables_kernel(int mode, AxisSpec a
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ay.out_n) {
         float* w = reinterpret_cast<float*>(ty_lo + 2 * ay.out_n) + (size_t)i * ay.max_taps;
-        axis_weights(mode, ay, i, ty_lo + i, ty_lo + ay.out_n + i, w);
+        if (mode == OTF_RESIZE_LANCZOS) lanczos_axis_weights(ay, i, ty_lo + i, ty_lo + ay.out_n + i, w);
+        else axis_weights(mode, ay, i, ty_lo + i, ty_lo + ay.out_n + i, w);
     } else if (i - ay.out_n < ax.out_n) {
         const int o = i - ay.out_n;
         float* w = reinterpret_cast<float*>(tx_lo + 2 * ax.out_n) + (size_t)o * ax.max_taps;
-        axis_weights(mode, ax, o, tx_lo + o, tx_lo + ax.out_n + o, w);
+        if (mode == OTF_RESIZE_LANCZOS) lanczos_axis_weights(ax, o, tx_lo + o, tx_lo + ax.out_n + o, w);
+        else axis_weights(mode, ax, o, tx_lo + o, tx_lo + ax.out_n + o, w);
     }
 }
 
@@ -448,10 +500,18 @@ static AxisSpec make_axis(int mode, int in_n, int out_n) {
         a.max_taps = (in_n + out_n - 1) / out_n + 1;
     } else if (mode == OTF_RESIZE_NEAREST_EXACT || mode == OTF_RESIZE_NEAREST) {
         a.max_taps = 1;
+    } else if (mode == OTF_RESIZE_LANCZOS && out_n < in_n) {
+        const int n = (int)ceil(3.0 / ((double)out_n / (double)in_n) + 1.0);  // prefilter: 2n - 3 taps, radius n - 2
+        a.max_taps = 4 + 2 * (n - 2);
     } else {
         a.max_taps = 4;
     }
     return a;
+}
+static bool lanczos_ok(int in_n, int out_n) {
+    if (out_n >= in_n) return true;
+    const int r = (int)ceil(3.0 / ((double)out_n / (double)in_n) + 1.0) - 2;
+    return r <= kLanczosMaxR && r < in_n;  // reflect padding needs r < extent (F.pad raises otherwise)
 }
 
 static size_t table_ints(const AxisSpec& a) { return (size_t)a.out_n * (2 + a.max_taps); }
@@ -460,7 +520,8 @@ static size_t table_ints(const AxisSpec& a) { return (size_t)a.out_n * (2 + a.ma
 
 extern "C" int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode) {
     using namespace otf;
-    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || mode < OTF_RESIZE_BILINEAR_AA || mode > OTF_RESIZE_NEAREST) return -1;
+    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || mode < OTF_RESIZE_BILINEAR_AA || mode > OTF_RESIZE_LANCZOS) return -1;
+    if (mode == OTF_RESIZE_LANCZOS && !(lanczos_ok(H, OH) && lanczos_ok(W, OW))) return -1;
     return (int64_t)(table_ints(make_axis(mode, H, OH)) + table_ints(make_axis(mode, W, OW))) * 4;
 }
 
@@ -470,7 +531,9 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
     using namespace otf;
     OTF_REQUIRE(img && out && img != out && workspace_dev, OTF_ERR_BAD_ARG, "resize: bad pointers");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && OH > 0 && OW > 0, OTF_ERR_BAD_ARG, "resize: bad extents");
-    OTF_REQUIRE(mode >= OTF_RESIZE_BILINEAR_AA && mode <= OTF_RESIZE_NEAREST, OTF_ERR_BAD_ARG, "resize: unknown mode %d", mode);
+    OTF_REQUIRE(mode >= OTF_RESIZE_BILINEAR_AA && mode <= OTF_RESIZE_LANCZOS, OTF_ERR_BAD_ARG, "resize: unknown mode %d", mode);
+    OTF_REQUIRE(mode != OTF_RESIZE_LANCZOS || (lanczos_ok(H, OH) && lanczos_ok(W, OW)), OTF_ERR_UNSUPPORTED,
+                "resize: lanczos prefilter radius above %d (or not below the extent)", kLanczosMaxR);
     OTF_REQUIRE(workspace_bytes >= otf_resize_workspace_bytes(H, W, OH, OW, mode), OTF_ERR_WORKSPACE, "resize: workspace too small");
     const AxisSpec ay = make_axis(mode, H, OH), ax = make_axis(mode, W, OW);
     int* ty_lo = (int*)workspace_dev;

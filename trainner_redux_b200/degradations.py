@@ -321,8 +321,11 @@ def resize_pt(img: Tensor, mode: str, scale_factor: float = 0, size: tuple[int, 
     x = _lib.dense_f32(img)
     b, c, h, w = x.shape
     oh, ow = int(size[0]), int(size[1])
+    if mode == "lanczos" and _lib.load().otf_resize_workspace_bytes(h, w, oh, ow, _lib.RESIZE_LANCZOS) > 0:
+        # degradations.py:961-1001 in ONE pass: the Lanczos prefilter of the shrinking axes composed with the bicubic sample
+        return _resize_call(x, oh, ow, _lib.RESIZE_LANCZOS, True)
     if mode == "lanczos":
-        # degradations.py:982-1001: prefilter only the shrinking axes, then plain bicubic + clamp
+        # extreme down-scales (prefilter radius > 62): prefilter passes, then plain bicubic + clamp
         cur = x
         if oh < h:
             taps = _lanczos_taps(oh / h)

@@ -120,7 +120,9 @@ class StageList:
         if scale_factor != 0:
             size = (round(self.h * scale_factor), round(self.w * scale_factor))
         oh, ow = int(size[0]), int(size[1])
-        if mode == "lanczos":  # prefilter the shrinking axes, then plain bicubic (degradations.py:982-1001)
+        if mode == "lanczos" and _lib.load().otf_resize_workspace_bytes(self.h, self.w, oh, ow, _lib.RESIZE_LANCZOS) > 0:
+            mode_id = _lib.RESIZE_LANCZOS  # prefilter and bicubic sample composed into one set of weight tables: one launch
+        elif mode == "lanczos":  # extreme down-scales: prefilter the shrinking axes, then plain bicubic (degradations.py:982-1001)
             for axis, (o, i) in enumerate(((oh, self.h), (ow, self.w))):
                 if o < i:
                     taps = D._lanczos_taps(o / i)
