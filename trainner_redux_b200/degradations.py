@@ -268,7 +268,7 @@ def _lanczos_taps(ratio: float, a: int = 3) -> np.ndarray:
 # keeps reading the same memory, so pinned tables live for the life of the process).
 _TABLE_CACHE: dict[tuple, tuple[Tensor, "torch.cuda.Event", int]] = {}
 _TABLE_PINNED: dict[tuple, Tensor] = {}
-_TABLE_CACHE_MAX = 64
+_TABLE_CACHE_MAX = 4096  # a few KB each; random schedules revisit a few hundred (H, W, OH, OW, mode) keys per stage
 
 
 def pin_resize_tables() -> int:
