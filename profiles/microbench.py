@@ -31,7 +31,7 @@ pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
 if os.path.exists(pk):
     peak = float(json.load(open(pk))["hbm_gbs"])
 FMA_PEAK = 148 * 128 * 2 * 1.965e9 / 1e12
-B = 64
+B = int(os.environ.get("OTF_MB_BATCH", "64"))
 ROTATE_BYTES = 256 * 1024 * 1024  # inputs rotate over > 2x the 126 MB L2, so every launch reads HBM
 
 
