@@ -141,7 +141,12 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = BATCH if args.steps + args.warmup <= 120 else 16
+    # each step = one bounded sample of the workload, sized so that K + W steps end within ~2 minutes on this host
+    # (the port runs at roughly 22 pairs/s per host thread)
+    budget_pairs = 120.0 * 22.0 * threads
+    batch = BATCH
+    while batch > 1 and batch * (args.steps + args.warmup) > budget_pairs:
+        batch //= 2
     val, ms = cpu_chain_pairs_per_s(batch, args.steps, args.warmup, threads)
     sample = f"each step = one batch of {batch} x {GT}^2 GT through the oracle port of the reference chain (torch CPU, {threads} threads)"
     line = {
