@@ -2,6 +2,8 @@
 oracle/make_goldens.py produced by running the REFERENCE's Python (bit for bit on the machine
 that generated them; a few ulp elsewhere because BLAS/oneDNN kernels differ by CPU)."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -168,3 +170,40 @@ def test_kernel_synthesis_oracle_and_draw_order(golden):
     for name, prm in (("k1", p1), ("k2", p2), ("sinc", p3)):
         assert np.abs(KS.synthesize(prm) - g[f"ks_ds_{name}"].numpy()).max() < 1e-9, name
     assert set(p1[:, 0].astype(int)) <= set(range(7)) and (p3[:, 0] >= 6).all()
+
+
+def test_config1_plumbing_batch8_256_scale4():
+    """BASELINE.json configs[0] (SURVEY.md §8d Config 1): batch 8 of synthetic 256x256 RGB GT, scale 4, the reference
+    order on the CPU — the host draws of the product's planner feed the oracle chain; shapes, value ranges, the 8-bit
+    lattice, the GT crop window and the pair-pool semantics are what `RealESRGANModel.feed_data` promises."""
+    from trainner_redux_b200.realesrgan_feed import HostRNG, OTFOptions, draw_plan
+
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    b, h, sc, gsz = 8, 256, 4, 224
+    opt = OTFOptions(scale=sc, gt_size=gsz, queue_size=16, blur_prob=1.0, blur_prob2=0.8, gaussian_noise_prob=1.0, noise_range=(1, 30),
+                     gray_noise_prob=0.4, gaussian_noise_prob2=1.0, noise_range2=(1, 25), gray_noise_prob2=0.4, jpeg_range=(30, 95),
+                     jpeg_range2=(30, 95), resize_mode_list=("bilinear", "bicubic", "area"), resize_mode_prob=(1 / 3,) * 3,
+                     resize_mode_list2=("bilinear", "bicubic", "area"), resize_mode_prob2=(1 / 3,) * 3,
+                     resize_mode_list3=("bilinear", "bicubic", "area"), resize_mode_prob3=(1 / 3,) * 3)
+    rng = HostRNG(0)
+    pool = O.PairPool(opt.queue_size)
+    k1, k2, sk = O.synth_blur_kernels(b, seed=1), O.synth_blur_kernels(b, seed=2), O.synth_sinc_or_pulse(b, seed=3)
+    g = torch.Generator().manual_seed(0)
+    outs = []
+    for step in range(3):
+        gt = O.synth_gt(b, h, h, "natural", seed=step)
+        plan = draw_plan(opt, b, h, h, rng)
+        assert set(plan) >= {"blur1", "resize1", "noise1", "jpeg1", "blur2", "resize2", "noise2", "final_order", "resize3_mode", "jpeg2", "crop"}
+        h1, h2 = round(h * plan["resize1"]["scale"]), int(h / sc * plan["resize2"]["scale"])
+        noise = {"noise1_color": torch.randn(b, 3, h1, h1, generator=g), "noise1_gray": torch.randn(h1, h1, generator=g),
+                 "noise2_color": torch.randn(b, 3, h2, h2, generator=g), "noise2_gray": torch.randn(h2, h2, generator=g)}
+        gt_c, lq_c = O.run_chain_b(gt, k1, k2, sk, plan, noise)
+        assert tuple(gt_c.shape) == (b, 3, gsz, gsz) and tuple(lq_c.shape) == (b, 3, gsz // sc, gsz // sc)
+        top, left = plan["crop"]
+        assert torch.equal(gt_c, gt[:, :, top * sc : top * sc + gsz, left * sc : left * sc + gsz])  # one offset for the whole batch
+        assert lq_c.min() >= 0 and lq_c.max() <= 1 and torch.equal(lq_c, torch.round(lq_c * 255) / 255)
+        lq_o, gt_o = pool.step(lq_c, gt_c, torch.randperm(opt.queue_size, generator=g))
+        outs.append((lq_c, lq_o))
+        assert lq_o.shape == lq_c.shape and gt_o.shape == gt_c.shape
+    assert torch.equal(outs[0][0], outs[0][1]) and torch.equal(outs[1][0], outs[1][1])  # queue of 16 fills in two steps: pass-through
+    assert not torch.equal(outs[2][0], outs[2][1])                                      # full: the batch comes out of the shuffled pool
