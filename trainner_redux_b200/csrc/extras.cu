@@ -58,8 +58,10 @@ __device__ __forceinline__ float bilinear_zero(const float* __restrict__ pl, int
     return __fmaf_rn(d, se, r);
 }
 
-// thread = output pixel (j fastest); loops over the C channels of its sample
-__global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W,
+// thread = output pixel (j fastest); loops over the C channels of its sample.  One instantiation per mode: the
+// three grids share little code, and a mode-specific kernel needs two thirds of the registers of the combined one.
+template <int MODE>
+__global__ void __launch_bounds__(256, 8) warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W,
                                                    WarpParams p) {
     // 16 x 16 output tile per CTA: the lens grid samples the TRANSPOSED position (see below), so a flat row of threads
     // would read one source column (32 sectors per load); a square tile touches a square source patch either way
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img
     const size_t plane = (size_t)H * W;
     const float* ip = img + (size_t)b * C * plane;
     float* op = out + (size_t)b * C * plane + (size_t)i * W + j;
-    if (p.mode == OTF_WARP_CHROMA) {
+    if (MODE == OTF_WARP_CHROMA) {
         // affine_grid(align_corners=False): base = linspace * (n-1) / n, then base * scale (theta is diagonal);
         // R sampled at scale 1.001, G untouched, B at 0.999; zeros padding; clamp(0,1) on all three
         const float bx = __fdiv_rn(__fmul_rn(lw, (float)(W - 1)), (float)W), by = __fdiv_rn(__fmul_rn(lh, (float)(H - 1)), (float)H);
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img
         return;
     }
     float gx, gy;
-    if (p.mode == OTF_WARP_LENS) {
+    if (MODE == OTF_WARP_LENS) {
         // paragon_otf_degradations.py:313-331 — note grid_x runs along the ROWS (meshgrid 'ij' of (H, W)) and is
         // stacked as the x coordinate: the reference samples the transposed position, reproduced as is
         const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(lh, lh), __fmul_rn(lw, lw)));
@@ -298,7 +300,11 @@ extern "C" int otf_warp_f32(const float* img, int B, int C, int H, int W, int mo
     p.p0 = p0;
     p.step_h = 2.0f / (float)(H - 1);
     p.step_w = 2.0f / (float)(W - 1);
-    warp_kernel<<<dim3(ceil_div(W, 16), ceil_div(H, 16), B), 256, 0, (cudaStream_t)stream>>>(img, out, C, H, W, p);
+    const dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == OTF_WARP_LENS) warp_kernel<OTF_WARP_LENS><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
+    else if (mode == OTF_WARP_SHUTTER) warp_kernel<OTF_WARP_SHUTTER><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
+    else warp_kernel<OTF_WARP_CHROMA><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
     OTF_LAUNCH_CHECK("warp_kernel");
     return OTF_OK;
 }
