@@ -44,6 +44,7 @@ def same(a: torch.Tensor, b: torch.Tensor, what: str) -> None:
 def base_opt(**kw) -> SimpleNamespace:
     """The reference's option fields for this path with the schema defaults (redux_options.py:525-700, :854-894)."""
     o = SimpleNamespace(
+        p_clean=0.0,  # ReduxOptions always defines it (redux_options.py), so the gate at realesrgan_model.py:487-489 always draws
         scale=4, blur_prob=0.0, lens_distort_prob=0.0, lens_distort_strength_range=(-0.3, 0.3), chromatic_aberration_prob=0.0,
         motion_blur_prob=0.0, motion_blur_kernel_size=(5, 15), motion_blur_angle_range=(0, 360), demosaic_prob=0.0,
         sensor_noise_prob=0.0, sensor_noise_std_range=(0.01, 0.1), rolling_shutter_prob=0.0, rolling_shutter_strength_range=(-0.1, 0.1),
@@ -188,6 +189,8 @@ def main() -> None:
     from trainner_redux_b200.realesrgan_feed import HostRNG, OTFOptions, draw_plan  # product-side host draws (checked here)
 
     def reference_chain(gt, k1, sk, opt):
+        if hasattr(opt, "p_clean") and R.RNG.get_rng().uniform() < opt.p_clean:   # :487-489 (drawn even at probability 0)
+            return torch.clamp((gt.clone() * 255.0).round(), 0, 255) / 255.0      # :491-493
         out = Ref.apply_lens_distortion(gt, opt)                       # :516
         out = Ref.apply_chromatic_aberration(out, opt)                 # :519 (the model's copy, :244-310, is the same code)
         out = Ref.apply_motion_blur(out, opt)                          # :522
@@ -227,6 +230,7 @@ def main() -> None:
         opt = base_opt(**probs)
         nr, pr = seed(1000 + s)
         ref = reference_chain(gt, k1, sk, opt)
+        assert not (nr.uniform() < opt.p_clean)  # the oracle's replay of the p_clean gate (:489)
         plan = P.draw_extras(opt, nr, pr)
         plan["scale"] = opt.scale
         torch.manual_seed(1000 + s + 2000)

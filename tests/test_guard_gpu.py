@@ -123,3 +123,42 @@ def test_guard_output_band_raw_abi(dev, case):
     _lib.call("otf_filter2d_f32", _lib.ptr(x), 2, 3, h, w, _lib.ptr(kd), 2, 21, _lib.ptr(scratch), 0, C.c_void_p(o2.data_ptr()), _lib.stream(), launches=3)
     torch.cuda.synchronize()
     assert torch.all(big2[:128] == SENT) and torch.all(big2[128 + n2 :] == SENT) and torch.isfinite(o2).all(), "filter2d wrote outside its output"
+
+
+def test_diffjpeg_refuses_to_drop_a_gradient(dev):
+    """The reference DiffJPEG is an autograd graph (diffjpeg.py:485-527); the kernel is forward-only and says so."""
+    import trainner_redux_b200 as T
+
+    jp = T.DiffJPEG(differentiable=True)
+    x = torch.rand(1, 3, 32, 32, device=dev, requires_grad=True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        jp(x, quality=80.0)
+    with torch.no_grad():
+        y = jp(x, quality=80.0)
+    assert y.shape == x.shape and not y.requires_grad
+    assert jp(x.detach(), quality=80.0).shape == x.shape
+
+
+def test_feed_accepts_a_frozen_redux_options_shaped_object(dev):
+    """ReduxOptions is a frozen struct without `order` / top-level `gt_size`; MoA lives under opt.train."""
+    import dataclasses
+
+    from test_host_cpu import _Frozen
+    from trainner_redux_b200.realesrgan_feed import OTFOptions, RealESRGANFeed
+
+    fields = {f.name: getattr(OTFOptions(), f.name) for f in dataclasses.fields(OTFOptions)}
+    for k in ("gt_size", "order", "use_moa", "moa_augs", "moa_probs"):
+        fields.pop(k)
+    fields.update(blur_prob=1.0, queue_size=8, compression_formats=["jpeg"], compression_weights=[1.0])
+    opt = _Frozen(**fields, datasets={"train": _Frozen(gt_size=64)},
+                  train=_Frozen(use_moa=True, moa_augs=["none", "mixup"], moa_probs=[0.5, 0.5], moa_debug=False, moa_debug_limit=0))
+    feed = RealESRGANFeed(opt, device=dev, manual_seed=1)
+    assert feed.order == "fork" and feed.gt_size == 64 and feed.batch_augment is not None
+    g = torch.Generator().manual_seed(0)
+    k = torch.zeros(4, 21, 21)
+    k[:, 8:13, 8:13] = 1 / 25
+    data = {"gt": torch.rand(4, 3, 96, 96, generator=g), "kernel1": k, "kernel2": k, "sinc_kernel": k}
+    for _ in range(3):
+        feed.feed_data(data)
+    assert tuple(feed.gt.shape) == (4, 3, 64, 64) and tuple(feed.lq.shape) == (4, 3, 16, 16)
+    assert feed.last_plan["order"] == "fork" and feed.last_plan["gt_size"] == 64

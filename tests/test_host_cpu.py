@@ -205,3 +205,51 @@ def test_lanczos_taps_host_side_match_oracle():
     for ratio in (0.4, 0.75, 0.25, 0.9, 117 / 288, 0.1):
         a, b = _lanczos_taps(ratio), O._lanczos_taps(ratio).numpy()
         assert a.shape == b.shape and np.abs(a - b).max() < 1e-7
+
+
+class _Frozen:
+    """Stand-in for the reference's msgspec StrictStruct options (redux_options.py): attributes can be read, never set."""
+
+    def __init__(self, **kw):
+        object.__setattr__(self, "_d", dict(kw))
+
+    def __getattr__(self, name):
+        try:
+            return object.__getattribute__(self, "_d")[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setattr__(self, name, value):
+        raise AttributeError(f"{type(self).__name__} is frozen (cannot set {name!r})")
+
+
+def test_redux_options_shaped_object_is_accepted_as_is():
+    """A ReduxOptions-shaped object: no `order`, no top-level `gt_size` (it lives in opt.datasets["train"]), MoA fields
+    under opt.train, every attribute read-only.  The feed resolves all of them without writing to the object."""
+    import dataclasses
+
+    from trainner_redux_b200.realesrgan_feed import HostRNG, OTFOptions, draw_plan, resolve_gt_size, resolve_order
+
+    fields = {f.name: getattr(OTFOptions(), f.name) for f in dataclasses.fields(OTFOptions)}
+    for k in ("gt_size", "order", "use_moa", "moa_augs", "moa_probs", "final_jpeg_first_prob", "noise_enabled", "fork_compression", "codec_fallback"):
+        fields.pop(k)
+    opt = _Frozen(**fields, datasets={"train": _Frozen(gt_size=128, lq_size=None)},
+                  train=_Frozen(use_moa=True, moa_augs=["none", "mixup"], moa_probs=[0.5, 0.5], moa_debug=False, moa_debug_limit=0))
+    with pytest.raises(AttributeError):
+        opt.gt_size = 128
+    assert resolve_gt_size(opt) == 128 and resolve_order(opt) == "fork"
+    assert resolve_gt_size(OTFOptions(gt_size=96)) == 96 and resolve_order(OTFOptions()) == "classic"
+    plan = draw_plan(opt, 4, 160, 160, HostRNG(5), gt_size=resolve_gt_size(opt), order=resolve_order(opt))
+    assert plan["order"] == "fork" and plan["gt_size"] == 128 and "resize3_mode" in plan and "resize1" not in plan
+    assert 0 <= plan["crop"][0] <= 160 // 4 - 32
+    # the p_clean gate is drawn first even at probability 0 (realesrgan_model.py:487-489): the lens gate sees the 2nd uniform
+    import numpy as np
+
+    ref = np.random.default_rng(5)
+    ref.uniform()
+    opt2 = _Frozen(**{**fields, "lens_distort_prob": 1.0}, datasets={"train": _Frozen(gt_size=128)})
+    plan2 = draw_plan(opt2, 4, 160, 160, HostRNG(5), gt_size=128, order="fork")
+    ref.uniform()  # lens gate
+    assert plan2["lens"] == float(ref.uniform(*opt2.lens_distort_strength_range))
+    # explicit overrides win
+    assert draw_plan(opt, 4, 160, 160, HostRNG(5), gt_size=64, order="classic")["order"] == "classic"

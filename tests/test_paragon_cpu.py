@@ -94,12 +94,15 @@ def test_product_draws_follow_the_reference_order():
         rng = HostRNG(0)
         rng.np, rng.py = np.random.default_rng(seed), random.Random(seed + 7)
         mine = draw_plan(opt, 2, 64, 48, rng)
-        want = P.draw_extras(opt, np.random.default_rng(seed), random.Random(seed + 7))
+        want_np = np.random.default_rng(seed)
+        want_np.uniform()  # the p_clean gate (realesrgan_model.py:487-489): drawn first, even at probability 0
+        want = P.draw_extras(opt, want_np, random.Random(seed + 7))
         for k, v in want.items():
             assert mine.get(k) == v, (seed, k)
         seen.update(want)
         # both consumed the same number of draws: the next values agree
         ref_np, ref_py = np.random.default_rng(seed), random.Random(seed + 7)
+        ref_np.uniform()
         P.draw_extras(opt, ref_np, ref_py)
         ref_py.randint(0, 64 // 4 - 8), ref_py.randint(0, 48 // 4 - 8)  # the crop offsets draw_plan takes afterwards
         assert rng.np.uniform() == ref_np.uniform() and rng.py.random() == ref_py.random()
@@ -107,14 +110,15 @@ def test_product_draws_follow_the_reference_order():
 
 
 def test_gates_draw_even_at_probability_zero():
-    """Every stage whose option fields exist consumes its gate draw (the reference's hasattr guards): 14 uniforms."""
+    """Every stage whose option fields exist consumes its gate draw (the reference's hasattr guards): 15 uniforms,
+    the p_clean gate first (ReduxOptions always defines it)."""
     opt = OTFOptions(order="fork", gt_size=32, compression_formats=("jpeg",), compression_weights=(1.0,))
     rng = HostRNG(3)
     plan = draw_plan(opt, 2, 64, 64, rng)
     assert not any(k in plan for k in ("lens", "chroma", "motion", "sensor", "shutter", "exposure", "color_temp", "oversharpen", "aliasing"))
     assert plan["compression"][0][0] == "jpeg" and 45 <= plan["compression"][0][1] <= 95
     ref = np.random.default_rng(3)
-    for _ in range(11):  # lens, chroma, motion, blur, demosaic, sensor, shutter, exposure, colour temp, oversharpen, aliasing
+    for _ in range(12):  # p_clean, lens, chroma, motion, blur, demosaic, sensor, shutter, exposure, colour temp, oversharpen, aliasing
         ref.uniform()
     ref.choice(["jpeg"], p=[1.0]); ref.uniform(45, 95); ref.uniform(); ref.uniform()  # format, quality, recompression, editing
     assert rng.np.uniform() == ref.uniform()

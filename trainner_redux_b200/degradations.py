@@ -294,6 +294,7 @@ def _resize_call(x: Tensor, oh: int, ow: int, mode_id: int, clamp: bool) -> Tens
             if not capturing:  # (event queries are illegal under capture: only pinned tables are used there)
                 if sid != cur.cuda_stream:
                     cur.wait_event(ev)
+                    tab.record_stream(cur)  # an eviction must not hand the block back while this stream still reads it
                 ws = tab
     ready = ws is not None
     if ws is None:

@@ -20,7 +20,11 @@ def quality_to_factor(quality: float) -> float:
 
 class DiffJPEG(nn.Module):
     """Batched JPEG simulation. ``differentiable=True`` selects the reference's cubic rounding
-    surrogate (forward values only — this path runs under no_grad in feed_data)."""
+    surrogate (forward values only — this path runs under no_grad in feed_data).
+
+    The reference module is an autograd graph (diffjpeg.py:485-527); this kernel is forward-only, so a call that
+    would need a gradient — grad mode on and an input that requires grad — raises instead of silently returning a
+    tensor with no ``grad_fn``."""
 
     def __init__(self, differentiable: bool = True) -> None:
         super().__init__()
@@ -35,6 +39,10 @@ class DiffJPEG(nn.Module):
                 per-sample factors, as the reference does (diffjpeg.py:512-514).
         """
         _lib.require_cuda(x)
+        if torch.is_grad_enabled() and (x.requires_grad or (isinstance(quality, Tensor) and quality.requires_grad)):
+            raise RuntimeError(
+                "trainner_redux_b200.DiffJPEG is forward-only (the OTF feed runs it under torch.no_grad, "
+                "realesrgan_model.py:455); call it under torch.no_grad() or detach the input — it cannot backpropagate")
         img = _lib.dense_f32(x)
         b, c, h, w = img.shape
         if c != 3:

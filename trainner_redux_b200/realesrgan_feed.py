@@ -218,12 +218,34 @@ def _draw_fork(opt: Any, rng: HostRNG) -> dict:
     return p
 
 
-def draw_plan(opt: Any, b: int, ori_h: int, ori_w: int, rng: HostRNG) -> dict:
+def resolve_gt_size(opt: Any, default: int | None = None) -> int | None:
+    """``gt_size`` as the reference reads it: ``opt.datasets["train"].gt_size`` (realesrgan_model.py:619); a flat
+    ``opt.gt_size`` (OTFOptions) wins when present."""
+    v = getattr(opt, "gt_size", None)
+    if v is None:
+        ds = getattr(opt, "datasets", None)
+        train = ds.get("train") if isinstance(ds, dict) else getattr(ds, "train", None)
+        v = getattr(train, "gt_size", None) if train is not None else None
+        if v is None and isinstance(train, dict):
+            v = train.get("gt_size")
+    return default if v is None else int(v)
+
+
+def resolve_order(opt: Any) -> str:
+    """Which composition runs: ``opt.order`` when the options object has one (OTFOptions: "classic" by default); an
+    object without the field — a real ``ReduxOptions`` — gets the order this fork's ``feed_data`` executes ("fork")."""
+    return getattr(opt, "order", None) or "fork"
+
+
+def draw_plan(opt: Any, b: int, ori_h: int, ori_w: int, rng: HostRNG, gt_size: int | None = None, order: str | None = None) -> dict:
     """Host-side decisions for one ``feed_data`` call, in the order of SURVEY.md appendix A.
-    The result is a plain dict (the format ``oracle.otf_oracle.run_chain_b`` consumes)."""
+    The result is a plain dict (the format ``oracle.otf_oracle.run_chain_b`` consumes).  ``gt_size`` / ``order``
+    override what the options object says (a frozen ``ReduxOptions`` struct cannot be given new attributes)."""
     scale = _opt(opt, "scale", 4)
-    plan: dict[str, Any] = {"scale": scale, "gt_size": _opt(opt, "gt_size", ori_h), "order": _opt(opt, "order", "classic")}
-    if _opt(opt, "p_clean", 0) and rng.np.uniform() < opt.p_clean:  # realesrgan_model.py:487-503
+    plan: dict[str, Any] = {"scale": scale, "gt_size": gt_size or resolve_gt_size(opt, ori_h), "order": order or resolve_order(opt)}
+    # the gate is drawn whenever the option exists — ReduxOptions always defines p_clean (default 0), so the reference
+    # consumes one numpy uniform here on every call (realesrgan_model.py:487-489, SURVEY.md appendix A draw #1)
+    if hasattr(opt, "p_clean") and rng.np.uniform() < opt.p_clean:  # realesrgan_model.py:487-503
         plan["clean"] = True
     elif plan["order"] == "fork":
         plan.update(_draw_fork(opt, rng))
@@ -326,8 +348,16 @@ class RealESRGANFeed:
     ``self.gt`` / ``self.lq`` on the device."""
 
     def __init__(self, opt: Any, device: torch.device | str = "cuda", manual_seed: int = 0, rank: int = 0,
-                 use_pool: bool = True) -> None:
+                 use_pool: bool = True, gt_size: int | None = None, order: str | None = None) -> None:
+        """``opt``: an ``OTFOptions`` or the reference's ``ReduxOptions`` (read-only: nothing is ever set on it).
+        ``gt_size`` defaults to ``opt.gt_size`` or ``opt.datasets["train"].gt_size`` (realesrgan_model.py:619);
+        ``order`` to ``opt.order`` or, for an options object without that field, "fork" — the order the reference's
+        own ``feed_data`` runs.  MoA fields are read from ``opt.train`` when ``opt`` has one (base_model.py:875-876)."""
         self.opt = opt
+        self.gt_size = gt_size or resolve_gt_size(opt)
+        self.order = order or resolve_order(opt)
+        if self.order not in ("classic", "fork"):
+            raise ValueError(f"order must be 'classic' or 'fork', got {self.order!r}")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("RealESRGANFeed runs on a CUDA device only (no CPU fallback)")
@@ -340,11 +370,13 @@ class RealESRGANFeed:
         self._usm: dict[int, USMSharp] = {}
         self.queue_size = _opt(opt, "queue_size", 120)
         self.pool = PairPool(self.queue_size, randperm=lambda n: torch.randperm(n, generator=self.rng.torch)) if use_pool else None
-        self.batch_augment = None  # base_model.py:875-876
-        if _opt(opt, "use_moa", False):
+        self.batch_augment = None  # base_model.py:875-876: BatchAugment(self.opt.scale, self.opt.train)
+        train_opt = getattr(opt, "train", None)
+        moa_opt = train_opt if train_opt is not None and hasattr(train_opt, "use_moa") else opt
+        if _opt(moa_opt, "use_moa", False):
             from .batchaug import BatchAugment
 
-            self.batch_augment = BatchAugment(_opt(opt, "scale", 4), opt, rng=self.rng)
+            self.batch_augment = BatchAugment(_opt(opt, "scale", 4), moa_opt, rng=self.rng)
         self.gt: Tensor | None = None
         self.lq: Tensor | None = None
         self.last_plan: dict | None = None
@@ -353,6 +385,7 @@ class RealESRGANFeed:
         self.stage_times: dict[str, list] = {}
         self.record_stage_fns = False
         self.stage_fns: dict[str, Callable[[], Tensor]] = {}
+        self.collect_taps: dict[str, Tensor] | None = None
         # launch the whole chain from ONE library call (stages.py / otf_run_stages_f32) instead of one Python call
         # per stage; same kernels, same arguments, bit-identical results.  The per-stage path stays for the stage hooks.
         self.native_chain = True
@@ -360,6 +393,9 @@ class RealESRGANFeed:
     def _timed(self, name: str, fn: Callable[[], Tensor]) -> Tensor:
         if self.record_stage_fns:
             self.stage_fns[name] = fn  # closure over this call's inputs: bench.py re-launches it in a graph
+        if self.collect_taps is not None:  # parity localisation (profiles/parity_localise.py): keep every intermediate
+            self.collect_taps[name] = out = fn()
+            return out
         if not self.time_stages:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -456,7 +492,7 @@ class RealESRGANFeed:
     def _native(self, plan: dict | None = None) -> bool:
         # the fork's extra stages are launched per stage from Python (they are not in the native executor's op table)
         extras = plan is not None and any(k in plan for k in EXTRA_KEYS)
-        return self.native_chain and not (self.time_stages or self.record_stage_fns or extras)
+        return self.native_chain and not (self.time_stages or self.record_stage_fns or self.collect_taps is not None or extras)
 
     def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
                 inject: dict | None = None) -> Tensor:
@@ -569,7 +605,7 @@ class RealESRGANFeed:
             gt = _lib.dense_f32(gt)
             ori_h, ori_w = gt.shape[2:4]
             if plan is None:
-                plan = draw_plan(self.opt, gt.size(0), ori_h, ori_w, self.rng)
+                plan = draw_plan(self.opt, gt.size(0), ori_h, ori_w, self.rng, gt_size=self.gt_size, order=self.order)
             self.last_plan = plan
             top, left = plan["crop"]
             if plan.get("clean") and plan["scale"] != 1:

@@ -149,6 +149,7 @@ class StageList:
             cur = torch.cuda.current_stream()
             if sid != cur.cuda_stream:
                 cur.wait_event(ev)
+                tab.record_stream(cur)  # an eviction must not hand the block back while this stream still reads it
             ready = True
         elif tab is None and key in _MISSED_ONCE and not torch.cuda.is_current_stream_capturing():
             nbytes = _lib.load().otf_resize_workspace_bytes(self.h, self.w, oh, ow, mode_id)
