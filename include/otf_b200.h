@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OTF_ABI_VERSION 1
+#define OTF_ABI_VERSION 2
 
 enum {
     OTF_OK = 0,
@@ -64,7 +64,9 @@ enum { OTF_TAPS_NONE = 0, OTF_TAPS_OVERSHARPEN = 1 };
 enum {
     OTF_NOISE_CLIP = 1,
     OTF_NOISE_ROUNDS = 2,
-    OTF_NOISE_FIELD_ONLY = 4 /* write the noise field itself (generate_*_noise_pt), no add/tail */
+    OTF_NOISE_FIELD_ONLY = 4, /* write the noise field itself (generate_*_noise_pt), no add/tail */
+    OTF_NOISE_RAW_FIELD = 16  /* Gaussian entry only: noise_color_dev holds the FINISHED noise field (what generate_*_noise_pt
+                                 returned); out = tail(img + field) — degradations.py:625 / :833 */
 };
 
 int otf_abi_version(void);
@@ -118,6 +120,9 @@ int otf_usm_sharp_f32(const float* img, int planes, int H, int W,
  * depend on (H, W, OH, OW, mode) only; a caller that kept a workspace filled by an earlier
  * call with the same five values passes tables_ready != 0 and skips the first launch. */
 int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode);
+/* Fill a workspace with the weight tables only (what otf_resize_f32 does first when tables_ready == 0): lets a caller
+ * build the tables of a chain before capturing it into a CUDA graph. */
+int otf_resize_tables_f32(int H, int W, int OH, int OW, int mode, void* workspace_dev, int64_t workspace_bytes, void* stream);
 int otf_resize_f32(const float* img, int planes, int H, int W,
                    float* out, int OH, int OW, int mode, int clamp01,
                    void* workspace_dev, int64_t workspace_bytes, int tables_ready, void* stream);
@@ -127,11 +132,14 @@ int otf_resize_f32(const float* img, int planes, int H, int W,
  * sigma_dev, gray_dev: fp32[B] (gray_dev may be NULL = colour noise only).
  * Either inject the standard-normal fields (noise_color_dev fp32[B,C,H,W],
  * noise_gray_dev fp32[H,W] — ONE field shared by the batch) or pass NULL for
- * both and give a Philox4x32-10 (seed, offset) pair. flags: OTF_NOISE_*. */
+ * both and give a Philox4x32-10 (seed, offset) pair. flags: OTF_NOISE_*.
+ * offset_dev (uint64 on the device, may be NULL) is added to `offset` by the kernel: a launch captured in a
+ * CUDA graph draws a fresh field on every replay once the caller advances that word (feed_data keeps it in
+ * the per-step parameter block it uploads anyway). */
 int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int W,
                            const float* sigma_dev, const float* gray_dev,
                            const float* noise_color_dev, const float* noise_gray_dev,
-                           uint64_t seed, uint64_t offset, int flags,
+                           uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int flags,
                            float* out, void* stream);
 /* Fill out[n] with Philox standard normals / uniforms (distribution tests). */
 int otf_philox_normal_f32(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
@@ -158,7 +166,7 @@ int otf_poisson_build_tables(void* tables_dev, void* stream);
 int otf_poisson_noise_f32(const float* img, int B, int C, int H, int W,
                           const float* scale_dev, const float* gray_dev,
                           const float* counts_color_dev, const float* counts_gray_dev,
-                          uint64_t seed, uint64_t offset, int flags,
+                          uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int flags,
                           uint32_t* masks_dev, const void* tables_dev, float* vals_out_dev,
                           float* lambda_color_dev, float* lambda_gray_dev,
                           float* out, void* stream);
@@ -186,10 +194,12 @@ int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* stream);
 
 /* ---- a8: paired crop — traiNNer/data/transforms.py:124-135 + .contiguous() ----
  * Copies the LQ window (top,left,p,p) and the GT window (top*scale,left*scale,
- * p*scale...) into dense outputs in one launch. */
+ * p*scale...) into dense outputs in one launch.  top_left_dev (int32[2] on the device, may be NULL)
+ * overrides (top, left): a captured launch then follows the offsets the caller uploads per step (they are
+ * clamped to the valid range on the device; the host validates them when it draws them). */
 int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
                       const float* lq, int Hl, int Wl,
-                      int top, int left, int lq_patch, int scale,
+                      int top, int left, const int32_t* top_left_dev, int lq_patch, int scale,
                       float* gt_out, float* lq_out, void* stream);
 
 /* uint8 image -> fp32 / 255 (the host-side normalisation of traiNNer/utils/img_util.py:65-109 `img2tensor`,
@@ -248,14 +258,15 @@ int otf_copy_box_f32(const float* src, int Hs, int Ws, int sy, int sx,
  *   OTF_OP_USM          p0 HOST taps, n = ntaps, f0 weight, f1 threshold
  *   OTF_OP_SEPCONV      p0 HOST taps, n = ntaps, mode = axis (0 vertical, 1 horizontal)
  *   OTF_OP_RESIZE       mode, oh, ow, flags&1 = clamp01, p0 = prebuilt tables or NULL (flags&2 = ready)
- *   OTF_OP_GAUSS        p0 sigma, p1 gray|NULL, p2/p3 injected fields|NULL, seed, offset, flags = OTF_NOISE_*
- *   OTF_OP_POISSON      p0 scale, p1 gray|NULL, p2/p3 injected counts|NULL, seed, offset, flags = OTF_NOISE_*;
+ *   OTF_OP_GAUSS        p0 sigma, p1 gray|NULL, p2/p3 injected fields|NULL, seed, offset, p4 = device offset word|NULL,
+ *                       flags = OTF_NOISE_*
+ *   OTF_OP_POISSON      p0 scale, p1 gray|NULL, p2/p3 injected counts|NULL, seed, offset, p4 as above, flags = OTF_NOISE_*;
  *                       with flags bit 3 (8) set, p2 is the universal CDF table block of otf_poisson_build_tables instead
  *   OTF_OP_JPEG         p0 per-sample factor/quality or NULL (f0 scalar), flags: 1 is_quality, 2 differentiable,
  *                       4 clamp_in, 8 round8_out
  *   OTF_OP_CLAMP_ROUND  -
  *   OTF_OP_CROP_PAIR    terminal: p0 = GT (B,C,H0,W0 of the chain input), oh = top, ow = left, n = lq_patch,
- *                       mode = scale; writes p1 = gt_out, p2 = lq_out
+ *                       mode = scale; writes p1 = gt_out, p2 = lq_out; p4 = device int32[2] (top, left) override|NULL
  * `final_h/final_w` (host, may be NULL) receive the extent of the last image-producing stage. */
 enum {
     OTF_OP_ANALYSE = 0, OTF_OP_FILTER2D = 1, OTF_OP_USM = 2, OTF_OP_SEPCONV = 3, OTF_OP_RESIZE = 4,
@@ -270,6 +281,7 @@ typedef struct OtfStage {
     const void* p2;
     const void* p3;
     void* dst;
+    const void* p4; /* per-step device parameters of a captured chain (see the op table) */
 } OtfStage;
 int64_t otf_run_stages_workspace_bytes(int B, int C, int H, int W, const OtfStage* stages, int nstages);
 int otf_run_stages_f32(const float* img, int B, int C, int H, int W, const OtfStage* stages, int nstages,

@@ -394,6 +394,9 @@ _FWD_SHIFT = torch.tensor([0.0, 128.0, 128.0])
 _INV_SHIFT = torch.tensor([0, -128.0, -128.0])
 
 
+_G = globals()  # diffjpeg() re-binds the constants above per call on the input's device
+
+
 def quality_to_factor(q: float) -> float:
     """diffjpeg.py:48-61."""
     q = 5000.0 / q if q < 50 else 200.0 - q * 2
@@ -436,6 +439,10 @@ def diffjpeg(x: Tensor, quality: float | Tensor, differentiable: bool = False) -
     h, w = x.shape[-2:]
     hp = (16 - h % 16) % 16
     wp = (16 - w % 16) % 16
+    dv = x.device  # the constants follow the input (CPU: `.to` returns the tensor itself; CUDA: bench.py's eager-ATen arm)
+    _RGB2YCC, _FWD_SHIFT, _DCT_SCALE, _DCT_T, _Y_TABLE, _C_TABLE, _IDCT_ALPHA, _IDCT_T, _INV_SHIFT, _YCC2RGB = (
+        t.to(dv) for t in (_G["_RGB2YCC"], _G["_FWD_SHIFT"], _G["_DCT_SCALE"], _G["_DCT_T"], _G["_Y_TABLE"], _G["_C_TABLE"],
+                           _G["_IDCT_ALPHA"], _G["_IDCT_T"], _G["_INV_SHIFT"], _G["_YCC2RGB"]))
     xp = F.pad(x, (0, wp, 0, hp), mode="constant", value=0)  # :515-522
     hh, ww = h + hp, w + wp
     nb = x.shape[0]
@@ -554,24 +561,20 @@ class PairPool:
 # ----------------------------------------------------------------------------
 
 
-def _apply_noise(out: Tensor, st: dict, noise: dict, key: str, poisson_fn) -> Tensor:
+def _apply_noise(out: Tensor, st: dict, noise: dict, key: str, poisson_fn, fields: dict | None = None) -> Tensor:
+    """``add_*_noise_pt`` written as generate + add + tail (degradations.py:625-632 / :833-841 do exactly that), so the
+    generated noise field can be exported (``fields[key + "_field"]``) for tests that inject the finished field."""
     kind = st["kind"]
     if kind == "gaussian":
-        return add_gaussian_noise(
-            out, st["sigma"], st["gray"], noise[f"{key}_color"], noise.get(f"{key}_gray"), clip=True, rounds=False
-        )
-    if kind == "poisson":
-        return add_poisson_noise(
-            out,
-            st["scale"],
-            st["gray"],
-            clip=True,
-            rounds=False,
-            poisson_fn=poisson_fn,
-            counts_color=noise.get(f"{key}_counts_color"),
-            counts_gray=noise.get(f"{key}_counts_gray"),
-        )
-    return out
+        f = gaussian_noise_field(out, st["sigma"], st["gray"], noise[f"{key}_color"], noise.get(f"{key}_gray"))
+    elif kind == "poisson":
+        f = poisson_noise_field(out, st["scale"], st["gray"], poisson_fn=poisson_fn,
+                                counts_color=noise.get(f"{key}_counts_color"), counts_gray=noise.get(f"{key}_counts_gray"))
+    else:
+        return out
+    if fields is not None:
+        fields[f"{key}_field"] = f.contiguous().clone()
+    return _finish_noise(out + f, True, False)
 
 
 def run_chain_b(
@@ -583,6 +586,7 @@ def run_chain_b(
     noise: dict,
     poisson_fn: Callable[[Tensor], Tensor] = torch.poisson,
     taps: dict | None = None,
+    fields: dict | None = None,
 ) -> tuple[Tensor, Tensor]:
     """Classical Real-ESRGAN second-order chain, SURVEY.md §3.2(B): every stage
     is one of the reference primitives above, driven by an explicit ``plan``.
@@ -612,7 +616,7 @@ def run_chain_b(
         r = plan["resize1"]
         out = tap("resize1", resize_pt(out, scale_factor=r["scale"], mode=r["mode"]))
     if plan.get("noise1"):
-        out = tap("noise1", _apply_noise(out, plan["noise1"], noise, "noise1", poisson_fn))
+        out = tap("noise1", _apply_noise(out, plan["noise1"], noise, "noise1", poisson_fn, fields))
     if plan.get("jpeg1") is not None:
         out = torch.clamp(out, 0, 1)
         out = tap("jpeg1", diffjpeg(out, plan["jpeg1"].clone(), differentiable=False).contiguous())
@@ -623,7 +627,7 @@ def run_chain_b(
         size = (int(ori_h / sc * r["scale"]), int(ori_w / sc * r["scale"]))  # quirk Q5: int() truncation
         out = tap("resize2", resize_pt(out, size=size, mode=r["mode"]))
     if plan.get("noise2"):
-        out = tap("noise2", _apply_noise(out, plan["noise2"], noise, "noise2", poisson_fn))
+        out = tap("noise2", _apply_noise(out, plan["noise2"], noise, "noise2", poisson_fn, fields))
 
     def final_resize_sinc(t: Tensor) -> Tensor:
         t = tap("resize3", resize_pt(t, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))

@@ -41,7 +41,30 @@ def main() -> None:
         rows.append({"stage": name, "free_running_maxabs": d.max().item(), "free_running_frac_1lsb": frac,
                      "n_gt_1e-5": int((d > 1e-5).sum().item()), "numel": d.numel()})
     frac, worst = lsb_fraction(feed.lq, want_lq)
-    out = {"case": args[:4], "final_frac_1lsb": frac, "final_max_lsb": worst, "stages": rows}
+    # the reference against ITSELF: the same chain of ATen calls on the CUDA device (what the reference executes in
+    # training) vs on the CPU, same inputs, same injected fields / counts — how far two builds of the reference's own
+    # arithmetic drift apart through the rounding cliffs
+    self_frac = self_worst = None
+    try:
+        from oracle import otf_oracle as O
+
+        def mv(v):
+            if torch.is_tensor(v):
+                return v.to(dev)
+            if isinstance(v, dict):
+                return {k: mv(x) for k, x in v.items()}
+            return v
+
+        _, lq_cuda = O.run_chain_b(case["gt"].to(dev), case["kernel1"].to(dev), case["kernel2"].to(dev), case["sinc_kernel"].to(dev),
+                                   mv(case["plan"]), mv(noise))
+        self_frac, self_worst = lsb_fraction(lq_cuda, want_lq)
+        mine_vs_cuda = lsb_fraction(feed.lq, lq_cuda)
+    except Exception as e:  # noqa: BLE001
+        mine_vs_cuda = (None, None)
+        self_frac = f"failed: {type(e).__name__}: {e}"
+    out = {"case": args[:4], "final_frac_1lsb": frac, "final_max_lsb": worst,
+           "reference_cuda_vs_reference_cpu_frac_1lsb": self_frac, "reference_cuda_vs_reference_cpu_max_lsb": self_worst,
+           "this_repo_vs_reference_cuda_frac_1lsb": mine_vs_cuda[0], "stages": rows}
     print(json.dumps(out, indent=1))
 
 

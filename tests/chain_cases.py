@@ -37,9 +37,10 @@ def make_case(config: str, noise_kind: str, final_order: str, gt_kind: str, seed
             "seed": seed}
 
 
-def run_oracle(case: dict, taps: dict | None = None) -> tuple[torch.Tensor, torch.Tensor, dict]:
+def run_oracle(case: dict, taps: dict | None = None, fields: dict | None = None) -> tuple[torch.Tensor, torch.Tensor, dict]:
     """Oracle pass: returns (gt_crop, lq_crop, noise) with ``noise`` holding every random field it consumed, keyed as
-    RealESRGANFeed's ``inject`` expects."""
+    RealESRGANFeed's ``inject`` expects; ``fields`` collects the finished noise fields (``noise1_field`` ...), the
+    other thing ``inject`` accepts."""
     b, size, scale, plan = case["b"], case["size"], case["scale"], case["plan"]
     gen = torch.Generator().manual_seed(77 + case["seed"])
     noise: dict = {}
@@ -56,7 +57,8 @@ def run_oracle(case: dict, taps: dict | None = None) -> tuple[torch.Tensor, torc
         calls.append(c)
         return c
 
-    gt_c, lq_c = O.run_chain_b(case["gt"], case["kernel1"], case["kernel2"], case["sinc_kernel"], plan, noise, poisson_fn=rec, taps=taps)
+    gt_c, lq_c = O.run_chain_b(case["gt"], case["kernel1"], case["kernel2"], case["sinc_kernel"], plan, noise, poisson_fn=rec, taps=taps,
+                                 fields=fields)
     it = iter(calls)
     for key in ("noise1", "noise2"):
         st = plan[key]

@@ -19,10 +19,11 @@ LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0
+ABI_VERSION = 2  # 2: device-side Philox offset word / crop offsets, OtfStage.p4, OTF_NOISE_RAW_FIELD
 RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST, RESIZE_LANCZOS = range(7)
 WARP_LENS, WARP_SHUTTER, WARP_CHROMA = range(3)
 TAPS_NONE, TAPS_OVERSHARPEN = 0, 1
-NOISE_CLIP, NOISE_ROUNDS, NOISE_FIELD_ONLY = 1, 2, 4
+NOISE_CLIP, NOISE_ROUNDS, NOISE_FIELD_ONLY, NOISE_RAW_FIELD = 1, 2, 4, 16
 
 _p, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 
@@ -38,18 +39,19 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_usm_workspace_bytes": (_i64, [_i, _i, _i]),
     "otf_usm_sharp_f32": (_i, [_p, _i, _i, _i, _p, _i, _f, _f, _p, _i64, _p, _p]),
     "otf_resize_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "otf_resize_tables_f32": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p]),
     "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i64, _i, _p]),
-    "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p]),
+    "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _p, _i, _p, _p]),
     "otf_philox_normal_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_philox_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_poisson_tables_bytes": (_i64, []),
     "otf_poisson_build_tables": (_i, [_p, _p]),
-    "otf_poisson_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "otf_poisson_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "otf_philox_poisson_f32": (_i, [_p, _p, _i64, _u64, _u64, _p]),
     "otf_quality_to_factor_f32": (_i, [_p, _i, _p]),
     "otf_diffjpeg_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _i, _p, _p]),
     "otf_clamp_round_f32": (_i, [_p, _i64, _p, _p]),
-    "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "otf_u8_to_f32": (_i, [_p, _i64, _p, _p]),
     "otf_copy_strided_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "otf_synth_kernels_f32": (_i, [_p, _i, _p, _p]),
@@ -77,7 +79,7 @@ class Stage(C.Structure):
     _fields_ = [("op", C.c_int32), ("mode", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32), ("n", C.c_int32),
                 ("kb", C.c_int32), ("K", C.c_int32), ("flags", C.c_int32), ("f0", C.c_float), ("f1", C.c_float),
                 ("seed", C.c_uint64), ("offset", C.c_uint64), ("p0", C.c_void_p), ("p1", C.c_void_p), ("p2", C.c_void_p),
-                ("p3", C.c_void_p), ("dst", C.c_void_p)]
+                ("p3", C.c_void_p), ("dst", C.c_void_p), ("p4", C.c_void_p)]
 
 
 _lib: C.CDLL | None = None
@@ -90,6 +92,7 @@ _LAUNCHES = {
     "otf_filter2d_f32": 3,  # kernel analysis + launch order + blocked kernel (callers pass the exact count)
     "otf_sepconv_reflect_f32": 1,
     "otf_usm_sharp_f32": 4,
+    "otf_resize_tables_f32": 1,
     "otf_resize_f32": 2,  # weight tables + resampler
     "otf_gaussian_noise_f32": 1,
     "otf_philox_normal_f32": 1,
@@ -138,7 +141,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.otf_abi_version() != 1:
+            if lib.otf_abi_version() != ABI_VERSION:
                 raise ImportError("libotf_b200.so ABI version mismatch")
             _lib = lib
     return _lib

@@ -139,13 +139,14 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
             }
             case OTF_OP_GAUSS:
                 rc = otf_gaussian_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1, (const float*)s.p2,
-                                            (const float*)s.p3, s.seed, s.offset, s.flags, out, stream);
+                                            (const float*)s.p3, s.seed, s.offset, (const uint64_t*)s.p4, s.flags, out, stream);
                 break;
             case OTF_OP_POISSON:
                 // flags bit 3: p2 carries the universal CDF tables (otf_poisson_build_tables) instead of injected counts
                 rc = otf_poisson_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1,
                                            (s.flags & 8) ? nullptr : (const float*)s.p2, (s.flags & 8) ? nullptr : (const float*)s.p3,
-                                           s.seed, s.offset, s.flags & 7, (uint32_t*)scratch, (s.flags & 8) ? s.p2 : nullptr,
+                                           s.seed, s.offset, (const uint64_t*)s.p4, s.flags & 7, (uint32_t*)scratch,
+                                           (s.flags & 8) ? s.p2 : nullptr,
                                            nullptr, nullptr, nullptr, out, stream);
                 break;
             case OTF_OP_JPEG:
@@ -157,7 +158,7 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
                 rc = otf_clamp_round_f32(cur, (int64_t)B * C * h * w, out, stream);
                 break;
             case OTF_OP_CROP_PAIR:
-                rc = otf_crop_pair_f32((const float*)s.p0, B * C, H, W, cur, h, w, s.oh, s.ow, s.n, s.mode,
+                rc = otf_crop_pair_f32((const float*)s.p0, B * C, H, W, cur, h, w, s.oh, s.ow, (const int32_t*)s.p4, s.n, s.mode,
                                        (float*)const_cast<void*>(s.p1), (float*)const_cast<void*>(s.p2), stream);
                 makes_image = false;
                 break;

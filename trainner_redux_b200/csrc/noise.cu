@@ -70,12 +70,15 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
                                                              int chw, int hw,
                                                              const float* __restrict__ sigma, const float* __restrict__ gray,
                                                              const float* __restrict__ ncol, const float* __restrict__ ngray,
-                                                             uint64_t seed, uint64_t offset, int flags) {
+                                                             uint64_t seed, uint64_t offset,
+                                                             const uint64_t* __restrict__ offset_dev, int flags) {
     const Philox ph(seed);
+    if (offset_dev) offset += *offset_dev;  // device-resident counter: a replayed CUDA graph draws a fresh field
     const int b = blockIdx.y;
-    const float sg = sigma[b];
+    const bool raw = (flags & OTF_NOISE_RAW_FIELD) != 0;  // ncol is the finished noise field: added as it is
+    const float sg = raw ? 0.0f : sigma[b];
     const float g = gray ? gray[b] : 0.0f;
-    const bool use_gray = gray != nullptr;
+    const bool use_gray = gray != nullptr && !raw;
     const float one_minus_g = __fsub_rn(1.0f, g);
     const float s255 = __fdiv_rn(sg, 255.0f);
     const float ca = use_gray ? s255 * one_minus_g : s255, cb = use_gray ? s255 * g : 0.0f;  // folded factors
@@ -101,7 +104,9 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float noise;
-                if (EXACT) {
+                if (EXACT && raw) {
+                    noise = gq[u].nc[k];  // degradations.py:625 / :833: out = img + noise, the field generated elsewhere
+                } else if (EXACT) {
                     // degradations.py:598: noise = randn * sigma / 255 ; :603: noise*(1-gray) + noise_gray*gray
                     noise = __fdiv_rn(__fmul_rn(gq[u].nc[k], sg), 255.0f);
                     if (use_gray) {
@@ -342,9 +347,11 @@ __device__ __forceinline__ void poisson_pixel_generic(const float* __restrict__ 
 __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restrict__ img, float* __restrict__ out, int hw,
                                                             const float* __restrict__ scale, const float* __restrict__ gray,
                                                             const float* __restrict__ counts_c, const float* __restrict__ counts_g,
-                                                            uint64_t seed, uint64_t offset, int flags,
+                                                            uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev,
+                                                            int flags,
                                                             const uint32_t* __restrict__ masks, float* __restrict__ vals_out,
                                                             float* __restrict__ lam_c_out, float* __restrict__ lam_g_out) {
+    if (offset_dev) offset += *offset_dev;
     const int b = blockIdx.y;
     __shared__ float s_vals[2];
     if (threadIdx.x < 2) {
@@ -430,8 +437,10 @@ __device__ __forceinline__ float poisson_by_table(const PoissonTables& tab, int 
 // pixel, one Philox call per pixel (3 of its 4 words for the colour channels, 1 for a gray sample).
 __global__ void __launch_bounds__(256) poisson_apply_table_kernel(const float* __restrict__ img, float* __restrict__ out, int hw,
                                                                   const float* __restrict__ scale, const float* __restrict__ gray,
-                                                                  uint64_t seed, uint64_t offset, int flags,
+                                                                  uint64_t seed, uint64_t offset,
+                                                                  const uint64_t* __restrict__ offset_dev, int flags,
                                                                   const uint32_t* __restrict__ masks, PoissonTables tab) {
+    if (offset_dev) offset += *offset_dev;
     const int b = blockIdx.y;
     const float gf = gray ? gray[b] : 0.0f;
     const bool is_gray = gray && gf == 1.0f;
@@ -508,13 +517,17 @@ static int stream_grid(int64_t work_items, int threads) {
 
 extern "C" int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int W, const float* sigma_dev,
                                       const float* gray_dev, const float* noise_color_dev, const float* noise_gray_dev,
-                                      uint64_t seed, uint64_t offset, int flags, float* out, void* stream) {
+                                      uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int flags, float* out,
+                                      void* stream) {
     using namespace otf;
-    OTF_REQUIRE(img && out && sigma_dev, OTF_ERR_BAD_ARG, "gaussian_noise: null pointer");
+    OTF_REQUIRE(img && out && (sigma_dev || (flags & OTF_NOISE_RAW_FIELD)), OTF_ERR_BAD_ARG, "gaussian_noise: null pointer");
+    OTF_REQUIRE(!(flags & OTF_NOISE_RAW_FIELD) || (noise_color_dev && !noise_gray_dev), OTF_ERR_BAD_ARG,
+                "gaussian_noise: OTF_NOISE_RAW_FIELD takes the finished field in noise_color_dev (and no gray field)");
     OTF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "gaussian_noise: bad extents");
     OTF_REQUIRE(!(noise_gray_dev && !noise_color_dev), OTF_ERR_BAD_ARG, "gaussian_noise: inject both fields or neither");
     OTF_REQUIRE((int64_t)C * H * W < (1ll << 30), OTF_ERR_UNSUPPORTED, "gaussian_noise: sample too large");
     OTF_REQUIRE(B <= 65535, OTF_ERR_UNSUPPORTED, "gaussian_noise: B > 65535");
+    if (flags & OTF_NOISE_RAW_FIELD) gray_dev = nullptr;
     const float* ng = gray_dev ? noise_gray_dev : nullptr;
     OTF_REQUIRE(!(gray_dev && noise_color_dev && !noise_gray_dev), OTF_ERR_BAD_ARG,
                 "gaussian_noise: gray flags with an injected colour field need the injected gray field too");
@@ -528,7 +541,7 @@ extern "C" int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int
     cudaStream_t st = (cudaStream_t)stream;
 #define OTF_GAUSS(V, E)                                                                                              \
     gaussian_noise_kernel<V, E><<<grid, 256, 0, st>>>(img, out, chw, H * W, sigma_dev, gray_dev, noise_color_dev, ng, \
-                                                      seed, offset, flags)
+                                                      seed, offset, offset_dev, flags)
     if (vec && exact) OTF_GAUSS(true, true);
     else if (vec) OTF_GAUSS(true, false);
     else if (exact) OTF_GAUSS(false, true);
@@ -577,9 +590,9 @@ extern "C" int otf_poisson_build_tables(void* tables_dev, void* stream) {
 
 extern "C" int otf_poisson_noise_f32(const float* img, int B, int C, int H, int W, const float* scale_dev,
                                      const float* gray_dev, const float* counts_color_dev, const float* counts_gray_dev,
-                                     uint64_t seed, uint64_t offset, int flags, uint32_t* masks_dev, const void* tables_dev,
-                                     float* vals_out_dev, float* lambda_color_dev, float* lambda_gray_dev, float* out,
-                                     void* stream) {
+                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int flags, uint32_t* masks_dev,
+                                     const void* tables_dev, float* vals_out_dev, float* lambda_color_dev, float* lambda_gray_dev,
+                                     float* out, void* stream) {
     using namespace otf;
     OTF_REQUIRE(img && out && scale_dev && masks_dev, OTF_ERR_BAD_ARG, "poisson_noise: null pointer");
     OTF_REQUIRE(C == 3, OTF_ERR_UNSUPPORTED, "poisson_noise: C must be 3 (rgb_to_grayscale), got %d", C);
@@ -602,13 +615,13 @@ extern "C" int otf_poisson_noise_f32(const float* img, int B, int C, int H, int 
     static const bool force_ptrs = [] { const char* e = getenv("OTF_POISSON_IMPL"); return e && e[0] == 'p'; }();
     const bool plain = !counts_color_dev && !counts_gray_dev && !vals_out_dev && !lambda_color_dev && !lambda_gray_dev;
     if (plain && !force_ptrs && tables_dev) {
-        poisson_apply_table_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, seed, offset, flags,
+        poisson_apply_table_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, seed, offset, offset_dev, flags,
                                                                      masks_dev, poisson_tables(tables_dev));
         OTF_LAUNCH_CHECK("poisson_apply_table_kernel");
         return OTF_OK;
     }
     poisson_apply_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, counts_color_dev,
-                                                           counts_gray_dev, seed, offset, flags, masks_dev, vals_out_dev,
+                                                           counts_gray_dev, seed, offset, offset_dev, flags, masks_dev, vals_out_dev,
                                                            lambda_color_dev, lambda_gray_dev);
     OTF_LAUNCH_CHECK("poisson_apply_kernel");
     return OTF_OK;

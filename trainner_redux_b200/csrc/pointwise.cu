@@ -80,8 +80,13 @@ __device__ __forceinline__ void copy_window(const float* __restrict__ src, int H
 template <bool VEC_GT, bool VEC_LQ>
 __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict__ gt, int Hg, int Wg,
                                                         const float* __restrict__ lq, int Hl, int Wl, int top, int left,
+                                                        const int32_t* __restrict__ top_left_dev,
                                                         int p, int scale, int planes, float* __restrict__ gt_out,
                                                         float* __restrict__ lq_out) {
+    if (top_left_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot read outside the image
+        top = clampi(top_left_dev[0], 0, Hl - p);
+        left = clampi(top_left_dev[1], 0, Wl - p);
+    }
     const int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, qs = (int64_t)gridDim.x * blockDim.x;
     copy_window<VEC_GT>(gt, Hg, Wg, top * scale, left * scale, p * scale, gt_out, planes, q0, qs);
     copy_window<VEC_LQ>(lq, Hl, Wl, top, left, p, lq_out, planes, q0, qs);
@@ -90,8 +95,13 @@ __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict_
 // any patch size (p % 4 != 0): one element per thread
 __global__ void __launch_bounds__(256) crop_pair_scalar_kernel(const float* __restrict__ gt, int Hg, int Wg,
                                                                const float* __restrict__ lq, int Hl, int Wl, int top,
-                                                               int left, int p, int scale, int planes,
+                                                               int left, const int32_t* __restrict__ top_left_dev, int p,
+                                                               int scale, int planes,
                                                                float* __restrict__ gt_out, float* __restrict__ lq_out) {
+    if (top_left_dev) {
+        top = clampi(top_left_dev[0], 0, Hl - p);
+        left = clampi(top_left_dev[1], 0, Wl - p);
+    }
     const int G = p * scale;
     const int64_t ng = (int64_t)planes * G * G, nl = (int64_t)planes * p * p;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ng + nl; i += (int64_t)gridDim.x * blockDim.x) {
@@ -198,7 +208,8 @@ extern "C" int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* st
 }
 
 extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, const float* lq, int Hl, int Wl, int top,
-                                 int left, int lq_patch, int scale, float* gt_out, float* lq_out, void* stream) {
+                                 int left, const int32_t* top_left_dev, int lq_patch, int scale, float* gt_out, float* lq_out,
+                                 void* stream) {
     using namespace otf;
     OTF_REQUIRE(gt && lq && gt_out && lq_out, OTF_ERR_BAD_ARG, "crop_pair: null pointer");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && scale > 0 && lq_patch > 0, OTF_ERR_BAD_ARG, "crop_pair: bad extents");
@@ -212,16 +223,17 @@ extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, co
     if (blocks < 1) blocks = 1;
     const bool quads = (lq_patch % 4 == 0) && ((((uintptr_t)gt_out | (uintptr_t)lq_out) & 15) == 0);
     if (!quads) {
-        crop_pair_scalar_kernel<<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
+        crop_pair_scalar_kernel<<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
         OTF_LAUNCH_CHECK("crop_pair_scalar_kernel");
         return OTF_OK;
     }
-    const bool vg = (Wg % 4 == 0) && ((left * scale) % 4 == 0) && (((uintptr_t)gt & 15) == 0);
-    const bool vl = (Wl % 4 == 0) && (left % 4 == 0) && (((uintptr_t)lq & 15) == 0);
-    if (vg && vl) crop_pair_kernel<true, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
-    else if (vg) crop_pair_kernel<true, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
-    else if (vl) crop_pair_kernel<false, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
-    else crop_pair_kernel<false, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, lq_patch, scale, planes, gt_out, lq_out);
+    // device-side offsets: the alignment of the window start is only known for the GT window at scale % 4 == 0
+    const bool vg = (Wg % 4 == 0) && (top_left_dev ? scale % 4 == 0 : (left * scale) % 4 == 0) && (((uintptr_t)gt & 15) == 0);
+    const bool vl = (Wl % 4 == 0) && !top_left_dev && (left % 4 == 0) && (((uintptr_t)lq & 15) == 0);
+    if (vg && vl) crop_pair_kernel<true, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
+    else if (vg) crop_pair_kernel<true, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
+    else if (vl) crop_pair_kernel<false, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
+    else crop_pair_kernel<false, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
     OTF_LAUNCH_CHECK("crop_pair_kernel");
     return OTF_OK;
 }

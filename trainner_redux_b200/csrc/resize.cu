@@ -525,6 +525,20 @@ extern "C" int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int 
     return (int64_t)(table_ints(make_axis(mode, H, OH)) + table_ints(make_axis(mode, W, OW))) * 4;
 }
 
+extern "C" int otf_resize_tables_f32(int H, int W, int OH, int OW, int mode, void* workspace_dev, int64_t workspace_bytes,
+                                     void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(workspace_dev, OTF_ERR_BAD_ARG, "resize_tables: null workspace");
+    const int64_t need = otf_resize_workspace_bytes(H, W, OH, OW, mode);
+    OTF_REQUIRE(need > 0, OTF_ERR_BAD_ARG, "resize_tables: mode %d or extents (%d, %d) -> (%d, %d) not supported", mode, H, W, OH, OW);
+    OTF_REQUIRE(workspace_bytes >= need, OTF_ERR_WORKSPACE, "resize_tables: workspace too small");
+    const AxisSpec ay = make_axis(mode, H, OH), ax = make_axis(mode, W, OW);
+    int* ty_lo = (int*)workspace_dev;
+    resize_tables_kernel<<<ceil_div(OH + OW, 128), 128, 0, (cudaStream_t)stream>>>(mode, ay, ax, ty_lo, ty_lo + table_ints(ay));
+    OTF_LAUNCH_CHECK("resize_tables_kernel");
+    return OTF_OK;
+}
+
 extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
                               int clamp_out, void* workspace_dev, int64_t workspace_bytes, int tables_ready,
                               void* stream) {

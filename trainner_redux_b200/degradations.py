@@ -62,6 +62,20 @@ def _per_sample(v: float | Tensor, b: int, device: torch.device) -> Tensor:
 # ------------------------------------------------------------------ Gaussian ----
 
 
+def add_noise_field_pt(img: Tensor, field: Tensor, clip: bool = True, rounds: bool = False) -> Tensor:
+    """``tail(img + field)`` — the last three statements of ``add_gaussian_noise_pt`` / ``add_poisson_noise_pt``
+    (degradations.py:625-632, :833-841) for a noise field that was generated elsewhere (e.g. by the reference, in a
+    parity test that injects the finished field)."""
+    _lib.require_cuda(img, field)
+    x = _lib.dense_f32(img)
+    b, c, h, w = x.shape
+    f = field.to(torch.float32).expand(b, c, h, w).contiguous()
+    out = torch.empty_like(x)
+    _lib.call("otf_gaussian_noise_f32", _lib.ptr(x), b, c, h, w, None, None, _lib.ptr(f), None, 0, 0, None,
+              _flags(clip, rounds) | _lib.NOISE_RAW_FIELD, _lib.ptr(out), _lib.stream())
+    return out
+
+
 def _gaussian(img, sigma, gray_noise, clip, rounds, add, noise=None, noise_gray=None, generator=None) -> Tensor:
     _lib.require_cuda(img)
     x = _lib.dense_f32(img)
@@ -81,7 +95,7 @@ def _gaussian(img, sigma, gray_noise, clip, rounds, add, noise=None, noise_gray=
     out = torch.empty_like(x)
     _lib.call(
         "otf_gaussian_noise_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(sg), _lib.ptr(gray), _lib.ptr(noise),
-        _lib.ptr(noise_gray), gen.seed, gen.next_offset(), _flags(clip, rounds) if add else _lib.NOISE_FIELD_ONLY,
+        _lib.ptr(noise_gray), gen.seed, gen.next_offset(), None, _flags(clip, rounds) if add else _lib.NOISE_FIELD_ONLY,
         _lib.ptr(out), _lib.stream(),
     )
     return out
@@ -191,7 +205,7 @@ def _poisson(img, scale, gray_noise, clip, rounds, add, counts=None, counts_gray
     out = torch.empty_like(x)
     _lib.call(
         "otf_poisson_noise_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(sc), _lib.ptr(gray), _lib.ptr(counts),
-        _lib.ptr(counts_gray), gen.seed, gen.next_offset(), _flags(clip, rounds) if add else _lib.NOISE_FIELD_ONLY, _lib.ptr(masks),
+        _lib.ptr(counts_gray), gen.seed, gen.next_offset(), None, _flags(clip, rounds) if add else _lib.NOISE_FIELD_ONLY, _lib.ptr(masks),
         _lib.ptr(tables), _lib.ptr(vals), _lib.ptr(lam_c), _lib.ptr(lam_g), _lib.ptr(out), _lib.stream(),
     )
     if export is not None:
@@ -278,6 +292,28 @@ def pin_resize_tables() -> int:
         ev.synchronize()
         _TABLE_PINNED[key] = tab
     return len(_TABLE_PINNED)
+
+
+def pinned_resize_table(device: torch.device, h: int, w: int, oh: int, ow: int, mode_id: int) -> Tensor:
+    """The weight tables of one (H, W, OH, OW, mode), built now if need be and kept for the life of the process — for
+    chains that are about to be captured into a CUDA graph (the capture starts with a device synchronise, so a table
+    launched here is complete before any captured kernel can read it)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), h, w, oh, ow, mode_id)
+    tab = _TABLE_PINNED.get(key)
+    if tab is None:
+        hit = _TABLE_CACHE.get(key)
+        if hit is not None:
+            hit[1].synchronize()
+            tab = hit[0]
+        else:
+            nbytes = _lib.load().otf_resize_workspace_bytes(h, w, oh, ow, mode_id)
+            if nbytes <= 0:
+                raise _lib.OtfError(f"resize tables: mode {mode_id} or extents ({h}, {w}) -> ({oh}, {ow}) not supported")
+            tab = torch.empty(nbytes // 4, dtype=torch.int32, device=device)
+            _lib.call("otf_resize_tables_f32", h, w, oh, ow, mode_id, _lib.ptr(tab), nbytes, _lib.stream())
+            torch.cuda.current_stream().synchronize()
+        _TABLE_PINNED[key] = tab
+    return tab
 
 
 def _resize_call(x: Tensor, oh: int, ow: int, mode_id: int, clamp: bool) -> Tensor:

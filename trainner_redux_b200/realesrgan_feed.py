@@ -32,6 +32,7 @@ from torch import Tensor
 
 from . import _lib
 from . import degradations as D
+from .chain_graph import ChainGraph, ChainGraphCache, ParamBlock, ParamCollector, plan_signature
 from .diffjpeg import DiffJPEG
 from .img_process_util import KernelAnalysis, USMSharp, filter2d
 from .stages import StageList
@@ -154,8 +155,9 @@ def _draw_noise(rng: HostRNG, b: int, gaussian_prob, noise_range, poisson_range,
     # gate first, then the primitive's own draws: rand(B) value, rand(B) gray (degradations.py:673-679)
     gaussian = rng.np.uniform() < gaussian_prob
     rr = noise_range if gaussian else poisson_range
-    val = torch.rand(b, generator=rng.torch) * (rr[1] - rr[0]) + rr[0]
-    gray = (torch.rand(b, generator=rng.torch) < gray_prob).float()
+    # (in-place forms of `rand * (hi - lo) + lo` and `(rand < p).float()`: same values, a third of the dispatches)
+    val = torch.rand(b, generator=rng.torch).mul_(rr[1] - rr[0]).add_(rr[0])
+    gray = torch.rand(b, generator=rng.torch).lt_(gray_prob)
     if gaussian:
         return {"kind": "gaussian", "sigma": val, "gray": gray}
     return {"kind": "poisson", "scale": val, "gray": gray}
@@ -389,6 +391,14 @@ class RealESRGANFeed:
         # launch the whole chain from ONE library call (stages.py / otf_run_stages_f32) instead of one Python call
         # per stage; same kernels, same arguments, bit-identical results.  The per-stage path stays for the stage hooks.
         self.native_chain = True
+        # Shape-stable schedules replay a captured chain (chain_graph.py): a plan signature seen twice is captured into
+        # a CUDA graph whose per-step numbers (per-sample sigma / scale / gray / quality, crop offsets, Philox position)
+        # live in a small device block, so a step costs the host one plan draw, one tiny H2D and one graph launch.
+        # NOTE: a replayed chain returns ``self.gt`` / ``self.lq`` in buffers the NEXT replay of the same chain
+        # overwrites (the reference returns fresh tensors); a caller that keeps batches across steps sets
+        # ``use_graphs = False`` or clones.  The pool (``use_pool``) copies what it keeps, so it is unaffected.
+        self.use_graphs = True
+        self.graphs = ChainGraphCache()
 
     def _timed(self, name: str, fn: Callable[[], Tensor]) -> Tensor:
         if self.record_stage_fns:
@@ -408,6 +418,8 @@ class RealESRGANFeed:
     # -- stages ---------------------------------------------------------------------------
     def _noise(self, out: Tensor, st: dict, inject: dict | None, key: str) -> Tensor:
         inject = inject or {}
+        if inject.get(f"{key}_field") is not None:
+            return D.add_noise_field_pt(out, inject[f"{key}_field"], clip=True, rounds=False)
         if st["kind"] == "gaussian":
             return D.add_gaussian_noise_pt(
                 out, st["sigma"].to(self.device, non_blocking=True), st["gray"].to(self.device, non_blocking=True),
@@ -440,7 +452,9 @@ class RealESRGANFeed:
         an = (lambda i: i) if joint else (lambda i: None)
 
         def noise(st: dict, key: str) -> None:
-            if st["kind"] == "gaussian":
+            if inject.get(f"{key}_field") is not None:  # the finished noise field of the reference (parity tests)
+                sl.noise_field(inject[f"{key}_field"])
+            elif st["kind"] == "gaussian":
                 sl.gaussian_noise(st["sigma"], st["gray"], self.rng.philox, noise=inject.get(f"{key}_color"),
                                   noise_gray=inject.get(f"{key}_gray"))
             else:
@@ -493,6 +507,65 @@ class RealESRGANFeed:
         # the fork's extra stages are launched per stage from Python (they are not in the native executor's op table)
         extras = plan is not None and any(k in plan for k in EXTRA_KEYS)
         return self.native_chain and not (self.time_stages or self.record_stage_fns or self.collect_taps is not None or extras)
+
+    # -- captured chains -------------------------------------------------------------------
+    def _graph_key(self, gt: Tensor, kernels: Sequence[Tensor], plan: dict, inject: dict | None) -> tuple | None:
+        if not self.use_graphs or inject or not self._native(plan) or torch.cuda.is_current_stream_capturing():
+            return None
+        if any(k.dtype != torch.float32 or not k.is_contiguous() or not k.is_cuda for k in kernels):
+            return None  # the stage list would work on a converted copy whose address is not the caller's
+        sig = plan_signature(plan, gt.size(2), gt.size(3))
+        if sig is None:
+            return None
+        return (gt.data_ptr(), tuple(gt.shape), *((k.data_ptr(), tuple(k.shape)) for k in kernels), sig)
+
+    def _fill_params(self, entry: ChainGraph, b: int, h: int, w: int, kernels: Sequence[Tensor], plan: dict) -> None:
+        """This step's numbers into the chain's parameter block (walks the same branches as the capture did)."""
+        pc = ParamCollector(entry.params, b, h, w)
+        self._record(pc, *kernels, plan)  # type: ignore[arg-type]
+        if (entry.params.rows, entry.params.noise_stages) != (entry.rows, entry.noise_stages):
+            raise RuntimeError("captured chain and plan disagree about the parameter block layout")  # signature bug
+        top, left = plan["crop"]
+        entry.params.set_header(self.rng.philox.offset, top, left)
+        self.rng.philox.offset += entry.noise_stages
+        cur = _lib.stream().value or 0
+        if entry.done is not None and entry.last_stream != cur:
+            torch.cuda.current_stream().wait_event(entry.done)  # the block must not change under a replay still in flight
+        entry.last_stream = cur
+        entry.params.upload()
+
+    def _replay(self, entry: ChainGraph) -> tuple[Tensor, Tensor]:
+        assert entry.graph is not None and entry.gt_out is not None and entry.lq_out is not None
+        entry.graph.replay()
+        if entry.done is None:
+            entry.done = torch.cuda.Event()
+        entry.done.record()
+        _lib.launch_count += entry.launches
+        return entry.gt_out, entry.lq_out
+
+    def _capture(self, key: tuple, gt: Tensor, kernels: Sequence[Tensor], plan: dict) -> ChainGraph | None:
+        """Record the chain against a parameter block and capture its launches into a CUDA graph."""
+        b, _, h, w = gt.shape
+        entry = ChainGraph(ParamBlock(b, self.device))
+        try:
+            sl = self._record(StageList(gt, params=entry.params), *kernels, plan)  # resize tables are built here, eagerly
+            entry.rows, entry.noise_stages = entry.params.rows, entry.params.noise_stages
+            top, left = plan["crop"]
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                entry.gt_out, entry.lq_out = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left))
+            entry.launches = _lib.launch_count - l0
+            _lib.launch_count = l0  # nothing ran yet: replays are what launches
+            entry.graph, entry.keep = g, sl
+        except Exception as e:  # noqa: BLE001  a chain that cannot be captured keeps running eagerly
+            import warnings
+
+            warnings.warn(f"RealESRGANFeed: chain capture failed ({type(e).__name__}: {e}); this plan shape stays eager", stacklevel=2)
+            self.graphs.seen[key] = -(1 << 30)
+            return None
+        self.graphs.put(key, entry)
+        return entry
 
     def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
                 inject: dict | None = None) -> Tensor:
@@ -616,8 +689,17 @@ class RealESRGANFeed:
             if self._native(plan):  # chain + crop from one library call
                 if plan["gt_size"] % plan["scale"]:
                     raise _lib.OtfError(f"gt_patch_size {plan['gt_size']} must be a multiple of scale {plan['scale']}")
-                sl = self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject)
-                self.gt, self.lq = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left))
+                kernels = (kernel1, kernel2, sinc_kernel)
+                key = self._graph_key(gt, kernels, plan, inject)
+                entry = self.graphs.get(key) if key is not None else None
+                if entry is None and key is not None and self.graphs.should_capture(key):
+                    entry = self._capture(key, gt, kernels, plan)
+                if entry is not None:  # a captured chain: refresh its parameter block, replay
+                    self._fill_params(entry, gt.size(0), ori_h, ori_w, kernels, plan)
+                    self.gt, self.lq = self._replay(entry)
+                else:
+                    sl = self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject)
+                    self.gt, self.lq = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left))
             else:
                 lq_full = self.degrade(gt, kernel1, kernel2, sinc_kernel, plan, inject)
                 self.gt, self.lq = crop_pair(gt, lq_full, plan["gt_size"], plan["scale"], top, left)

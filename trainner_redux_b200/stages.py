@@ -32,8 +32,14 @@ _MISSED_ONCE: set[tuple] = set()  # resize-table keys that missed the cache once
 class StageList:
     """Accumulates ``OtfStage`` records for one batch; tracks the image extent as stages are added."""
 
-    def __init__(self, img: Tensor) -> None:
+    def __init__(self, img: Tensor, params: Any | None = None) -> None:
+        """``params`` (a ``chain_graph.ParamBlock``): per-sample vectors, the Philox offset and the crop offsets are read
+        by the kernels from that device block instead of being baked into the launches — the form a chain takes when it
+        is captured into a CUDA graph (the caller fills and uploads the block before every run / replay)."""
         _lib.require_cuda(img)
+        self.params = params
+        if params is not None:
+            params.begin()
         self.img = _lib.dense_f32(img)
         self.b, self.c, self.h, self.w = self.img.shape
         self.device = self.img.device
@@ -66,6 +72,11 @@ class StageList:
         """Point ``stage.fld`` at a length-B fp32 device vector: device tensors are used in place, CPU tensors
         and scalars are collected and uploaded by ONE copy in run()."""
         if v is None:
+            return
+        if self.params is not None:
+            if isinstance(v, Tensor) and v.is_cuda:
+                raise RuntimeError("a chain with a parameter block takes its per-sample vectors from the host")
+            setattr(stage, fld, self.params.add_row(v))
             return
         if isinstance(v, Tensor) and v.is_cuda:
             t = v.reshape(self.b).to(torch.float32).contiguous()
@@ -143,6 +154,8 @@ class StageList:
         shape-stable workload, not the usual freshly drawn scale) gets a table of its own, published by run()."""
         key = (self.device.index, self.h, self.w, oh, ow, mode_id)
         tab = D._TABLE_PINNED.get(key)
+        if tab is None and self.params is not None:  # about to be captured: build the tables now, keep them for good
+            tab = D.pinned_resize_table(self.device, self.h, self.w, oh, ow, mode_id)
         ready = tab is not None
         if tab is None and key in D._TABLE_CACHE and not torch.cuda.is_current_stream_capturing():
             tab, ev, sid = D._TABLE_CACHE[key]
@@ -174,10 +187,23 @@ class StageList:
             gray = None
         if noise is not None and noise_gray is None:
             gray = None
-        s = self._add(_lib.OP_GAUSS, seed=gen.seed, offset=gen.next_offset(), flags=D._flags(clip, rounds),
+        s = self._add(_lib.OP_GAUSS, seed=gen.seed, flags=D._flags(clip, rounds), **self._offset(gen),
                       p2=self._dev_ptr(noise), p3=self._dev_ptr(noise_gray) if noise is not None else None)
         self._per_sample(s, "p0", sigma)
         self._per_sample(s, "p1", gray)
+        self.launches += 1
+
+    def _offset(self, gen: D.PhiloxState) -> dict:
+        """Philox position of a noise stage: the generator's running offset, or — with a parameter block — the stage's
+        index inside the chain plus the base the block carries (the caller advances the generator per run)."""
+        if self.params is None:
+            return {"offset": gen.next_offset()}
+        return {"offset": self.params.next_noise_index(), "p4": self.params.offset_ptr}
+
+    def noise_field(self, field: Tensor, clip: bool = True, rounds: bool = False) -> None:
+        """degradations.add_noise_field_pt: ``tail(img + field)`` for a field generated elsewhere (parity tests)."""
+        f = field.to(torch.float32).expand(self.b, self.c, self.h, self.w)
+        self._add(_lib.OP_GAUSS, flags=D._flags(clip, rounds) | _lib.NOISE_RAW_FIELD, p2=self._dev_ptr(f))
         self.launches += 1
 
     def poisson_noise(self, scale: float | Tensor, gray: float | Tensor | None, gen: D.PhiloxState, clip: bool = True,
@@ -189,10 +215,10 @@ class StageList:
             gray = None
         tables = D.poisson_tables(self.device) if counts is None else None  # exact table inversion when the counts are drawn here
         if tables is not None:
-            s = self._add(_lib.OP_POISSON, seed=gen.seed, offset=gen.next_offset(), flags=D._flags(clip, rounds) | 8,
+            s = self._add(_lib.OP_POISSON, seed=gen.seed, flags=D._flags(clip, rounds) | 8, **self._offset(gen),
                           p2=tables.data_ptr())  # (raw table block: owned by degradations._POISSON_TABLES for the life of the process)
         else:
-            s = self._add(_lib.OP_POISSON, seed=gen.seed, offset=gen.next_offset(), flags=D._flags(clip, rounds),
+            s = self._add(_lib.OP_POISSON, seed=gen.seed, flags=D._flags(clip, rounds), **self._offset(gen),
                           p2=self._dev_ptr(counts), p3=self._dev_ptr(counts_gray) if counts is not None else None)
         self._per_sample(s, "p0", scale)
         self._per_sample(s, "p1", gray)
@@ -202,7 +228,7 @@ class StageList:
         """DiffJPEG.forward(x, quality) with the conversion of the quality fused into the kernel."""
         flags = JPEG_IS_QUALITY | (JPEG_DIFFERENTIABLE if differentiable else 0) | (JPEG_CLAMP_IN if clamp_in else 0) | \
             (JPEG_ROUND8 if round8 else 0)
-        if isinstance(quality, Tensor):
+        if isinstance(quality, Tensor) or self.params is not None:  # (a parameter block carries scalars as rows too)
             s = self._add(_lib.OP_JPEG, flags=flags)
             self._per_sample(s, "p0", quality)
         else:
@@ -225,7 +251,8 @@ class StageList:
             p = gt_patch // scale
             gt_out = torch.empty((self.b, self.c, p * scale, p * scale), dtype=torch.float32, device=self.device)
             lq_out = torch.empty((self.b, self.c, p, p), dtype=torch.float32, device=self.device)
-            self._add(_lib.OP_CROP_PAIR, p0=self._dev_ptr(gt), p1=gt_out.data_ptr(), p2=lq_out.data_ptr(), oh=top, ow=left, n=p, mode=scale)
+            self._add(_lib.OP_CROP_PAIR, p0=self._dev_ptr(gt), p1=gt_out.data_ptr(), p2=lq_out.data_ptr(), oh=top, ow=left, n=p, mode=scale,
+                      p4=None if self.params is None else self.params.crop_ptr)
             self.launches += 1
             outs = (gt_out, lq_out)
         else:
