@@ -224,6 +224,12 @@ int otf_gather_slots_f32(const float* src, const int32_t* idx_host, int n,
                          int64_t slot_elems, float* dst, void* stream);
 int otf_scatter_slots_f32(const float* src, const int32_t* idx_host, int n,
                           int64_t slot_elems, float* dst, void* stream);
+/* One pool step (traiNNer/models/realesrgan_model.py:430-447) in one launch: for slot idx_host[i] of BOTH queues the
+ * stored pair goes to out_*[i] (dequeue; pass NULL for both while the pool is still filling) and in_*[i] takes its
+ * place (enqueue).  lq_elems / gt_elems: floats per slot. */
+int otf_pool_exchange_f32(float* queue_lq, float* queue_gt, const int32_t* idx_host, int n,
+                          int64_t lq_elems, int64_t gt_elems, const float* in_lq, const float* in_gt,
+                          float* out_lq, float* out_gt, void* stream);
 
 /* ---- f4: MoA batch augment on the finished pair — traiNNer/ops/batchaug.py:21-509 ----------------
  * The host draws the augmentation, ratio, permutation and box exactly as the reference does; the

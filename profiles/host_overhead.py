@@ -36,8 +36,7 @@ opt = OTFOptions(scale=4, gt_size=args.gt - 32, blur_prob=1.0, blur_prob2=0.8, g
 if args.stable:  # every draw still happens; only the shapes repeat (bench.py's headline workload)
     import dataclasses
 
-    opt = dataclasses.replace(opt, blur_prob2=1.0, gaussian_noise_prob=1.0, gaussian_noise_prob2=1.0, resize_prob=(0, 1, 0),
-                              resize_range=(0.75, 0.75), resize_mode_list=["bicubic"], resize_mode_prob=[1.0], resize_prob2=(0, 0, 1),
+    opt = dataclasses.replace(opt, blur_prob2=1.0, gaussian_noise_prob=1.0, gaussian_noise_prob2=1.0, resize_prob=(0, 0, 1), resize_mode_list=["bicubic"], resize_mode_prob=[1.0], resize_prob2=(0, 0, 1),
                               resize_mode_list2=["bilinear"], resize_mode_prob2=[1.0], resize_mode_list3=["area"], resize_mode_prob3=[1.0],
                               final_jpeg_first_prob=0.0)
 feed = RealESRGANFeed(opt, device=dev, manual_seed=0)

@@ -19,7 +19,7 @@ def _opt(noise: str, b: int, **kw) -> OTFOptions:
                 gray_noise_prob=0.4, gaussian_noise_prob2=g, noise_range2=(1, 25), poisson_scale_range2=(0.05, 2.5), gray_noise_prob2=0.4,
                 jpeg_range=(30, 95), jpeg_range2=(30, 95), resize_prob=(0, 0, 1), resize_mode_list=["bicubic"], resize_mode_prob=[1],
                 resize_prob2=(0, 0, 1), resize_mode_list2=["bilinear"], resize_mode_prob2=[1], resize_mode_list3=["area"],
-                resize_mode_prob3=[1], queue_size=4 * b)
+                resize_mode_prob3=[1], final_jpeg_first_prob=0.0, queue_size=4 * b)
     base.update(kw)
     return OTFOptions(**base)
 
@@ -85,11 +85,12 @@ def test_same_counter_same_field_different_counter_different_field(dev):
 
 
 def test_noise_field_injection_is_the_reference_tail(dev):
-    x = torch.rand(3, 3, 20, 28, device=dev) * 1.2 - 0.1
-    f = torch.randn(3, 3, 20, 28, device=dev) * 0.05
-    assert torch.equal(D.add_noise_field_pt(x, f), (x + f).clamp(0, 1))
-    assert torch.equal(D.add_noise_field_pt(x, f, clip=True, rounds=True), ((x + f) * 255.0).round().clamp(0, 255) / 255.0)
-    assert torch.equal(D.add_noise_field_pt(x, f, clip=False), x + f)
+    xc = torch.rand(3, 3, 20, 28) * 1.2 - 0.1  # expectations on the CPU: ATen's CUDA `x / 255.0` multiplies by a reciprocal
+    fc = torch.randn(3, 3, 20, 28) * 0.05
+    x, f = xc.to(dev), fc.to(dev)
+    assert torch.equal(D.add_noise_field_pt(x, f).cpu(), (xc + fc).clamp(0, 1))
+    assert torch.equal(D.add_noise_field_pt(x, f, clip=True, rounds=True).cpu(), ((xc + fc) * 255.0).round().clamp(0, 255) / 255.0)
+    assert torch.equal(D.add_noise_field_pt(x, f, clip=False).cpu(), xc + fc)
 
 
 def test_prefetcher_static_slots_and_feed(dev):

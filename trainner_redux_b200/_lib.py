@@ -57,6 +57,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_synth_kernels_f32": (_i, [_p, _i, _p, _p]),
     "otf_gather_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
     "otf_scatter_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),
+    "otf_pool_exchange_f32": (_i, [_p, _p, _p, _i, _i64, _i64, _p, _p, _p, _p, _p]),
     "otf_mixup_f32": (_i, [_p, _p, _i, _i64, _f, _f, _p, _p]),
     "otf_copy_box_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "otf_warp_f32": (_i, [_p, _i, _i, _i, _i, _i, _f, _p, _p]),
@@ -109,6 +110,7 @@ _LAUNCHES = {
     "otf_synth_kernels_f32": 1,
     "otf_gather_slots_f32": 1,
     "otf_scatter_slots_f32": 1,
+    "otf_pool_exchange_f32": 1,
     "otf_mixup_f32": 1,
     "otf_copy_box_f32": 1,
     "otf_warp_f32": 1,

@@ -184,10 +184,17 @@ class ChainGraph:
 
 class ChainGraphCache:
     """LRU of captured chains keyed by (input addresses, batch shape, plan signature).  A key is captured the SECOND
-    time it is seen — a freshly drawn resize scale rarely repeats, a shape-stable schedule repeats at once."""
+    time it is seen — a freshly drawn resize scale rarely repeats, a shape-stable schedule repeats at once.
 
-    def __init__(self, capacity: int = 8, capture_after: int = 2) -> None:
+    A capture costs milliseconds (torch synchronises the device and collects garbage around it), so captures are
+    rationed: the cache starts with a few capture credits, every replay earns a fraction of one back.  A shape-stable
+    schedule pays for its handful of graphs at once and then only replays; a random schedule whose shapes recur now and
+    then (a resize scale drawn from a continuum) spends its credits, finds that replays do not pay them back, and stays
+    on the eager path instead of capturing-and-evicting forever."""
+
+    def __init__(self, capacity: int = 8, capture_after: int = 2, credits: float = 4.0, credit_per_hit: float = 0.02) -> None:
         self.capacity, self.capture_after = capacity, capture_after
+        self.credits, self.max_credits, self.credit_per_hit = credits, credits, credit_per_hit
         self.entries: OrderedDict[tuple, ChainGraph] = OrderedDict()
         self.seen: OrderedDict[tuple, int] = OrderedDict()
         self.hits = self.misses = self.captures = 0
@@ -197,6 +204,7 @@ class ChainGraphCache:
         if e is not None:
             self.entries.move_to_end(key)
             self.hits += 1
+            self.credits = min(self.max_credits, self.credits + self.credit_per_hit)
         else:
             self.misses += 1
         return e
@@ -207,7 +215,10 @@ class ChainGraphCache:
         self.seen.move_to_end(key)
         while len(self.seen) > 512:
             self.seen.popitem(last=False)
-        return n >= self.capture_after
+        if n < self.capture_after or self.credits < 1.0:
+            return False
+        self.credits -= 1.0
+        return True
 
     def put(self, key: tuple, entry: ChainGraph) -> None:
         self.entries[key] = entry

@@ -23,7 +23,8 @@ namespace otf {
 // ---- per-kernel analysis: true support, rank-1 factors, processing order --------------
 // One CTA, one warp per kernel.
 //   support[kb]  largest |offset| with a non-zero tap (kernels arrive zero-padded to 21x21);
-//   rank1[kb]    1 when the kernel is an outer product u v^T to within fp32 rounding of its own
+//   rank1[kb]    bit 1 (value 2): the kernel is left-right mirror symmetric (horizontal fold);
+//                bit 0: set when the kernel is an outer product u v^T to within fp32 rounding of its own
 //                taps (isotropic Gaussians — 45 % of the reference's default kernel_prob — and the
 //                USM kernel are), with the factors in uv[kb][0][*] (rows) and uv[kb][1][*] (columns),
 //                stored centred in 21 slots; the blur is then evaluated as K + K taps instead of K*K.
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_consta
     // scan them (support, pivot, rank-1 residual) — three short passes instead of a 14-deep serial loop per lane
     __shared__ float sk[32 * 32];
     __shared__ float s_red[4];
-    __shared__ int s_idx[4], s_r[4], s_ok[4];
+    __shared__ int s_idx[4], s_r[4], s_ok[4], s_sym[4];
     const float* kern = sets.ptr[blockIdx.y];
     int32_t* scratch = scratch_base + (size_t)blockIdx.y * scratch_words(kernel_batch);
     int32_t* support = scratch;
@@ -94,9 +95,18 @@ __global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_consta
         }
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) s_ok[warp] = ok;
+    // left-right mirror symmetry, K[i][j] == K[i][K-1-j] bit for bit (every isotropic family and the sinc kernels are:
+    // the generators evaluate a function of x^2): such kernels are evaluated with the horizontal fold
+    bool sym = true;
+    for (int idx = tid; idx < n; idx += 128) {
+        const int i = idx / K, j = idx - i * K;
+        sym = sym && (sk[idx] == sk[i * K + (K - 1 - j)]);
+    }
+    sym = __all_sync(0xffffffffu, sym);
+    if (lane == 0) { s_ok[warp] = ok; s_sym[warp] = sym; }
     __syncthreads();
     ok = s_ok[0] && s_ok[1] && s_ok[2] && s_ok[3];
+    sym = s_sym[0] && s_sym[1] && s_sym[2] && s_sym[3];
     if (tid < kUVPitch) {
         // centred in 21 slots: slot s <-> offset s - 10
         const int t = tid - 10 + c;  // tap index for this slot
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_consta
         uv[((size_t)kb * 2 + 0) * kUVPitch + tid] = (ok && in) ? sk[t * K + pj] : 0.0f;
         uv[((size_t)kb * 2 + 1) * kUVPitch + tid] = (ok && in) ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
     }
-    if (tid == 0) { support[kb] = r; rank1[kb] = ok ? 1 : 0; }
+    if (tid == 0) { support[kb] = r; rank1[kb] = (ok ? 1 : 0) | (sym ? 2 : 0); }
 }
 
 // order[0..kb): sample indices sorted by support, largest first (stable).  One small CTA per kernel set.
@@ -261,6 +271,73 @@ __device__ __forceinline__ void accumulate_rows_packed(const float* __restrict__
         }
 }
 
+// Horizontal fold for left-right mirror-symmetric kernels (w[i][R+t] == w[i][R-t]): the two pixels that share a tap
+// are added first, s = p[x+t] + p[x-t], and the sum feeds the FFMA2 of both vertically paired output rows — per image
+// row and output column R FADDs + 2(R+1) FFMA2 instead of 2(2R+1) FFMA2: 1.56x fewer FMA-pipe cycles at K = 21.
+// wsm2f row i holds the paired taps (w[i][R+t], w[i-1][R+t]) for t = 0..R.  The summation order differs from the
+// unfolded loop (pairs are pre-added), i.e. by a few ulp — inside the 1e-5 bar like every other order.
+template <int TX, int TY, int KT, int PMASK>
+__device__ __forceinline__ void fold_row(const float* __restrict__ rowp, const float2* __restrict__ wsm2f, int r,
+                                         float2 (&acc2)[TY / 2][TX]) {
+    constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
+    constexpr int NROW = TX + 2 * RA;
+    float row[NROW];
+    const float4* rp = reinterpret_cast<const float4*>(rowp);
+#pragma unroll
+    for (int q = 0; q < NROW / 4; ++q) {
+        const float4 v = rp[q];
+        row[4 * q + 0] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int q = 0; q < (R + 2) / 2; ++q) {  // taps t = 2q, 2q + 1
+        float4 w4[TY / 2];
+#pragma unroll
+        for (int p = 0; p < TY / 2; ++p)
+            if ((PMASK >> p) & 1) w4[p] = reinterpret_cast<const float4*>(wsm2f + (r - 2 * p) * kW2Pitch)[q];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = 2 * q + u;
+            if (t <= R) {
+#pragma unroll
+                for (int ox = 0; ox < TX; ++ox) {
+                    const int c = OFF + ox + R;
+                    const float sv = t == 0 ? row[c] : __fadd_rn(row[c + t], row[c - t]);
+                    const float2 s2 = make_float2(sv, sv);
+#pragma unroll
+                    for (int p = 0; p < TY / 2; ++p)
+                        if ((PMASK >> p) & 1)
+                            ffma2(acc2[p][ox], s2, u == 0 ? make_float2(w4[p].x, w4[p].y) : make_float2(w4[p].z, w4[p].w));
+                }
+            }
+        }
+    }
+}
+
+template <int TX, int TY, int KT>
+__device__ __forceinline__ void accumulate_rows_folded(const float* __restrict__ tile_thread, int pitch,
+                                                       const float2* __restrict__ wsm2f, float (&acc)[TY][TX]) {
+    static_assert(TY == 4, "two vertical output pairs");
+    float2 acc2[TY / 2][TX];
+#pragma unroll
+    for (int p = 0; p < TY / 2; ++p)
+#pragma unroll
+        for (int ox = 0; ox < TX; ++ox) acc2[p][ox] = make_float2(0.0f, 0.0f);
+    // output pair p takes kernel rows (i, i - 1) with i = r - 2p from image row r: valid while 0 <= i <= KT
+    fold_row<TX, TY, KT, 1>(tile_thread, wsm2f, 0, acc2);
+    fold_row<TX, TY, KT, 1>(tile_thread + pitch, wsm2f, 1, acc2);
+#pragma unroll 1
+    for (int r = 2; r <= KT; ++r) fold_row<TX, TY, KT, 3>(tile_thread + r * pitch, wsm2f, r, acc2);
+    fold_row<TX, TY, KT, 2>(tile_thread + (KT + 1) * pitch, wsm2f, KT + 1, acc2);
+    fold_row<TX, TY, KT, 2>(tile_thread + (KT + 2) * pitch, wsm2f, KT + 2, acc2);
+#pragma unroll
+    for (int p = 0; p < TY / 2; ++p)
+#pragma unroll
+        for (int ox = 0; ox < TX; ++ox) {
+            acc[2 * p][ox] = acc2[p][ox].x;
+            acc[2 * p + 1][ox] = acc2[p][ox].y;
+        }
+}
+
 // Rank-1 kernels: out = u (x) v correlated with the tile, evaluated per thread as a horizontal
 // K-tap pass over each row of its window (kept in registers) followed by the vertical accumulation.
 // u and v sit centred in 21 slots (tap t of a KT-tap kernel is slot 10 - R + t).
@@ -355,7 +432,9 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     const int kb = kernel_batch == 1 ? 0 : b;
     const int32_t* support = scratch;
     const int R_ = scratch ? min(scratch[kb], K / 2) : K / 2;
-    const bool rank1 = scratch && R_ >= 2 && scratch[2 * kernel_batch + kb] != 0;
+    const int kflags = scratch ? scratch[2 * kernel_batch + kb] : 0;
+    const bool rank1 = R_ >= 2 && (kflags & 1) != 0;
+    const bool fold = PACKED && TY == 4 && !rank1 && R_ >= 2 && (kflags & 2) != 0;
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.x;
     const int R = support ? min(support[kb], K / 2) : K / 2;  // true radius (block-uniform)
@@ -403,6 +482,17 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     if (rank1) {
         const float* uv = reinterpret_cast<const float*>(scratch + 3 * kernel_batch) + (size_t)kb * 2 * kUVPitch;
         for (int idx = tid; idx < 2 * kUVPitch; idx += NT) wsm[idx] = uv[idx];
+    } else if (fold) {
+        // folded paired taps: row i holds (w[i][R+t], w[i-1][R+t]) for t = 0..R (the right half of the mirror-symmetric rows)
+        float2* w2 = reinterpret_cast<float2*>(wsm);
+        auto tap = [&](int i, int t) {
+            const int si = c - R + i, sj = c + t;
+            return (i >= 0 && i < KT && t <= R && si >= 0 && si < K && sj < K) ? kp[si * K + sj] : 0.0f;
+        };
+        for (int idx = tid; idx < 22 * kW2Pitch; idx += NT) {
+            const int i = idx / kW2Pitch, t = idx - i * kW2Pitch;
+            w2[idx] = make_float2(tap(i, t), tap(i - 1, t));
+        }
     } else if (PACKED && R >= 1) {
         // paired taps: row i holds (w[i][j], w[i-1][j]) for i = 0..KT, zeros outside the KT x KT centre
         float2* w2 = reinterpret_cast<float2*>(wsm);
@@ -475,6 +565,21 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
             case 8: accumulate_rank1<TX, TY, 17>(tt, P, u, v, acc); break;
             case 9: accumulate_rank1<TX, TY, 19>(tt, P, u, v, acc); break;
             default: accumulate_rank1<TX, TY, 21>(tt, P, u, v, acc); break;
+        }
+    } else if (fold) {
+        if constexpr (PACKED && TY == 4) {
+            const float2* w2 = reinterpret_cast<const float2*>(wsm);
+            switch (R) {
+                case 2: accumulate_rows_folded<TX, TY, 5>(tt, P, w2, acc); break;
+                case 3: accumulate_rows_folded<TX, TY, 7>(tt, P, w2, acc); break;
+                case 4: accumulate_rows_folded<TX, TY, 9>(tt, P, w2, acc); break;
+                case 5: accumulate_rows_folded<TX, TY, 11>(tt, P, w2, acc); break;
+                case 6: accumulate_rows_folded<TX, TY, 13>(tt, P, w2, acc); break;
+                case 7: accumulate_rows_folded<TX, TY, 15>(tt, P, w2, acc); break;
+                case 8: accumulate_rows_folded<TX, TY, 17>(tt, P, w2, acc); break;
+                case 9: accumulate_rows_folded<TX, TY, 19>(tt, P, w2, acc); break;
+                default: accumulate_rows_folded<TX, TY, 21>(tt, P, w2, acc); break;
+            }
         }
     } else if (PACKED && R >= 1) {
         const float2* w2 = reinterpret_cast<const float2*>(wsm);

@@ -171,7 +171,60 @@ static int move_slots(const float* src, const int32_t* idx_host, int n, int64_t 
     return OTF_OK;
 }
 
+// One pool step in ONE launch (realesrgan_model.py:430-447): for every listed slot of both queues, hand the stored
+// pair out (dequeue; skipped while the pool is still filling) and store the new pair in its place (enqueue).
+// grid = (chunks, n, 2): z selects the LQ or the GT queue.
+__global__ void __launch_bounds__(256) pool_exchange_kernel(float* __restrict__ q_lq, float* __restrict__ q_gt,
+                                                            const float* __restrict__ in_lq, const float* __restrict__ in_gt,
+                                                            float* __restrict__ out_lq, float* __restrict__ out_gt,
+                                                            int64_t lq_elems, int64_t gt_elems, const __grid_constant__ SlotIdx map) {
+    const int s = blockIdx.y;
+    const bool gt = blockIdx.z != 0;
+    const int64_t n = gt ? gt_elems : lq_elems;
+    float* qp = (gt ? q_gt : q_lq) + (int64_t)map.idx[s] * n;
+    const float* ip = (gt ? in_gt : in_lq) + (int64_t)s * n;
+    float* op = gt ? out_gt : out_lq;
+    if (op) op += (int64_t)s * n;
+    const bool vec = (n % 4 == 0) && ((((uintptr_t)qp | (uintptr_t)ip | (uintptr_t)op) & 15) == 0);
+    if (vec) {
+        const int64_t nq = n >> 2;
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+            const float4 fresh = __ldg(reinterpret_cast<const float4*>(ip) + q);
+            if (op) reinterpret_cast<float4*>(op)[q] = reinterpret_cast<const float4*>(qp)[q];
+            reinterpret_cast<float4*>(qp)[q] = fresh;
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            const float fresh = __ldg(ip + i);
+            if (op) op[i] = qp[i];
+            qp[i] = fresh;
+        }
+    }
+}
+
 }  // namespace otf
+
+extern "C" int otf_pool_exchange_f32(float* queue_lq, float* queue_gt, const int32_t* idx_host, int n, int64_t lq_elems,
+                                     int64_t gt_elems, const float* in_lq, const float* in_gt, float* out_lq, float* out_gt,
+                                     void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(queue_lq && queue_gt && idx_host && in_lq && in_gt, OTF_ERR_BAD_ARG, "pool_exchange: null pointer");
+    OTF_REQUIRE((out_lq == nullptr) == (out_gt == nullptr), OTF_ERR_BAD_ARG, "pool_exchange: give both outputs or neither");
+    OTF_REQUIRE(n > 0 && n <= 512 && lq_elems > 0 && gt_elems > 0, OTF_ERR_BAD_ARG, "pool_exchange: need 0 < n <= 512 (got %d)", n);
+    SlotIdx m;
+    memset(&m, 0, sizeof(m));
+    for (int i = 0; i < n; ++i) {
+        OTF_REQUIRE(idx_host[i] >= 0, OTF_ERR_BAD_ARG, "pool_exchange: negative slot index");
+        m.idx[i] = idx_host[i];
+    }
+    const int64_t big = gt_elems > lq_elems ? gt_elems : lq_elems;
+    int bx = ceil_div(big / 4 + 1, 256 * 4);
+    if (bx > 64) bx = 64;
+    pool_exchange_kernel<<<dim3(bx, n, 2), 256, 0, (cudaStream_t)stream>>>(queue_lq, queue_gt, in_lq, in_gt, out_lq, out_gt, lq_elems,
+                                                                        gt_elems, m);
+    OTF_LAUNCH_CHECK("pool_exchange_kernel");
+    return OTF_OK;
+}
 
 extern "C" int otf_abi_version(void) { return OTF_ABI_VERSION; }
 extern "C" const char* otf_last_error(void) { return otf::g_err; }

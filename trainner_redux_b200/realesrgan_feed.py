@@ -301,6 +301,19 @@ class SlotMover:
         arr = (C.c_int32 * n)(*idx)
         _lib.call("otf_scatter_slots_f32", _lib.ptr(_lib.dense_f32(src)), arr, n, dst[0].numel(), _lib.ptr(dst), _lib.stream())
 
+    def exchange(self, queue_lr: Tensor, queue_gt: Tensor, idx: Sequence[int], lq: Tensor, gt: Tensor,
+                 dequeue: bool) -> tuple[Tensor, Tensor]:
+        """One pool step in one launch: enqueue ``lq`` / ``gt`` into the listed slots and, when ``dequeue``, hand out
+        what they held (otherwise the new pair is passed through, as the reference does while the pool fills)."""
+        n = len(idx)
+        arr = (C.c_int32 * n)(*idx)
+        lq, gt = _lib.dense_f32(lq), _lib.dense_f32(gt)
+        lq_out = torch.empty_like(lq) if dequeue else None
+        gt_out = torch.empty_like(gt) if dequeue else None
+        _lib.call("otf_pool_exchange_f32", _lib.ptr(queue_lr), _lib.ptr(queue_gt), arr, n, lq[0].numel(), gt[0].numel(), _lib.ptr(lq),
+                  _lib.ptr(gt), _lib.ptr(lq_out), _lib.ptr(gt_out), _lib.stream())
+        return (lq_out, gt_out) if dequeue else (lq, gt)
+
 
 class PairPool:
     """Training pair pool (realesrgan_model.py:403-453) without the full-queue gather.
@@ -332,15 +345,19 @@ class PairPool:
             idx = self.randperm(self.queue_size).tolist()
             self.slot_of = [self.slot_of[i] for i in idx]
             slots = self.slot_of[:b]
+            if hasattr(self.mover, "exchange"):
+                return self.mover.exchange(self.queue_lr, self.queue_gt, slots, lq, gt, True)
             lq_out = self.mover.gather(self.queue_lr, slots)
             gt_out = self.mover.gather(self.queue_gt, slots)
             self.mover.scatter(self.queue_lr, slots, lq)
             self.mover.scatter(self.queue_gt, slots, gt)
             return lq_out, gt_out
         slots = self.slot_of[self.queue_ptr : self.queue_ptr + b]
+        self.queue_ptr += b
+        if hasattr(self.mover, "exchange"):
+            return self.mover.exchange(self.queue_lr, self.queue_gt, slots, lq, gt, False)
         self.mover.scatter(self.queue_lr, slots, lq)
         self.mover.scatter(self.queue_gt, slots, gt)
-        self.queue_ptr += b
         return lq, gt
 
 
