@@ -13,13 +13,26 @@ GT per GPU, scale 4, the classical second-order chain with every stage on:
 A "step" is one pass of that chain over one batch.  The batch shards per sample, so every rank
 runs its own batch with no collective on the data path ("scaling": "weak").
 
-One JSON line on stdout (rank 0).  `value` = pairs/s with inputs resident in HBM, `--streams` (default 4)
-batches in flight as CUDA-graph replays on as many streams (`value_one_batch_in_flight` = one stream);
-`e2e` = the same metric through RealESRGANFeed.feed_data() from pinned HOST fp32 buffers (H2D of the batch
-and its kernels prefetched on a copy stream) with the finished LQ read back every step; `e2e_u8` = the
-uint8-GT upload extension; `roofline` describes the dominant kernel (blur1 filter2d) from CUDA-event
-timings of graph replays; `cpu_baseline` is the oracle port of the reference pipeline on this box's host
-cores (`--impl reference` runs only that).
+EVERY number of the GPU arm goes through the product's public call, ``RealESRGANFeed.feed_data`` (the drop-in for
+traiNNer/models/realesrgan_model.py:455-650), with a plan drawn afresh for every step by the product's own
+``draw_plan`` — per-sample sigma / gray flags / JPEG qualities, crop offsets and the Philox position change every step;
+only the resize scale of stage 1 is pinned to the workload's 0.75.  The chain's shapes repeat, so feed_data replays its
+captured chain (trainner_redux_b200/chain_graph.py) after the second step.
+
+One JSON line on stdout (rank 0):
+  value                        pairs/s, inputs resident in HBM (rotating over 4 distinct batches), `--streams` (default 4)
+                               feed_data calls in flight on as many streams;
+  value_feed_data              the same loop on ONE stream (what a plain training loop gets);
+  value_graph_replay           bare replays of the same captured chains, no host work per step (upper bound);
+  e2e                          feed_data fed by the package's CUDAPrefetcher from pinned HOST fp32 batches (H2D inside the
+                               timed region, LQ read back to the host every step), wall clock;
+  e2e_u8                       the uint8-GT + kernel-parameter upload extension (SURVEY.md §8 f2/f4);
+  roofline                     the dominant kernel (blur1 filter2d) from CUDA-event timings of graph replays;
+  cpu_baseline / --impl reference   the oracle port of the reference pipeline on this box's host cores;
+  reference_torch_cuda         the same oracle (the reference's own ATen call sequence) run on the CUDA device: PyTorch-eager
+                               on the same B200, the GPU path a user of the reference has today;
+  parity                       final-LQ agreement of feed_data with the oracle on this workload (injected noise fields);
+  poisson, c3                  short runs of Config 2's Poisson variant and of BASELINE configs[2] (32 x 512^2 x2).
 """
 
 from __future__ import annotations
@@ -38,11 +51,55 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "degraded LR/HR pairs/sec at 256^2 GT x4"
 UNIT = "pairs/s"
-GT, SCALE, BATCH, GT_CROP = 256, 4, 64, 224
 S1, S2 = 0.75, 1.0
 N_ROTATE = int(os.environ.get("OTF_BENCH_ROTATE", "4"))  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
+
+
+class Workload:
+    """c2 (default, the config the metric is quoted on): B=64 x 256^2 GT x4 per GPU, weak scaling.
+    c3 (BASELINE.json configs[2]): ONE batch of 32 x 512^2 GT x2 sharded per sample over the ranks, strong scaling."""
+
+    def __init__(self, name: str, world: int, noise: str = "gaussian") -> None:
+        self.name, self.noise = name, noise
+        if name == "c3":
+            self.gt, self.scale, self.crop, self.scaling = 512, 2, 480, "strong"
+            self.batch = max(1, 32 // world)
+            self.metric = "degraded LR/HR pairs/sec at 512^2 GT x2 (batch 32 sharded over the ranks)"
+        else:
+            self.gt, self.scale, self.crop, self.scaling, self.batch = 256, 4, 224, "weak", 64
+            self.metric = "degraded LR/HR pairs/sec at 256^2 GT x4"
+
+    def describe(self) -> str:
+        lq = self.gt // self.scale
+        return (f"Real-ESRGAN OTF second-order chain incl. DiffJPEG + sinc, batch {self.batch} synthetic {self.gt}^2 GT x{self.scale} "
+                f"per GPU (blur1, bicubic x0.75, {self.noise}, jpeg, blur2, bilinear, {self.noise}, area->{lq}^2, sinc, jpeg, "
+                f"clamp/round, crop {self.crop}/{self.crop // self.scale})")
+
+    def config(self, batch: int | None = None) -> dict:
+        """Identical keys in both arms (the driver compares them)."""
+        return {"workload": self.describe(), "batch_per_step": batch or self.batch, "gt": self.gt, "scale": self.scale,
+                "noise": self.noise}
+
+    def options(self):
+        from trainner_redux_b200.realesrgan_feed import OTFOptions
+
+        g = 1.0 if self.noise == "gaussian" else 0.0
+        return OTFOptions(
+            scale=self.scale, gt_size=self.crop, queue_size=self.batch * 2, blur_prob=1.0, blur_prob2=1.0, gaussian_noise_prob=g,
+            noise_range=(1, 30), poisson_scale_range=(0.05, 3.0), gray_noise_prob=0.4, jpeg_prob=1.0, jpeg_range=(30, 95),
+            gaussian_noise_prob2=g, noise_range2=(1, 25), poisson_scale_range2=(0.05, 2.5), gray_noise_prob2=0.4, jpeg_prob2=1.0,
+            jpeg_range2=(30, 95), resize_prob=(0, 0, 1), resize_mode_list=["bicubic"], resize_mode_prob=[1.0], resize_prob2=(0, 0, 1),
+            resize_mode_list2=["bilinear"], resize_mode_prob2=[1.0], resize_mode_list3=["area"], resize_mode_prob3=[1.0],
+            final_jpeg_first_prob=0.0)
+
+    def algorithmic_bytes_per_pair(self) -> int:
+        """Stage-sum model of SURVEY.md §8d."""
+        a = 3 * self.gt * self.gt * 4
+        b1 = int(round(self.gt * S1)) ** 2 * 3 * 4
+        c = (self.gt // self.scale) ** 2 * 3 * 4
+        b2 = int(self.gt / self.scale * S2) ** 2 * 3 * 4
+        return 2 * a + (a + b1) + 2 * b1 + 2 * b1 + (b1 + b2) + (b2 + c) + 2 * c + 2 * c
 
 
 def peaks() -> dict:
@@ -54,7 +111,7 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "sm_max_mhz": 1965.0}
 
 
-def make_inputs(seed: int, batch: int, device=None):
+def make_inputs(wl: Workload, seed: int, device=None) -> dict:
     """Synthetic GT + kernels as SURVEY.md §8d specifies: U[0,1) GT; blur kernels from the reference's
     `random_mixed_kernels` distribution (default kernel_list / kernel_prob, odd sizes 7..21 zero-padded to 21,
     sinc_prob 0.1), final sinc w.p. 0.8 else the pulse.  The parameter tables are drawn once (dataset order);
@@ -62,7 +119,7 @@ def make_inputs(seed: int, batch: int, device=None):
     the oracle of those generators (device None) — the two agree to 1e-7 (tests/test_parity_gpu.py)."""
     from trainner_redux_b200.synthetic import synth_gt, synth_kernel_params
 
-    p1, p2, p3 = synth_kernel_params(batch, seed)
+    p1, p2, p3 = synth_kernel_params(wl.batch, seed)
     if device is None:
         from oracle import kernel_synth_oracle as KS  # CPU reference arm only
 
@@ -71,114 +128,90 @@ def make_inputs(seed: int, batch: int, device=None):
         from trainner_redux_b200.kernels import synthesize_kernels
 
         k1, k2, k3 = (synthesize_kernels(p, device).cpu() for p in (p1, p2, p3))
-    return {"gt": synth_gt(batch, GT, GT, "uniform", seed=1234 + seed), "kernel1": k1, "kernel2": k2, "sinc_kernel": k3}
+    return {"gt": synth_gt(wl.batch, wl.gt, wl.gt, "uniform", seed=1234 + seed), "kernel1": k1, "kernel2": k2, "sinc_kernel": k3,
+            "kernel_params": (p1, p2, p3)}
 
 
-NOISE = "gaussian"  # --noise poisson: the Poisson variant of SURVEY.md §8d Config 2 (scale ~ U[0.05, 3] / U[0.05, 2.5])
+def fixed_plan(wl: Workload, seed: int) -> dict:
+    """The workload's plan with seeded per-sample draws (the CPU arms and the parity check use it)."""
+    from trainner_redux_b200.realesrgan_feed import HostRNG, draw_plan
 
-
-def make_plan(batch: int, seed: int) -> dict:
-    g = torch.Generator().manual_seed(seed)
-    plan = _make_plan(batch, g)
-    if NOISE == "poisson":
-        for key, hi in (("noise1", 3.0), ("noise2", 2.5)):
-            plan[key] = {"kind": "poisson", "scale": torch.rand(batch, generator=g) * (hi - 0.05) + 0.05, "gray": plan[key]["gray"]}
+    plan = draw_plan(wl.options(), wl.batch, wl.gt, wl.gt, HostRNG(1000 + seed))
+    plan["resize1"] = {"scale": S1, "mode": "bicubic"}
+    plan["crop"] = (4, 4)
     return plan
 
 
-def _make_plan(batch: int, g) -> dict:
-    return {
-        "scale": SCALE, "gt_size": GT_CROP, "order": "classic", "blur1": True,
-        "resize1": {"scale": S1, "mode": "bicubic"},
-        "noise1": {"kind": "gaussian", "sigma": torch.rand(batch, generator=g) * 29 + 1, "gray": (torch.rand(batch, generator=g) < 0.4).float()},
-        "jpeg1": torch.rand(batch, generator=g) * 65 + 30, "blur2": True,
-        "resize2": {"scale": S2, "mode": "bilinear"},
-        "noise2": {"kind": "gaussian", "sigma": torch.rand(batch, generator=g) * 24 + 1, "gray": (torch.rand(batch, generator=g) < 0.4).float()},
-        "final_order": "resize_first", "resize3_mode": "area", "jpeg2": torch.rand(batch, generator=g) * 65 + 30,
-        "crop": (4, 4),
-    }
-
-
-def algorithmic_bytes_per_pair() -> int:
-    """Stage-sum model of SURVEY.md §8d (noise counted with its own read+write here because it is a
-    separate kernel in this round)."""
-    a = 3 * GT * GT * 4
-    b1 = int(round(GT * S1)) ** 2 * 3 * 4
-    c = (GT // SCALE) ** 2 * 3 * 4
-    b2 = int(GT / SCALE * S2) ** 2 * 3 * 4
-    return 2 * a + (a + b1) + 2 * b1 + 2 * b1 + (b1 + b2) + (b2 + c) + 2 * c + 2 * c
-
-
 # ------------------------------------------------------------------ CPU reference arm ----
-def cpu_chain_pairs_per_s(batch: int, steps: int, warmup: int, threads: int) -> tuple[float, float]:
-    """Times the oracle port of the reference pipeline (same plan, same inputs) on host cores."""
+def oracle_chain(wl: Workload, batch: int, steps: int, warmup: int, threads: int, device: str = "cpu", keep: dict | None = None):
+    """Times the oracle port of the reference pipeline (same plan shape, same inputs): (pairs/s, ms/step)."""
     from oracle import otf_oracle as O
 
     torch.set_num_threads(threads)
-    data = make_inputs(0, batch)
-    plan = make_plan(batch, 0)
+    data = {k: (v[:batch] if torch.is_tensor(v) else v) for k, v in make_inputs(wl, 0).items()}
+    plan = fixed_plan(wl, 0)
+    for key in ("noise1", "noise2"):
+        plan[key] = {k: (v[:batch] if torch.is_tensor(v) else v) for k, v in plan[key].items()}
+    plan["jpeg1"], plan["jpeg2"] = plan["jpeg1"][:batch], plan["jpeg2"][:batch]
     g = torch.Generator().manual_seed(0)
-    h1 = int(round(GT * S1))
-    h2 = int(GT / SCALE * S2)
+    h1, h2 = int(round(wl.gt * S1)), int(wl.gt / wl.scale * S2)
+    dev = torch.device(device)
+
+    def mv(v):
+        if torch.is_tensor(v):
+            return v.to(dev)
+        if isinstance(v, dict):
+            return {k: mv(x) for k, x in v.items()}
+        return v
+
+    d_dev, plan_dev = mv({k: data[k] for k in ("gt", "kernel1", "kernel2", "sinc_kernel")}), mv(plan)
 
     def one():
-        noise = {"noise1_color": torch.randn(batch, 3, h1, h1, generator=g), "noise1_gray": torch.randn(h1, h1, generator=g),
-                 "noise2_color": torch.randn(batch, 3, h2, h2, generator=g), "noise2_gray": torch.randn(h2, h2, generator=g)}
-        return O.run_chain_b(data["gt"], data["kernel1"], data["kernel2"], data["sinc_kernel"], plan, noise)
+        noise = {}
+        if wl.noise == "gaussian":
+            noise = {"noise1_color": torch.randn(batch, 3, h1, h1, generator=g), "noise1_gray": torch.randn(h1, h1, generator=g),
+                     "noise2_color": torch.randn(batch, 3, h2, h2, generator=g), "noise2_gray": torch.randn(h2, h2, generator=g)}
+        fields: dict = {} if keep is not None else None  # type: ignore[assignment]
+        out = O.run_chain_b(d_dev["gt"], d_dev["kernel1"], d_dev["kernel2"], d_dev["sinc_kernel"], plan_dev, mv(noise), fields=fields)
+        if keep is not None:
+            keep.update(plan=plan, data=data, fields=fields, out=out)
+        return out
 
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
     with torch.no_grad():
         for _ in range(warmup):
             one()
+        sync()
         t0 = time.perf_counter()
         for _ in range(steps):
             one()
+        sync()
         dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps * 1e3
 
 
-def run_reference(args) -> None:
+def run_reference(args, wl: Workload) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     # each step = one bounded sample of the workload, sized so that K + W steps end within ~2 minutes on this host
-    # (the port runs at roughly 22 pairs/s per host thread)
-    budget_pairs = 120.0 * 22.0 * threads
-    batch = BATCH
+    # (the port runs at roughly 22 pairs/s per host thread at 256^2)
+    budget_pairs = 120.0 * 22.0 * threads * (256.0 / wl.gt) ** 2
+    batch = wl.batch
     while batch > 1 and batch * (args.steps + args.warmup) > budget_pairs:
         batch //= 2
-    val, ms = cpu_chain_pairs_per_s(batch, args.steps, args.warmup, threads)
-    sample = f"each step = one batch of {batch} x {GT}^2 GT through the oracle port of the reference chain (torch CPU, {threads} threads)"
+    val, ms = oracle_chain(wl, batch, args.steps, args.warmup, threads)
+    sample = f"each step = one batch of {batch} x {wl.gt}^2 GT through the oracle port of the reference chain (torch CPU, {threads} threads)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "batch_per_step": batch, "gt": GT, "scale": SCALE},
+        "impl": "reference", "metric": wl.metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": wl.config(),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-SCALING = "weak"
-
-
-def set_workload(name: str, world: int) -> None:
-    """c2 (default, the config the metric is quoted on): B=64 x 256^2 GT x4 per GPU, weak scaling.
-    c3 (BASELINE.json configs[2]): ONE batch of 32 x 512^2 GT x2 sharded per sample over the ranks, strong scaling."""
-    global GT, SCALE, BATCH, GT_CROP, SCALING, METRIC
-    if name == "c3":
-        GT, SCALE, GT_CROP, SCALING = 512, 2, 480, "strong"
-        BATCH = max(1, 32 // world)
-        METRIC = "degraded LR/HR pairs/sec at 512^2 GT x2 (batch 32 sharded over the ranks)"
-
-
-def workload_name() -> str:
-    lq = GT // SCALE
-    return (f"Real-ESRGAN OTF second-order chain incl. DiffJPEG + sinc, batch {BATCH} synthetic {GT}^2 GT x{SCALE} per GPU "
-            f"(blur1, bicubic x0.75, {NOISE}, jpeg, blur2, bilinear, {NOISE}, area->{lq}^2, sinc, jpeg, clamp/round, "
-            f"crop {GT_CROP}/{GT_CROP // SCALE})")
 
 
 # ------------------------------------------------------------------------- clocks ----
@@ -190,14 +223,14 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
     def stop(self) -> dict:
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -218,20 +251,36 @@ class ClockSampler:
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # the sampler spans warm-up, the timed regions and the e2e loops: report the clock under load (upper half)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gpu_numa_node(index: int):
+    """(node, why): the NUMA node the GPU hangs off, from sysfs."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+        if not os.path.exists(path):
+            return None, f"{path} does not exist (PCI topology not exposed in this container)"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, f"{path} = {node}: the platform reports no NUMA affinity for this device (single-node guest)"
+        return node, "sysfs"
+    except Exception as e:  # noqa: BLE001
+        return None, f"{type(e).__name__}: {e}"
 
 
 def bind_to_gpu_numa_node(index: int):
     """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA
     node the GPU hangs off, so that N ranks do not all pull their H2D traffic through one socket."""
+    node, why = gpu_numa_node(index)
+    if node is None:
+        return None, why
     try:
-        pr = torch.cuda.get_device_properties(index)
-        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
             for part in f.read().strip().split(","):
@@ -240,19 +289,189 @@ def bind_to_gpu_numa_node(index: int):
         allowed = os.sched_getaffinity(0) & cpus
         if allowed:
             os.sched_setaffinity(0, allowed)
-            return node
-    except Exception:  # noqa: BLE001  (topology files missing in a container: stay unbound)
-        return None
-    return None
+            return node, f"bound to {len(allowed)} CPUs of node {node}"
+        return None, f"none of node {node}'s CPUs is in this process's affinity mask"
+    except Exception as e:  # noqa: BLE001
+        return None, f"{type(e).__name__}: {e}"
 
 
 # ---------------------------------------------------------------------------- main ----
-def run_b200(args) -> None:
+class Arm:
+    """One workload on this rank: device-resident inputs, a feed, and the loops that are timed."""
+
+    def __init__(self, wl: Workload, dev, rank: int, world: int, dist) -> None:
+        from trainner_redux_b200.realesrgan_feed import RealESRGANFeed, draw_plan
+
+        self.wl, self.dev, self.rank, self.world, self.dist = wl, dev, rank, world, dist
+        self.opt = wl.options()
+        self.feed = RealESRGANFeed(self.opt, device=dev, manual_seed=0, rank=rank, use_pool=False)
+        self.draw_plan = draw_plan
+        self.host = [make_inputs(wl, rank * N_ROTATE + i, dev) for i in range(N_ROTATE)]
+        keys = ("gt", "kernel1", "kernel2", "sinc_kernel")
+        self.devd = [{k: d[k].to(dev) for k in keys} for d in self.host]
+
+    def plan(self) -> dict:
+        """A fresh plan for this step from the product's own draw_plan: every host draw of the chain happens (per-sample
+        sigma, gray flags, qualities, crop offsets); the workload pins stage 1 to its x0.75 bicubic."""
+        p = self.draw_plan(self.opt, self.wl.batch, self.wl.gt, self.wl.gt, self.feed.rng)
+        p["resize1"] = {"scale": S1, "mode": "bicubic"}
+        return p
+
+    def step(self, i: int) -> None:
+        self.feed.feed_data(self.devd[i % N_ROTATE], plan=self.plan())
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, steps: int, n_streams: int, replay_only: bool = False) -> float:
+        """K steps, one batch each; max over ranks of the device time (CUDA events on the launching stream).  With
+        several streams consecutive feed_data calls run on different streams (step i on stream i % n): every call is the
+        whole chain of its own batch, but the tail of one step's small kernels overlaps the next step's work — what a
+        prefetching loader gets when it degrades batch i+1 while batch i is being consumed."""
+        main = torch.cuda.current_stream()
+        lanes = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else [main]
+        entries = list(self.feed.graphs.entries.values())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for ln in lanes:
+            if ln is not main:
+                ln.wait_stream(main)
+        for i in range(steps):
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                if replay_only:
+                    entries[i % len(entries)].graph.replay()
+                else:
+                    self.step(i)  # N_ROTATE is a multiple of the lane count: a captured chain always replays on the same lane
+        for ln in lanes:
+            if ln is not main:
+                main.wait_stream(ln)
+        e1.record()
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def pairs_per_s(self, steps: int, ms_total: float) -> float:
+        return self.world * self.wl.batch * steps / (ms_total / 1e3)
+
+    # ---- e2e: CUDAPrefetcher (pinned host batches -> static device slots on a copy stream) + feed_data + D2H of the LQ ----
+    def e2e(self, steps: int, warmup: int, u8: bool) -> tuple[float, int, int]:
+        from trainner_redux_b200.prefetch import CUDAPrefetcher
+
+        wl = self.wl
+        batches = []
+        for d in self.host:
+            if u8:  # extension: 8-bit GT (what the dataset decodes) + three (B,8) kernel-parameter tables
+                b = {"gt": (d["gt"] * 255.0).round().clamp(0, 255).to(torch.uint8).pin_memory(),
+                     "kernel_params": tuple(torch.as_tensor(p, dtype=torch.float64).pin_memory() for p in d["kernel_params"])}
+            else:  # the reference's host format: fp32 GT and three (B,21,21) kernels (realesrgan_dataset.py:213-219)
+                b = {k: d[k].pin_memory() for k in ("gt", "kernel1", "kernel2", "sinc_kernel")}
+            batches.append(b)
+        lq_host = torch.empty((wl.batch, 3, wl.crop // wl.scale, wl.crop // wl.scale), dtype=torch.float32).pin_memory()
+
+        def loader(n):
+            for i in range(n):
+                yield batches[i % N_ROTATE]
+
+        def run(n: int) -> int:
+            pf = CUDAPrefetcher(loader(n), device=self.dev, slots=2)
+            h2d = 0
+            batch = pf.next()
+            while batch is not None:
+                h2d = pf.h2d_bytes
+                self.feed.feed_data(batch, plan=self.plan())
+                lq_host.copy_(self.feed.lq, non_blocking=True)
+                batch = pf.next()
+            torch.cuda.synchronize()
+            return h2d
+
+        run(max(warmup, 4))  # (two static slots: the chain of each is captured on its second sighting)
+        self.barrier()
+        t0 = time.perf_counter()
+        h2d = run(steps)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        params_h2d = 16 + 4 * wl.batch * 6  # the chain's per-step parameter block (chain_graph.ParamBlock)
+        return self.world * wl.batch * steps / t.item(), h2d + params_h2d, lq_host.numel() * 4
+
+    # ---- per-stage GPU durations: every stage re-captured alone (x REP) and replayed, CUDA events ----
+    def stage_ms(self) -> dict:
+        feed = self.feed
+        feed.record_stage_fns = True
+        d, p = self.devd[0], self.plan()
+        for key in ("noise1", "noise2"):
+            p[key] = {k: (v.to(self.dev) if torch.is_tensor(v) else v) for k, v in p[key].items()}
+        p["jpeg1"], p["jpeg2"] = p["jpeg1"].to(self.dev), p["jpeg2"].to(self.dev)
+        from trainner_redux_b200.transforms import crop_pair
+
+        lq_full = feed.degrade(d["gt"], d["kernel1"], d["kernel2"], d["sinc_kernel"], p)
+        feed.stage_fns["crop"] = lambda: crop_pair(d["gt"], lq_full, self.wl.crop, self.wl.scale, 4, 4)
+        feed.record_stage_fns = False
+        torch.cuda.synchronize()
+        from trainner_redux_b200.degradations import pin_resize_tables
+
+        pin_resize_tables()
+        rep, out = 20, {}
+        side = torch.cuda.Stream()
+        for name, fn in feed.stage_fns.items():
+            g = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(rep):
+                        fn()
+            torch.cuda.current_stream().wait_stream(side)
+            g.replay()
+            best = float("inf")
+            for _ in range(3):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                g.replay()
+                s1.record()
+                torch.cuda.synchronize()
+                best = min(best, s0.elapsed_time(s1) / rep)
+            out[name] = best
+            del g
+        feed.stage_fns = {}
+        return out
+
+    def executed_ops(self) -> dict:
+        """FP32-pipe lane operations the blur1 launch EXECUTES per output pixel, from the device-side kernel analysis
+        (true radius R, rank-1 and mirror-symmetry flags): dense K^2 FMAs; rank-1 K + K(4+K-1)/4 (the horizontal pass runs
+        once per image row of the 4-row register block); folded K(R+1) FMAs + R(4+K-1)/4 adds."""
+        from trainner_redux_b200.img_process_util import KernelAnalysis
+
+        k1 = self.devd[0]["kernel1"]
+        ka = KernelAnalysis([k1])
+        torch.cuda.synchronize()
+        kb = k1.size(0)
+        s = ka.scratch[: 3 * kb].cpu().tolist()
+        ops, kinds = 0.0, {"rank1": 0, "folded": 0, "dense": 0, "identity": 0}
+        for r, fl in zip(s[:kb], s[2 * kb:3 * kb]):
+            kt = 2 * r + 1
+            if r == 0:
+                ops, kinds["identity"] = ops + 1, kinds["identity"] + 1
+            elif r >= 2 and fl & 1:
+                ops, kinds["rank1"] = ops + kt + kt * (4 + kt - 1) / 4, kinds["rank1"] + 1
+            elif r >= 2 and fl & 2:
+                ops, kinds["folded"] = ops + kt * (r + 1) + r * (4 + kt - 1) / 4, kinds["folded"] + 1
+            else:
+                ops, kinds["dense"] = ops + kt * kt, kinds["dense"] + 1
+        return {"lane_ops_per_output_mean": ops / kb, "kinds": kinds,
+                "nonzero_taps_mean": float((k1 != 0).flatten(1).sum(1).float().mean().item())}
+
+
+def run_b200(args, wl: Workload) -> None:
     import torch.distributed as dist
 
     from trainner_redux_b200 import _lib
-    from trainner_redux_b200.realesrgan_feed import OTFOptions, RealESRGANFeed
-    from trainner_redux_b200.transforms import crop_pair
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -261,245 +480,117 @@ def run_b200(args) -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
+    sampler = ClockSampler(local) if rank == 0 else None  # spans warm-up, every timed region and the e2e loops
+    numa, numa_why = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
     if world > 1:
-        # stdout carries the one JSON line only: NCCL's banner ("NCCL version ...", NCCL_DEBUG output) goes to stderr —
-        # file descriptor 1 points at stderr while the communicator is created
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        # NCCL's banner lines go wherever NCCL sends them (stderr); stdout carries the one JSON line, printed last
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
     _lib.load()
 
-    feed = RealESRGANFeed(OTFOptions(scale=SCALE, gt_size=GT_CROP, queue_size=BATCH * 2), device=dev, manual_seed=0, rank=rank,
-                          use_pool=False)
-    feed.stage_times = {}
-    host = [make_inputs(rank * N_ROTATE + i, BATCH, dev) for i in range(N_ROTATE)]
-    for d in host:
-        for k in d:
-            d[k] = d[k].pin_memory()
-    devd = [{k: v.to(dev) for k, v in d.items()} for d in host]
-    plans = []
-    for i in range(N_ROTATE):
-        p = make_plan(BATCH, rank * N_ROTATE + i)
-        for key in ("noise1", "noise2"):
-            for kk in ("sigma", "scale", "gray"):
-                if kk in p[key]:
-                    p[key][kk] = p[key][kk].to(dev)
-        for key in ("jpeg1", "jpeg2"):
-            p[key] = p[key].to(dev)
-        plans.append(p)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_resident(i: int):
-        d, p = devd[i % N_ROTATE], plans[i % N_ROTATE]
-        lq_full = feed.degrade(d["gt"], d["kernel1"], d["kernel2"], d["sinc_kernel"], p)
-        return crop_pair(d["gt"], lq_full, GT_CROP, SCALE, *p["crop"])
-
-    # ---- value: device-resident inputs, CUDA events, max over ranks ----
-    # The chain has fixed shapes here, so each rotated input set is captured once into a CUDA graph
-    # (one launch of ~16 kernel nodes per step) and the timed region replays the graphs.  --no-graph
-    # times the eager Python-driven launches instead.
-    for i in range(max(args.warmup, N_ROTATE)):
-        step_resident(i)
-    barrier()
-    graphs, graph_out, kernels_per_step = [], [], None
-    if not args.no_graph:
-        from trainner_redux_b200.degradations import pin_resize_tables
-
-        pin_resize_tables()  # the warm-up steps filled the weight-table cache; captured graphs may read it
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(N_ROTATE):
-                g = torch.cuda.CUDAGraph()
-                l_before = _lib.launch_count
-                with torch.cuda.graph(g, stream=side):
-                    graph_out.append(step_resident(i))
-                kernels_per_step = _lib.launch_count - l_before
-                graphs.append(g)
-        torch.cuda.current_stream().wait_stream(side)
-        for i in range(args.warmup):
-            graphs[i % N_ROTATE].replay()
-    barrier()
-    def timed_region(n_streams: int) -> float:
-        """K steps, one batch each.  With 2 streams consecutive batches overlap (step i on stream i % 2): every
-        batch runs the identical chain, but the tail of one step's small kernels fills with the next step's work —
-        what a prefetching loader gets when it degrades batch i+1 while batch i is being consumed."""
-        main = torch.cuda.current_stream()
-        lanes = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else [main]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for ln in lanes:
-            if ln is not main:
-                ln.wait_stream(main)
-        for i in range(args.steps):
-            with torch.cuda.stream(lanes[i % len(lanes)]):
-                if graphs:
-                    graphs[i % N_ROTATE].replay()  # lanes divides N_ROTATE: a graph always replays on the same lane
-                else:
-                    step_resident(i)
-        for ln in lanes:
-            if ln is not main:
-                main.wait_stream(ln)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    l0 = _lib.launch_count
-    n_streams = 1 if args.no_graph else max(1, min(args.streams, N_ROTATE))
+    arm = Arm(wl, dev, rank, world, dist)
+    n_streams = max(1, min(args.streams, N_ROTATE))
     while N_ROTATE % n_streams:
         n_streams -= 1
-    ms_total = timed_region(n_streams)
-    launches = kernels_per_step * args.steps if graphs else _lib.launch_count - l0
-    clocks = sampler.stop() if sampler else None
-    value = world * BATCH * args.steps / (ms_total / 1e3)
-    ms_single = timed_region(1) if n_streams > 1 else ms_total
-    value_single = world * BATCH * args.steps / (ms_single / 1e3)
-    # per-stage GPU durations for the roofline.  CUDA events cannot be read back from inside a replayed
-    # graph, and around eager launches they would include the Python launch gap, so every stage of the
-    # chain (on the tensors of one real pass) is re-captured into its own graph of REP launches and that
-    # graph's replay is timed with an event pair: kernel time only, measured live in this run.
-    feed.record_stage_fns = not args.no_stage_timing
-    step_resident(0)
-    feed.record_stage_fns = False
-    torch.cuda.synchronize()
-    REP = 20
-    stage_ms = {}
-    side = torch.cuda.Stream()
-    for name, fn in feed.stage_fns.items():
-        g = torch.cuda.CUDAGraph()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            fn()
-            with torch.cuda.graph(g, stream=side):
-                for _ in range(REP):
-                    fn()
-        torch.cuda.current_stream().wait_stream(side)
-        g.replay()
-        best = float("inf")
-        for _ in range(3):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            g.replay()
-            s1.record()
-            torch.cuda.synchronize()
-            best = min(best, s0.elapsed_time(s1) / REP)
-        stage_ms[name] = best
-        del g
-    feed.stage_fns = {}
+    for i in range(max(args.warmup, 3 * N_ROTATE)):  # every rotated input set is seen (and its chain captured) before timing
+        arm.step(i)
+    arm.barrier()
+    arm.timed(min(args.steps, 2 * N_ROTATE), n_streams)  # lanes warmed up
+    l0 = _lib.launch_count
+    ms_total = arm.timed(args.steps, n_streams)
+    launches = _lib.launch_count - l0
+    value = arm.pairs_per_s(args.steps, ms_total)
+    ms_single = arm.timed(args.steps, 1)
+    ms_replay = arm.timed(args.steps, n_streams, replay_only=True) if arm.feed.graphs.entries else float("nan")
+    graphs = arm.feed.graphs
+    stage_ms = {} if args.no_stage_timing else arm.stage_ms()
 
-    # ---- e2e: feed_data() from pinned HOST buffers + D2H of the LQ batch, wall clock, max over ranks ----
-    # As in the reference's training loop the upload of batch i+1 overlaps the degradation of batch i
-    # (CUDAPrefetcher: side-stream H2D joined by wait_stream, prefetch_dataloader.py:476-493); the GT
-    # crop stays on the device for the network, the LQ result is read back every step.
-    lq_host = torch.empty((BATCH, 3, GT_CROP // SCALE, GT_CROP // SCALE), dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream()
-    plans_host = [make_plan(BATCH, rank * N_ROTATE + i) for i in range(N_ROTATE)]
+    e2e_value, h2d, d2h = arm.e2e(args.steps, args.warmup, u8=False)
+    e2e_u8_value, h2d_u8, _ = arm.e2e(args.steps, args.warmup, u8=True)
 
-    def upload(i: int):
-        with torch.cuda.stream(copy_stream):
-            d = {k: v.to(dev, non_blocking=True) for k, v in host[i % N_ROTATE].items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return d, ev
-
-    def run_e2e(n: int):
-        nxt = upload(0)
-        for i in range(n):
-            d, ev = nxt
-            if i + 1 < n:
-                nxt = upload(i + 1)
-            torch.cuda.current_stream().wait_event(ev)
-            for v in d.values():
-                v.record_stream(torch.cuda.current_stream())
-            feed.feed_data(d, plan=plans_host[i % N_ROTATE])
-            lq_host.copy_(feed.lq, non_blocking=True)
-        torch.cuda.synchronize()
-
-    def timed_e2e() -> float:
-        run_e2e(args.warmup)
-        barrier()
-        t0 = time.perf_counter()
-        run_e2e(args.steps)
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * BATCH * args.steps / t.item()
-
-    e2e_value = timed_e2e()
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values()) + 6 * BATCH * 4
-    d2h = lq_host.numel() * 4
-    # extension, reported beside the contract's fp32 number: the same loop with the GT batch uploaded as uint8
-    # (what the dataset decodes) and normalised on the device — SURVEY.md §8 f4
-    for d in host:
-        d["gt"] = (d["gt"] * 255.0).round().clamp(0, 255).to(torch.uint8).pin_memory()
-    e2e_u8_value = timed_e2e()
-    h2d_u8 = sum(v.numel() * v.element_size() for v in host[0].values()) + 6 * BATCH * 4
+    extras = {}
+    if not args.no_extras and wl.name == "c2" and wl.noise == "gaussian":
+        # short runs of the two other workloads SURVEY.md §8d names, so that they are measured by the same command
+        for key, w2 in (("poisson", Workload("c2", world, "poisson")), ("c3", Workload("c3", world))):
+            a2 = Arm(w2, dev, rank, world, dist)
+            for i in range(3 * N_ROTATE):
+                a2.step(i)
+            n2 = max(20, min(args.steps, 200))
+            a2.timed(2 * N_ROTATE, n_streams)
+            ms2 = a2.timed(n2, n_streams)
+            extras[key] = {"metric": w2.metric, "value": a2.pairs_per_s(n2, ms2), "unit": UNIT, "ms_per_step": ms2 / n2, "steps": n2,
+                           "scaling": w2.scaling, "config": w2.config()}
+            del a2
+            torch.cuda.empty_cache()
 
     if rank == 0:
         pk = peaks()
         k_ms = stage_ms.get("blur1", float("nan"))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):  # dram__bytes_read+write of this kernel from the committed ncu --set full capture
+        if os.path.exists(tpath):  # dram__bytes_read+write of this kernel from the committed ncu --set full capture, per workload
             with open(tpath) as f:
-                traffic = json.load(f).get("filter2d_blur1_dram_bytes_per_launch")
-        blur_bytes = BATCH * (2 * 3 * GT * GT * 4 + 21 * 21 * 4)
+                traffic = (json.load(f).get(wl.name) or {}).get("filter2d_blur1_dram_bytes_per_launch")
+        blur_bytes = wl.batch * (2 * 3 * wl.gt * wl.gt * 4 + 21 * 21 * 4)
         achieved = blur_bytes / (k_ms * 1e-3) / 1e9
-        true_k2 = float((devd[0]["kernel1"] != 0).flatten(1).sum(1).float().mean().item())
-        flops = 2.0 * 21 * 21 * 3 * GT * GT * BATCH
+        ex = arm.executed_ops()
+        outputs = 3.0 * wl.gt * wl.gt * wl.batch
         fma_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-        chain_bytes = algorithmic_bytes_per_pair()
-        cpu = None
+        exec_tflops = 2.0 * ex["lane_ops_per_output_mean"] * outputs / (k_ms * 1e-3) / 1e12
+        chain_bytes = wl.algorithmic_bytes_per_pair()
+        cpu = parity = torch_cuda = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cval, cms = cpu_chain_pairs_per_s(BATCH, 8, 1, threads)
+            keep: dict = {}
+            n_cpu = 8 if wl.gt <= 256 else 2
+            cval, cms = oracle_chain(wl, wl.batch, n_cpu, 1, threads, keep=keep)
             cpu = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"8 batches of {BATCH} x {GT}^2 GT (+1 warm-up) through the oracle port of the reference chain, torch CPU {threads} threads, {cms:.0f} ms/batch"}
+                   "sample": f"{n_cpu} batches of {wl.batch} x {wl.gt}^2 GT (+1 warm-up) through the oracle port of the reference chain, torch CPU {threads} threads, {cms:.0f} ms/batch"}
+            # parity on this very workload: feed_data with the oracle's finished noise fields injected vs the oracle's LQ
+            from trainner_redux_b200.realesrgan_feed import RealESRGANFeed
+
+            pf = RealESRGANFeed(arm.opt, device=dev, use_pool=False)
+            pf.feed_data({k: keep["data"][k] for k in ("gt", "kernel1", "kernel2", "sinc_kernel")}, plan=keep["plan"],
+                         inject={k: v.to(dev) for k, v in keep["fields"].items()})
+            diff = (pf.lq.cpu() - keep["out"][1]).abs()
+            parity = {"lq_within_1lsb_frac": (diff <= 1 / 255 + 1e-6).float().mean().item(), "max_lsb": diff.max().item() * 255,
+                      "gt_crop_bit_identical": bool(torch.equal(pf.gt.cpu(), keep["out"][0])), "bar": 0.999,
+                      "how": "feed_data vs oracle.run_chain_b, same plan / inputs / injected noise fields, full batch"}
+            tval, tms = oracle_chain(wl, wl.batch, 5, 2, threads, device=f"cuda:{local}")
+            torch_cuda = {"value": tval, "unit": UNIT, "ms_per_step": tms,
+                          "what": "the oracle's ATen call sequence (= the reference's primitives) on the CUDA device: PyTorch-eager on this B200"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
+            "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "batch_per_gpu": BATCH, "gt": GT, "scale": SCALE,
-                       "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * BATCH * 3 * GT * GT * 4 / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "eager" if args.no_graph else f"CUDA graph replay ({kernels_per_step} kernels/step), {n_streams} batches in flight on {n_streams} streams; stage_ms: each stage re-captured alone (x20) and replayed",
-                       "parallelism": f"per-sample shards x{world}, no collective", "numa_node_rank0": numa},
-            "value_one_batch_in_flight": value_single, "ms_per_step_one_batch_in_flight": ms_single / args.steps,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "config": dict(wl.config(),
+                           l2=f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * wl.batch * 3 * wl.gt * wl.gt * 4 / 1e6:.0f} MB > 126 MB L2)",
+                           launch=f"RealESRGANFeed.feed_data, a fresh draw_plan per step, captured chains replayed ({graphs.captures} captures, "
+                                  f"{graphs.hits} replays so far), {n_streams} calls in flight on {n_streams} streams",
+                           parallelism=f"per-sample shards x{world}, no collective", numa_node_rank0=numa, numa_note=numa_why),
+            "value_feed_data": arm.pairs_per_s(args.steps, ms_single), "ms_per_step_feed_data": ms_single / args.steps,
+            "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_gbs_per_rank": h2d * e2e_value / world / wl.batch / 1e9},
             "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
-                       "note": "extension: uint8 GT upload + on-device /255 (not the reference's fp32 host format)"},
+                       "h2d_gbs_per_rank": h2d_u8 * e2e_u8_value / world / wl.batch / 1e9,
+                       "note": "extension: uint8 GT + kernel-parameter tables uploaded, /255 and kernel synthesis on the device (not the reference's fp32 host format)"},
             "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"kernel": f"filter2d_kernel (blur1, {BATCH}x3x{GT}x{GT}, per-sample kernels zero-padded to 21x21: default kernel_list mix, sizes 7..21)", "bound": "hbm",
-                         "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "clocks": sampler.stop() if sampler else None,
+            "roofline": {"kernel": f"filter2d_kernel (blur1, {wl.batch}x3x{wl.gt}x{wl.gt}, per-sample kernels zero-padded to 21x21: default kernel_list mix, sizes 7..21)",
+                         "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": traffic, "peak_source": pk["source"], "ms_per_launch": k_ms,
-                         "fma": {"achieved_tflops_true_taps": flops * (true_k2 / 441.0) / (k_ms * 1e-3) / 1e12,
-                                 "frac_of_fma_peak": flops * (true_k2 / 441.0) / (k_ms * 1e-3) / 1e12 / fma_peak,
-                                 "peak_tflops": fma_peak, "mean_nonzero_taps": true_k2,
-                                 "note": "filter2d is FP32-FMA bound above K~9 (SURVEY.md H1); both roofs reported"}},
+                         "fma": {"executed_tflops": exec_tflops, "frac_of_fma_peak": exec_tflops / fma_peak, "peak_tflops": fma_peak,
+                                 **ex, "note": "filter2d is FP32-FMA bound above K~9 (SURVEY.md H1); executed FP32-pipe operations, not nominal K^2 taps"}},
             "chain": {"algorithmic_bytes_per_pair": chain_bytes, "achieved_gbs": chain_bytes * value / world / 1e9,
-                      "frac_of_hbm_peak": chain_bytes * value / world / 1e9 / pk["hbm_gbs"], "stage_ms": stage_ms},
-            "cpu_baseline": cpu,
+                      "frac_of_hbm_peak": chain_bytes * value / world / 1e9 / pk["hbm_gbs"], "stage_ms": stage_ms,
+                      "kernels_per_step": launches / args.steps},
+            "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "parity": parity, **extras,
         }
         print(json.dumps(line), flush=True)
+    elif sampler:
+        sampler.stop()
     if world > 1:
         dist.destroy_process_group()
 
@@ -513,18 +604,16 @@ def main() -> None:
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: 64 x 256^2 x4 per GPU (default); c3: 32 x 512^2 x2 sharded")
     ap.add_argument("--noise", default="gaussian", choices=["gaussian", "poisson"], help="noise kind of both noise stages")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--streams", type=int, default=4, help="batches in flight during the timed region (graph mode)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short Poisson / c3 runs of the default line")
+    ap.add_argument("--streams", type=int, default=4, help="feed_data calls in flight during the timed region")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-capture pass (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    set_workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")))
-    global NOISE
-    NOISE = args.noise
+    wl = Workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")), args.noise)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_b200(args)
+        run_b200(args, wl)
 
 
 if __name__ == "__main__":

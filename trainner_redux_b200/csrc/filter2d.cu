@@ -209,7 +209,7 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_t
 // (acc[2p][ox], acc[2p+1][ox]).  Each lane is an ordinary IEEE fp32 FMA: results are bit-identical
 // to the scalar loop.
 #ifndef OTF_F2D_MINB
-#define OTF_F2D_MINB 4
+#define OTF_F2D_MINB 5
 #endif
 constexpr int kW2Pitch = 24;  // float2 per paired tap row
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {

@@ -92,8 +92,9 @@ def draw_kernel_params(opt: Any, batch: int, py, nprng) -> tuple[np.ndarray, np.
     return np.asarray(p1, np.float64), np.asarray(p2, np.float64), np.asarray(p3, np.float64)
 
 
-def synthesize_kernels(params: np.ndarray | Tensor, device: torch.device | str = "cuda") -> Tensor:
-    """(B,8) parameter table -> (B,21,21) fp32 kernels on the device (one launch)."""
+def synthesize_kernels(params: np.ndarray | Tensor, device: torch.device | str = "cuda", out: Tensor | None = None) -> Tensor:
+    """(B,8) parameter table -> (B,21,21) fp32 kernels on the device (one launch).  ``out``: write into this buffer
+    (feed_data keeps one per upload slot so that the kernels' addresses repeat and its captured chains are replayed)."""
     t = torch.as_tensor(params, dtype=torch.float64)
     if t.dim() != 2 or t.size(1) != 8:
         raise ValueError("params must have shape (B, 8)")
@@ -101,6 +102,7 @@ def synthesize_kernels(params: np.ndarray | Tensor, device: torch.device | str =
     if dev.type != "cuda":
         raise RuntimeError("kernel synthesis runs on a CUDA device only (no CPU fallback)")
     t = t.contiguous().to(dev, non_blocking=True)
-    out = torch.empty((t.size(0), 21, 21), dtype=torch.float32, device=dev)
+    if out is None or tuple(out.shape) != (t.size(0), 21, 21) or out.dtype != torch.float32 or not out.is_contiguous():
+        out = torch.empty((t.size(0), 21, 21), dtype=torch.float32, device=dev)
     _lib.call("otf_synth_kernels_f32", _lib.ptr(t), t.size(0), _lib.ptr(out), _lib.stream())
     return out
