@@ -23,7 +23,8 @@ One JSON line on stdout (rank 0):
   value                        pairs/s, inputs resident in HBM (rotating over 4 distinct batches), `--streams` (default 4)
                                feed_data calls in flight on as many streams;
   value_feed_data              the same loop on ONE stream (what a plain training loop gets);
-  value_graph_replay           bare replays of the same captured chains, no host work per step (upper bound);
+  value_graph_replay[_one_stream]  bare replays of the same captured chains, no host work per step (upper bounds of the two above);
+  pcie_measured_gbs            raw pinned-host <-> device copy bandwidth of this box (the ceiling of e2e);
   e2e                          feed_data fed by the package's CUDAPrefetcher from pinned HOST fp32 batches (H2D inside the
                                timed region, LQ read back to the host every step), wall clock;
   e2e_u8                       the uint8-GT + kernel-parameter upload extension (SURVEY.md §8 f2/f4);
@@ -355,6 +356,25 @@ class Arm:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t.item()
 
+    def pcie_gbs(self) -> dict:
+        """Raw pinned-host <-> device copy bandwidth of THIS box's link (256 MB, best of 3, CUDA events): the ceiling the
+        end-to-end number is measured against."""
+        n = 64 * 1024 * 1024
+        h = torch.empty(n, dtype=torch.float32).pin_memory()
+        d = torch.empty(n, dtype=torch.float32, device=self.dev)
+        out = {}
+        for name, (dst, src) in (("h2d", (d, h)), ("d2h", (h, d))):
+            best = float("inf")
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dst.copy_(src, non_blocking=True)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name] = n * 4 / best / 1e6
+        return out
+
     def pairs_per_s(self, steps: int, ms_total: float) -> float:
         return self.world * self.wl.batch * steps / (ms_total / 1e3)
 
@@ -502,6 +522,8 @@ def run_b200(args, wl: Workload) -> None:
     launches = _lib.launch_count - l0
     value = arm.pairs_per_s(args.steps, ms_total)
     ms_single = arm.timed(args.steps, 1)
+    ms_replay1 = arm.timed(args.steps, 1, replay_only=True) if arm.feed.graphs.entries else float("nan")
+    pcie = arm.pcie_gbs()
     ms_replay = arm.timed(args.steps, n_streams, replay_only=True) if arm.feed.graphs.entries else float("nan")
     graphs = arm.feed.graphs
     stage_ms = {} if args.no_stage_timing else arm.stage_ms()
@@ -571,6 +593,8 @@ def run_b200(args, wl: Workload) -> None:
                            parallelism=f"per-sample shards x{world}, no collective", numa_node_rank0=numa, numa_note=numa_why),
             "value_feed_data": arm.pairs_per_s(args.steps, ms_single), "ms_per_step_feed_data": ms_single / args.steps,
             "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,
+            "value_graph_replay_one_stream": arm.pairs_per_s(args.steps, ms_replay1),
+            "pcie_measured_gbs": pcie,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "h2d_gbs_per_rank": h2d * e2e_value / world / wl.batch / 1e9},
             "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,

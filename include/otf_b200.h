@@ -126,6 +126,17 @@ int otf_resize_tables_f32(int H, int W, int OH, int OW, int mode, void* workspac
 int otf_resize_f32(const float* img, int planes, int H, int W,
                    float* out, int OH, int OW, int mode, int clamp01,
                    void* workspace_dev, int64_t workspace_bytes, int tables_ready, void* stream);
+/* a3 + a4 in ONE launch: the resampler with the Gaussian-noise stage that follows it in the chain
+ * (realesrgan_model.py:531-546, :553-562: resize_pt then add_gaussian_noise_pt) as its epilogue — the resampled,
+ * clamped pixel gets its noise and the noise tail before it is stored, so the intermediate image never reaches HBM.
+ * The Philox positions are otf_gaussian_noise_f32's: the result is BIT-IDENTICAL to otf_resize_f32 followed by
+ * otf_gaussian_noise_f32(sigma_dev, gray_dev, seed, offset, offset_dev, noise_flags).  Only the plain / clip tails
+ * (noise_flags = 0 or OTF_NOISE_CLIP) and generated fields are fused. */
+int otf_resize_gauss_f32(const float* img, int B, int C, int H, int W,
+                         float* out, int OH, int OW, int mode, int clamp01,
+                         void* workspace_dev, int64_t workspace_bytes, int tables_ready,
+                         const float* sigma_dev, const float* gray_dev, uint64_t seed, uint64_t offset,
+                         const uint64_t* offset_dev, int noise_flags, void* stream);
 
 /* ---- a4: Gaussian noise — degradations.py:569-633 -----------------------------
  * out = tail(img + mix(N*sigma[b]/255, G*sigma[b]/255, gray[b])).
@@ -188,6 +199,16 @@ int otf_diffjpeg_f32(const float* img, int B, int H, int W,
                      const float* factor_dev, float factor_scalar, int factor_is_quality,
                      int differentiable, int clamp_in, int round8_out, float* out, void* stream);
 
+/* The chain's usual last three steps in ONE launch: DiffJPEG with the 8-bit lattice on its output (a6 + a7), the LQ crop
+ * window stored straight into the dense (B,3,p,p) `lq_out`, and the GT crop window (a8) copied by the CTAs behind the
+ * codec's.  Arguments as otf_diffjpeg_f32 (round8_out implied) + otf_crop_pair_f32.  The GT patch must be a multiple of 4
+ * pixels wide. */
+int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
+                               const float* factor_dev, float factor_scalar, int factor_is_quality,
+                               int differentiable, int clamp_in,
+                               const float* gt, int Hg, int Wg, int top, int left, const int32_t* top_left_dev,
+                               int lq_patch, int scale, float* gt_out, float* lq_out, void* stream);
+
 /* ---- a7: clamp/round — traiNNer/models/realesrgan_model.py:616 ----------------
  * out = clamp(round(x*255),0,255)/255, round half to even. In place allowed. */
 int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* stream);
@@ -196,10 +217,11 @@ int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* stream);
  * Copies the LQ window (top,left,p,p) and the GT window (top*scale,left*scale,
  * p*scale...) into dense outputs in one launch.  top_left_dev (int32[2] on the device, may be NULL)
  * overrides (top, left): a captured launch then follows the offsets the caller uploads per step (they are
- * clamped to the valid range on the device; the host validates them when it draws them). */
+ * clamped to the valid range on the device; the host validates them when it draws them).  lq_round8 != 0 applies
+ * the 8-bit lattice of a7 to the LQ window on the way (clamp/round + crop in one launch). */
 int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
                       const float* lq, int Hl, int Wl,
-                      int top, int left, const int32_t* top_left_dev, int lq_patch, int scale,
+                      int top, int left, const int32_t* top_left_dev, int lq_patch, int scale, int lq_round8,
                       float* gt_out, float* lq_out, void* stream);
 
 /* uint8 image -> fp32 / 255 (the host-side normalisation of traiNNer/utils/img_util.py:65-109 `img2tensor`,
@@ -292,6 +314,11 @@ typedef struct OtfStage {
 int64_t otf_run_stages_workspace_bytes(int B, int C, int H, int W, const OtfStage* stages, int nstages);
 int otf_run_stages_f32(const float* img, int B, int C, int H, int W, const OtfStage* stages, int nstages,
                        void* workspace_dev, int64_t workspace_bytes, int* final_h, int* final_w, void* stream);
+/* Kernels the calling thread's last otf_run_stages_f32 launched.  The executor fuses adjacent stages where a fused
+ * kernel exists (resize + Gaussian noise; DiffJPEG + clamp/round + both crops; clamp/round + both crops; a same-size
+ * resize of a clamped image is dropped): fewer launches, bit-identical results.  OTF_FUSE=0 in the environment turns
+ * the fusions off (the unfused path the tests compare against). */
+int otf_run_stages_launches(void);
 
 /* ---- f3: fork extras — traiNNer/models/paragon_otf_degradations.py:251-572 ----------------
  * otf_warp_f32: analytic sampling grid + F.grid_sample(bilinear, align_corners=False) in one pass.

@@ -78,7 +78,7 @@ rows = []
 
 def add(name, fn, nbytes, flops=None, x=None):
     """fn(x) runs the kernel on input tensor x; x is cloned into the rotation buffers."""
-    if args.only and args.only not in name:
+    if args.only and not any(o in name for o in args.only.split(",")):
         return
     xs = {}
 
@@ -147,6 +147,34 @@ usm = T.USMSharp().to(dev)
 add("usm 256^2 (4 launches)", lambda t: usm(t), 2 * N(x256), x=x256)
 add("clamp_round 64^2", lambda t: clamp_round(t), 2 * N(x64), x=x64)
 add("crop_pair 256/64 -> 224/56", lambda t: crop_pair(t, x64, 224, 4, 4, 4), 2 * B * 3 * (224 * 224 + 56 * 56) * 4, x=x256)
+
+# ---- row g1: the executor's fused launches beside the launches they replace ---------------------------------------
+from trainner_redux_b200 import _lib as L  # noqa: E402
+
+
+def _fused_resize_gauss(t, oh, mode_id, gp, fused=True):
+    b, c, h, w = t.shape
+    tab = D.pinned_resize_table(dev, h, w, oh, oh, mode_id)
+    nb = L.load().otf_resize_workspace_bytes(h, w, oh, oh, mode_id)
+    out = torch.empty(b, c, oh, oh, device=dev)
+    L.call("otf_resize_gauss_f32", L.ptr(t), b, c, h, w, L.ptr(out), oh, oh, mode_id, 1, L.ptr(tab), nb, 1, L.ptr(sigma), L.ptr(gp),
+           7, 1, None, L.NOISE_CLIP, L.stream())
+    return out
+
+
+for gp, lab in ((None, "colour"), (gray, "40% gray")):
+    add(f"g1 resize bicubic 256->192 + gaussian {lab} (1 launch)", lambda t, gp=gp: _fused_resize_gauss(t, 192, L.RESIZE_BICUBIC_AA, gp),
+        N(x256) + N(x192), x=x256)
+    add(f"g1 resize bilinear 192->64 + gaussian {lab} (1 launch)", lambda t, gp=gp: _fused_resize_gauss(t, 64, L.RESIZE_BILINEAR_AA, gp),
+        N(x192) + N(x64), x=x192)
+gt_out = torch.empty(B, 3, 224, 224, device=dev)
+lq_out = torch.empty(B, 3, 56, 56, device=dev)
+add("g1 diffjpeg 64^2 + lattice + LQ crop + GT crop 224 (1 launch)",
+    lambda t: L.call("otf_diffjpeg_crop_pair_f32", L.ptr(t), B, 64, 64, L.ptr(q), 0.0, 1, 0, 1, L.ptr(x256), 256, 256, 4, 4, None, 56, 4,
+                     L.ptr(gt_out), L.ptr(lq_out), L.stream()), N(x64) + 2 * B * 3 * 224 * 224 * 4 + B * 3 * 56 * 56 * 4, x=x64)
+add("g1 clamp/round + crop_pair 256/64 -> 224/56 (1 launch)",
+    lambda t: L.call("otf_crop_pair_f32", L.ptr(t), B * 3, 256, 256, L.ptr(x64), 64, 64, 4, 4, None, 56, 4, 1, L.ptr(gt_out), L.ptr(lq_out),
+                     L.stream()), 2 * B * 3 * (224 * 224 + 56 * 56) * 4, x=x256)
 
 # ---- "next" rows of SURVEY.md §8f: pair pool (f1), kernel synthesis (f2), uint8 upload + MoA (f4) --------------
 import random  # noqa: E402

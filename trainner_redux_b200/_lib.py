@@ -41,6 +41,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_resize_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "otf_resize_tables_f32": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p]),
     "otf_resize_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i64, _i, _p]),
+    "otf_resize_gauss_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i64, _i, _p, _p, _u64, _u64, _p, _i, _p]),
     "otf_gaussian_noise_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _u64, _u64, _p, _i, _p, _p]),
     "otf_philox_normal_f32": (_i, [_p, _i64, _u64, _u64, _p]),
     "otf_philox_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
@@ -50,8 +51,9 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_philox_poisson_f32": (_i, [_p, _p, _i64, _u64, _u64, _p]),
     "otf_quality_to_factor_f32": (_i, [_p, _i, _p]),
     "otf_diffjpeg_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _i, _p, _p]),
+    "otf_diffjpeg_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _f, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "otf_clamp_round_f32": (_i, [_p, _i64, _p, _p]),
-    "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
     "otf_u8_to_f32": (_i, [_p, _i64, _p, _p]),
     "otf_copy_strided_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "otf_synth_kernels_f32": (_i, [_p, _i, _p, _p]),
@@ -68,6 +70,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_demosaic_f32": (_i, [_p, _i, _i, _i, _p, _p]),
     "otf_run_stages_workspace_bytes": (_i64, [_i, _i, _i, _i, _p, _i]),
     "otf_run_stages_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i64, _p, _p, _p]),
+    "otf_run_stages_launches": (_i, []),
 }
 
 (OP_ANALYSE, OP_FILTER2D, OP_USM, OP_SEPCONV, OP_RESIZE, OP_GAUSS, OP_POISSON, OP_JPEG, OP_CLAMP_ROUND,
@@ -89,12 +92,13 @@ launch_count = 0  # kernels enqueued through this binding (bench.py reports it)
 
 # launches behind each entry point (see the .cu files)
 _LAUNCHES = {
-    "otf_filter2d_analyse_f32": 2,  # analysis + launch order
-    "otf_filter2d_f32": 3,  # kernel analysis + launch order + blocked kernel (callers pass the exact count)
+    "otf_filter2d_analyse_f32": 1,  # analysis + launch order, one launch
+    "otf_filter2d_f32": 2,  # kernel analysis + blocked kernel (callers pass the exact count)
     "otf_sepconv_reflect_f32": 1,
     "otf_usm_sharp_f32": 4,
     "otf_resize_tables_f32": 1,
     "otf_resize_f32": 2,  # weight tables + resampler
+    "otf_resize_gauss_f32": 2,
     "otf_gaussian_noise_f32": 1,
     "otf_philox_normal_f32": 1,
     "otf_philox_uniform_f32": 1,
@@ -103,6 +107,7 @@ _LAUNCHES = {
     "otf_philox_poisson_f32": 1,
     "otf_quality_to_factor_f32": 1,
     "otf_diffjpeg_f32": 1,
+    "otf_diffjpeg_crop_pair_f32": 1,
     "otf_clamp_round_f32": 1,
     "otf_crop_pair_f32": 1,
     "otf_u8_to_f32": 1,

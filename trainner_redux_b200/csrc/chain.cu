@@ -2,9 +2,29 @@
 // See include/otf_b200.h "native stage executor".  Nothing here touches pixels: every stage is one
 // of the library's own entry points, called in sequence on the caller's stream, with the image
 // threaded through two ping-pong buffers carved out of the caller's workspace.
+// Adjacent stages that have a fused kernel run as ONE launch:
+//   resize + Gaussian noise            -> otf_resize_gauss_f32          (resize.cu, noise epilogue)
+//   DiffJPEG(+8-bit lattice) + crop    -> otf_diffjpeg_crop_pair_f32    (diffjpeg.cu, crop tail)
+//   clamp/round + crop                 -> otf_crop_pair_f32(lq_round8)  (pointwise.cu)
+// each bit-identical to the two launches it replaces (tests/test_chain_native_gpu.py); OTF_FUSE=0 turns them off.
+#include <stdlib.h>
+
 #include "otf_common.cuh"
 
 namespace otf {
+
+static thread_local int g_last_launches = 0;
+
+static bool fuse_enabled() {
+    const char* e = getenv("OTF_FUSE");
+    return !(e && e[0] == '0');
+}
+
+// resize followed by a Gaussian stage the resize epilogue can draw itself (no injected field, plain / clip tail)
+static bool fusable_resize_gauss(const OtfStage& r, const OtfStage& g) {
+    return r.op == OTF_OP_RESIZE && g.op == OTF_OP_GAUSS && !r.dst && g.p0 && !g.p2 && !g.p3 &&
+           !(g.flags & (OTF_NOISE_ROUNDS | OTF_NOISE_FIELD_ONLY | OTF_NOISE_RAW_FIELD));
+}
 
 static inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -95,6 +115,9 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
     bool analysed = false;
     int analysed_kb = 0, analysed_sets = 0;
 
+    const bool fuse = fuse_enabled();
+    int launches = 0;
+    g_last_launches = 0;
     const float* cur = img;
     int h = H, w = W, which = 0;
     for (int i = 0; i < nstages; ++i) {
@@ -102,10 +125,47 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
         float* out = s.dst ? reinterpret_cast<float*>(s.dst) : pong[which];
         int rc = OTF_OK;
         bool makes_image = true;
+        const OtfStage* nx = i + 1 < nstages ? &stages[i + 1] : nullptr;
+        if (fuse && nx && fusable_resize_gauss(s, *nx)) {  // resize + noise + clamp: one launch, one image write
+            float* fout = nx->dst ? reinterpret_cast<float*>(nx->dst) : pong[which];
+            void* tables = s.p0 ? const_cast<void*>(s.p0) : scratch;
+            const int ready = (s.p0 && (s.flags & 2)) ? 1 : 0;
+            rc = otf_resize_gauss_f32(cur, B, C, h, w, fout, s.oh, s.ow, s.mode, s.flags & 1, tables,
+                                      otf_resize_workspace_bytes(h, w, s.oh, s.ow, s.mode), ready, (const float*)nx->p0,
+                                      (const float*)nx->p1, nx->seed, nx->offset, (const uint64_t*)nx->p4, nx->flags, stream);
+            if (rc != OTF_OK) return rc;
+            launches += ready ? 1 : 2;
+            h = s.oh;
+            w = s.ow;
+            cur = fout;
+            if (!nx->dst) which ^= 1;
+            ++i;
+            continue;
+        }
+        if (fuse && nx && nx->op == OTF_OP_CROP_PAIR && !s.dst && C == 3 && s.op == OTF_OP_JPEG && ((s.flags >> 3) & 1) &&
+            (nx->n * nx->mode) % 4 == 0 && (reinterpret_cast<uintptr_t>(nx->p1) & 15) == 0) {
+            // the last codec pass stores only the crop window; the GT window rides in the same launch
+            rc = otf_diffjpeg_crop_pair_f32(cur, B, h, w, (const float*)s.p0, s.f0, s.flags & 1, (s.flags >> 1) & 1, (s.flags >> 2) & 1,
+                                            (const float*)nx->p0, H, W, nx->oh, nx->ow, (const int32_t*)nx->p4, nx->n, nx->mode,
+                                            (float*)const_cast<void*>(nx->p1), (float*)const_cast<void*>(nx->p2), stream);
+            if (rc != OTF_OK) return rc;
+            launches += 1;
+            ++i;
+            continue;
+        }
+        if (fuse && nx && nx->op == OTF_OP_CROP_PAIR && !s.dst && s.op == OTF_OP_CLAMP_ROUND) {
+            rc = otf_crop_pair_f32((const float*)nx->p0, B * C, H, W, cur, h, w, nx->oh, nx->ow, (const int32_t*)nx->p4, nx->n, nx->mode, 1,
+                                   (float*)const_cast<void*>(nx->p1), (float*)const_cast<void*>(nx->p2), stream);
+            if (rc != OTF_OK) return rc;
+            launches += 1;
+            ++i;
+            continue;
+        }
         switch (s.op) {
             case OTF_OP_ANALYSE: {
                 const float* sets[4] = {(const float*)s.p0, (const float*)s.p1, (const float*)s.p2, (const float*)s.p3};
                 rc = otf_filter2d_analyse_f32(sets, s.n, s.kb, s.K, analysis, stream);
+                launches += 1;
                 analysed = true;
                 analysed_kb = s.kb;
                 analysed_sets = s.n;
@@ -118,21 +178,26 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
                                 "run_stages[%d]: filter2d refers to analysis set %d that no earlier analyse stage produced", i, s.n);
                     rc = otf_filter2d_f32(cur, B, C, h, w, (const float*)s.p0, s.kb, s.K,
                                           analysis + (int64_t)s.n * otf_filter2d_scratch_words(s.kb), 1, out, stream);
+                    launches += 1;
                 } else {
                     rc = otf_filter2d_f32(cur, B, C, h, w, (const float*)s.p0, s.kb, s.K, (int32_t*)scratch, 0, out, stream);
+                    launches += s.K > 21 ? 1 : 2;
                 }
                 break;
             case OTF_OP_USM:
                 rc = otf_usm_sharp_f32(cur, B * C, h, w, (const float*)s.p0, s.n, s.f0, s.f1, scratch,
                                        otf_usm_workspace_bytes(B * C, h, w), out, stream);
+                launches += 4;
                 break;
             case OTF_OP_SEPCONV:
                 rc = otf_sepconv_reflect_f32(cur, B * C, h, w, (const float*)s.p0, s.n, s.mode, out, stream);
+                launches += 1;
                 break;
             case OTF_OP_RESIZE: {
                 void* tables = s.p0 ? const_cast<void*>(s.p0) : scratch;
                 rc = otf_resize_f32(cur, B * C, h, w, out, s.oh, s.ow, s.mode, s.flags & 1, tables,
                                     otf_resize_workspace_bytes(h, w, s.oh, s.ow, s.mode), (s.p0 && (s.flags & 2)) ? 1 : 0, stream);
+                launches += (s.p0 && (s.flags & 2)) ? 1 : 2;
                 h = s.oh;
                 w = s.ow;
                 break;
@@ -140,6 +205,7 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
             case OTF_OP_GAUSS:
                 rc = otf_gaussian_noise_f32(cur, B, C, h, w, (const float*)s.p0, (const float*)s.p1, (const float*)s.p2,
                                             (const float*)s.p3, s.seed, s.offset, (const uint64_t*)s.p4, s.flags, out, stream);
+                launches += 1;
                 break;
             case OTF_OP_POISSON:
                 // flags bit 3: p2 carries the universal CDF tables (otf_poisson_build_tables) instead of injected counts
@@ -148,28 +214,36 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
                                            s.seed, s.offset, (const uint64_t*)s.p4, s.flags & 7, (uint32_t*)scratch,
                                            (s.flags & 8) ? s.p2 : nullptr,
                                            nullptr, nullptr, nullptr, out, stream);
+                launches += 2;
                 break;
             case OTF_OP_JPEG:
                 OTF_REQUIRE(C == 3, OTF_ERR_BAD_ARG, "run_stages[%d]: DiffJPEG needs 3 channels", i);
                 rc = otf_diffjpeg_f32(cur, B, h, w, (const float*)s.p0, s.f0, s.flags & 1, (s.flags >> 1) & 1, (s.flags >> 2) & 1,
                                       (s.flags >> 3) & 1, out, stream);
+                launches += 1;
                 break;
             case OTF_OP_CLAMP_ROUND:
                 rc = otf_clamp_round_f32(cur, (int64_t)B * C * h * w, out, stream);
+                launches += 1;
                 break;
             case OTF_OP_CROP_PAIR:
-                rc = otf_crop_pair_f32((const float*)s.p0, B * C, H, W, cur, h, w, s.oh, s.ow, (const int32_t*)s.p4, s.n, s.mode,
+                rc = otf_crop_pair_f32((const float*)s.p0, B * C, H, W, cur, h, w, s.oh, s.ow, (const int32_t*)s.p4, s.n, s.mode, 0,
                                        (float*)const_cast<void*>(s.p1), (float*)const_cast<void*>(s.p2), stream);
+                launches += 1;
                 makes_image = false;
                 break;
         }
         if (rc != OTF_OK) return rc;  // the entry point has set the message
+        g_last_launches = launches;
         if (makes_image) {
             cur = out;
             if (!s.dst) which ^= 1;
         }
     }
+    g_last_launches = launches;
     if (final_h) *final_h = h;
     if (final_w) *final_w = w;
     return OTF_OK;
 }
+
+extern "C" int otf_run_stages_launches(void) { return otf::g_last_launches; }

@@ -11,6 +11,8 @@
 // Arithmetic order (documented for parity): 1-D DCT-II with the orthonormal matrix
 // C[k][n] = 0.5*alpha_k*cos((2n+1)k*pi/16), sums taken n = 0..7 with FFMA; quantisation divides by
 // fl(table*factor) exactly as the reference (no reciprocal), torch.round = rintf (half to even).
+#include <string.h>
+
 #include "otf_common.cuh"
 
 namespace otf {
@@ -121,10 +123,36 @@ __device__ __forceinline__ float quality_to_factor_dev(float v) {
     return __fdiv_rn(f, 100.0f);
 }
 
+// Optional fused tail (the chain's last launch): instead of the full image the kernel stores only the LQ crop window
+// (traiNNer/data/transforms.py:133-135 + .contiguous(), realesrgan_model.py:627) into a dense (B,3,p,p) tensor, and the CTAs
+// behind the codec's copy the GT crop window (transforms.py:124) — clamp/round, both crops and the JPEG in ONE launch.
+struct CropTail {
+    float* lq_out;           // nullptr: no fused crop, `out` receives the full image
+    const float* gt;
+    float* gt_out;
+    const int32_t* tl_dev;   // device (top, left) override or nullptr
+    int top, left, p, scale, Hg, Wg, planes, jpeg_ctas, vec_gt;
+};
+
 __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
                                                        float factor_scalar, int differentiable, int clamp_in,
-                                                       int round8_out, int vec_ok, int factor_is_quality) {
+                                                       int round8_out, int vec_ok, int factor_is_quality,
+                                                       const __grid_constant__ CropTail ct) {
+    int top = ct.top, left = ct.left;
+    if (ct.lq_out) {
+        if (ct.tl_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot leave the image
+            top = clampi(ct.tl_dev[0], 0, H - ct.p);
+            left = clampi(ct.tl_dev[1], 0, W - ct.p);
+        }
+        if ((int)blockIdx.x >= ct.jpeg_ctas) {  // the GT crop rides in the same launch
+            const int64_t q0 = (int64_t)(blockIdx.x - ct.jpeg_ctas) * blockDim.x + threadIdx.x;
+            const int64_t qs = (int64_t)(gridDim.x - ct.jpeg_ctas) * blockDim.x;
+            if (ct.vec_gt) copy_window<true>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
+            else copy_window<false>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
+            return;
+        }
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t total = (int64_t)B * mcu_x * mcu_y;
@@ -235,6 +263,19 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
         res[0][k] = R; res[1][k] = G; res[2][k] = Bc;
     }
     if (!row_ok) return;
+    if (ct.lq_out) {  // only the crop window, into the dense (B,3,p,p) output
+        const int yy = y - top;
+        if (yy < 0 || yy >= ct.p) return;
+        float* lp = ct.lq_out + ((size_t)b * 3 * ct.p + yy) * ct.p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int xx = x0 + k - left;
+                if (xx >= 0 && xx < ct.p && x0 + k < W) lp[(size_t)c * ct.p * ct.p + xx] = res[c][k];
+            }
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (full && vec_ok) {
@@ -274,9 +315,44 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
     // one warp per MCU; few MCUs (64^2 LQ stage) -> one-warp CTAs so they spread over all 148 SMs
     const int wpc = warps >= (int64_t)kNumSMs * 32 ? 4 : 1;
+    CropTail ct;
+    memset(&ct, 0, sizeof(ct));
     diffjpeg_kernel<<<ceil_div(warps, wpc), 32 * wpc, 0, (cudaStream_t)stream>>>(img, out, B, H, W, mcu_x, mcu_y, factor_dev,
                                                                              factor_scalar, differentiable, clamp_in,
-                                                                             round8_out, vec_ok, factor_is_quality);
+                                                                             round8_out, vec_ok, factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W, const float* factor_dev, float factor_scalar,
+                                          int factor_is_quality, int differentiable, int clamp_in, const float* gt, int Hg, int Wg,
+                                          int top, int left, const int32_t* top_left_dev, int lq_patch, int scale, float* gt_out,
+                                          float* lq_out, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(img && gt && gt_out && lq_out, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: null pointer");
+    OTF_REQUIRE(B > 0 && B * 3 <= 65535 && H > 0 && W > 0 && scale > 0 && lq_patch > 0, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: bad extents");
+    OTF_REQUIRE(Hg == H * scale && Wg == W * scale, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: GT (%d, %d) is not %dx LQ (%d, %d)", Hg, Wg, scale, H, W);
+    OTF_REQUIRE(top >= 0 && left >= 0 && top + lq_patch <= H && left + lq_patch <= W, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: window outside LQ");
+    OTF_REQUIRE((lq_patch * scale) % 4 == 0 && (((uintptr_t)gt_out) & 15) == 0, OTF_ERR_UNSUPPORTED,
+                "diffjpeg_crop_pair: GT patch must be a multiple of 4 pixels wide (use otf_diffjpeg_f32 + otf_crop_pair_f32)");
+    const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
+    const int64_t warps = (int64_t)B * mcu_x * mcu_y;
+    const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
+    const int wpc = 4;
+    CropTail ct;
+    memset(&ct, 0, sizeof(ct));
+    ct.lq_out = lq_out; ct.gt = gt; ct.gt_out = gt_out; ct.tl_dev = top_left_dev;
+    ct.top = top; ct.left = left; ct.p = lq_patch; ct.scale = scale; ct.Hg = Hg; ct.Wg = Wg; ct.planes = B * 3;
+    ct.jpeg_ctas = ceil_div(warps, wpc);
+    // device-side offsets: the alignment of the GT window start is only known when scale % 4 == 0
+    ct.vec_gt = (Wg % 4 == 0) && (top_left_dev ? scale % 4 == 0 : (left * scale) % 4 == 0) && (((uintptr_t)gt & 15) == 0);
+    const int64_t gquads = (int64_t)B * 3 * lq_patch * scale * (lq_patch * scale / 4);
+    int copy_ctas = (int)((gquads / 4 + 127) / 128);
+    if (copy_ctas > kNumSMs * 8) copy_ctas = kNumSMs * 8;
+    if (copy_ctas < 1) copy_ctas = 1;
+    diffjpeg_kernel<<<ct.jpeg_ctas + copy_ctas, 32 * wpc, 0, (cudaStream_t)stream>>>(img, nullptr, B, H, W, mcu_x, mcu_y, factor_dev,
+                                                                                  factor_scalar, differentiable, clamp_in, 1, vec_ok,
+                                                                                  factor_is_quality, ct);
+    OTF_LAUNCH_CHECK("diffjpeg_kernel (fused crop)");
     return OTF_OK;
 }

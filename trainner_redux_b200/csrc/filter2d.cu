@@ -21,7 +21,6 @@
 namespace otf {
 
 // ---- per-kernel analysis: true support, rank-1 factors, processing order --------------
-// One CTA, one warp per kernel.
 //   support[kb]  largest |offset| with a non-zero tap (kernels arrive zero-padded to 21x21);
 //   rank1[kb]    bit 1 (value 2): the kernel is left-right mirror symmetric (horizontal fold);
 //                bit 0: set when the kernel is an outer product u v^T to within fp32 rounding of its own
@@ -40,89 +39,70 @@ struct KernelSets {
     const float* ptr[4];  // up to 4 kernel tensors (kernel1, kernel2, sinc_kernel, ...) analysed by one launch
 };
 
-__global__ void __launch_bounds__(128) kernel_support_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch,
-                                                             int32_t* __restrict__ scratch_base) {
-    // one CTA per kernel: the K*K taps go to shared memory with one coalesced pass, then 128 threads
-    // scan them (support, pivot, rank-1 residual) — three short passes instead of a 14-deep serial loop per lane
-    __shared__ float sk[32 * 32];
-    __shared__ float s_red[4];
-    __shared__ int s_idx[4], s_r[4], s_ok[4], s_sym[4];
-    const float* kern = sets.ptr[blockIdx.y];
-    int32_t* scratch = scratch_base + (size_t)blockIdx.y * scratch_words(kernel_batch);
+// One CTA per kernel tensor, one WARP per kernel (warp w takes kernels w, w + 16, ...), then the same CTA ranks the
+// samples — analysis and launch order in ONE launch (they used to be two).
+constexpr int kAnalyseWarps = 16;
+__global__ void __launch_bounds__(kAnalyseWarps * 32) kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K,
+                                                                            int kernel_batch, int32_t* __restrict__ scratch_base) {
+    __shared__ float sk_all[kAnalyseWarps][21 * 21 + 7];
+    extern __shared__ int s_sup[];  // [kernel_batch] supports, for the ranking pass
+    const float* kern = sets.ptr[blockIdx.x];
+    int32_t* scratch = scratch_base + (size_t)blockIdx.x * scratch_words(kernel_batch);
     int32_t* support = scratch;
     int32_t* rank1 = scratch + 2 * kernel_batch;
     float* uv = reinterpret_cast<float*>(scratch + 3 * kernel_batch);
-    const int c = K / 2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kb = blockIdx.x;
-    const float* kp = kern + (size_t)kb * K * K;
+    const int c = K / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = K * K;  // K <= 21 on this path
-    int r = 0;
-    float amax = 0.0f;
-    int imax = 0;
-    for (int idx = tid; idx < n; idx += 128) {
-        const float v = kp[idx];
-        sk[idx] = v;
-        if (v != 0.0f) {
-            const int i = idx / K, j = idx - i * K;
-            r = max(r, max(abs(i - c), abs(j - c)));
+    float* sk = sk_all[warp];
+    for (int kb = warp; kb < kernel_batch; kb += kAnalyseWarps) {
+        const float* kp = kern + (size_t)kb * n;
+        int r = 0, imax = 0;
+        float amax = 0.0f;
+        for (int idx = lane; idx < n; idx += 32) {
+            const float v = kp[idx];
+            sk[idx] = v;
+            if (v != 0.0f) {
+                const int i = idx / K, j = idx - i * K;
+                r = max(r, max(abs(i - c), abs(j - c)));
+            }
+            if (fabsf(v) > amax) { amax = fabsf(v); imax = idx; }
         }
-        if (fabsf(v) > amax) { amax = fabsf(v); imax = idx; }
-    }
-    r = __reduce_max_sync(0xffffffffu, r);
+        r = __reduce_max_sync(0xffffffffu, r);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {  // pivot = the largest |tap| (ties -> lowest index)
-        const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
-        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
-    }
-    if (lane == 0) { s_red[warp] = amax; s_idx[warp] = imax; s_r[warp] = r; }
-    __syncthreads();
-    amax = s_red[0]; imax = s_idx[0]; r = s_r[0];
-#pragma unroll
-    for (int w = 1; w < 4; ++w) {
-        if (s_red[w] > amax || (s_red[w] == amax && s_idx[w] < imax)) { amax = s_red[w]; imax = s_idx[w]; }
-        r = max(r, s_r[w]);
-    }
-    const int pi = imax / K, pj = imax - pi * K;
-    const float piv = sk[imax];
-    bool ok = amax > 0.0f;
-    if (ok) {
-        for (int idx = tid; idx < n; idx += 128) {
+        for (int o = 16; o > 0; o >>= 1) {  // pivot = the largest |tap| (ties -> lowest index)
+            const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
+            if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
+        }
+        __syncwarp();
+        const int pi = imax / K, pj = imax - pi * K;
+        const float piv = sk[imax];
+        bool ok = amax > 0.0f, sym = true;
+        for (int idx = lane; idx < n; idx += 32) {
             const int i = idx / K, j = idx - i * K;
             const float kij = sk[idx];
-            const float sep = sk[i * K + pj] * __fdiv_rn(sk[pi * K + j], piv);
-            ok = ok && (fabsf(kij - sep) <= 4e-7f * fabsf(kij) + 1e-9f * amax);
+            if (ok) {
+                const float sep = sk[i * K + pj] * __fdiv_rn(sk[pi * K + j], piv);
+                ok = fabsf(kij - sep) <= 4e-7f * fabsf(kij) + 1e-9f * amax;
+            }
+            // left-right mirror symmetry, K[i][j] == K[i][K-1-j] bit for bit (every isotropic family and the sinc kernels
+            // are: the generators evaluate a function of x^2): such kernels are evaluated with the horizontal fold
+            sym = sym && (kij == sk[i * K + (K - 1 - j)]);
         }
+        ok = __all_sync(0xffffffffu, ok);
+        sym = __all_sync(0xffffffffu, sym);
+        if (lane < kUVPitch) {
+            // centred in 21 slots: slot s <-> offset s - 10
+            const int t = lane - 10 + c;  // tap index for this slot
+            const bool in = lane < 21 && t >= 0 && t < K;
+            uv[((size_t)kb * 2 + 0) * kUVPitch + lane] = (ok && in) ? sk[t * K + pj] : 0.0f;
+            uv[((size_t)kb * 2 + 1) * kUVPitch + lane] = (ok && in) ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
+        }
+        if (lane == 0) { support[kb] = r; rank1[kb] = (ok ? 1 : 0) | (sym ? 2 : 0); s_sup[kb] = r; }
+        __syncwarp();
     }
-    ok = __all_sync(0xffffffffu, ok);
-    // left-right mirror symmetry, K[i][j] == K[i][K-1-j] bit for bit (every isotropic family and the sinc kernels are:
-    // the generators evaluate a function of x^2): such kernels are evaluated with the horizontal fold
-    bool sym = true;
-    for (int idx = tid; idx < n; idx += 128) {
-        const int i = idx / K, j = idx - i * K;
-        sym = sym && (sk[idx] == sk[i * K + (K - 1 - j)]);
-    }
-    sym = __all_sync(0xffffffffu, sym);
-    if (lane == 0) { s_ok[warp] = ok; s_sym[warp] = sym; }
     __syncthreads();
-    ok = s_ok[0] && s_ok[1] && s_ok[2] && s_ok[3];
-    sym = s_sym[0] && s_sym[1] && s_sym[2] && s_sym[3];
-    if (tid < kUVPitch) {
-        // centred in 21 slots: slot s <-> offset s - 10
-        const int t = tid - 10 + c;  // tap index for this slot
-        const bool in = tid < 21 && t >= 0 && t < K;
-        uv[((size_t)kb * 2 + 0) * kUVPitch + tid] = (ok && in) ? sk[t * K + pj] : 0.0f;
-        uv[((size_t)kb * 2 + 1) * kUVPitch + tid] = (ok && in) ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
-    }
-    if (tid == 0) { support[kb] = r; rank1[kb] = (ok ? 1 : 0) | (sym ? 2 : 0); }
-}
-
-// order[0..kb): sample indices sorted by support, largest first (stable).  One small CTA per kernel set.
-__global__ void __launch_bounds__(1024) kernel_order_kernel(int kernel_batch, int32_t* __restrict__ scratch_base) {
-    extern __shared__ int s_sup[];
-    int32_t* scratch = scratch_base + (size_t)blockIdx.x * scratch_words(kernel_batch);
-    for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) s_sup[t] = scratch[t];
-    __syncthreads();
+    // order[0..kb): sample indices sorted by support, largest first (stable)
     for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
         const int mine = s_sup[t];
         int rank = 0;
@@ -133,15 +113,11 @@ __global__ void __launch_bounds__(1024) kernel_order_kernel(int kernel_batch, in
 
 static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch, int K, int32_t* scratch, cudaStream_t st) {
     OTF_REQUIRE(nsets >= 1 && nsets <= 4, OTF_ERR_BAD_ARG, "filter2d_analyse: 1..4 kernel sets per call");
-    OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 8192, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..8192");
+    OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 4096, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..4096");
     KernelSets sets;
     for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
-    kernel_support_kernel<<<dim3(kernel_batch, nsets), 128, 0, st>>>(sets, K, kernel_batch, scratch);
-    OTF_LAUNCH_CHECK("kernel_support_kernel");
-    if (kernel_batch > 1) {
-        kernel_order_kernel<<<nsets, 1024, kernel_batch * sizeof(int), st>>>(kernel_batch, scratch);
-        OTF_LAUNCH_CHECK("kernel_order_kernel");
-    }
+    kernel_analyse_kernel<<<nsets, kAnalyseWarps * 32, kernel_batch * sizeof(int), st>>>(sets, K, kernel_batch, scratch);
+    OTF_LAUNCH_CHECK("kernel_analyse_kernel");
     return OTF_OK;
 }
 

@@ -21,17 +21,24 @@ namespace otf {
 // block-uniform factors first — N*(sigma/255*(1-g)) + G*(sigma/255*g) — which differs from the
 // reference by <= 2 ulp of the noise (~1e-9 on a [0,1] image) and costs 2 FMAs instead of 2 IEEE
 // divisions + 5 ops per element: at 6.4 TB/s an elementwise kernel has ~6 issue slots per float4.
+// Philox positions are laid out per image ROW: a quad is four consecutive pixels of one row, quad (row, xq) of sample b
+// has index b*(C*H*QW) + row*QW + xq with QW = ceil(W/4) (row = c*H + y), the shared gray field uses y*QW + xq.  For
+// W % 4 == 0 this is the flat quad numbering; for any other width rows simply end with a partial quad.  The row layout is
+// what lets the resize kernels draw the very same field in their epilogue (resize.cu: four lanes own four consecutive
+// output columns), so that the fused resize + noise launch is bit-identical to resize followed by this kernel.
 struct GaussQuad {
     float v[4], nc[4], ng[4];
 };
 
 template <bool VEC, bool EXACT>
 __device__ __forceinline__ void gauss_load(GaussQuad& g, const Philox& ph, const float* __restrict__ ip, int q, int nq,
-                                           int chw, int hw, size_t base, int b, const float* __restrict__ ncol,
+                                           int W, int QW, int H, size_t base, int b, const float* __restrict__ ncol,
                                            const float* __restrict__ ngray, bool need_color, bool need_gray,
                                            uint64_t offset) {
-    const int e0 = q << 2;
-    const int cnt = min(4, chw - e0);
+    // VEC: W % 4 == 0, the quad's first element is 4q;  otherwise row = q / QW, xq = q % QW
+    const int row = VEC ? 0 : q / QW, xq = VEC ? 0 : q - row * QW;
+    const int e0 = VEC ? (q << 2) : row * W + (xq << 2);
+    const int cnt = VEC ? 4 : min(4, W - (xq << 2));
 #pragma unroll
     for (int k = 0; k < 4; ++k) { g.v[k] = 0.f; g.nc[k] = 0.f; g.ng[k] = 0.f; }
     if (VEC) {
@@ -47,27 +54,22 @@ __device__ __forceinline__ void gauss_load(GaussQuad& g, const Philox& ph, const
         g.nc[0] = t.x; g.nc[1] = t.y; g.nc[2] = t.z; g.nc[3] = t.w;
     }
     if (need_gray) {
+        const int hw = H * W;
         const int p0 = e0 % hw;  // pixel index of the first element inside its channel plane
         if (ngray) {
-            for (int k = 0; k < cnt; ++k) { int p = p0 + k; if (p >= hw) p -= hw; g.ng[k] = ngray[p]; }
-        } else if ((p0 & 3) == 0 && p0 + 3 < hw) {
-            // ONE (h,w) field shared by the whole batch and all channels (degradations.py:593-596)
-            const float4 t = normal4(ph, (uint64_t)(p0 >> 2), offset * 8 + STREAM_GRAY);
-            g.ng[0] = t.x; g.ng[1] = t.y; g.ng[2] = t.z; g.ng[3] = t.w;
+            for (int k = 0; k < cnt; ++k) g.ng[k] = ngray[p0 + k];
         } else {
-            for (int k = 0; k < cnt; ++k) {
-                int p = p0 + k; if (p >= hw) p -= hw;
-                const float4 t = normal4(ph, (uint64_t)(p >> 2), offset * 8 + STREAM_GRAY);
-                const float tt[4] = {t.x, t.y, t.z, t.w};
-                g.ng[k] = tt[p & 3];
-            }
+            // ONE (h,w) field shared by the whole batch and all channels (degradations.py:593-596)
+            const int gq = VEC ? (p0 >> 2) : (row % H) * QW + xq;
+            const float4 t = normal4(ph, (uint64_t)gq, offset * 8 + STREAM_GRAY);
+            g.ng[0] = t.x; g.ng[1] = t.y; g.ng[2] = t.z; g.ng[3] = t.w;
         }
     }
 }
 
 template <bool VEC, bool EXACT>
 __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __restrict__ img, float* __restrict__ out,
-                                                             int chw, int hw,
+                                                             int C, int H, int W,
                                                              const float* __restrict__ sigma, const float* __restrict__ gray,
                                                              const float* __restrict__ ncol, const float* __restrict__ ngray,
                                                              uint64_t seed, uint64_t offset,
@@ -82,7 +84,9 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
     const float one_minus_g = __fsub_rn(1.0f, g);
     const float s255 = __fdiv_rn(sg, 255.0f);
     const float ca = use_gray ? s255 * one_minus_g : s255, cb = use_gray ? s255 * g : 0.0f;  // folded factors
-    const int nq = (chw + 3) >> 2;
+    const int QW = (W + 3) >> 2;
+    const int chw = C * H * W;
+    const int nq = C * H * QW;
     const size_t base = (size_t)b * chw;
     const float* ip = img + base;
     float* op = out + base;
@@ -94,12 +98,13 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
         const int qs[2] = {q0, q0 + stride};
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-            if (qs[u] < nq) gauss_load<VEC, EXACT>(gq[u], ph, ip, qs[u], nq, chw, hw, base, b, ncol, ngray, need_color, need_gray, offset);
+            if (qs[u] < nq) gauss_load<VEC, EXACT>(gq[u], ph, ip, qs[u], nq, W, QW, H, base, b, ncol, ngray, need_color, need_gray, offset);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (qs[u] >= nq) continue;
-            const int e0 = qs[u] << 2;
-            const int cnt = min(4, chw - e0);
+            const int row = VEC ? 0 : qs[u] / QW, xq = VEC ? 0 : qs[u] - row * QW;
+            const int e0 = VEC ? (qs[u] << 2) : row * W + (xq << 2);
+            const int cnt = VEC ? 4 : min(4, W - (xq << 2));
             float r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -531,16 +536,15 @@ extern "C" int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int
     const float* ng = gray_dev ? noise_gray_dev : nullptr;
     OTF_REQUIRE(!(gray_dev && noise_color_dev && !noise_gray_dev), OTF_ERR_BAD_ARG,
                 "gaussian_noise: gray flags with an injected colour field need the injected gray field too");
-    const int chw = C * H * W;
-    const bool vec = (chw % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
-    int chunks = ceil_div((chw + 3) / 4, 512);
+    const bool vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
+    int chunks = ceil_div((int64_t)C * H * ((W + 3) / 4), 512);
     const int cap = ceil_div(kNumSMs * 16, B);
     if (chunks > cap) chunks = cap;
     const dim3 grid(chunks, B);
     const bool exact = noise_color_dev != nullptr || (flags & OTF_NOISE_ROUNDS);
     cudaStream_t st = (cudaStream_t)stream;
 #define OTF_GAUSS(V, E)                                                                                              \
-    gaussian_noise_kernel<V, E><<<grid, 256, 0, st>>>(img, out, chw, H * W, sigma_dev, gray_dev, noise_color_dev, ng, \
+    gaussian_noise_kernel<V, E><<<grid, 256, 0, st>>>(img, out, C, H, W, sigma_dev, gray_dev, noise_color_dev, ng, \
                                                       seed, offset, offset_dev, flags)
     if (vec && exact) OTF_GAUSS(true, true);
     else if (vec) OTF_GAUSS(true, false);

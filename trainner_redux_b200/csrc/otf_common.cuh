@@ -110,6 +110,41 @@ __device__ __forceinline__ float4 normal4(const Philox& ph, uint64_t quad, uint6
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ---- a8: traiNNer/data/transforms.py:124-135 followed by .contiguous() --------------------
+// One launch copies both windows.  A thread moves one quad (4 consecutive output pixels) per
+// iteration and keeps UNR of them in flight; 16-byte loads when the window start is aligned.
+template <bool VEC, bool ROUND8 = false>
+__device__ __forceinline__ void copy_window(const float* __restrict__ src, int Hs, int Ws, int top, int left, int n,
+                                            float* __restrict__ dst, int planes, int64_t q0, int64_t qstride) {
+    const int qrow = n >> 2;                          // quads per output row (n % 4 == 0 on this path)
+    const int64_t nq = (int64_t)planes * n * qrow;
+    constexpr int UNR = 4;
+    for (int64_t qb = q0; qb < nq; qb += qstride * UNR) {
+        float4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t q = qb + u * qstride;
+            if (q < nq) {
+                const int xq = (int)(q % qrow);
+                const int64_t t = q / qrow;
+                const int y = (int)(t % n);
+                const int64_t pl = t / n;
+                const float* sp = src + ((size_t)pl * Hs + (top + y)) * Ws + left + 4 * xq;
+                if (VEC) v[u] = __ldg(reinterpret_cast<const float4*>(sp));
+                else v[u] = make_float4(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2), __ldg(sp + 3));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t q = qb + u * qstride;
+            if (q < nq) {
+                if (ROUND8) v[u] = make_float4(quantise8(v[u].x), quantise8(v[u].y), quantise8(v[u].z), quantise8(v[u].w));  // a7 fused
+                reinterpret_cast<float4*>(dst)[q] = v[u];
+            }
+        }
+    }
+}
+
 // streams used by the noise kernels (hi 64 bits of the Philox counter = offset*8 + id)
 enum { STREAM_COLOR = 0, STREAM_GRAY = 1, STREAM_POIS_COLOR = 2, STREAM_POIS_GRAY = 3 };
 

@@ -45,39 +45,8 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restric
     if (tail < n) dst[tail] = __fdiv_rn((float)src[tail], 255.0f);
 }
 
-// ---- a8: traiNNer/data/transforms.py:124-135 followed by .contiguous() --------------------
-// One launch copies both windows.  A thread moves one quad (4 consecutive output pixels) per
-// iteration and keeps UNR of them in flight; 16-byte loads when the window start is aligned.
-template <bool VEC>
-__device__ __forceinline__ void copy_window(const float* __restrict__ src, int Hs, int Ws, int top, int left, int n,
-                                            float* __restrict__ dst, int planes, int64_t q0, int64_t qstride) {
-    const int qrow = n >> 2;                          // quads per output row (n % 4 == 0 on this path)
-    const int64_t nq = (int64_t)planes * n * qrow;
-    constexpr int UNR = 4;
-    for (int64_t qb = q0; qb < nq; qb += qstride * UNR) {
-        float4 v[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int64_t q = qb + u * qstride;
-            if (q < nq) {
-                const int xq = (int)(q % qrow);
-                const int64_t t = q / qrow;
-                const int y = (int)(t % n);
-                const int64_t pl = t / n;
-                const float* sp = src + ((size_t)pl * Hs + (top + y)) * Ws + left + 4 * xq;
-                if (VEC) v[u] = __ldg(reinterpret_cast<const float4*>(sp));
-                else v[u] = make_float4(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2), __ldg(sp + 3));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int64_t q = qb + u * qstride;
-            if (q < nq) reinterpret_cast<float4*>(dst)[q] = v[u];
-        }
-    }
-}
-
-template <bool VEC_GT, bool VEC_LQ>
+// (copy_window, the quad-per-thread window copy of a8, lives in otf_common.cuh: the fused DiffJPEG + crop launch uses it too)
+template <bool VEC_GT, bool VEC_LQ, bool ROUND8>
 __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict__ gt, int Hg, int Wg,
                                                         const float* __restrict__ lq, int Hl, int Wl, int top, int left,
                                                         const int32_t* __restrict__ top_left_dev,
@@ -89,14 +58,14 @@ __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict_
     }
     const int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, qs = (int64_t)gridDim.x * blockDim.x;
     copy_window<VEC_GT>(gt, Hg, Wg, top * scale, left * scale, p * scale, gt_out, planes, q0, qs);
-    copy_window<VEC_LQ>(lq, Hl, Wl, top, left, p, lq_out, planes, q0, qs);
+    copy_window<VEC_LQ, ROUND8>(lq, Hl, Wl, top, left, p, lq_out, planes, q0, qs);
 }
 
 // any patch size (p % 4 != 0): one element per thread
 __global__ void __launch_bounds__(256) crop_pair_scalar_kernel(const float* __restrict__ gt, int Hg, int Wg,
                                                                const float* __restrict__ lq, int Hl, int Wl, int top,
                                                                int left, const int32_t* __restrict__ top_left_dev, int p,
-                                                               int scale, int planes,
+                                                               int scale, int planes, int round8,
                                                                float* __restrict__ gt_out, float* __restrict__ lq_out) {
     if (top_left_dev) {
         top = clampi(top_left_dev[0], 0, Hl - p);
@@ -113,7 +82,8 @@ __global__ void __launch_bounds__(256) crop_pair_scalar_kernel(const float* __re
             const int64_t j = i - ng;
             const int x = (int)(j % p), y = (int)((j / p) % p);
             const int64_t pl = j / ((int64_t)p * p);
-            lq_out[j] = __ldg(lq + ((size_t)pl * Hl + top + y) * Wl + left + x);
+            const float v = __ldg(lq + ((size_t)pl * Hl + top + y) * Wl + left + x);
+            lq_out[j] = round8 ? quantise8(v) : v;
         }
     }
 }
@@ -261,8 +231,8 @@ extern "C" int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* st
 }
 
 extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, const float* lq, int Hl, int Wl, int top,
-                                 int left, const int32_t* top_left_dev, int lq_patch, int scale, float* gt_out, float* lq_out,
-                                 void* stream) {
+                                 int left, const int32_t* top_left_dev, int lq_patch, int scale, int lq_round8, float* gt_out,
+                                 float* lq_out, void* stream) {
     using namespace otf;
     OTF_REQUIRE(gt && lq && gt_out && lq_out, OTF_ERR_BAD_ARG, "crop_pair: null pointer");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && scale > 0 && lq_patch > 0, OTF_ERR_BAD_ARG, "crop_pair: bad extents");
@@ -276,17 +246,23 @@ extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, co
     if (blocks < 1) blocks = 1;
     const bool quads = (lq_patch % 4 == 0) && ((((uintptr_t)gt_out | (uintptr_t)lq_out) & 15) == 0);
     if (!quads) {
-        crop_pair_scalar_kernel<<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
+        crop_pair_scalar_kernel<<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, lq_round8, gt_out, lq_out);
         OTF_LAUNCH_CHECK("crop_pair_scalar_kernel");
         return OTF_OK;
     }
     // device-side offsets: the alignment of the window start is only known for the GT window at scale % 4 == 0
     const bool vg = (Wg % 4 == 0) && (top_left_dev ? scale % 4 == 0 : (left * scale) % 4 == 0) && (((uintptr_t)gt & 15) == 0);
     const bool vl = (Wl % 4 == 0) && !top_left_dev && (left % 4 == 0) && (((uintptr_t)lq & 15) == 0);
-    if (vg && vl) crop_pair_kernel<true, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
-    else if (vg) crop_pair_kernel<true, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
-    else if (vl) crop_pair_kernel<false, true><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
-    else crop_pair_kernel<false, false><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out);
+#define OTF_CROP(VG, VL, R8) \
+    crop_pair_kernel<VG, VL, R8><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out)
+    if (lq_round8) {
+        if (vg && vl) OTF_CROP(true, true, true); else if (vg) OTF_CROP(true, false, true);
+        else if (vl) OTF_CROP(false, true, true); else OTF_CROP(false, false, true);
+    } else {
+        if (vg && vl) OTF_CROP(true, true, false); else if (vg) OTF_CROP(true, false, false);
+        else if (vl) OTF_CROP(false, true, false); else OTF_CROP(false, false, false);
+    }
+#undef OTF_CROP
     OTF_LAUNCH_CHECK("crop_pair_kernel");
     return OTF_OK;
 }

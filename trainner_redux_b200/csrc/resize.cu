@@ -11,6 +11,7 @@
 // pass (result kept in smem), then the vertical pass — the same order ATen uses (W first, then H).
 // HBM-bound: the source is read once per tile (+ halo, served by L2), the output written once.
 #include <stdlib.h>
+#include <string.h>
 
 #include "otf_common.cuh"
 
@@ -176,6 +177,84 @@ __global__ void __launch_bounds__(128) resize_tables_kernel(int mode, AxisSpec a
     }
 }
 
+
+// ---- fused Gaussian-noise epilogue (row g1: resize + noise + clamp in one launch) ----------------------------
+// What otf_gaussian_noise_f32 would do to this launch's output (degradations.py:569-633 after :1004-1021), applied
+// to the resampled pixel before it is stored.  The Philox positions are the noise kernel's (noise.cu: quad = four
+// consecutive pixels of an output row), so the fused launch is BIT-IDENTICAL to resize followed by the noise kernel.
+// Four lanes own four consecutive output columns (one quad) and four output rows each: lane j of the group draws the
+// quad of row j (one Philox call, two Box-Muller pairs), a 4x4 exchange inside the group hands every lane the normal
+// of its own column for each of the four rows — one Philox call per four pixels, as in the stand-alone kernel.
+struct NoiseEpi {
+    const float* sigma;          // fp32[B]
+    const float* gray;           // fp32[B] or nullptr
+    const uint64_t* offset_dev;  // device offset word or nullptr
+    uint64_t seed, offset;
+    int C, flags;
+};
+
+struct NoiseCtx {  // per-CTA constants (a CTA works inside one plane)
+    float ca, cb;
+    bool need_color, need_gray;
+    uint64_t color_base, stream_color, stream_gray;
+    int QW, flags;
+};
+
+__device__ __forceinline__ NoiseCtx noise_ctx(const NoiseEpi& ne, int plane, int OH, int OW) {
+    NoiseCtx nc;
+    const int b = plane / ne.C, c = plane - b * ne.C;
+    const float sg = ne.sigma[b];
+    const float g = ne.gray ? ne.gray[b] : 0.0f;
+    const bool use_gray = ne.gray != nullptr;
+    const float s255 = __fdiv_rn(sg, 255.0f);
+    nc.ca = use_gray ? s255 * __fsub_rn(1.0f, g) : s255;  // the folded factors of gaussian_noise_kernel
+    nc.cb = use_gray ? s255 * g : 0.0f;
+    nc.need_color = !(use_gray && g == 1.0f);
+    nc.need_gray = use_gray && g != 0.0f;
+    nc.QW = (OW + 3) >> 2;
+    const uint64_t off = ne.offset + (ne.offset_dev ? *ne.offset_dev : 0);
+    nc.color_base = (uint64_t)b * ((uint64_t)ne.C * OH * nc.QW) + (uint64_t)c * OH * nc.QW;
+    nc.stream_color = off * 8 + STREAM_COLOR;
+    nc.stream_gray = off * 8 + STREAM_GRAY;
+    nc.flags = ne.flags;
+    return nc;
+}
+
+// The four noise values of output column x (x - (lane & 3) is a multiple of 4: the group's quad) at rows y[0..3].
+// Must be called by all 32 lanes; rows >= OH are skipped (their value is unspecified).
+__device__ __forceinline__ void noise_rows4(const Philox& ph, const NoiseCtx& nc, int OH, int x, const int (&y)[4], int lane,
+                                            float (&nz)[4]) {
+    const int j = lane & 3;
+    const int my = j == 0 ? y[0] : j == 1 ? y[1] : j == 2 ? y[2] : y[3];
+    const int xq = x >> 2;
+    float q[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (my < OH) {
+        float4 n = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nc.need_color) n = normal4(ph, nc.color_base + (uint64_t)my * nc.QW + xq, nc.stream_color);
+        if (nc.need_gray) g = normal4(ph, (uint64_t)my * nc.QW + xq, nc.stream_gray);
+        q[0] = fmaf(g.x, nc.cb, n.x * nc.ca);  // gaussian_noise_kernel: noise = fmaf(ng, cb, nc * ca)
+        q[1] = fmaf(g.y, nc.cb, n.y * nc.ca);
+        q[2] = fmaf(g.z, nc.cb, n.z * nc.ca);
+        q[3] = fmaf(g.w, nc.cb, n.w * nc.ca);
+    }
+    // 4x4 exchange: in step s lane j sends component (j + s) & 3 of its row to lane (j + s) & 3, i.e. lane j receives,
+    // from lane i = (j - s) & 3, the component j of row i
+    float r[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int comp = (j + s) & 3;
+        const float send = comp == 0 ? q[0] : comp == 1 ? q[1] : comp == 2 ? q[2] : q[3];
+        r[s] = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((j - s) & 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int s = (j - i) & 3;
+        nz[i] = s == 0 ? r[0] : s == 1 ? r[1] : s == 2 ? r[2] : r[3];
+    }
+}
+
+__device__ __forceinline__ float noise_finish(float v, float nz, int flags) { return noise_tail(__fadd_rn(v, nz), flags); }
+
 __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -191,11 +270,11 @@ __device__ __forceinline__ void cp_async_f32x4(float* smem_dst, const float* gsr
 // registers (broadcast) and each lane produces CW columns; clamp fused.  Taps beyond a window's true
 // length are zero and read zero-filled padding, so the unrolled loops need no predicates.
 // smem: wx[TW][NT] wy[tile_h][NT] xlo[TW] ylo[tile_h] | src[rows_cap][SP] | tmp[rows_cap + NT][TW]
-template <int NT, int CW>
+template <int NT, int CW, bool NOISE>
 __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ img, float* __restrict__ out,
                                                      AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
                                                      const int* __restrict__ tx_lo, int tile_h, int rows_cap,
-                                                     int cols_cap, int clamp_out, int vec_ok) {
+                                                     int cols_cap, int clamp_out, int vec_ok, const __grid_constant__ NoiseEpi ne) {
     constexpr int TW = 32 * CW;
     extern __shared__ __align__(16) float sm[];
     const int SP = (cols_cap + NT + 3) & ~3;  // src row pitch: >= NT zero columns behind every row, 16-byte rows
@@ -277,6 +356,41 @@ __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ i
     __syncthreads();
     // vertical pass: warp = output row, lane = CW columns
     float* op = out + (size_t)plane * ay.out_n * ax.out_n;
+    if (NOISE) {
+        // four output rows per trip (t, t + 8, t + 16, t + 24: tile_h <= 32) so that the noise epilogue can share one
+        // Philox call between the four lanes of a quad
+        const Philox ph(ne.seed);
+        const NoiseCtx nc = noise_ctx(ne, plane, ay.out_n, ax.out_n);
+        float acc[4][CW];
+        int yy[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = wid + 8 * i;
+            yy[i] = t < th ? oy0 + t : ay.out_n;  // (out_n = "no such row")
+#pragma unroll
+            for (int k = 0; k < CW; ++k) acc[i][k] = 0.0f;
+            if (t < th) {
+                const float* tp = tmp + ylo[t] * TW + lane;
+#pragma unroll
+                for (int ii = 0; ii < NT; ++ii) {
+                    const float wv = wy[t * NT + ii];
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) acc[i][k] = fmaf(wv, tp[ii * TW + 32 * k], acc[i][k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+            const int x = ox0 + lane + 32 * k;
+            float nz[4];
+            noise_rows4(ph, nc, ay.out_n, x, yy, lane, nz);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (yy[i] < ay.out_n && x < ax.out_n)
+                    op[(size_t)yy[i] * ax.out_n + x] = noise_finish(clamp_out ? clamp01(acc[i][k]) : acc[i][k], nz[i], nc.flags);
+        }
+        return;
+    }
     for (int t = wid; t < th; t += 8) {
         float w[NT];
 #pragma unroll
@@ -308,11 +422,11 @@ __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ i
 //       NT LDS + NT FFMA per output, clamp fused, coalesced 128 B stores.
 // NT == 0 selects run-time tap counts (long windows of extreme down-scales) with the horizontal taps in smem.
 // Rounding order differs from ATen's (W then H) by ~1e-7, inside the 1e-5 bar of the path.
-template <int NT, bool VEC>
+template <int NT, bool VEC, bool NOISE>
 __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict__ img, float* __restrict__ out,
                                                         AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
                                                         const int* __restrict__ tx_lo, int TW, int TH, int pitch,
-                                                        int clamp_out) {
+                                                        int clamp_out, const __grid_constant__ NoiseEpi ne) {
     extern __shared__ __align__(16) float sm[];
     const int nty = NT ? NT : ay.max_taps, ntx = NT ? NT : ax.max_taps;
     const int wxp = ntx | 1;  // odd pitch of the run-time horizontal tap table: conflict-free column reads
@@ -435,7 +549,48 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
     }
     __syncthreads();
     // ---- horizontal pass: vbuf -> global ----
-    {
+    if (NOISE) {
+        // the same sums, four output rows per trip (rows ph + (4g + i) * PH) so that the noise epilogue can share one
+        // Philox call between the four lanes of a quad; every lane takes part in the exchange, stores are predicated
+        const int col = tid % TW, ph = tid / TW, PH = 256 / TW;
+        const int x = ox0 + col, lane = tid & 31;
+        const bool colok = col < tw;
+        const Philox phx(ne.seed);
+        const NoiseCtx nc = noise_ctx(ne, plane, ay.out_n, ax.out_n);
+        float* op = out + (size_t)plane * ay.out_n * ax.out_n + x;
+        const float* vp = vbuf + (colok ? xlo[col] : 0);
+        float w[NT ? NT : 1];
+        if (NT) {
+#pragma unroll
+            for (int j = 0; j < (NT ? NT : 1); ++j) w[j] = colok ? wxs[col * wxp + j] : 0.0f;
+        }
+        const float* wp = wxs + (colok ? col : 0) * wxp;
+        for (int t0 = ph; t0 < th; t0 += 4 * PH) {
+            float acc[4];
+            int yy[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i * PH;
+                yy[i] = t < th ? oy0 + t : ay.out_n;
+                acc[i] = 0.0f;
+                if (t < th && colok) {
+                    const float* rp = vp + t * pitch;
+                    if (NT) {
+#pragma unroll
+                        for (int j = 0; j < (NT ? NT : 1); ++j) acc[i] = fmaf(w[j], rp[j], acc[i]);
+                    } else {
+                        for (int j = 0; j < ntx; ++j) acc[i] = fmaf(wp[j], rp[j], acc[i]);
+                    }
+                }
+            }
+            float nz[4];
+            noise_rows4(phx, nc, ay.out_n, x, yy, lane, nz);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (yy[i] < ay.out_n && colok)
+                    op[(size_t)yy[i] * ax.out_n] = noise_finish(clamp_out ? clamp01(acc[i]) : acc[i], nz[i], nc.flags);
+        }
+    } else {
         const int col = tid % TW, ph = tid / TW, PH = 256 / TW;
         const int x = ox0 + col;
         if (col < tw) {
@@ -467,9 +622,11 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
 
 // Fallback for extreme down-scales (> 64 taps per output on an axis): one thread per output pixel,
 // horizontal sums nested inside the vertical sum, everything straight from L1/L2.  Correct, not fast.
+template <bool NOISE>
 __global__ void __launch_bounds__(256) resize_generic_kernel(const float* __restrict__ img, float* __restrict__ out,
                                                              AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
-                                                             const int* __restrict__ tx_lo, int clamp_out) {
+                                                             const int* __restrict__ tx_lo, int clamp_out,
+                                                             const __grid_constant__ NoiseEpi ne) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= ax.out_n || y >= ay.out_n) return;
     const float* wx = reinterpret_cast<const float*>(tx_lo + 2 * ax.out_n) + (size_t)x * ax.max_taps;
@@ -483,7 +640,18 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(const float* __rest
         for (int j = 0; j < xn; ++j) h = fmaf(wx[j], __ldg(rp + j), h);
         acc = fmaf(wy[i], h, acc);
     }
-    out[(size_t)blockIdx.z * ay.out_n * ax.out_n + (size_t)y * ax.out_n + x] = clamp_out ? clamp01(acc) : acc;
+    float v = clamp_out ? clamp01(acc) : acc;
+    if (NOISE) {  // (rare path: every thread draws its own quad and keeps one component)
+        const Philox ph(ne.seed);
+        const NoiseCtx nc = noise_ctx(ne, blockIdx.z, ay.out_n, ax.out_n);
+        float4 n = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nc.need_color) n = normal4(ph, nc.color_base + (uint64_t)y * nc.QW + (x >> 2), nc.stream_color);
+        if (nc.need_gray) g = normal4(ph, (uint64_t)y * nc.QW + (x >> 2), nc.stream_gray);
+        const int k = x & 3;
+        const float nn = k == 0 ? n.x : k == 1 ? n.y : k == 2 ? n.z : n.w, gg = k == 0 ? g.x : k == 1 ? g.y : k == 2 ? g.z : g.w;
+        v = noise_finish(v, fmaf(gg, nc.cb, nn * nc.ca), nc.flags);
+    }
+    out[(size_t)blockIdx.z * ay.out_n * ax.out_n + (size_t)y * ax.out_n + x] = v;
 }
 
 static AxisSpec make_axis(int mode, int in_n, int out_n) {
@@ -539,10 +707,15 @@ extern "C" int otf_resize_tables_f32(int H, int W, int OH, int OW, int mode, voi
     return OTF_OK;
 }
 
-extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
-                              int clamp_out, void* workspace_dev, int64_t workspace_bytes, int tables_ready,
-                              void* stream) {
-    using namespace otf;
+namespace otf {
+static int resize_impl(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
+                       int clamp_out, void* workspace_dev, int64_t workspace_bytes, int tables_ready,
+                       void* stream, const NoiseEpi* nep) {
+    NoiseEpi ne;
+    memset(&ne, 0, sizeof(ne));
+    if (nep) ne = *nep;
+    const bool noise = nep != nullptr;
+
     OTF_REQUIRE(img && out && img != out && workspace_dev, OTF_ERR_BAD_ARG, "resize: bad pointers");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && OH > 0 && OW > 0, OTF_ERR_BAD_ARG, "resize: bad extents");
     OTF_REQUIRE(mode >= OTF_RESIZE_BILINEAR_AA && mode <= OTF_RESIZE_LANCZOS, OTF_ERR_BAD_ARG, "resize: unknown mode %d", mode);
@@ -581,17 +754,18 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
         }
         if (smem <= 200 * 1024) {
             const dim3 grid(ceil_div(OW, TW), ceil_div(OH, TH), planes);
+#define OTF_RESIZE_VH2(NT_, V_, N_)                                                                                       \
+    do {                                                                                                                  \
+        auto kfn = resize_vh_kernel<NT_, V_, N_>;                                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, TW, TH, pitch, clamp_out, ne);                       \
+    } while (0)
 #define OTF_RESIZE_VH(NT_)                                                                                                \
     do {                                                                                                                  \
-        if (vec) {                                                                                                        \
-            auto kfn = resize_vh_kernel<NT_, true>;                                                                       \
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-            kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, TW, TH, pitch, clamp_out);                       \
-        } else {                                                                                                          \
-            auto kfn = resize_vh_kernel<NT_, false>;                                                                      \
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-            kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, TW, TH, pitch, clamp_out);                       \
-        }                                                                                                                 \
+        if (vec && noise) OTF_RESIZE_VH2(NT_, true, true);                                                                \
+        else if (vec) OTF_RESIZE_VH2(NT_, true, false);                                                                   \
+        else if (noise) OTF_RESIZE_VH2(NT_, false, true);                                                                 \
+        else OTF_RESIZE_VH2(NT_, false, false);                                                                           \
     } while (0)
             switch (NTv) {
                 case 1: OTF_RESIZE_VH(1); break;
@@ -609,7 +783,8 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
         }
     }
     if (mt > 64) {
-        resize_generic_kernel<<<dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes), 256, 0, st>>>(img, out, ay, ax, ty_lo, tx_lo, clamp_out);
+        if (noise) resize_generic_kernel<true><<<dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes), 256, 0, st>>>(img, out, ay, ax, ty_lo, tx_lo, clamp_out, ne);
+        else resize_generic_kernel<false><<<dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes), 256, 0, st>>>(img, out, ay, ax, ty_lo, tx_lo, clamp_out, ne);
         OTF_LAUNCH_CHECK("resize_generic_kernel");
         return OTF_OK;
     }
@@ -641,12 +816,17 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
     const dim3 grid(ceil_div(OW, 32 * CW), ceil_div(OH, tile_h), planes);
 #define OTF_RESIZE_LAUNCH(NT_, CW_)                                                                                       \
     do {                                                                                                                  \
-        auto kfn = resize_kernel<NT_, CW_>;                                                                               \
+        if (noise) OTF_RESIZE_LAUNCH2(NT_, CW_, true);                                                                    \
+        else OTF_RESIZE_LAUNCH2(NT_, CW_, false);                                                                         \
+    } while (0)
+#define OTF_RESIZE_LAUNCH2(NT_, CW_, N_)                                                                                  \
+    do {                                                                                                                  \
+        auto kfn = resize_kernel<NT_, CW_, N_>;                                                                           \
         if (smem > 48 * 1024) {                                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
             if (e != cudaSuccess) return cuda_fail(e, "resize smem attribute");                                           \
         }                                                                                                                 \
-        kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, tile_h, rows_cap, cols_cap, clamp_out, vec_ok);            \
+        kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, tile_h, rows_cap, cols_cap, clamp_out, vec_ok, ne);        \
     } while (0)
 #define OTF_RESIZE_CW(NT_)                                  \
     do {                                                    \
@@ -668,4 +848,28 @@ extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float*
     }
     OTF_LAUNCH_CHECK("resize_kernel");
     return OTF_OK;
+}
+}  // namespace otf
+
+extern "C" int otf_resize_f32(const float* img, int planes, int H, int W, float* out, int OH, int OW, int mode,
+                              int clamp_out, void* workspace_dev, int64_t workspace_bytes, int tables_ready,
+                              void* stream) {
+    return otf::resize_impl(img, planes, H, W, out, OH, OW, mode, clamp_out, workspace_dev, workspace_bytes, tables_ready, stream,
+                            nullptr);
+}
+
+extern "C" int otf_resize_gauss_f32(const float* img, int B, int C, int H, int W, float* out, int OH, int OW, int mode,
+                                    int clamp_out, void* workspace_dev, int64_t workspace_bytes, int tables_ready,
+                                    const float* sigma_dev, const float* gray_dev, uint64_t seed, uint64_t offset,
+                                    const uint64_t* offset_dev, int noise_flags, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(sigma_dev, OTF_ERR_BAD_ARG, "resize_gauss: null sigma");
+    OTF_REQUIRE(B > 0 && C > 0, OTF_ERR_BAD_ARG, "resize_gauss: bad extents");
+    OTF_REQUIRE(!(noise_flags & (OTF_NOISE_ROUNDS | OTF_NOISE_FIELD_ONLY | OTF_NOISE_RAW_FIELD)), OTF_ERR_UNSUPPORTED,
+                "resize_gauss: only the plain / clip tails are fused (rounds, field-only and injected fields take two launches)");
+    NoiseEpi ne;
+    memset(&ne, 0, sizeof(ne));
+    ne.sigma = sigma_dev; ne.gray = gray_dev; ne.offset_dev = offset_dev; ne.seed = seed; ne.offset = offset; ne.C = C;
+    ne.flags = noise_flags;
+    return resize_impl(img, B * C, H, W, out, OH, OW, mode, clamp_out, workspace_dev, workspace_bytes, tables_ready, stream, &ne);
 }

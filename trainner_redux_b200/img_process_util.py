@@ -49,7 +49,7 @@ class KernelAnalysis:
         self.scratch = torch.empty(len(kernels) * self.words, dtype=torch.int32, device=kernels[0].device)
         ptrs = (C.c_void_p * len(kernels))(*[t.data_ptr() for t in self.kernels])
         _lib.call("otf_filter2d_analyse_f32", ptrs, len(kernels), kb, k, _lib.ptr(self.scratch), _lib.stream(),
-                  launches=2 if kb > 1 else 1)
+                  launches=1)
 
     def scratch_ptr(self, i: int) -> C.c_void_p:
         return C.c_void_p(self.scratch.data_ptr() + 4 * i * self.words)
@@ -87,7 +87,7 @@ def filter2d(img: Tensor, kernel: Tensor, *, _analysis: tuple[KernelAnalysis, in
     # per-kernel analysis scratch: true radii, launch order, rank-1 flags and factors
     scratch = torch.empty(_lib.load().otf_filter2d_scratch_words(kb), dtype=torch.int32, device=x.device)
     _lib.call("otf_filter2d_f32", _lib.ptr(x), b, c, h, w, _lib.ptr(kern), kb, k, _lib.ptr(scratch), 0, _lib.ptr(out), _lib.stream(),
-              launches=1 if k > 21 else (3 if kb > 1 else 2))
+              launches=1 if k > 21 else 2)
     return out
 
 

@@ -49,6 +49,7 @@ class StageList:
         self._host_vecs: list[Tensor] = []  # per-sample CPU vectors, uploaded together by run()
         self._host_slots: list[tuple[int, str]] = []  # (stage index, field) to patch with the uploaded address
         self._new_tables: list[tuple[tuple, Tensor]] = []  # resize weight tables this run builds (published by run())
+        self.unit_range = False  # the running image is known to lie in [0, 1] (after a clamping stage)
 
     # -- helpers ------------------------------------------------------------------------------
     def _add(self, op: int, **kw: Any) -> _lib.Stage:
@@ -96,7 +97,7 @@ class StageList:
         self._sets = list(ptrs)
         self._sets_shape = (kb, k)
         self._add(_lib.OP_ANALYSE, n=len(kernels), kb=kb, K=k, **{f"p{i}": p for i, p in enumerate(ptrs)})
-        self.launches += 2 if kb > 1 else 1
+        self.launches += 1
 
     def filter2d(self, kernel: Tensor, analysed_set: int | None = None) -> None:
         k, kb = kernel.size(-1), kernel.size(0)
@@ -111,9 +112,11 @@ class StageList:
         if analysed_set is not None and k <= 21:
             self._add(_lib.OP_FILTER2D, p0=self._sets[analysed_set], kb=kb, K=k, n=analysed_set)
             self.launches += 1
+            self.unit_range = False
         else:
             self._add(_lib.OP_FILTER2D, p0=self._dev_ptr(kernel), kb=kb, K=k, n=-1)
-            self.launches += 1 if k > 21 else (3 if kb > 1 else 2)
+            self.launches += 1 if k > 21 else 2
+            self.unit_range = False
 
     def usm(self, taps: np.ndarray, weight: float, threshold: float) -> None:
         n = len(taps)
@@ -123,6 +126,7 @@ class StageList:
         self._keep.append(taps)
         self._add(_lib.OP_USM, p0=taps.ctypes.data, n=n, f0=float(weight), f1=float(threshold))
         self.launches += 4
+        self.unit_range = False
 
     def resize(self, mode: str, scale_factor: float = 0, size: tuple[int, int] = (0, 0)) -> None:
         """degradations.resize_pt: ``size`` wins, else round(extent * scale_factor); always clamps."""
@@ -131,6 +135,12 @@ class StageList:
         if scale_factor != 0:
             size = (round(self.h * scale_factor), round(self.w * scale_factor))
         oh, ow = int(size[0]), int(size[1])
+        if (oh, ow) == (self.h, self.w) and self.unit_range and (mode in D._MODE_ID or mode == "lanczos"):
+            # A same-size resample is the identity in every mode of resize_pt — the window weights evaluate to exactly
+            # (1, 0, ...) (cubic pieces vanish at 1 and 2 in fp32, area / nearest windows have one tap, the lanczos
+            # prefilter only runs on shrinking axes) — and the trailing clamp(0, 1) is the identity on an image a clamping
+            # stage produced: no launch (realesrgan_model.py:564-571 with ori_h // scale equal to the current extent).
+            return
         if mode == "lanczos" and _lib.load().otf_resize_workspace_bytes(self.h, self.w, oh, ow, _lib.RESIZE_LANCZOS) > 0:
             mode_id = _lib.RESIZE_LANCZOS  # prefilter and bicubic sample composed into one set of weight tables: one launch
         elif mode == "lanczos":  # extreme down-scales: prefilter the shrinking axes, then plain bicubic (degradations.py:982-1001)
@@ -140,6 +150,7 @@ class StageList:
                     self._keep.append(taps)
                     self._add(_lib.OP_SEPCONV, p0=taps.ctypes.data, n=len(taps), mode=axis)
                     self.launches += 1
+                    self.unit_range = False
             mode_id = _lib.RESIZE_BICUBIC
         elif mode in D._MODE_ID:
             mode_id = D._MODE_ID[mode]
@@ -179,6 +190,7 @@ class StageList:
                   p0=None if tab is None else tab.data_ptr())
         self.launches += 1 if ready else 2
         self.h, self.w = oh, ow
+        self.unit_range = bool(clamp)
 
     def gaussian_noise(self, sigma: float | Tensor, gray: float | Tensor | None, gen: D.PhiloxState, clip: bool = True,
                        rounds: bool = False, noise: Tensor | None = None, noise_gray: Tensor | None = None) -> None:
@@ -192,6 +204,7 @@ class StageList:
         self._per_sample(s, "p0", sigma)
         self._per_sample(s, "p1", gray)
         self.launches += 1
+        self.unit_range = bool(clip)
 
     def _offset(self, gen: D.PhiloxState) -> dict:
         """Philox position of a noise stage: the generator's running offset, or — with a parameter block — the stage's
@@ -205,6 +218,7 @@ class StageList:
         f = field.to(torch.float32).expand(self.b, self.c, self.h, self.w)
         self._add(_lib.OP_GAUSS, flags=D._flags(clip, rounds) | _lib.NOISE_RAW_FIELD, p2=self._dev_ptr(f))
         self.launches += 1
+        self.unit_range = bool(clip)
 
     def poisson_noise(self, scale: float | Tensor, gray: float | Tensor | None, gen: D.PhiloxState, clip: bool = True,
                       rounds: bool = False, counts: Tensor | None = None, counts_gray: Tensor | None = None) -> None:
@@ -223,6 +237,7 @@ class StageList:
         self._per_sample(s, "p0", scale)
         self._per_sample(s, "p1", gray)
         self.launches += 2
+        self.unit_range = bool(clip)
 
     def jpeg(self, quality: float | Tensor, differentiable: bool = False, clamp_in: bool = True, round8: bool = False) -> None:
         """DiffJPEG.forward(x, quality) with the conversion of the quality fused into the kernel."""
@@ -234,10 +249,12 @@ class StageList:
         else:
             self._add(_lib.OP_JPEG, flags=flags, f0=float(quality))
         self.launches += 1
+        self.unit_range = True  # diffjpeg.py:476-479: clamp to [0, 255], then / 255
 
     def clamp_round(self) -> None:
         self._add(_lib.OP_CLAMP_ROUND)
         self.launches += 1
+        self.unit_range = True
 
     # -- execution ----------------------------------------------------------------------------
     def run(self, crop: tuple[Tensor, int, int, int, int] | None = None) -> Tensor | tuple[Tensor, Tensor]:
@@ -275,7 +292,11 @@ class StageList:
             raise _lib.OtfError(f"otf_run_stages_workspace_bytes failed ({ws_bytes}): {_lib.last_error()}")
         ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.int32, device=self.device)
         _lib.call("otf_run_stages_f32", _lib.ptr(self.img), b, c, h0, w0, arr, n, _lib.ptr(ws), ws_bytes, None, None, _lib.stream(),
-                  launches=self.launches)
+                  launches=0)
+        # the executor fuses adjacent stages where it has a fused kernel (csrc/chain.cu): what it launched is its count,
+        # self.launches stays the unfused figure (one entry point per stage)
+        self.launched = lib.otf_run_stages_launches()
+        _lib.launch_count += self.launched
         if self._new_tables:  # one event covers every table this run built
             cur = torch.cuda.current_stream()
             ev = torch.cuda.Event()

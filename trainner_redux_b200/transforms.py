@@ -50,7 +50,7 @@ def crop_pair(img_gt: Tensor, img_lq: Tensor, gt_patch_size: int, scale: int, to
     gt_out = torch.empty((b, c, g, g), dtype=torch.float32, device=gt.device)
     lq_out = torch.empty((b, c, p, p), dtype=torch.float32, device=gt.device)
     _lib.call(
-        "otf_crop_pair_f32", _lib.ptr(gt), b * c, hg, wg, _lib.ptr(lq), hl, wl, top, left, None, p, scale,
+        "otf_crop_pair_f32", _lib.ptr(gt), b * c, hg, wg, _lib.ptr(lq), hl, wl, top, left, None, p, scale, 0,
         _lib.ptr(gt_out), _lib.ptr(lq_out), _lib.stream(),
     )
     return gt_out, lq_out
