@@ -47,6 +47,18 @@ for it in range(3):
         T.filter2d(x64, sk)
     if want("poisson"):
         D.add_poisson_noise_pt(x192, sigma / 10, True, False, gray)
+    if want("g1"):
+        from trainner_redux_b200 import _lib as L
+        for (x, oh, mode_id) in ((gt, 192, L.RESIZE_BICUBIC_AA), (x192, 64, L.RESIZE_BILINEAR_AA)):
+            b, c, h, w = x.shape
+            tab = D.pinned_resize_table(dev, h, w, oh, oh, mode_id)
+            nb = L.load().otf_resize_workspace_bytes(h, w, oh, oh, mode_id)
+            o = torch.empty(b, c, oh, oh, device=dev)
+            L.call("otf_resize_gauss_f32", L.ptr(x), b, c, h, w, L.ptr(o), oh, oh, mode_id, 1, L.ptr(tab), nb, 1, L.ptr(sigma), L.ptr(gray),
+                   7, 1, None, L.NOISE_CLIP, L.stream())
+        go, lo = torch.empty(B, 3, 224, 224, device=dev), torch.empty(B, 3, 56, 56, device=dev)
+        L.call("otf_diffjpeg_crop_pair_f32", L.ptr(x64), B, 64, 64, L.ptr(q), 0.0, 1, 0, 1, L.ptr(gt), 256, 256, 4, 4, None, 56, 4,
+               L.ptr(go), L.ptr(lo), L.stream())
     if want("usm"):
         T.USMSharp().to(dev)(gt)
 torch.cuda.synchronize()

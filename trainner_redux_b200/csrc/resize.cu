@@ -162,8 +162,25 @@ __device__ void lanczos_axis_weights(const AxisSpec& ax, int o, int* lo_out, int
 // ---- pass 0: per-launch weight tables ------------------------------------------------------
 // table layout for an axis with out_n outputs and T = max_taps: int lo[out_n], int n[out_n],
 // float w[out_n][T].  One thread per output index; the tables are a few KB and stay in L2.
+//
+// Shapes the register-blocked kernel (resize_rb_kernel below) takes get a second block behind the two tables: the
+// windows of every group of GV output rows / GH output columns expanded into DENSE weight matrices (zeros where a
+// tap does not reach), laid out exactly as a CTA wants them in shared memory, so that the resampler's prologue is a
+// straight cp.async copy of its slice instead of a per-CTA scatter with dependent table lookups:
+//   int   vbase[ngy]            first source row of row group g            (ngy = tiles_y * TH / GV, padded to whole tiles)
+//   float wv[ngy][RV][GV]       wv[g][r][i] = weight of source row vbase[g] + r for output row g * GV + i
+//   int   hbase[ngx]            first ibuf column of column group k's span, a multiple of 4, relative to its tile's c0
+//   float whs[ngx][GH * 4SH + 4]  whs[k][i * 4SH + c] = weight of ibuf column hbase[k] + c for output column k * GH + i
+//   int   tc0[tiles_x], tnq[tiles_x]   first source column of the tile (multiple of 4) and its count of column quads
+struct RbPlan {
+    int cfg;  // -1: shape not covered
+    int GV, RV, GH, SH, TW, TH, pitch, tiles_x, tiles_y;
+    int off_vbase, off_wv, off_hbase, off_whs, off_tc0, off_tnq, total_ints;  // in 4-byte words from the block's start
+    int smem;
+};
+
 __global__ void __launch_bounds__(128) resize_tables_kernel(int mode, AxisSpec ay, AxisSpec ax, int* __restrict__ ty_lo,
-                                                            int* __restrict__ tx_lo) {
+                                                            int* __restrict__ tx_lo, RbPlan pl, int* __restrict__ dense) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ay.out_n) {
         float* w = reinterpret_cast<float*>(ty_lo + 2 * ay.out_n) + (size_t)i * ay.max_taps;
@@ -175,8 +192,56 @@ __global__ void __launch_bounds__(128) resize_tables_kernel(int mode, AxisSpec a
         if (mode == OTF_RESIZE_LANCZOS) lanczos_axis_weights(ax, o, tx_lo + o, tx_lo + ax.out_n + o, w);
         else axis_weights(mode, ax, o, tx_lo + o, tx_lo + ax.out_n + o, w);
     }
+    if (pl.cfg < 0) return;
+    // dense block: thread = one (possibly padded) output index; it owns one column of its group's matrix
+    constexpr int kMaxT = 16;  // rb shapes have max_taps <= 13
+    float w[kMaxT], w2[kMaxT];
+    auto window = [&](const AxisSpec& a, int o, int* lo, int* n, float* wp) {
+        if (mode == OTF_RESIZE_LANCZOS) lanczos_axis_weights(a, o, lo, n, wp);
+        else axis_weights(mode, a, o, lo, n, wp);
+    };
+    const int rows_pad = pl.tiles_y * pl.TH, cols_pad = pl.tiles_x * pl.TW;
+    if (i < rows_pad) {
+        const int t = i, g = t / pl.GV, ii = t - g * pl.GV;
+        float* col = reinterpret_cast<float*>(dense + pl.off_wv) + (size_t)g * pl.RV * pl.GV + ii;
+        for (int r = 0; r < pl.RV; ++r) col[r * pl.GV] = 0.0f;
+        int lo0 = 0, n0 = 0;
+        if (g * pl.GV < ay.out_n) window(ay, g * pl.GV, &lo0, &n0, w2);
+        if (ii == 0) dense[pl.off_vbase + g] = lo0;
+        if (t < ay.out_n) {
+            int lo, n;
+            window(ay, t, &lo, &n, w);
+            for (int j = 0; j < n; ++j) {
+                const int r = lo - lo0 + j;
+                if (r >= 0 && r < pl.RV) col[r * pl.GV] = w[j];
+            }
+        }
+    } else if (i - rows_pad < cols_pad) {
+        const int o = i - rows_pad, k = o / pl.GH, ii = o - k * pl.GH, tile = o / pl.TW, SPAN = 4 * pl.SH, WHP = pl.GH * SPAN + 4;
+        float* row = reinterpret_cast<float*>(dense + pl.off_whs) + (size_t)k * WHP + ii * SPAN;
+        for (int c = 0; c < SPAN; ++c) row[c] = 0.0f;
+        if (ii == 0)
+            for (int c = 0; c < 4; ++c) row[pl.GH * SPAN + c] = 0.0f;  // (the pad words)
+        int lo, n, lot = 0, lok = 0;
+        window(ax, min(tile * pl.TW, ax.out_n - 1), &lot, &n, w2);
+        const int c0 = lot & ~3;
+        window(ax, min(k * pl.GH, ax.out_n - 1), &lok, &n, w2);
+        const int hb = (lok - c0) & ~3;
+        if (ii == 0) dense[pl.off_hbase + k] = hb;
+        if (o < ax.out_n) {
+            window(ax, o, &lo, &n, w);
+            for (int j = 0; j < n; ++j) {
+                const int c = lo - c0 - hb + j;
+                if (c >= 0 && c < SPAN) row[c] = w[j];
+            }
+        }
+        if (o == tile * pl.TW) {
+            window(ax, min(tile * pl.TW + pl.TW, ax.out_n) - 1, &lo, &n, w2);
+            dense[pl.off_tc0 + tile] = c0;
+            dense[pl.off_tnq + tile] = min((min(lo + n, ax.in_n) - c0 + 3) >> 2, (pl.pitch - SPAN) >> 2);
+        }
+    }
 }
-
 
 // ---- fused Gaussian-noise epilogue (row g1: resize + noise + clamp in one launch) ----------------------------
 // What otf_gaussian_noise_f32 would do to this launch's output (degradations.py:569-633 after :1004-1021), applied
@@ -620,6 +685,176 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
     }
 }
 
+// ---- pass 1 (v6): register-blocked dense windows ---------------------------------------------------------------
+// Both passes of the vertical-first kernel above pay one load per tap per output (NT LDG.128 per intermediate quad,
+// NT LDS per output) plus the index arithmetic around them: ~130 warp instructions per 32 outputs at 256->192, issue-
+// and latency-bound at a quarter of the HBM roof.  Here a task produces a BLOCK of outputs along the resampled axis
+// from the union of their windows, with the block's windows expanded into a small dense weight matrix (zeros where a
+// tap does not reach): every source value is loaded once per block and feeds all the block's outputs from registers.
+//   (V) task = (source column quad, group of GV output rows): RV coalesced LDG.128 straight from global memory (all
+//       independent: one round trip per task), RV broadcast LDS.128 of the group's weights [r][GV], GV*RV FMA4,
+//       GV STS.128 into ibuf[TH][pitch];
+//   (H) thread = a group of GH output columns with its dense GH x 4SH weights in REGISTERS, walking down the tile's
+//       rows: SH LDS.128 + GH*4SH FMAs per GH outputs, then clamp (+ the Gaussian-noise epilogue: with GH = 4 the
+//       thread's outputs are exactly one Philox quad of the stand-alone noise kernel) and one 16-byte store.
+// The zero taps cost FMAs (~1.6x the minimum) — the FMA pipe is nowhere near busy here — and buy a 3x cut in load
+// instructions and no per-tap index arithmetic at all.  Summation order inside a window is unchanged (taps in
+// ascending source order, zeros in between are exact no-ops), so results equal the vertical-first kernel's bit for bit.
+template <int GV, int RV, int GH, int SH, bool VEC, bool NOISE>
+__global__ void __launch_bounds__(128, 4) resize_rb_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                           AxisSpec ay, AxisSpec ax, const int* __restrict__ dense,
+                                                           const __grid_constant__ RbPlan pl, int clamp_out, int vec_out,
+                                                           const __grid_constant__ NoiseEpi ne) {
+    constexpr int SPAN = 4 * SH, WHP = GH * SPAN + 4;  // (+4: consecutive column groups start 4 banks apart)
+    extern __shared__ __align__(16) float sm[];
+    const int TW = pl.TW, TH = pl.TH, pitch = pl.pitch;
+    const int NG = TH / GV, KP = TW / GH;
+    float* ibuf = sm;                                   // [TH][pitch]  vertical-pass result
+    float* wv = ibuf + (size_t)TH * pitch;              // [NG][RV][GV] dense vertical weights of each row group
+    float* whs = wv + NG * RV * GV;                     // [KP][WHP]    dense horizontal weights of each column group
+    int* hbase = reinterpret_cast<int*>(whs + KP * WHP);  // [KP] first ibuf column of the group's span (multiple of 4)
+
+    const int plane = blockIdx.z;
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+    const int tw = min(TW, ax.out_n - ox0), th = min(TH, ay.out_n - oy0);
+    const int H = ay.in_n, W = ax.in_n;
+    // this CTA's slices of the dense block -> shared memory, asynchronously (16-byte pieces; every slice starts on a
+    // 16-byte boundary: TH / GV * RV * GV, TW / GH * WHP and TW / GH words are multiples of 4)
+    {
+        const float* gwv = reinterpret_cast<const float*>(dense + pl.off_wv) + (size_t)blockIdx.y * NG * RV * GV;
+        const float* gwh = reinterpret_cast<const float*>(dense + pl.off_whs) + (size_t)blockIdx.x * KP * WHP;
+        const float* ghb = reinterpret_cast<const float*>(dense + pl.off_hbase) + (size_t)blockIdx.x * KP;
+        for (int i = tid; i < NG * RV * GV / 4; i += 128) cp_async_f32x4(wv + 4 * i, gwv + 4 * i);
+        for (int i = tid; i < KP * WHP / 4; i += 128) cp_async_f32x4(whs + 4 * i, gwh + 4 * i);
+        for (int i = tid; i < KP / 4; i += 128) cp_async_f32x4(reinterpret_cast<float*>(hbase) + 4 * i, ghb + 4 * i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int c0 = __ldg(dense + pl.off_tc0 + blockIdx.x), nq = __ldg(dense + pl.off_tnq + blockIdx.x);
+    const int* gvb = dense + pl.off_vbase + blockIdx.y * NG;
+    // columns behind the span: zero-weight taps of the last column groups read them (SPAN words per row suffice)
+    for (int i = tid; i < TH * SH; i += 128) {
+        const int r = i / SH, c = i - r * SH;
+        *reinterpret_cast<float4*>(ibuf + (size_t)r * pitch + 4 * (nq + c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- vertical pass: global -> ibuf ----
+    {
+        const float* ip = img + (size_t)plane * H * W;
+        const int ntask = nq * ((th + GV - 1) / GV);
+        int task = tid;
+        float4 v[RV];
+        auto load = [&](int tk) {
+            const int g = tk / nq, q = tk - g * nq;
+            const int r0 = __ldg(gvb + g), col = c0 + 4 * q;
+            const int last = H - 1 - r0;  // rows past the image only meet zero weights: hold the last row
+            const float* p0 = ip + (size_t)r0 * W + col;
+#pragma unroll
+            for (int r = 0; r < RV; ++r) {
+                const float* p = p0 + min(r, last) * W;
+                if (VEC) {
+                    v[r] = __ldg(reinterpret_cast<const float4*>(p));
+                } else {
+                    v[r].x = col < W ? __ldg(p) : 0.0f;
+                    v[r].y = col + 1 < W ? __ldg(p + 1) : 0.0f;
+                    v[r].z = col + 2 < W ? __ldg(p + 2) : 0.0f;
+                    v[r].w = col + 3 < W ? __ldg(p + 3) : 0.0f;
+                }
+            }
+        };
+        if (task < ntask) load(task);  // in flight while the weights arrive
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        while (task < ntask) {
+            const int g = task / nq, q = task - g * nq;
+            const float* wg = wv + g * RV * GV;
+            float4 acc[GV];
+#pragma unroll
+            for (int i = 0; i < GV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < RV; ++r) {
+                float w[GV];
+                if (GV == 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wg + r * GV);
+                    w[0] = w4.x; w[1] = w4.y; w[2 % GV] = w4.z; w[3 % GV] = w4.w;
+                } else {
+                    const float2 w2 = *reinterpret_cast<const float2*>(wg + r * GV);
+                    w[0] = w2.x; w[1] = w2.y;
+                }
+#pragma unroll
+                for (int i = 0; i < GV; ++i) {
+                    acc[i].x = fmaf(w[i], v[r].x, acc[i].x); acc[i].y = fmaf(w[i], v[r].y, acc[i].y);
+                    acc[i].z = fmaf(w[i], v[r].z, acc[i].z); acc[i].w = fmaf(w[i], v[r].w, acc[i].w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < GV; ++i) *reinterpret_cast<float4*>(ibuf + (size_t)(g * GV + i) * pitch + 4 * q) = acc[i];
+            task += 128;
+            if (task < ntask) load(task);
+        }
+    }
+    __syncthreads();
+    // ---- horizontal pass: ibuf -> global ----
+    const int k = tid & (KP - 1), ph = tid / KP, PH = 128 / KP;
+    const int x0 = ox0 + k * GH;
+    if (k * GH >= tw) return;
+    float wr[GH][SPAN];
+#pragma unroll
+    for (int i = 0; i < GH; ++i)
+#pragma unroll
+        for (int s4 = 0; s4 < SH; ++s4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(whs + k * WHP + i * SPAN + 4 * s4);
+            wr[i][4 * s4] = t4.x; wr[i][4 * s4 + 1] = t4.y; wr[i][4 * s4 + 2] = t4.z; wr[i][4 * s4 + 3] = t4.w;
+        }
+    const float* rp0 = ibuf + hbase[k];
+    float* op = out + (size_t)plane * ay.out_n * ax.out_n + x0;
+    const Philox phx(NOISE ? ne.seed : 0);
+    NoiseCtx nc;
+    if (NOISE) nc = noise_ctx(ne, plane, ay.out_n, ax.out_n);
+    for (int t = ph; t < th; t += PH) {
+        float in[SPAN];
+#pragma unroll
+        for (int s4 = 0; s4 < SH; ++s4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(rp0 + (size_t)t * pitch + 4 * s4);
+            in[4 * s4] = t4.x; in[4 * s4 + 1] = t4.y; in[4 * s4 + 2] = t4.z; in[4 * s4 + 3] = t4.w;
+        }
+        float acc[GH];
+#pragma unroll
+        for (int i = 0; i < GH; ++i) {
+            float a = 0.0f;
+#pragma unroll
+            for (int c = 0; c < SPAN; ++c) a = fmaf(wr[i][c], in[c], a);
+            acc[i] = clamp_out ? clamp01(a) : a;
+        }
+        const int y = oy0 + t;
+        if (NOISE) {
+            // the quad of gaussian_noise_kernel that holds these outputs: x0 is a multiple of GH, GH divides 4
+            float4 n = make_float4(0.f, 0.f, 0.f, 0.f), gq = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int xq = x0 >> 2;
+            if (nc.need_color) n = normal4(phx, nc.color_base + (uint64_t)y * nc.QW + xq, nc.stream_color);
+            if (nc.need_gray) gq = normal4(phx, (uint64_t)y * nc.QW + xq, nc.stream_gray);
+            const float nn[4] = {n.x, n.y, n.z, n.w}, gg[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+            for (int i = 0; i < GH; ++i) {
+                const int comp = GH == 4 ? i : ((x0 & 3) + i);
+                float nv = 0.0f, gv = 0.0f;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (m == comp) { nv = nn[m]; gv = gg[m]; }
+                acc[i] = noise_finish(acc[i], fmaf(gv, nc.cb, nv * nc.ca), nc.flags);
+            }
+        }
+        float* orow = op + (size_t)y * ax.out_n;
+        if (vec_out) {
+            if (GH == 4) *reinterpret_cast<float4*>(orow) = make_float4(acc[0], acc[1], acc[2 % GH], acc[3 % GH]);
+            else *reinterpret_cast<float2*>(orow) = make_float2(acc[0], acc[1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < GH; ++i)
+                if (x0 + i < ax.out_n) orow[i] = acc[i];
+        }
+    }
+}
+
 // Fallback for extreme down-scales (> 64 taps per output on an axis): one thread per output pixel,
 // horizontal sums nested inside the vertical sum, everything straight from L1/L2.  Correct, not fast.
 template <bool NOISE>
@@ -684,13 +919,67 @@ static bool lanczos_ok(int in_n, int out_n) {
 
 static size_t table_ints(const AxisSpec& a) { return (size_t)a.out_n * (2 + a.max_taps); }
 
+// source extent covered by nout consecutive outputs (an upper bound)
+static int span(const AxisSpec& a, int nout) {
+    int v = (int)ceilf(a.scale * (float)(nout - 1)) + a.max_taps + 2;
+    return v > a.in_n ? a.in_n : v;
+}
+
+// Which register-blocked configuration (if any) takes this shape, its tile and the layout of its dense block.
+// Window bound for G consecutive outputs: lo(o + G - 1) - lo(o) <= floor((G - 1) * scale) + 1 and a window has at most
+// max_taps entries; the horizontal span additionally starts on a multiple of 4 (up to 3 words of slack).
+static RbPlan rb_plan(const AxisSpec& ay, const AxisSpec& ax) {
+    RbPlan p;
+    memset(&p, 0, sizeof(p));
+    p.cfg = -1;
+    auto need = [](const AxisSpec& a, int G) { return (int)floorf((float)(G - 1) * a.scale + 1e-3f) + 2 + a.max_taps; };
+    if (need(ay, 4) <= 10 && need(ax, 4) + 3 <= 12) { p.cfg = 0; p.GV = 4; p.RV = 10; p.GH = 4; p.SH = 3; }
+    else if (need(ay, 4) <= 13 && need(ax, 4) + 3 <= 16) { p.cfg = 1; p.GV = 4; p.RV = 13; p.GH = 4; p.SH = 4; }
+    else if (need(ay, 2) <= 12 && need(ax, 2) + 3 <= 16) { p.cfg = 2; p.GV = 2; p.RV = 12; p.GH = 2; p.SH = 4; }
+    else return p;
+    const int OH = ay.out_n, OW = ax.out_n, WHP = p.GH * 4 * p.SH + 4;
+    p.TW = OW >= 96 ? 128 : OW >= 48 ? 64 : 32;
+    p.TH = OH >= 24 ? 32 : 16;
+    for (;;) {
+        p.pitch = ((span(ax, p.TW) + 3 + 3) & ~3) + 4 * p.SH;
+        p.smem = (p.TH * p.pitch + (p.TH / p.GV) * p.RV * p.GV + (p.TW / p.GH) * WHP + p.TW / p.GH) * 4;
+        if (p.smem <= 44 * 1024 || p.TW == 32) break;
+        p.TW /= 2;
+    }
+    if (p.smem > 100 * 1024) { p.cfg = -1; return p; }
+    p.tiles_x = ceil_div(OW, p.TW);
+    p.tiles_y = ceil_div(OH, p.TH);
+    const int ngy = p.tiles_y * (p.TH / p.GV), ngx = p.tiles_x * (p.TW / p.GH);
+    int off = 0;
+    auto take = [&](int words) { const int o = off; off += (words + 3) & ~3; return o; };  // every array 16-byte aligned
+    p.off_vbase = take(ngy);
+    p.off_wv = take(ngy * p.RV * p.GV);
+    p.off_hbase = take(ngx);
+    p.off_whs = take(ngx * WHP);
+    p.off_tc0 = take(p.tiles_x);
+    p.off_tnq = take(p.tiles_x);
+    p.total_ints = off;
+    return p;
+}
+static size_t sparse_ints(const AxisSpec& ay, const AxisSpec& ax) { return (table_ints(ay) + table_ints(ax) + 3) & ~(size_t)3; }
+static int launch_tables(int mode, const AxisSpec& ay, const AxisSpec& ax, int* ws, cudaStream_t st) {
+    const RbPlan pl = rb_plan(ay, ax);
+    int n = ay.out_n + ax.out_n;
+    if (pl.cfg >= 0 && pl.tiles_y * pl.TH + pl.tiles_x * pl.TW > n) n = pl.tiles_y * pl.TH + pl.tiles_x * pl.TW;
+    resize_tables_kernel<<<ceil_div(n, 128), 128, 0, st>>>(mode, ay, ax, ws, ws + table_ints(ay), pl, ws + sparse_ints(ay, ax));
+    OTF_LAUNCH_CHECK("resize_tables_kernel");
+    return OTF_OK;
+}
+
 }  // namespace otf
 
 extern "C" int64_t otf_resize_workspace_bytes(int H, int W, int OH, int OW, int mode) {
     using namespace otf;
     if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || mode < OTF_RESIZE_BILINEAR_AA || mode > OTF_RESIZE_LANCZOS) return -1;
     if (mode == OTF_RESIZE_LANCZOS && !(lanczos_ok(H, OH) && lanczos_ok(W, OW))) return -1;
-    return (int64_t)(table_ints(make_axis(mode, H, OH)) + table_ints(make_axis(mode, W, OW))) * 4;
+    const AxisSpec ay = make_axis(mode, H, OH), ax = make_axis(mode, W, OW);
+    const RbPlan pl = rb_plan(ay, ax);
+    return (int64_t)(sparse_ints(ay, ax) + (pl.cfg >= 0 ? (size_t)pl.total_ints : 0)) * 4;
 }
 
 extern "C" int otf_resize_tables_f32(int H, int W, int OH, int OW, int mode, void* workspace_dev, int64_t workspace_bytes,
@@ -701,10 +990,7 @@ extern "C" int otf_resize_tables_f32(int H, int W, int OH, int OW, int mode, voi
     OTF_REQUIRE(need > 0, OTF_ERR_BAD_ARG, "resize_tables: mode %d or extents (%d, %d) -> (%d, %d) not supported", mode, H, W, OH, OW);
     OTF_REQUIRE(workspace_bytes >= need, OTF_ERR_WORKSPACE, "resize_tables: workspace too small");
     const AxisSpec ay = make_axis(mode, H, OH), ax = make_axis(mode, W, OW);
-    int* ty_lo = (int*)workspace_dev;
-    resize_tables_kernel<<<ceil_div(OH + OW, 128), 128, 0, (cudaStream_t)stream>>>(mode, ay, ax, ty_lo, ty_lo + table_ints(ay));
-    OTF_LAUNCH_CHECK("resize_tables_kernel");
-    return OTF_OK;
+    return launch_tables(mode, ay, ax, (int*)workspace_dev, (cudaStream_t)stream);
 }
 
 namespace otf {
@@ -727,19 +1013,44 @@ static int resize_impl(const float* img, int planes, int H, int W, float* out, i
     int* tx_lo = ty_lo + table_ints(ay);
     cudaStream_t st = (cudaStream_t)stream;
     if (!tables_ready) {  // the tables depend on (H, W, OH, OW, mode) only: a caller may keep and reuse them
-        resize_tables_kernel<<<ceil_div(OH + OW, 128), 128, 0, st>>>(mode, ay, ax, ty_lo, tx_lo);
-        OTF_LAUNCH_CHECK("resize_tables_kernel");
+        if (int rc = launch_tables(mode, ay, ax, ty_lo, st)) return rc;
     }
-    auto span = [](const AxisSpec& a, int nout) {  // source extent covered by nout consecutive outputs
-        int v = (int)ceilf(a.scale * (float)(nout - 1)) + a.max_taps + 2;
-        return v > a.in_n ? a.in_n : v;
-    };
     const int mt = ay.max_taps > ax.max_taps ? ay.max_taps : ax.max_taps;
     // Two tiled kernels: the vertical-first kernel wins when the image shrinks (long windows, output smaller than the
     // source: 256->102 bicubic 0.037 vs 0.072 ms), the staged horizontal-first kernel when it grows (0.052 vs 0.063 ms
     // at 256->384 bilinear).  OTF_RESIZE_IMPL=3|4 forces one of them for A/B runs.
     static const int forced = [] { const char* e = getenv("OTF_RESIZE_IMPL"); return e ? atoi(e) : 0; }();
-    const int impl = forced ? forced : (ay.scale >= 1.0f && ax.scale >= 1.0f ? 4 : 3);
+    const int impl = forced ? forced : (ay.scale >= 1.0f && ax.scale >= 1.0f ? 4 : 3);  // (the fallbacks' choice; 6 = rb only where it fits)
+    // The register-blocked kernel takes every shape whose block windows fit its dense matrices (moderate scales: the
+    // chain's usual x0.4 .. x1.5 steps with bilinear / bicubic / area / nearest windows); the two tiled kernels below stay
+    // for long windows (lanczos prefilters, extreme down-scales).
+    if (forced == 0 || forced == 6) {
+        const RbPlan pl = rb_plan(ay, ax);
+        if (pl.cfg >= 0) {
+            const int vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
+            const int vec_out = (OW % pl.GH == 0) && (((uintptr_t)out & (4 * pl.GH - 1)) == 0);
+            const int* dense = ty_lo + sparse_ints(ay, ax);
+            const dim3 grid(pl.tiles_x, pl.tiles_y, planes);
+#define OTF_RESIZE_RB3(GV_, RV_, GH_, SH_, V_, N_)                                                                        \
+    do {                                                                                                                  \
+        auto kfn = resize_rb_kernel<GV_, RV_, GH_, SH_, V_, N_>;                                                          \
+        if (pl.smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);         \
+        kfn<<<grid, 128, pl.smem, st>>>(img, out, ay, ax, dense, pl, clamp_out, vec_out, ne);                             \
+    } while (0)
+#define OTF_RESIZE_RB(GV_, RV_, GH_, SH_)                                                                                 \
+    do {                                                                                                                  \
+        if (vec && noise) OTF_RESIZE_RB3(GV_, RV_, GH_, SH_, true, true);                                                 \
+        else if (vec) OTF_RESIZE_RB3(GV_, RV_, GH_, SH_, true, false);                                                    \
+        else if (noise) OTF_RESIZE_RB3(GV_, RV_, GH_, SH_, false, true);                                                  \
+        else OTF_RESIZE_RB3(GV_, RV_, GH_, SH_, false, false);                                                            \
+    } while (0)
+            if (pl.cfg == 0) OTF_RESIZE_RB(4, 10, 4, 3);
+            else if (pl.cfg == 1) OTF_RESIZE_RB(4, 13, 4, 4);
+            else OTF_RESIZE_RB(2, 12, 2, 4);
+            OTF_LAUNCH_CHECK("resize_rb_kernel");
+            return OTF_OK;
+        }
+    }
     if (impl == 4) {
         const int vec = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
         const int NTv = mt <= 1 ? 1 : mt <= 2 ? 2 : mt <= 3 ? 3 : mt <= 4 ? 4 : mt <= 6 ? 6 : mt <= 8 ? 8 : mt <= 12 ? 12 : mt <= 16 ? 16 : 0;
