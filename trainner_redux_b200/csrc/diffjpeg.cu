@@ -3,32 +3,20 @@
 //  IDCT -> chroma x2 -> YCbCr2RGB -> clamp -> /255 -> crop), which the reference runs as ~60 ATen
 // launches and ~25 image-sized HBM round trips.  Here the image is read once and written once.
 //
-// Mapping: one warp = one 16x16 MCU (4 Y blocks + Cb + Cr).  Lane l owns the 8-pixel row segment
-// (block yb = l>>3, row r = l&7) of the MCU, i.e. row (yb>>1)*8+r, columns (yb&1)*8..+7 — 32 B per
-// channel per lane, float4-vectorised.  The 8x8 DCT is register resident: an 8-point transform
-// along the lane's own row, an 8x8 transpose across the 8 lanes of the block (12 shuffles), a second
-// 8-point transform; chroma rows are gathered onto lanes 0-7 (Cb) / 8-15 (Cr) with shuffles.
+// Mapping: one warp = two horizontally adjacent 16x16 MCUs (8 Y blocks + 2 Cb + 2 Cr).  Lane l owns the 8-pixel row
+// segment (block yb = l>>3, row r = l&7) of each MCU, i.e. row (yb>>1)*8+r, columns (yb&1)*8..+7 — 32 B per channel per
+// lane, float4-vectorised.  The 8x8 DCT is register resident: an 8-point transform along the lane's own row, an 8x8
+// transpose across the 8 lanes of the block (through the warp's shared-memory scratch), a second 8-point transform;
+// the four chroma blocks of the pair fill one 32-lane pass.
 // Arithmetic order (documented for parity): 1-D DCT-II with the orthonormal matrix
-// C[k][n] = 0.5*alpha_k*cos((2n+1)k*pi/16), sums taken n = 0..7 with FFMA; quantisation divides by
-// fl(table*factor) exactly as the reference (no reciprocal), torch.round = rintf (half to even).
+// C[k][n] = 0.5*alpha_k*cos((2n+1)k*pi/16) evaluated by even/odd decomposition; quantisation divides by
+// fl(table*factor) as the reference does (quotient within 1 ulp of IEEE), torch.round = rintf (half to even).
 #include <string.h>
 
 #include "otf_common.cuh"
 
 namespace otf {
 
-// C[k][n] = 0.5*alpha_k*cos((2n+1)k*pi/16) rounded to fp32 (orthonormal DCT-II; the reference's
-// 0.25*alpha_u*alpha_v*cos*cos of diffjpeg.py:155-164 is its outer product)
-__constant__ float c_dct[8][8] = {
-    {3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f},
-    {4.903926253e-01f, 4.157347977e-01f, 2.777851224e-01f, 9.754516184e-02f, -9.754516184e-02f, -2.777851224e-01f, -4.157347977e-01f, -4.903926253e-01f},
-    {4.619397521e-01f, 1.913417131e-01f, -1.913417131e-01f, -4.619397521e-01f, -4.619397521e-01f, -1.913417131e-01f, 1.913417131e-01f, 4.619397521e-01f},
-    {4.157347977e-01f, -9.754516184e-02f, -4.903926253e-01f, -2.777851224e-01f, 2.777851224e-01f, 4.903926253e-01f, 9.754516184e-02f, -4.157347977e-01f},
-    {3.535533845e-01f, -3.535533845e-01f, -3.535533845e-01f, 3.535533845e-01f, 3.535533845e-01f, -3.535533845e-01f, -3.535533845e-01f, 3.535533845e-01f},
-    {2.777851224e-01f, -4.903926253e-01f, 9.754516184e-02f, 4.157347977e-01f, -4.157347977e-01f, -9.754516184e-02f, 4.903926253e-01f, -2.777851224e-01f},
-    {1.913417131e-01f, -4.619397521e-01f, 4.619397521e-01f, -1.913417131e-01f, -1.913417131e-01f, 4.619397521e-01f, -4.619397521e-01f, 1.913417131e-01f},
-    {9.754516184e-02f, -2.777851224e-01f, 4.157347977e-01f, -4.903926253e-01f, 4.903926253e-01f, -4.157347977e-01f, 2.777851224e-01f, -9.754516184e-02f},
-};
 // Quantisation tables indexed [u][v] exactly as the reference stores them: the Annex-K luminance
 // table TRANSPOSED (diffjpeg.py:18-31) and the chroma table (:32-37, symmetric).
 __constant__ float c_ytab[8][8] = {
@@ -42,77 +30,104 @@ __constant__ float c_ctab[8][8] = {
     {99, 99, 99, 99, 99, 99, 99, 99}, {99, 99, 99, 99, 99, 99, 99, 99},
 };
 
-// y[k] = sum_n C[k][n] x[n]   (forward)      x[n] = sum_k C[k][n] y[k]   (inverse)
+// 8-point orthonormal DCT-II, C[k][n] = 0.5*alpha_k*cos((2n+1)k*pi/16), by even/odd decomposition (the reference's
+// 0.25*alpha_u*alpha_v*cos*cos tensor of diffjpeg.py:155-164 is the outer product of two of these): the mirror
+// symmetry C[k][7-n] = (-1)^k C[k][n] halves the sums, the even half splits once more — 36 FP32 operations instead of
+// the 64 FMAs of the dense matrix.  Rounding differs from the dense order by a few ulp of the coefficients (~1e-4 on a
+// 0..2040 scale), i.e. by as much as the dense order differs from the reference's 64-term tensordot.
+#define OTF_C4 3.535533845e-01f
+#define OTF_C1 4.903926253e-01f
+#define OTF_C2 4.619397521e-01f
+#define OTF_C3 4.157347977e-01f
+#define OTF_C5 2.777851224e-01f
+#define OTF_C6 1.913417131e-01f
+#define OTF_C7 9.754516184e-02f
+// y[k] = sum_n C[k][n] x[n]
 __device__ __forceinline__ void dct8(float (&x)[8]) {
-    float y[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float s = c_dct[k][0] * x[0];
-#pragma unroll
-        for (int n = 1; n < 8; ++n) s = fmaf(c_dct[k][n], x[n], s);
-        y[k] = s;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = y[k];
+    const float s0 = x[0] + x[7], s1 = x[1] + x[6], s2 = x[2] + x[5], s3 = x[3] + x[4];
+    const float d0 = x[0] - x[7], d1 = x[1] - x[6], d2 = x[2] - x[5], d3 = x[3] - x[4];
+    const float e0 = s0 + s3, e1 = s1 + s2, f0 = s0 - s3, f1 = s1 - s2;
+    x[0] = OTF_C4 * (e0 + e1);
+    x[4] = OTF_C4 * (e0 - e1);
+    x[2] = fmaf(OTF_C6, f1, OTF_C2 * f0);
+    x[6] = fmaf(-OTF_C2, f1, OTF_C6 * f0);
+    x[1] = fmaf(OTF_C7, d3, fmaf(OTF_C5, d2, fmaf(OTF_C3, d1, OTF_C1 * d0)));
+    x[3] = fmaf(-OTF_C5, d3, fmaf(-OTF_C1, d2, fmaf(-OTF_C7, d1, OTF_C3 * d0)));
+    x[5] = fmaf(OTF_C3, d3, fmaf(OTF_C7, d2, fmaf(-OTF_C1, d1, OTF_C5 * d0)));
+    x[7] = fmaf(-OTF_C1, d3, fmaf(OTF_C3, d2, fmaf(-OTF_C5, d1, OTF_C7 * d0)));
 }
+// x[n] = sum_k C[k][n] y[k]
 __device__ __forceinline__ void idct8(float (&y)[8]) {
-    float x[8];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-        float s = c_dct[0][n] * y[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) s = fmaf(c_dct[k][n], y[k], s);
-        x[n] = s;
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) y[n] = x[n];
+    const float a0 = OTF_C4 * y[0], a4 = OTF_C4 * y[4];
+    const float p0 = a0 + a4, p1 = a0 - a4;
+    const float q0 = fmaf(OTF_C6, y[6], OTF_C2 * y[2]), q1 = fmaf(-OTF_C2, y[6], OTF_C6 * y[2]);
+    const float e0 = p0 + q0, e3 = p0 - q0, e1 = p1 + q1, e2 = p1 - q1;
+    const float o0 = fmaf(OTF_C7, y[7], fmaf(OTF_C5, y[5], fmaf(OTF_C3, y[3], OTF_C1 * y[1])));
+    const float o1 = fmaf(-OTF_C5, y[7], fmaf(-OTF_C1, y[5], fmaf(-OTF_C7, y[3], OTF_C3 * y[1])));
+    const float o2 = fmaf(OTF_C3, y[7], fmaf(OTF_C7, y[5], fmaf(-OTF_C1, y[3], OTF_C5 * y[1])));
+    const float o3 = fmaf(-OTF_C1, y[7], fmaf(OTF_C3, y[5], fmaf(-OTF_C5, y[3], OTF_C7 * y[1])));
+    y[0] = e0 + o0; y[7] = e0 - o0;
+    y[1] = e1 + o1; y[6] = e1 - o1;
+    y[2] = e2 + o2; y[5] = e2 - o2;
+    y[3] = e3 + o3; y[4] = e3 - o3;
 }
 
-// 8x8 transpose across the 8 lanes of a group: lane g holds row g in a[0..7]; afterwards lane g
-// holds column g.
-__device__ __forceinline__ void transpose8(float (&a)[8], int lane) {
+// x / 255 with IEEE rounding in three FP32-pipe operations instead of the ~10 of a general division: q = x * RN(1/255),
+// one exact residual, one correction (Markstein).  Equal to __fdiv_rn(x, 255.0f) for EVERY float in [0, 255] — checked
+// exhaustively on the device (profiles/experiments/div255_exact.cu) — which is the whole range this file divides.
+__device__ __forceinline__ float div255(float x) {
+    const float y = 3.9215688593685627e-03f;  // RN(1 / 255) = 0x3B808081
+    const float q = __fmul_rn(x, y);
+    return fmaf(fmaf(-q, 255.0f, x), y, q);
+}
+// clamp(round(x * 255), 0, 255) / 255 for x already in [0, 1] (quantise8 of otf_common.cuh with the cheap division)
+__device__ __forceinline__ float quantise8_unit(float x) { return div255(fminf(fmaxf(rintf(__fmul_rn(x, 255.0f)), 0.0f), 255.0f)); }
+
+// 8x8 transpose across the 8 lanes of a group through the warp's shared-memory scratch (pitch 9: both the row
+// writes and the column reads are conflict-free): lane g of a group holds row g in a[0..7]; afterwards column g.
+// 16 shared-memory operations instead of 12 shuffles + 24 selects.
+__device__ __forceinline__ void transpose8(float (&a)[8], float* __restrict__ scratch, int lane) {
+    float* wp = scratch + lane * 9;
 #pragma unroll
-    for (int s = 1; s < 8; s <<= 1) {
-        const bool up = lane & s;
+    for (int k = 0; k < 8; ++k) wp[k] = a[k];
+    __syncwarp();
+    const float* rp = scratch + (lane & ~7) * 9 + (lane & 7);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i & s) continue;
-            const float send = up ? a[i] : a[i | s];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, s);
-            if (up) a[i] = recv; else a[i | s] = recv;
-        }
-    }
+    for (int k = 0; k < 8; ++k) a[k] = rp[k * 9];
+    __syncwarp();
 }
 
-// Quantise + dequantise an 8x8 block held as: lane v (within its group of 8) owns coefficients
-// D[u][v], u = register index.  tab is [u][v]: luma or chroma table, selected at run time so that the
-// codec below is ONE loop body for both planes (half the code: the fully unrolled kernel overflowed
-// the instruction cache — "no_instruction" was its second largest stall in profiles/).
-__device__ __forceinline__ void quant_dequant(float (&d)[8], int v, bool luma, float factor, bool differentiable) {
-    const float(*tab)[8] = luma ? c_ytab : c_ctab;
+// Quantise + dequantise an 8x8 block held as: lane v (within its group of 8) owns coefficients D[u][v], u = register
+// index; t[u] = fl(table[u][v] * factor) (diffjpeg.py:207-212 divides by exactly this product).  The quotient is
+// d * rcp(t) corrected once with the exact residual: within 1 ulp of the IEEE quotient (correctly rounded in all but
+// rare cases, exact whenever the quotient is representable, e.g. the half-integers torch.round ties on).
+__device__ __forceinline__ void quant_dequant(float (&d)[8], const float (&t)[8], bool differentiable) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        const float t = __fmul_rn(tab[u][v], factor);  // table * factor
-        const float x = __fdiv_rn(d[u], t);            // diffjpeg.py:207-212
-        float q = rintf(x);                            // torch.round
+        float y;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t[u]));
+        const float q0 = d[u] * y;
+        const float x = fmaf(fmaf(-q0, t[u], d[u]), y, q0);
+        float q = rintf(x);  // torch.round
         if (differentiable) {
             const float e = __fsub_rn(x, q);
             q = __fadd_rn(q, __fmul_rn(__fmul_rn(e, e), e));  // :40-42
         }
-        d[u] = __fmul_rn(q, t);  // :300-306
+        d[u] = __fmul_rn(q, t[u]);  // :300-306
     }
 }
 
 // Full 2-D DCT -> quantise -> dequantise -> 2-D IDCT on the block whose row `lane&7` is in f[].
 // Input is level-shifted (f-128); output has +128 restored.
-__device__ __forceinline__ void block_codec(float (&f)[8], int lane, bool luma, float factor, bool differentiable) {
-    dct8(f);             // along the row (y index -> v)
-    transpose8(f, lane); // lane now = v, registers = x (row index)
-    dct8(f);             // along x -> u
-    quant_dequant(f, lane & 7, luma, factor, differentiable);
-    idct8(f);            // u -> x
-    transpose8(f, lane); // lane = x, registers = v
-    idct8(f);            // v -> y
+__device__ __forceinline__ void block_codec(float (&f)[8], float* __restrict__ scratch, int lane, const float (&t)[8],
+                                            bool differentiable) {
+    dct8(f);                      // along the row (y index -> v)
+    transpose8(f, scratch, lane); // lane now = v, registers = x (row index)
+    dct8(f);                      // along x -> u
+    quant_dequant(f, t, differentiable);
+    idct8(f);                     // u -> x
+    transpose8(f, scratch, lane); // lane = x, registers = v
+    idct8(f);                     // v -> y
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] += 128.0f;
 }
@@ -134,11 +149,19 @@ struct CropTail {
     int top, left, p, scale, Hg, Wg, planes, jpeg_ctas, vec_gt;
 };
 
+// One warp = a PAIR of horizontally adjacent 16x16 MCUs (A | B).  Lane l owns, in each MCU, the 8-pixel row segment
+// (block yb = l>>3, row r = l&7): row (yb>>1)*8+r, columns (yb&1)*8..+7.  The eight luma blocks take two codec passes
+// of 32 lanes (MCU A, MCU B); the four chroma blocks (Cb A, Cb B, Cr A, Cr B) take ONE pass — with a single MCU per warp
+// half the lanes of the chroma pass were idle.  Chroma rows travel between the pixel lanes and the chroma lanes through
+// the warp's own 1 KB of shared memory (2 STS.128 + 2 LDS.128 per lane and direction) instead of 32 shuffles.
+constexpr int kJpegWarpFloats = 4 * 64 + 32 * 9 + 8;  // chroma staging [4 blocks][8][8] + transpose scratch [32][9] (+ pad to 16 B)
+
 __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
                                                        float factor_scalar, int differentiable, int clamp_in,
                                                        int round8_out, int vec_ok, int factor_is_quality,
                                                        const __grid_constant__ CropTail ct) {
+    __shared__ __align__(16) float s_warp[4][kJpegWarpFloats];
     int top = ct.top, left = ct.left;
     if (ct.lq_out) {
         if (ct.tl_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot leave the image
@@ -155,136 +178,139 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
     }
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t total = (int64_t)B * mcu_x * mcu_y;
+    const int pairs_x = (mcu_x + 1) >> 1;
+    const int64_t total = (int64_t)B * pairs_x * mcu_y;
     if (warp >= total) return;  // warp-uniform
-    const int b = (int)(warp / ((int64_t)mcu_x * mcu_y));
-    const int m = (int)(warp - (int64_t)b * mcu_x * mcu_y);
-    const int my = m / mcu_x, mx = m - my * mcu_x;
+    float* chroma = s_warp[threadIdx.x >> 5];   // [blk = comp * 2 + mcu][row][col]
+    float* scratch = chroma + 4 * 64;
+    const int b = (int)(warp / ((int64_t)pairs_x * mcu_y));
+    const int m = (int)(warp - (int64_t)b * pairs_x * mcu_y);
+    const int my = m / pairs_x, mx0 = 2 * (m - my * pairs_x);
     float factor = factor_dev ? factor_dev[b] : factor_scalar;
     if (factor_is_quality) factor = quality_to_factor_dev(factor);  // diffjpeg.py:57-61 fused (no extra launch)
+    float ty[8], tc[8];  // this lane's column (v = lane & 7) of table * factor
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        ty[u] = __fmul_rn(c_ytab[u][lane & 7], factor);
+        tc[u] = __fmul_rn(c_ctab[u][lane & 7], factor);
+    }
 
     const int yb = lane >> 3, r = lane & 7;
     const int by = yb >> 1, bx = yb & 1;
     const int y = my * 16 + by * 8 + r;
-    const int x0 = mx * 16 + bx * 8;
     const size_t hw = (size_t)H * W;
-    const float* ip = img + (size_t)b * 3 * hw + (size_t)y * W + x0;
     const bool row_ok = y < H;
-    const bool full = row_ok && (x0 + 8 <= W);
 
-    // ---- load 8 px x 3 channels (zero padding outside the image: diffjpeg.py:515-522) ----
-    float px[3][8];
+    float yv[2][8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (full && vec_ok) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(ip + c * hw));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(ip + c * hw) + 1);
-            px[c][0] = a.x; px[c][1] = a.y; px[c][2] = a.z; px[c][3] = a.w;
-            px[c][4] = d.x; px[c][5] = d.y; px[c][6] = d.z; px[c][7] = d.w;
-        } else {
+    for (int p = 0; p < 2; ++p) {
+        const int x0 = (mx0 + p) * 16 + bx * 8;
+        const float* ip = img + (size_t)b * 3 * hw + (size_t)y * W + x0;
+        const bool full = row_ok && (x0 + 8 <= W);
+        // ---- load 8 px x 3 channels (zero padding outside the image: diffjpeg.py:515-522) ----
+        float px[3][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) px[c][k] = (row_ok && x0 + k < W) ? __ldg(ip + c * hw + k) : 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            if (full && vec_ok) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ip + c * hw));
+                const float4 d = __ldg(reinterpret_cast<const float4*>(ip + c * hw) + 1);
+                px[c][0] = a.x; px[c][1] = a.y; px[c][2] = a.z; px[c][3] = a.w;
+                px[c][4] = d.x; px[c][5] = d.y; px[c][6] = d.z; px[c][7] = d.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) px[c][k] = (row_ok && x0 + k < W) ? __ldg(ip + c * hw + k) : 0.0f;
+            }
         }
-    }
-    // ---- x255, RGB -> YCbCr (diffjpeg.py:70-91), level shift for Y folded in ----
-    float yv[8], cb[8], cr[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float R = px[0][k], G = px[1][k], Bc = px[2][k];
-        if (clamp_in) { R = clamp01(R); G = clamp01(G); Bc = clamp01(Bc); }
-        R = __fmul_rn(R, 255.0f); G = __fmul_rn(G, 255.0f); Bc = __fmul_rn(Bc, 255.0f);
-        yv[k] = fmaf(Bc, 0.114f, fmaf(G, 0.587f, R * 0.299f)) - 128.0f;
-        cb[k] = fmaf(Bc, 0.5f, fmaf(G, -0.331264f, R * -0.168736f));  // the +128 shift is folded away, see below
-        cr[k] = fmaf(Bc, -0.081312f, fmaf(G, -0.418688f, R * 0.5f));
-    }
-    // ---- chroma 2x2 mean (diffjpeg.py:112-125); the +128 shift and the -128 level shift cancel ----
-    float cbs[4], crs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float s0 = cb[2 * k] + cb[2 * k + 1], s1 = cr[2 * k] + cr[2 * k + 1];
-        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-        cbs[k] = s0 * 0.25f;
-        crs[k] = s1 * 0.25f;
-    }
-    // gather chroma rows: target lane t (&15): comp = t>>3 (0 Cb, 1 Cr), chroma row mrow = t&7
-    //   source block row by' = mrow>>2, source lane row r' = (mrow&3)*2, left half from bx'=0, right from bx'=1
-    float ch[8];
-    {
-        const int t = lane & 15, mrow = t & 7;
-        const int src_l = (((mrow >> 2) * 2 + 0) << 3) + (mrow & 3) * 2;
-        const int src_r = (((mrow >> 2) * 2 + 1) << 3) + (mrow & 3) * 2;
-        const bool is_cr = t >> 3;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float lb = __shfl_sync(0xffffffffu, cbs[k], src_l), lr = __shfl_sync(0xffffffffu, crs[k], src_l);
-            const float rb = __shfl_sync(0xffffffffu, cbs[k], src_r), rr = __shfl_sync(0xffffffffu, crs[k], src_r);
-            ch[k] = is_cr ? lr : lb;
-            ch[4 + k] = is_cr ? rr : rb;
-        }
-    }
-    // ---- codec: one loop body, pass 0 = the four luma blocks, pass 1 = Cb | Cr (lanes 16-31 redo 0-15) ----
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        float blk[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) blk[k] = pass ? ch[k] : yv[k];
-        block_codec(blk, lane, pass == 0, factor, differentiable);
+        // ---- x255, RGB -> YCbCr (diffjpeg.py:70-91), level shift for Y folded in ----
+        float cb[8], cr[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (pass) ch[k] = blk[k]; else yv[k] = blk[k];
+            float R = px[0][k], G = px[1][k], Bc = px[2][k];
+            if (clamp_in) { R = clamp01(R); G = clamp01(G); Bc = clamp01(Bc); }
+            R = __fmul_rn(R, 255.0f); G = __fmul_rn(G, 255.0f); Bc = __fmul_rn(Bc, 255.0f);
+            yv[p][k] = fmaf(Bc, 0.114f, fmaf(G, 0.587f, R * 0.299f)) - 128.0f;
+            cb[k] = fmaf(Bc, 0.5f, fmaf(G, -0.331264f, R * -0.168736f));  // the +128 shift is folded away, see below
+            cr[k] = fmaf(Bc, -0.081312f, fmaf(G, -0.418688f, R * 0.5f));
         }
-    }
-    // ---- chroma back to pixel lanes: nearest x2 (diffjpeg.py:397-402) ----
-    {
-        const int mrow = by * 4 + (r >> 1);
+        // ---- chroma 2x2 mean (diffjpeg.py:112-125); the +128 shift and the -128 level shift cancel ----
+        float cbs[4], crs[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float b_lo = __shfl_sync(0xffffffffu, ch[k], mrow), b_hi = __shfl_sync(0xffffffffu, ch[4 + k], mrow);
-            const float r_lo = __shfl_sync(0xffffffffu, ch[k], 8 + mrow), r_hi = __shfl_sync(0xffffffffu, ch[4 + k], 8 + mrow);
-            const float vb = bx ? b_hi : b_lo, vr = bx ? r_hi : r_lo;
-            cb[2 * k] = vb; cb[2 * k + 1] = vb;
-            cr[2 * k] = vr; cr[2 * k + 1] = vr;
+            float s0 = cb[2 * k] + cb[2 * k + 1], s1 = cr[2 * k] + cr[2 * k + 1];
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            cbs[k] = s0 * 0.25f;
+            crs[k] = s1 * 0.25f;
+        }
+        if (!(r & 1)) {  // chroma row by*4 + r/2, columns bx*4..+3 of blocks (Cb, p) and (Cr, p)
+            const int off = (by * 4 + (r >> 1)) * 8 + bx * 4;
+            *reinterpret_cast<float4*>(chroma + (0 * 2 + p) * 64 + off) = make_float4(cbs[0], cbs[1], cbs[2], cbs[3]);
+            *reinterpret_cast<float4*>(chroma + (1 * 2 + p) * 64 + off) = make_float4(crs[0], crs[1], crs[2], crs[3]);
         }
     }
-    // ---- YCbCr -> RGB (diffjpeg.py:415-431), clamp, /255 (:476-479), optional 8-bit lattice ----
-    float* op = out + (size_t)b * 3 * hw + (size_t)y * W + x0;
-    float res[3][8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float Y = yv[k], Cb = cb[k] - 128.0f, Cr = cr[k] - 128.0f;   // block_codec restored +128 on every plane
-        float R = fmaf(Cr, 1.402f, Y);
-        float G = fmaf(Cr, -0.714136f, fmaf(Cb, -0.344136f, Y));
-        float Bc = fmaf(Cb, 1.772f, Y);
-        R = __fdiv_rn(fminf(fmaxf(R, 0.0f), 255.0f), 255.0f);
-        G = __fdiv_rn(fminf(fmaxf(G, 0.0f), 255.0f), 255.0f);
-        Bc = __fdiv_rn(fminf(fmaxf(Bc, 0.0f), 255.0f), 255.0f);
-        if (round8_out) { R = quantise8(R); G = quantise8(G); Bc = quantise8(Bc); }
-        res[0][k] = R; res[1][k] = G; res[2][k] = Bc;
+    __syncwarp();
+    // ---- codec: the four luma blocks of A, of B, then Cb A | Cb B | Cr A | Cr B (lane>>3 = chroma block) ----
+    block_codec(yv[0], scratch, lane, ty, differentiable);
+    block_codec(yv[1], scratch, lane, ty, differentiable);
+    {
+        float ch[8];
+        const float4 c0 = *reinterpret_cast<const float4*>(chroma + lane * 8), c1 = *reinterpret_cast<const float4*>(chroma + lane * 8 + 4);
+        ch[0] = c0.x; ch[1] = c0.y; ch[2] = c0.z; ch[3] = c0.w; ch[4] = c1.x; ch[5] = c1.y; ch[6] = c1.z; ch[7] = c1.w;
+        block_codec(ch, scratch, lane, tc, differentiable);
+        __syncwarp();
+        *reinterpret_cast<float4*>(chroma + lane * 8) = make_float4(ch[0], ch[1], ch[2], ch[3]);
+        *reinterpret_cast<float4*>(chroma + lane * 8 + 4) = make_float4(ch[4], ch[5], ch[6], ch[7]);
+        __syncwarp();
     }
     if (!row_ok) return;
-    if (ct.lq_out) {  // only the crop window, into the dense (B,3,p,p) output
-        const int yy = y - top;
-        if (yy < 0 || yy >= ct.p) return;
-        float* lp = ct.lq_out + ((size_t)b * 3 * ct.p + yy) * ct.p;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+    for (int p = 0; p < 2; ++p) {
+        const int x0 = (mx0 + p) * 16 + bx * 8;
+        if (x0 >= W) break;
+        // ---- chroma back to the pixel lanes: nearest x2 (diffjpeg.py:397-402) ----
+        const int off = (by * 4 + (r >> 1)) * 8 + bx * 4;
+        const float4 vb = *reinterpret_cast<const float4*>(chroma + (0 * 2 + p) * 64 + off);
+        const float4 vr = *reinterpret_cast<const float4*>(chroma + (1 * 2 + p) * 64 + off);
+        const float cbv[4] = {vb.x, vb.y, vb.z, vb.w}, crv[4] = {vr.x, vr.y, vr.z, vr.w};
+        // ---- YCbCr -> RGB (diffjpeg.py:415-431), clamp, /255 (:476-479), optional 8-bit lattice ----
+        float res[3][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int xx = x0 + k - left;
-                if (xx >= 0 && xx < ct.p && x0 + k < W) lp[(size_t)c * ct.p * ct.p + xx] = res[c][k];
+        for (int k = 0; k < 8; ++k) {
+            const float Y = yv[p][k], Cb = cbv[k >> 1] - 128.0f, Cr = crv[k >> 1] - 128.0f;   // block_codec restored +128 on every plane
+            float R = fmaf(Cr, 1.402f, Y);
+            float G = fmaf(Cr, -0.714136f, fmaf(Cb, -0.344136f, Y));
+            float Bc = fmaf(Cb, 1.772f, Y);
+            R = div255(fminf(fmaxf(R, 0.0f), 255.0f));
+            G = div255(fminf(fmaxf(G, 0.0f), 255.0f));
+            Bc = div255(fminf(fmaxf(Bc, 0.0f), 255.0f));
+            if (round8_out) { R = quantise8_unit(R); G = quantise8_unit(G); Bc = quantise8_unit(Bc); }
+            res[0][k] = R; res[1][k] = G; res[2][k] = Bc;
+        }
+        if (ct.lq_out) {  // only the crop window, into the dense (B,3,p,p) output
+            const int yy = y - top;
+            if (yy < 0 || yy >= ct.p) continue;
+            float* lp = ct.lq_out + ((size_t)b * 3 * ct.p + yy) * ct.p;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int xx = x0 + k - left;
+                    if (xx >= 0 && xx < ct.p && x0 + k < W) lp[(size_t)c * ct.p * ct.p + xx] = res[c][k];
+                }
+            continue;
+        }
+        float* op = out + (size_t)b * 3 * hw + (size_t)y * W + x0;
+        const bool full = x0 + 8 <= W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (full && vec_ok) {
+                reinterpret_cast<float4*>(op + c * hw)[0] = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
+                reinterpret_cast<float4*>(op + c * hw)[1] = make_float4(res[c][4], res[c][5], res[c][6], res[c][7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (x0 + k < W) op[c * hw + k] = res[c][k];
             }
-        return;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (full && vec_ok) {
-            reinterpret_cast<float4*>(op + c * hw)[0] = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
-            reinterpret_cast<float4*>(op + c * hw)[1] = make_float4(res[c][4], res[c][5], res[c][6], res[c][7]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (x0 + k < W) op[c * hw + k] = res[c][k];
         }
     }
 }
@@ -311,9 +337,9 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     OTF_REQUIRE(img && out, OTF_ERR_BAD_ARG, "diffjpeg: null pointer");
     OTF_REQUIRE(B > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "diffjpeg: bad extents");
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
-    const int64_t warps = (int64_t)B * mcu_x * mcu_y;
+    const int64_t warps = (int64_t)B * ((mcu_x + 1) / 2) * mcu_y;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
-    // one warp per MCU; few MCUs (64^2 LQ stage) -> one-warp CTAs so they spread over all 148 SMs
+    // one warp per pair of MCUs; few MCUs (64^2 LQ stage) -> one-warp CTAs so they spread over all 148 SMs
     const int wpc = warps >= (int64_t)kNumSMs * 32 ? 4 : 1;
     CropTail ct;
     memset(&ct, 0, sizeof(ct));
@@ -336,9 +362,9 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     OTF_REQUIRE((lq_patch * scale) % 4 == 0 && (((uintptr_t)gt_out) & 15) == 0, OTF_ERR_UNSUPPORTED,
                 "diffjpeg_crop_pair: GT patch must be a multiple of 4 pixels wide (use otf_diffjpeg_f32 + otf_crop_pair_f32)");
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
-    const int64_t warps = (int64_t)B * mcu_x * mcu_y;
+    const int64_t warps = (int64_t)B * ((mcu_x + 1) / 2) * mcu_y;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
-    const int wpc = 4;
+    const int wpc = 4;  // (the GT copy behind the codec wants full CTAs)
     CropTail ct;
     memset(&ct, 0, sizeof(ct));
     ct.lq_out = lq_out; ct.gt = gt; ct.gt_out = gt_out; ct.tl_dev = top_left_dev;
