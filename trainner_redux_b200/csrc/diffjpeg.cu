@@ -19,12 +19,12 @@ namespace otf {
 
 // Quantisation tables indexed [u][v] exactly as the reference stores them: the Annex-K luminance
 // table TRANSPOSED (diffjpeg.py:18-31) and the chroma table (:32-37, symmetric).
-__constant__ float c_ytab[8][8] = {
+__device__ const float c_ytab[8][8] = {
     {16, 12, 14, 14, 18, 24, 49, 72},     {11, 12, 13, 17, 22, 35, 64, 92},   {10, 14, 16, 22, 37, 55, 78, 95},
     {16, 19, 24, 29, 56, 64, 87, 98},     {24, 26, 40, 51, 68, 81, 103, 112}, {40, 58, 57, 87, 109, 104, 121, 100},
     {51, 60, 69, 80, 103, 113, 120, 103}, {61, 55, 56, 62, 77, 92, 101, 99},
 };
-__constant__ float c_ctab[8][8] = {
+__device__ const float c_ctab[8][8] = {
     {17, 18, 24, 47, 99, 99, 99, 99}, {18, 21, 26, 66, 99, 99, 99, 99}, {24, 26, 56, 99, 99, 99, 99, 99},
     {47, 66, 99, 99, 99, 99, 99, 99}, {99, 99, 99, 99, 99, 99, 99, 99}, {99, 99, 99, 99, 99, 99, 99, 99},
     {99, 99, 99, 99, 99, 99, 99, 99}, {99, 99, 99, 99, 99, 99, 99, 99},
@@ -156,7 +156,7 @@ struct CropTail {
 // the warp's own 1 KB of shared memory (2 STS.128 + 2 LDS.128 per lane and direction) instead of 32 shuffles.
 constexpr int kJpegWarpFloats = 4 * 64 + 32 * 9 + 8;  // chroma staging [4 blocks][8][8] + transpose scratch [32][9] (+ pad to 16 B)
 
-__global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
+__global__ void __launch_bounds__(128, 5) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
                                                        float factor_scalar, int differentiable, int clamp_in,
                                                        int round8_out, int vec_ok, int factor_is_quality,
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
     float ty[8], tc[8];  // this lane's column (v = lane & 7) of table * factor
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        ty[u] = __fmul_rn(c_ytab[u][lane & 7], factor);
-        tc[u] = __fmul_rn(c_ctab[u][lane & 7], factor);
+        ty[u] = __fmul_rn(__ldg(&c_ytab[u][lane & 7]), factor);  // (global, L1-resident: a lane-varying index would serialise the constant bank)
+        tc[u] = __fmul_rn(__ldg(&c_ctab[u][lane & 7]), factor);
     }
 
     const int yb = lane >> 3, r = lane & 7;
@@ -201,31 +201,40 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
     const size_t hw = (size_t)H * W;
     const bool row_ok = y < H;
 
+    // ---- load 2 x 8 px x 3 channels, all twelve 16-byte loads in flight at once (zero padding outside the image:
+    //      diffjpeg.py:515-522).  pair_full is warp-uniform: both MCUs lie inside an aligned image. ----
+    const bool pair_full = vec_ok && (my * 16 + 16 <= H) && ((mx0 + 2) * 16 <= W);
+    float px[2][3][8];
+    {
+        const float* ip0 = img + (size_t)b * 3 * hw + (size_t)y * W + mx0 * 16 + bx * 8;
+        if (pair_full) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(ip0 + p * 16 + c * hw));
+                    const float4 d = __ldg(reinterpret_cast<const float4*>(ip0 + p * 16 + c * hw) + 1);
+                    px[p][c][0] = a.x; px[p][c][1] = a.y; px[p][c][2] = a.z; px[p][c][3] = a.w;
+                    px[p][c][4] = d.x; px[p][c][5] = d.y; px[p][c][6] = d.z; px[p][c][7] = d.w;
+                }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        px[p][c][k] = (row_ok && (mx0 + p) * 16 + bx * 8 + k < W) ? __ldg(ip0 + p * 16 + c * hw + k) : 0.0f;
+        }
+    }
     float yv[2][8];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        const int x0 = (mx0 + p) * 16 + bx * 8;
-        const float* ip = img + (size_t)b * 3 * hw + (size_t)y * W + x0;
-        const bool full = row_ok && (x0 + 8 <= W);
-        // ---- load 8 px x 3 channels (zero padding outside the image: diffjpeg.py:515-522) ----
-        float px[3][8];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (full && vec_ok) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(ip + c * hw));
-                const float4 d = __ldg(reinterpret_cast<const float4*>(ip + c * hw) + 1);
-                px[c][0] = a.x; px[c][1] = a.y; px[c][2] = a.z; px[c][3] = a.w;
-                px[c][4] = d.x; px[c][5] = d.y; px[c][6] = d.z; px[c][7] = d.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) px[c][k] = (row_ok && x0 + k < W) ? __ldg(ip + c * hw + k) : 0.0f;
-            }
-        }
         // ---- x255, RGB -> YCbCr (diffjpeg.py:70-91), level shift for Y folded in ----
         float cb[8], cr[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float R = px[0][k], G = px[1][k], Bc = px[2][k];
+            float R = px[p][0][k], G = px[p][1][k], Bc = px[p][2][k];
             if (clamp_in) { R = clamp01(R); G = clamp01(G); Bc = clamp01(Bc); }
             R = __fmul_rn(R, 255.0f); G = __fmul_rn(G, 255.0f); Bc = __fmul_rn(Bc, 255.0f);
             yv[p][k] = fmaf(Bc, 0.114f, fmaf(G, 0.587f, R * 0.299f)) - 128.0f;
@@ -300,10 +309,9 @@ __global__ void __launch_bounds__(128) diffjpeg_kernel(const float* __restrict__
             continue;
         }
         float* op = out + (size_t)b * 3 * hw + (size_t)y * W + x0;
-        const bool full = x0 + 8 <= W;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (full && vec_ok) {
+            if (pair_full) {
                 reinterpret_cast<float4*>(op + c * hw)[0] = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
                 reinterpret_cast<float4*>(op + c * hw)[1] = make_float4(res[c][4], res[c][5], res[c][6], res[c][7]);
             } else {
@@ -340,7 +348,7 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     const int64_t warps = (int64_t)B * ((mcu_x + 1) / 2) * mcu_y;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
     // one warp per pair of MCUs; few MCUs (64^2 LQ stage) -> one-warp CTAs so they spread over all 148 SMs
-    const int wpc = warps >= (int64_t)kNumSMs * 32 ? 4 : 1;
+    const int wpc = warps >= (int64_t)kNumSMs * 8 ? 4 : 1;
     CropTail ct;
     memset(&ct, 0, sizeof(ct));
     diffjpeg_kernel<<<ceil_div(warps, wpc), 32 * wpc, 0, (cudaStream_t)stream>>>(img, out, B, H, W, mcu_x, mcu_y, factor_dev,

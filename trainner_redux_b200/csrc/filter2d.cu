@@ -12,6 +12,7 @@
 //     kernels of true size 7..21 are the norm: realesrgan_dataset.py:171-172), found
 //     on the device so the host never synchronises.
 // Summation order per output: kernel rows ascending, taps left to right, one FFMA each.
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,22 +40,23 @@ struct KernelSets {
     const float* ptr[4];  // up to 4 kernel tensors (kernel1, kernel2, sinc_kernel, ...) analysed by one launch
 };
 
-// One CTA per kernel tensor, one WARP per kernel (warp w takes kernels w, w + 16, ...), then the same CTA ranks the
-// samples — analysis and launch order in ONE launch (they used to be two).
-constexpr int kAnalyseWarps = 16;
-__global__ void __launch_bounds__(kAnalyseWarps * 32) kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K,
-                                                                            int kernel_batch, int32_t* __restrict__ scratch_base) {
+// One thread-block CLUSTER of 8 CTAs per kernel tensor, one WARP per kernel (64 warps: a batch of 64 kernels is analysed in
+// one pass, larger batches loop), then — behind the cluster barrier, which orders the CTAs' global writes — CTA 0 of the
+// cluster ranks the samples: analysis and launch order in ONE launch with no host-initialised ticket.
+constexpr int kAnalyseWarps = 8, kAnalyseCluster = 8;
+__global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnalyseWarps * 32)
+    kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch, int32_t* __restrict__ scratch_base) {
     __shared__ float sk_all[kAnalyseWarps][21 * 21 + 7];
-    extern __shared__ int s_sup[];  // [kernel_batch] supports, for the ranking pass
-    const float* kern = sets.ptr[blockIdx.x];
-    int32_t* scratch = scratch_base + (size_t)blockIdx.x * scratch_words(kernel_batch);
+    extern __shared__ int s_sup[];  // [kernel_batch] supports, for the ranking pass (CTA 0 of the cluster)
+    const float* kern = sets.ptr[blockIdx.y];
+    int32_t* scratch = scratch_base + (size_t)blockIdx.y * scratch_words(kernel_batch);
     int32_t* support = scratch;
     int32_t* rank1 = scratch + 2 * kernel_batch;
     float* uv = reinterpret_cast<float*>(scratch + 3 * kernel_batch);
     const int c = K / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = K * K;  // K <= 21 on this path
     float* sk = sk_all[warp];
-    for (int kb = warp; kb < kernel_batch; kb += kAnalyseWarps) {
+    for (int kb = blockIdx.x * kAnalyseWarps + warp; kb < kernel_batch; kb += kAnalyseWarps * kAnalyseCluster) {
         const float* kp = kern + (size_t)kb * n;
         int r = 0, imax = 0;
         float amax = 0.0f;
@@ -98,9 +100,12 @@ __global__ void __launch_bounds__(kAnalyseWarps * 32) kernel_analyse_kernel(cons
             uv[((size_t)kb * 2 + 0) * kUVPitch + lane] = (ok && in) ? sk[t * K + pj] : 0.0f;
             uv[((size_t)kb * 2 + 1) * kUVPitch + lane] = (ok && in) ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
         }
-        if (lane == 0) { support[kb] = r; rank1[kb] = (ok ? 1 : 0) | (sym ? 2 : 0); s_sup[kb] = r; }
+        if (lane == 0) { support[kb] = r; rank1[kb] = (ok ? 1 : 0) | (sym ? 2 : 0); }
         __syncwarp();
     }
+    cooperative_groups::this_cluster().sync();  // (release / acquire at cluster scope: every CTA's supports are visible)
+    if (blockIdx.x != 0) return;
+    for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) s_sup[t] = support[t];
     __syncthreads();
     // order[0..kb): sample indices sorted by support, largest first (stable)
     for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
@@ -116,7 +121,7 @@ static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch
     OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 4096, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..4096");
     KernelSets sets;
     for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
-    kernel_analyse_kernel<<<nsets, kAnalyseWarps * 32, kernel_batch * sizeof(int), st>>>(sets, K, kernel_batch, scratch);
+    kernel_analyse_kernel<<<dim3(kAnalyseCluster, nsets), kAnalyseWarps * 32, kernel_batch * sizeof(int), st>>>(sets, K, kernel_batch, scratch);
     OTF_LAUNCH_CHECK("kernel_analyse_kernel");
     return OTF_OK;
 }
@@ -736,9 +741,12 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
     }
     // small planes: 64x32 tiles (64 threads) keep the 8x4 register block and halve the tile
     const int64_t mid_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 32) * B * C;
-    if (mid_tiles >= 2 * kNumSMs && W >= 48) {
+    // (few tiles: the thread count, not the FMA pipe, is the limit — at 64x3x64^2 the 64x32 tiling gives 5 warps per SM and
+    // each thread walks 24 rows of 8 columns alone; the 32x32 tiling below doubles the threads and halves their work)
+    if (mid_tiles >= 4 * kNumSMs && W >= 48) {
         if (scalar) return launch_blocked<8, 4, 8, 8, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
         return launch_blocked<8, 4, 8, 8, true>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
     }
-    return launch_blocked<4, 4, 8, 8, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    if (scalar) return launch_blocked<4, 4, 8, 8, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+    return launch_blocked<4, 4, 8, 8, true>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
 }
