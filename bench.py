@@ -62,7 +62,7 @@ class Workload:
     c3 (BASELINE.json configs[2]): ONE batch of 32 x 512^2 GT x2 sharded per sample over the ranks, strong scaling."""
 
     def __init__(self, name: str, world: int, noise: str = "gaussian") -> None:
-        self.name, self.noise = name, noise
+        self.name, self.noise, self.world = name, noise, world
         if name == "c3":
             self.gt, self.scale, self.crop, self.scaling = 512, 2, 480, "strong"
             self.batch = max(1, 32 // world)
@@ -80,7 +80,9 @@ class Workload:
     def config(self, batch: int | None = None) -> dict:
         """Identical keys in both arms (the driver compares them)."""
         return {"workload": self.describe(), "batch_per_step": batch or self.batch, "gt": self.gt, "scale": self.scale,
-                "noise": self.noise}
+                "noise": self.noise,
+                "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * self.batch * 3 * self.gt * self.gt * 4 / 1e6:.0f} MB > 126 MB L2)",
+                "parallelism": f"per-sample shards x{self.world}, no collective"}
 
     def options(self):
         from trainner_redux_b200.realesrgan_feed import OTFOptions
@@ -433,6 +435,50 @@ class Arm:
         lq_full = feed.degrade(d["gt"], d["kernel1"], d["kernel2"], d["sinc_kernel"], p)
         feed.stage_fns["crop"] = lambda: crop_pair(d["gt"], lq_full, self.wl.crop, self.wl.scale, 4, 4)
         feed.record_stage_fns = False
+        # the launches feed_data's native executor actually makes where it fuses adjacent stages (csrc/chain.cu, row g1):
+        # resize + Gaussian noise, and the last DiffJPEG + 8-bit lattice + both crops.  Inputs: the unfused path's intermediates.
+        from trainner_redux_b200.stages import StageList
+
+        feed.collect_taps = {}
+        feed.degrade(d["gt"], d["kernel1"], d["kernel2"], d["sinc_kernel"], p)
+        taps, feed.collect_taps = feed.collect_taps, None
+        sc, h0 = self.wl.scale, self.wl.gt
+
+        def fused_resize_noise(src, rs, ns, size=None):
+            from trainner_redux_b200 import degradations as D
+
+            hh, ww = src.shape[2:]
+            oh, ow = size if size is not None else (round(hh * rs["scale"]), round(ww * rs["scale"]))
+            D.pinned_resize_table(self.dev, hh, ww, int(oh), int(ow), D._MODE_ID[rs["mode"]])  # tables outside the timed launches
+
+            def fn():
+                sl = StageList(src)
+                if size is None:
+                    sl.resize(rs["mode"], scale_factor=rs["scale"])
+                else:
+                    sl.resize(rs["mode"], size=size)
+                sl.gaussian_noise(ns["sigma"], ns["gray"], feed.rng.philox)
+                return sl.run()
+            return fn
+
+        def fused_tail():
+            from trainner_redux_b200 import _lib
+
+            x, gt, pch = taps["sinc"], d["gt"], self.wl.crop // sc
+            b = x.size(0)
+            gt_out = torch.empty((b, 3, self.wl.crop, self.wl.crop), dtype=torch.float32, device=self.dev)
+            lq_out = torch.empty((b, 3, pch, pch), dtype=torch.float32, device=self.dev)
+            _lib.call("otf_diffjpeg_crop_pair_f32", _lib.ptr(x), b, x.size(2), x.size(3), _lib.ptr(p["jpeg2"]), 0.0, 1, 0, 1, _lib.ptr(gt),
+                      gt.size(2), gt.size(3), 4, 4, None, pch, sc, _lib.ptr(gt_out), _lib.ptr(lq_out), _lib.stream())
+            return lq_out
+
+        if p["noise1"]["kind"] == "gaussian" and "blur1" in taps and "blur2" in taps:
+            feed.stage_fns["fused resize1+noise1"] = fused_resize_noise(taps["blur1"], p["resize1"], p["noise1"])
+            s2 = p["resize2"]["scale"]
+            feed.stage_fns["fused resize2+noise2"] = fused_resize_noise(taps["blur2"], p["resize2"], p["noise2"],
+                                                                        size=(int(h0 / sc * s2), int(h0 / sc * s2)))
+        if "sinc" in taps and p.get("final_order", "resize_first") == "resize_first":
+            feed.stage_fns["fused jpeg2+round+crop"] = fused_tail
         torch.cuda.synchronize()
         from trainner_redux_b200.degradations import pin_resize_tables
 
@@ -586,11 +632,10 @@ def run_b200(args, wl: Workload) -> None:
             "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(wl.config(),
-                           l2=f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * wl.batch * 3 * wl.gt * wl.gt * 4 / 1e6:.0f} MB > 126 MB L2)",
-                           launch=f"RealESRGANFeed.feed_data, a fresh draw_plan per step, captured chains replayed ({graphs.captures} captures, "
-                                  f"{graphs.hits} replays so far), {n_streams} calls in flight on {n_streams} streams",
-                           parallelism=f"per-sample shards x{world}, no collective", numa_node_rank0=numa, numa_note=numa_why),
+            "config": wl.config(),  # (the same dict in both arms: the driver compares them)
+            "run": {"launch": f"RealESRGANFeed.feed_data, a fresh draw_plan per step, captured chains replayed ({graphs.captures} captures, "
+                              f"{graphs.hits} replays so far), {n_streams} calls in flight on {n_streams} streams",
+                    "numa_node_rank0": numa, "numa_note": numa_why},
             "value_feed_data": arm.pairs_per_s(args.steps, ms_single), "ms_per_step_feed_data": ms_single / args.steps,
             "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,
             "value_graph_replay_one_stream": arm.pairs_per_s(args.steps, ms_replay1),

@@ -6,10 +6,10 @@ when the GPU feed drives a x4 SR training step under DDP.
 
 Shapes follow the reference's SPAN OTF template (options/_templates/train/SPAN/SPAN_OTF_fidelity.yml: batch 16 per GPU,
 lq_size 64, scale 4, AdamW 5e-4, Charbonnier loss, bf16 autocast, channels_last); the dataset hands feed_data
-(gt_size + 32)^2 GT crops.  The network is a consumer stand-in written here, NOT the reference's arch file: a
-52-channel, six-block 3x3-conv net with sigmoid-gated residuals and a pixel-shuffle tail (the same size class as
-SPAN).  Networks, losses and optimisers are outside this repo's scope; only their cost relative to the feed is
-measured.  Per rank: pinned-host batch -> H2D on a copy stream -> RealESRGANFeed.feed_data (classical order, random
+(gt_size + 32)^2 GT crops.  The network is SPAN's structure restated here (SpanShapedSR below: training-time Conv3XC
+branches, six SPAB blocks, conv_cat fusion, pixel-shuffle tail, 52 channels — traiNNer/archs/span_arch.py:97-345), random
+initialised, NOT the reference's arch file.  Networks, losses and optimisers are outside this repo's scope; only their
+cost relative to the feed is measured.  Per rank: pinned-host batch -> H2D on a copy stream -> RealESRGANFeed.feed_data (classical order, random
 plans, pair pool on) -> forward / loss / backward (DDP all-reduce) / AdamW step.  CUDA events bracket the feed and the
 optimisation separately and are read after the run (the host queues work ahead of the GPU, as a training loop does;
 --sync-every-step shows the host-bound figure instead); the report is the median over the timed steps, max over ranks.
@@ -34,35 +34,59 @@ from trainner_redux_b200.kernels import synthesize_kernels  # noqa: E402
 from trainner_redux_b200.realesrgan_feed import OTFOptions, RealESRGANFeed  # noqa: E402
 
 
-class GatedBlock(nn.Module):
+class RepConv3(nn.Module):
+    """Training-time form of SPAN's re-parameterisable 3x3 convolution (traiNNer/archs/span_arch.py:97-216 `Conv3XC`):
+    a 1x1 widening (gain), an unpadded 3x3 on the zero-padded input and a 1x1 narrowing, plus a 1x1 skip branch.  The
+    eval-time merged 3x3 of the reference is not needed here: only the training step is timed."""
+
+    def __init__(self, c_in: int, c_out: int, gain: int = 2) -> None:
+        super().__init__()
+        self.skip = nn.Conv2d(c_in, c_out, 1)
+        self.widen = nn.Conv2d(c_in, c_in * gain, 1)
+        self.mix = nn.Conv2d(c_in * gain, c_out * gain, 3)
+        self.narrow = nn.Conv2d(c_out * gain, c_out, 1)
+
+    def forward(self, x):
+        return self.narrow(self.mix(self.widen(nn.functional.pad(x, (1, 1, 1, 1))))) + self.skip(x)
+
+
+class AttnBlock(nn.Module):
+    """SPAN's parameter-free attention block (span_arch.py:219-248 `SPAB`): three RepConv3 with SiLU in between, the
+    residual sum gated by sigmoid(out) - 0.5; also returns the first convolution's output (block 6's feeds conv_cat)."""
+
     def __init__(self, c: int) -> None:
         super().__init__()
-        self.c1, self.c2, self.c3 = (nn.Conv2d(c, c, 3, padding=1) for _ in range(3))
+        self.c1, self.c2, self.c3 = RepConv3(c, c), RepConv3(c, c), RepConv3(c, c)
         self.act = nn.SiLU(inplace=True)
 
     def forward(self, x):
-        y = self.c3(self.act(self.c2(self.act(self.c1(x)))))
-        return (y + x) * (torch.sigmoid(y) - 0.5)
+        o1 = self.c1(x)
+        o3 = self.c3(self.act(self.c2(self.act(o1.clone()))))
+        return (o3 + x) * (torch.sigmoid(o3) - 0.5), o1
 
 
-class StandInSR(nn.Module):
-    def __init__(self, c: int = 52, blocks: int = 6, scale: int = 4) -> None:
+class SpanShapedSR(nn.Module):
+    """The SPAN network restated from its structure (span_arch.py:251-345; option template
+    options/_templates/train/SPAN/SPAN_OTF_fidelity.yml: `type: span`, 52 feature channels, x4): head RepConv3, six
+    attention blocks, RepConv3, a 1x1 fusion of [head, tail, block 1, first conv of block 6], 3x3 + pixel shuffle.
+    Random-initialised; written here, the reference's arch file is neither imported nor copied."""
+
+    def __init__(self, c: int = 52, scale: int = 4) -> None:
         super().__init__()
-        self.head = nn.Conv2d(3, c, 3, padding=1)
-        self.body = nn.ModuleList(GatedBlock(c) for _ in range(blocks))
+        self.head = RepConv3(3, c)
+        self.blocks = nn.ModuleList(AttnBlock(c) for _ in range(6))
+        self.tail = RepConv3(c, c)
         self.fuse = nn.Conv2d(4 * c, c, 1)
-        self.tail = nn.Sequential(nn.Conv2d(c, 3 * scale * scale, 3, padding=1), nn.PixelShuffle(scale))
+        self.up = nn.Sequential(nn.Conv2d(c, 3 * scale * scale, 3, padding=1), nn.PixelShuffle(scale))
 
     def forward(self, x):
         f = self.head(x)
-        y, first, last = f, None, None
-        for i, b in enumerate(self.body):
-            y = b(y)
+        y, b1, o1 = f, None, None
+        for i, blk in enumerate(self.blocks):
+            y, o1 = blk(y)
             if i == 0:
-                first = y
-            if i == len(self.body) - 2:
-                last = y
-        return self.tail(self.fuse(torch.cat([f, y, first, last], 1)))
+                b1 = y
+        return self.up(self.fuse(torch.cat([f, self.tail(y), b1, o1], 1)))
 
 
 def main() -> None:
@@ -92,7 +116,7 @@ def main() -> None:
         host.append({"gt": S.synth_gt(B, GTS + 32, GTS + 32, "uniform", seed=rank * 4 + i).pin_memory(),
                      "kernel1": synthesize_kernels(p1, dev).cpu().pin_memory(), "kernel2": synthesize_kernels(p2, dev).cpu().pin_memory(),
                      "sinc_kernel": synthesize_kernels(p3, dev).cpu().pin_memory()})
-    net = StandInSR(scale=SC).to(dev).to(memory_format=torch.channels_last)
+    net = SpanShapedSR(scale=SC).to(dev).to(memory_format=torch.channels_last)
     if world > 1:
         net = nn.parallel.DistributedDataParallel(net, device_ids=[local])
     optim = torch.optim.AdamW(net.parameters(), lr=5e-4, betas=(0.9, 0.99), fused=True)
@@ -144,7 +168,7 @@ def main() -> None:
     if rank == 0:
         f, o, wall_ms = res.tolist()
         line = {"config": "x4 SR training step with GPU OTF feed (BASELINE.json configs[4])", "n_gpus": world, "batch_per_gpu": B,
-                "gt": GTS, "scale": SC, "net": "52-ch 6-block gated 3x3 stand-in (SPAN size class), bf16 autocast, channels_last, AdamW fused",
+                "gt": GTS, "scale": SC, "net": "SPAN structure restated (52 ch, 6 SPAB, training-time Conv3XC branches, x4 pixel shuffle), random init, bf16 autocast, channels_last, AdamW fused",
                 "params": sum(p.numel() for p in net.parameters()), "feed_ms": f, "optimize_ms": o, "degradation_share": f / (f + o),
                 "wall_ms_per_step": wall_ms, "pairs_per_s_job": world * B / (wall_ms / 1e3),
                 "timing": "per-step sync" if args.sync_every_step else "events read after the run: the host queues ahead as in a real training loop", "steps": args.steps, "loss": float(loss)}

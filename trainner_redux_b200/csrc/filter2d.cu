@@ -257,7 +257,7 @@ __device__ __forceinline__ void accumulate_rows_packed(const float* __restrict__
 // row and output column R FADDs + 2(R+1) FFMA2 instead of 2(2R+1) FFMA2: 1.56x fewer FMA-pipe cycles at K = 21.
 // wsm2f row i holds the paired taps (w[i][R+t], w[i-1][R+t]) for t = 0..R.  The summation order differs from the
 // unfolded loop (pairs are pre-added), i.e. by a few ulp — inside the 1e-5 bar like every other order.
-template <int TX, int TY, int KT, int PMASK>
+template <int TX, int TY, int KT, bool ALL>
 __device__ __forceinline__ void fold_row(const float* __restrict__ rowp, const float2* __restrict__ wsm2f, int r,
                                          float2 (&acc2)[TY / 2][TX]) {
     constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
@@ -269,12 +269,16 @@ __device__ __forceinline__ void fold_row(const float* __restrict__ rowp, const f
         const float4 v = rp[q];
         row[4 * q + 0] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
     }
+    // output pair p takes kernel rows (i, i - 1) with i = r - 2p from image row r: live while 0 <= i <= KT (block-uniform)
+    bool live[TY / 2];
+#pragma unroll
+    for (int p = 0; p < TY / 2; ++p) live[p] = ALL || (r - 2 * p >= 0 && r - 2 * p <= KT);
 #pragma unroll
     for (int q = 0; q < (R + 2) / 2; ++q) {  // taps t = 2q, 2q + 1
         float4 w4[TY / 2];
 #pragma unroll
         for (int p = 0; p < TY / 2; ++p)
-            if ((PMASK >> p) & 1) w4[p] = reinterpret_cast<const float4*>(wsm2f + (r - 2 * p) * kW2Pitch)[q];
+            if (live[p]) w4[p] = reinterpret_cast<const float4*>(wsm2f + (r - 2 * p) * kW2Pitch)[q];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int t = 2 * q + u;
@@ -286,7 +290,7 @@ __device__ __forceinline__ void fold_row(const float* __restrict__ rowp, const f
                     const float2 s2 = make_float2(sv, sv);
 #pragma unroll
                     for (int p = 0; p < TY / 2; ++p)
-                        if ((PMASK >> p) & 1)
+                        if (live[p])
                             ffma2(acc2[p][ox], s2, u == 0 ? make_float2(w4[p].x, w4[p].y) : make_float2(w4[p].z, w4[p].w));
                 }
             }
@@ -297,19 +301,26 @@ __device__ __forceinline__ void fold_row(const float* __restrict__ rowp, const f
 template <int TX, int TY, int KT>
 __device__ __forceinline__ void accumulate_rows_folded(const float* __restrict__ tile_thread, int pitch,
                                                        const float2* __restrict__ wsm2f, float (&acc)[TY][TX]) {
-    static_assert(TY == 4, "two vertical output pairs");
+    static_assert(TY % 2 == 0, "pairs of output rows");
     float2 acc2[TY / 2][TX];
 #pragma unroll
     for (int p = 0; p < TY / 2; ++p)
 #pragma unroll
         for (int ox = 0; ox < TX; ++ox) acc2[p][ox] = make_float2(0.0f, 0.0f);
-    // output pair p takes kernel rows (i, i - 1) with i = r - 2p from image row r: valid while 0 <= i <= KT
-    fold_row<TX, TY, KT, 1>(tile_thread, wsm2f, 0, acc2);
-    fold_row<TX, TY, KT, 1>(tile_thread + pitch, wsm2f, 1, acc2);
+    // image rows 0 .. TY + KT - 2: every pair is live for rows TY - 2 .. KT (one loop body without predicates when that
+    // range is not empty), the ramps on either side test the pairs one by one
+    constexpr int LO = TY - 2, HI = KT, LAST = TY + KT - 2;
+    if constexpr (LO <= HI) {
 #pragma unroll 1
-    for (int r = 2; r <= KT; ++r) fold_row<TX, TY, KT, 3>(tile_thread + r * pitch, wsm2f, r, acc2);
-    fold_row<TX, TY, KT, 2>(tile_thread + (KT + 1) * pitch, wsm2f, KT + 1, acc2);
-    fold_row<TX, TY, KT, 2>(tile_thread + (KT + 2) * pitch, wsm2f, KT + 2, acc2);
+        for (int r = 0; r < LO; ++r) fold_row<TX, TY, KT, false>(tile_thread + r * pitch, wsm2f, r, acc2);
+#pragma unroll 1
+        for (int r = LO; r <= HI; ++r) fold_row<TX, TY, KT, true>(tile_thread + r * pitch, wsm2f, r, acc2);
+#pragma unroll 1
+        for (int r = HI + 1; r <= LAST; ++r) fold_row<TX, TY, KT, false>(tile_thread + r * pitch, wsm2f, r, acc2);
+    } else {
+#pragma unroll 1
+        for (int r = 0; r <= LAST; ++r) fold_row<TX, TY, KT, false>(tile_thread + r * pitch, wsm2f, r, acc2);
+    }
 #pragma unroll
     for (int p = 0; p < TY / 2; ++p)
 #pragma unroll
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     const int R_ = scratch ? min(scratch[kb], K / 2) : K / 2;
     const int kflags = scratch ? scratch[2 * kernel_batch + kb] : 0;
     const bool rank1 = R_ >= 2 && (kflags & 1) != 0;
-    const bool fold = PACKED && TY == 4 && !rank1 && R_ >= 2 && (kflags & 2) != 0;
+    const bool fold = PACKED && !rank1 && R_ >= 2 && (kflags & 2) != 0;
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.x;
     const int R = support ? min(support[kb], K / 2) : K / 2;  // true radius (block-uniform)
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
             default: accumulate_rank1<TX, TY, 21>(tt, P, u, v, acc); break;
         }
     } else if (fold) {
-        if constexpr (PACKED && TY == 4) {
+        if constexpr (PACKED) {
             const float2* w2 = reinterpret_cast<const float2*>(wsm);
             switch (R) {
                 case 2: accumulate_rows_folded<TX, TY, 5>(tt, P, w2, acc); break;
@@ -735,8 +746,15 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
     // big planes: 64x64 tiles, 8x4 outputs per thread (128 threads); tiny planes: 32x32 tiles, 4x4 per thread
     const int64_t big_tiles = (int64_t)ceil_div(W, 64) * ceil_div(H, 64) * B * C;
     static const bool scalar = getenv("OTF_F2D_SCALAR") != nullptr;  // A/B switch: scalar FFMA instead of packed FFMA2
+    static const bool tall = getenv("OTF_F2D_TALL") != nullptr;      // A/B switch: 4 columns x 8 rows per thread
     if (big_tiles >= 2 * kNumSMs) {
         if (scalar) return launch_blocked<8, 4, 8, 16, false>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
+        // Measured alternative (profiles/r02_microbench_f2d_blocks.txt): a 4 x 8 block makes the row loads conflict-free (the
+        // eight threads of a quarter-warp read eight consecutive 16-byte chunks; with 8 columns per thread chunks tx and
+        // tx + 4 share their banks) and shares each image row's horizontal pass among 8 output rows: rank-1 kernels run 11 %
+        // faster, dense and folded ones 4 % slower (twice the weight loads, 28 row iterations instead of 24) — a wash on the
+        // default kernel mix, so the 8 x 4 block stays.
+        if (tall) return launch_blocked<4, 8, 16, 8, true>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
         return launch_blocked<8, 4, 8, 16, true>(img, B, C, H, W, kernel, kernel_batch, K, support_dev, use_order, out, st);
     }
     // small planes: 64x32 tiles (64 threads) keep the 8x4 register block and halve the tile
