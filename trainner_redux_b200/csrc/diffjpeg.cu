@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(128, 5) diffjpeg_kernel(const float* __restric
                                                        float factor_scalar, int differentiable, int clamp_in,
                                                        int round8_out, int vec_ok, int factor_is_quality,
                                                        const __grid_constant__ CropTail ct) {
+    pdl_enter();
     __shared__ __align__(16) float s_warp[4][kJpegWarpFloats];
     int top = ct.top, left = ct.left;
     if (ct.lq_out) {
@@ -351,7 +352,7 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     const int wpc = warps >= (int64_t)kNumSMs * 8 ? 4 : 1;
     CropTail ct;
     memset(&ct, 0, sizeof(ct));
-    diffjpeg_kernel<<<ceil_div(warps, wpc), 32 * wpc, 0, (cudaStream_t)stream>>>(img, out, B, H, W, mcu_x, mcu_y, factor_dev,
+    launch_chain(diffjpeg_kernel, dim3(ceil_div(warps, wpc)), dim3(32 * wpc), 0, (cudaStream_t)stream, img, out, B, H, W, mcu_x, mcu_y, factor_dev,
                                                                              factor_scalar, differentiable, clamp_in,
                                                                              round8_out, vec_ok, factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel");
@@ -384,7 +385,7 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     int copy_ctas = (int)((gquads / 4 + 127) / 128);
     if (copy_ctas > kNumSMs * 8) copy_ctas = kNumSMs * 8;
     if (copy_ctas < 1) copy_ctas = 1;
-    diffjpeg_kernel<<<ct.jpeg_ctas + copy_ctas, 32 * wpc, 0, (cudaStream_t)stream>>>(img, nullptr, B, H, W, mcu_x, mcu_y, factor_dev,
+    launch_chain(diffjpeg_kernel, dim3(ct.jpeg_ctas + copy_ctas), dim3(32 * wpc), 0, (cudaStream_t)stream, img, nullptr, B, H, W, mcu_x, mcu_y, factor_dev,
                                                                                   factor_scalar, differentiable, clamp_in, 1, vec_ok,
                                                                                   factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel (fused crop)");

@@ -46,6 +46,7 @@ struct KernelSets {
 constexpr int kAnalyseWarps = 8, kAnalyseCluster = 8;
 __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnalyseWarps * 32)
     kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch, int32_t* __restrict__ scratch_base) {
+    pdl_enter();
     __shared__ float sk_all[kAnalyseWarps][21 * 21 + 7];
     extern __shared__ int s_sup[];  // [kernel_batch] supports, for the ranking pass (CTA 0 of the cluster)
     const float* kern = sets.ptr[blockIdx.y];
@@ -121,7 +122,7 @@ static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch
     OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 4096, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..4096");
     KernelSets sets;
     for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
-    kernel_analyse_kernel<<<dim3(kAnalyseCluster, nsets), kAnalyseWarps * 32, kernel_batch * sizeof(int), st>>>(sets, K, kernel_batch, scratch);
+    launch_chain(kernel_analyse_kernel, dim3(dim3(kAnalyseCluster, nsets)), dim3(kAnalyseWarps * 32), kernel_batch * sizeof(int), st, sets, K, kernel_batch, scratch);
     OTF_LAUNCH_CHECK("kernel_analyse_kernel");
     return OTF_OK;
 }
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
                                                           const int32_t* __restrict__ scratch, int use_order,
                                                           float* __restrict__ out, int C, int H, int W, int K,
                                                           int kernel_batch, int vec_ok, int use_tma) {
+    pdl_enter();
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY, NT = BX * BY;
     constexpr int P = TILE_W + 2 * kMaxRA;     // smem row pitch = TMA box width (multiple of 4)
     constexpr int ROWS = TILE_H + 2 * kMaxRT;  // TMA box height
@@ -699,7 +701,7 @@ static int launch_blocked(const float* img, int B, int C, int H, int W, const fl
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         use_tma = (r == CUDA_SUCCESS);
     }
-    kfn<<<grid, BX * BY, smem, st>>>(tmap, img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok, use_tma);
+    launch_chain(kfn, dim3(grid), dim3(BX * BY), smem, st, tmap, img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok, use_tma);
     OTF_LAUNCH_CHECK("filter2d_kernel");
     return OTF_OK;
 }

@@ -13,6 +13,7 @@
 namespace otf {
 
 __global__ void __launch_bounds__(128) synth_kernels_kernel(const double* __restrict__ params, float* __restrict__ out) {
+    pdl_enter();
     __shared__ double vals[21 * 21];
     __shared__ double red[4];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) synth_kernels_kernel(const double* __rest
 extern "C" int otf_synth_kernels_f32(const double* params_dev, int B, float* out, void* stream) {
     using namespace otf;
     OTF_REQUIRE(params_dev && out && B > 0, OTF_ERR_BAD_ARG, "synth_kernels: bad args");
-    synth_kernels_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(params_dev, out);
+    launch_chain(synth_kernels_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, params_dev, out);
     OTF_LAUNCH_CHECK("synth_kernels_kernel");
     return OTF_OK;
 }

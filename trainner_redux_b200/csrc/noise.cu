@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
                                                              const float* __restrict__ ncol, const float* __restrict__ ngray,
                                                              uint64_t seed, uint64_t offset,
                                                              const uint64_t* __restrict__ offset_dev, int flags) {
+    pdl_enter();
     const Philox ph(seed);
     if (offset_dev) offset += *offset_dev;  // device-resident counter: a replayed CUDA graph draws a fresh field
     const int b = blockIdx.y;
@@ -242,6 +243,7 @@ __device__ __forceinline__ int level8(float x) {  // clamp(round(x*255),0,255) a
 // masks[b*16 + 0..7] colour, [b*16 + 8..15] gray.  grid = (chunks, B).
 __global__ void __launch_bounds__(256) poisson_presence_kernel(const float* __restrict__ img, int hw,
                                                                uint32_t* __restrict__ masks) {
+    pdl_enter();
     // One byte flag per level in shared memory: setting it is a plain store (every writer stores the same 1, so the
     // race is benign) — 4 stores per pixel instead of the ~100 select instructions of per-thread register masks or the
     // contended atomics of a shared bit mask.  At the end 16 ballots pack the flags into the sample's 2 x 256-bit masks.
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restr
                                                             int flags,
                                                             const uint32_t* __restrict__ masks, float* __restrict__ vals_out,
                                                             float* __restrict__ lam_c_out, float* __restrict__ lam_g_out) {
+    pdl_enter();
     if (offset_dev) offset += *offset_dev;
     const int b = blockIdx.y;
     __shared__ float s_vals[2];
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(256) poisson_apply_table_kernel(const float* _
                                                                   uint64_t seed, uint64_t offset,
                                                                   const uint64_t* __restrict__ offset_dev, int flags,
                                                                   const uint32_t* __restrict__ masks, PoissonTables tab) {
+    pdl_enter();
     if (offset_dev) offset += *offset_dev;
     const int b = blockIdx.y;
     const float gf = gray ? gray[b] : 0.0f;
@@ -544,7 +548,7 @@ extern "C" int otf_gaussian_noise_f32(const float* img, int B, int C, int H, int
     const bool exact = noise_color_dev != nullptr || (flags & OTF_NOISE_ROUNDS);
     cudaStream_t st = (cudaStream_t)stream;
 #define OTF_GAUSS(V, E)                                                                                              \
-    gaussian_noise_kernel<V, E><<<grid, 256, 0, st>>>(img, out, C, H, W, sigma_dev, gray_dev, noise_color_dev, ng, \
+    launch_chain(gaussian_noise_kernel<V, E>, dim3(grid), dim3(256), 0, st, img, out, C, H, W, sigma_dev, gray_dev, noise_color_dev, ng, \
                                                       seed, offset, offset_dev, flags)
     if (vec && exact) OTF_GAUSS(true, true);
     else if (vec) OTF_GAUSS(true, false);
@@ -610,7 +614,7 @@ extern "C" int otf_poisson_noise_f32(const float* img, int B, int C, int H, int 
     const int max_chunks = ceil_div(kNumSMs * 8, B);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
-    poisson_presence_kernel<<<dim3(chunks, B), 256, 0, st>>>(img, hw, masks_dev);
+    launch_chain(poisson_presence_kernel, dim3(dim3(chunks, B)), dim3(256), 0, st, img, hw, masks_dev);
     OTF_LAUNCH_CHECK("poisson_presence_kernel");
     int chunks2 = ceil_div(hw, 256);
     const int max_chunks2 = ceil_div(kNumSMs * 16, B);
@@ -619,12 +623,12 @@ extern "C" int otf_poisson_noise_f32(const float* img, int B, int C, int H, int 
     static const bool force_ptrs = [] { const char* e = getenv("OTF_POISSON_IMPL"); return e && e[0] == 'p'; }();
     const bool plain = !counts_color_dev && !counts_gray_dev && !vals_out_dev && !lambda_color_dev && !lambda_gray_dev;
     if (plain && !force_ptrs && tables_dev) {
-        poisson_apply_table_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, seed, offset, offset_dev, flags,
+        launch_chain(poisson_apply_table_kernel, dim3(dim3(chunks2, B)), dim3(256), 0, st, img, out, hw, scale_dev, gray_dev, seed, offset, offset_dev, flags,
                                                                      masks_dev, poisson_tables(tables_dev));
         OTF_LAUNCH_CHECK("poisson_apply_table_kernel");
         return OTF_OK;
     }
-    poisson_apply_kernel<<<dim3(chunks2, B), 256, 0, st>>>(img, out, hw, scale_dev, gray_dev, counts_color_dev,
+    launch_chain(poisson_apply_kernel, dim3(dim3(chunks2, B)), dim3(256), 0, st, img, out, hw, scale_dev, gray_dev, counts_color_dev,
                                                            counts_gray_dev, seed, offset, offset_dev, flags, masks_dev, vals_out_dev,
                                                            lambda_color_dev, lambda_gray_dev);
     OTF_LAUNCH_CHECK("poisson_apply_kernel");

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/otf_b200.h"
 
@@ -34,6 +35,35 @@ int cuda_fail(cudaError_t e, const char* what);
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized against this
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------ programmatic dependent launch ----
+// The chain's kernels are launched back to back on one stream (or as consecutive nodes of a captured graph).  With
+// programmatic stream serialisation the NEXT kernel's CTAs may become resident while the last wave of this one drains:
+// every kernel on the chain starts with pdl_enter() — wait for the predecessor grid to complete (nothing of its output
+// is touched before, so plain stream order is preserved, ping-pong buffers included), then allow the successor's launch.
+// What is saved is the launch latency and CTA ramp-up at each of the ~8 kernel boundaries of a step (single stream:
+// ~4 us each).  The attribute is only attached with OTF_PDL=1 in the environment (see pdl_enabled(): it measured
+// slower); without it griddepcontrol.* are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // --------------------------------------------------------------- indexing ---
 // torch F.pad(mode="reflect"): mirror without repeating the edge sample.

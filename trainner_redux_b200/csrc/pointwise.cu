@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "otf_common.cuh"
 
 namespace otf {
@@ -15,6 +17,13 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+bool pdl_enabled() {
+    // off by default: measured on B200 (profiles/r02_pdl_ab.json) the early-resident dependents cost more than the launch
+    // gaps they hide — single-stream feed_data 227 k pairs/s with the attribute vs 248 k without, and the prefetcher loop
+    // (copy stream + events around the captured chain) collapses; OTF_PDL=1 turns the attribute on for further study
+    static const bool on = [] { const char* e = getenv("OTF_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return OTF_ERR_CUDA;
@@ -22,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // ---- a7: traiNNer/models/realesrgan_model.py:616 ------------------------------------------
 __global__ void __launch_bounds__(256) clamp_round_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+    pdl_enter();
     const int64_t nq = n >> 2;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[q];
@@ -35,6 +45,7 @@ __global__ void __launch_bounds__(256) clamp_round_kernel(const float* __restric
 // The reference normalises on the host (traiNNer/utils/img_util.py:65-109 `img2tensor`: float32(img) / 255) and
 // ships fp32 over PCIe; uploading the 8-bit image and dividing here moves 4x fewer bytes.  Same IEEE division.
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    pdl_enter();
     const int64_t nq = n >> 2;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         const uchar4 u = reinterpret_cast<const uchar4*>(src)[q];
@@ -52,6 +63,7 @@ __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ top_left_dev,
                                                         int p, int scale, int planes, float* __restrict__ gt_out,
                                                         float* __restrict__ lq_out) {
+    pdl_enter();
     if (top_left_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot read outside the image
         top = clampi(top_left_dev[0], 0, Hl - p);
         left = clampi(top_left_dev[1], 0, Wl - p);
@@ -67,6 +79,7 @@ __global__ void __launch_bounds__(256) crop_pair_scalar_kernel(const float* __re
                                                                int left, const int32_t* __restrict__ top_left_dev, int p,
                                                                int scale, int planes, int round8,
                                                                float* __restrict__ gt_out, float* __restrict__ lq_out) {
+    pdl_enter();
     if (top_left_dev) {
         top = clampi(top_left_dev[0], 0, Hl - p);
         left = clampi(top_left_dev[1], 0, Wl - p);
@@ -213,7 +226,7 @@ extern "C" int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* 
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     if (blocks < 1) blocks = 1;
-    clamp_round_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    launch_chain(clamp_round_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, x, out, n);
     OTF_LAUNCH_CHECK("clamp_round_kernel");
     return OTF_OK;
 }
@@ -225,7 +238,7 @@ extern "C" int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* st
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     if (blocks < 1) blocks = 1;
-    u8_to_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    launch_chain(u8_to_f32_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, src, dst, n);
     OTF_LAUNCH_CHECK("u8_to_f32_kernel");
     return OTF_OK;
 }
@@ -246,7 +259,7 @@ extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, co
     if (blocks < 1) blocks = 1;
     const bool quads = (lq_patch % 4 == 0) && ((((uintptr_t)gt_out | (uintptr_t)lq_out) & 15) == 0);
     if (!quads) {
-        crop_pair_scalar_kernel<<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, lq_round8, gt_out, lq_out);
+        launch_chain(crop_pair_scalar_kernel, dim3(blocks), dim3(256), 0, st, gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, lq_round8, gt_out, lq_out);
         OTF_LAUNCH_CHECK("crop_pair_scalar_kernel");
         return OTF_OK;
     }
@@ -254,7 +267,7 @@ extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, co
     const bool vg = (Wg % 4 == 0) && (top_left_dev ? scale % 4 == 0 : (left * scale) % 4 == 0) && (((uintptr_t)gt & 15) == 0);
     const bool vl = (Wl % 4 == 0) && !top_left_dev && (left % 4 == 0) && (((uintptr_t)lq & 15) == 0);
 #define OTF_CROP(VG, VL, R8) \
-    crop_pair_kernel<VG, VL, R8><<<blocks, 256, 0, st>>>(gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out)
+    launch_chain(crop_pair_kernel<VG, VL, R8>, dim3(blocks), dim3(256), 0, st, gt, Hg, Wg, lq, Hl, Wl, top, left, top_left_dev, lq_patch, scale, planes, gt_out, lq_out)
     if (lq_round8) {
         if (vg && vl) OTF_CROP(true, true, true); else if (vg) OTF_CROP(true, false, true);
         else if (vl) OTF_CROP(false, true, true); else OTF_CROP(false, false, true);

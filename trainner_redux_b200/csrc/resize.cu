@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ i
                                                      AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
                                                      const int* __restrict__ tx_lo, int tile_h, int rows_cap,
                                                      int cols_cap, int clamp_out, int vec_ok, const __grid_constant__ NoiseEpi ne) {
+    pdl_enter();
     constexpr int TW = 32 * CW;
     extern __shared__ __align__(16) float sm[];
     const int SP = (cols_cap + NT + 3) & ~3;  // src row pitch: >= NT zero columns behind every row, 16-byte rows
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
                                                         AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
                                                         const int* __restrict__ tx_lo, int TW, int TH, int pitch,
                                                         int clamp_out, const __grid_constant__ NoiseEpi ne) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];
     const int nty = NT ? NT : ay.max_taps, ntx = NT ? NT : ax.max_taps;
     const int wxp = ntx | 1;  // odd pitch of the run-time horizontal tap table: conflict-free column reads
@@ -705,6 +707,7 @@ __global__ void __launch_bounds__(128, 4) resize_rb_kernel(const float* __restri
                                                            AxisSpec ay, AxisSpec ax, const int* __restrict__ dense,
                                                            const __grid_constant__ RbPlan pl, int clamp_out, int vec_out,
                                                            const __grid_constant__ NoiseEpi ne) {
+    pdl_enter();
     constexpr int SPAN = 4 * SH, WHP = GH * SPAN + 4;  // (+4: consecutive column groups start 4 banks apart)
     extern __shared__ __align__(16) float sm[];
     const int TW = pl.TW, TH = pl.TH, pitch = pl.pitch;
@@ -862,6 +865,7 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(const float* __rest
                                                              AxisSpec ay, AxisSpec ax, const int* __restrict__ ty_lo,
                                                              const int* __restrict__ tx_lo, int clamp_out,
                                                              const __grid_constant__ NoiseEpi ne) {
+    pdl_enter();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= ax.out_n || y >= ay.out_n) return;
     const float* wx = reinterpret_cast<const float*>(tx_lo + 2 * ax.out_n) + (size_t)x * ax.max_taps;
@@ -1035,7 +1039,7 @@ static int resize_impl(const float* img, int planes, int H, int W, float* out, i
     do {                                                                                                                  \
         auto kfn = resize_rb_kernel<GV_, RV_, GH_, SH_, V_, N_>;                                                          \
         if (pl.smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);         \
-        kfn<<<grid, 128, pl.smem, st>>>(img, out, ay, ax, dense, pl, clamp_out, vec_out, ne);                             \
+        launch_chain(kfn, dim3(grid), dim3(128), pl.smem, st, img, out, ay, ax, dense, pl, clamp_out, vec_out, ne);                             \
     } while (0)
 #define OTF_RESIZE_RB(GV_, RV_, GH_, SH_)                                                                                 \
     do {                                                                                                                  \
@@ -1069,7 +1073,7 @@ static int resize_impl(const float* img, int planes, int H, int W, float* out, i
     do {                                                                                                                  \
         auto kfn = resize_vh_kernel<NT_, V_, N_>;                                                                         \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, TW, TH, pitch, clamp_out, ne);                       \
+        launch_chain(kfn, dim3(grid), dim3(256), smem, st, img, out, ay, ax, ty_lo, tx_lo, TW, TH, pitch, clamp_out, ne);                       \
     } while (0)
 #define OTF_RESIZE_VH(NT_)                                                                                                \
     do {                                                                                                                  \
@@ -1094,8 +1098,8 @@ static int resize_impl(const float* img, int planes, int H, int W, float* out, i
         }
     }
     if (mt > 64) {
-        if (noise) resize_generic_kernel<true><<<dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes), 256, 0, st>>>(img, out, ay, ax, ty_lo, tx_lo, clamp_out, ne);
-        else resize_generic_kernel<false><<<dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes), 256, 0, st>>>(img, out, ay, ax, ty_lo, tx_lo, clamp_out, ne);
+        if (noise) launch_chain(resize_generic_kernel<true>, dim3(dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes)), dim3(256), 0, st, img, out, ay, ax, ty_lo, tx_lo, clamp_out, ne);
+        else launch_chain(resize_generic_kernel<false>, dim3(dim3(ceil_div(OW, 32), ceil_div(OH, 8), planes)), dim3(256), 0, st, img, out, ay, ax, ty_lo, tx_lo, clamp_out, ne);
         OTF_LAUNCH_CHECK("resize_generic_kernel");
         return OTF_OK;
     }
@@ -1137,7 +1141,7 @@ static int resize_impl(const float* img, int planes, int H, int W, float* out, i
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
             if (e != cudaSuccess) return cuda_fail(e, "resize smem attribute");                                           \
         }                                                                                                                 \
-        kfn<<<grid, 256, smem, st>>>(img, out, ay, ax, ty_lo, tx_lo, tile_h, rows_cap, cols_cap, clamp_out, vec_ok, ne);        \
+        launch_chain(kfn, dim3(grid), dim3(256), smem, st, img, out, ay, ax, ty_lo, tx_lo, tile_h, rows_cap, cols_cap, clamp_out, vec_ok, ne);        \
     } while (0)
 #define OTF_RESIZE_CW(NT_)                                  \
     do {                                                    \
