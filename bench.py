@@ -510,8 +510,8 @@ class Arm:
 
     def executed_ops(self) -> dict:
         """FP32-pipe lane operations the blur1 launch EXECUTES per output pixel, from the device-side kernel analysis
-        (true radius R, rank-1 and mirror-symmetry flags): dense K^2 FMAs; rank-1 K + K(4+K-1)/4 (the horizontal pass runs
-        once per image row of the 4-row register block); folded K(R+1) FMAs + R(4+K-1)/4 adds."""
+        (true radius R, rank-1 and mirror-symmetry flags): dense K^2 FMAs; rank-1 K + K(64+K-1)/64 (the horizontal pass runs
+        once per row of the CTA's 64-row tile, through shared memory); folded K(R+1) FMAs + R(4+K-1)/4 adds."""
         from trainner_redux_b200.img_process_util import KernelAnalysis
 
         k1 = self.devd[0]["kernel1"]
@@ -525,7 +525,7 @@ class Arm:
             if r == 0:
                 ops, kinds["identity"] = ops + 1, kinds["identity"] + 1
             elif r >= 2 and fl & 1:
-                ops, kinds["rank1"] = ops + kt + kt * (4 + kt - 1) / 4, kinds["rank1"] + 1
+                ops, kinds["rank1"] = ops + kt + kt * (64 + kt - 1) / 64, kinds["rank1"] + 1
             elif r >= 2 and fl & 2:
                 ops, kinds["folded"] = ops + kt * (r + 1) + r * (4 + kt - 1) / 4, kinds["folded"] + 1
             else:

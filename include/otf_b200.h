@@ -77,13 +77,15 @@ int otf_device_cc(void);
 /* ---- a1: filter2d — traiNNer/utils/img_process_util.py:8-32 -------------------
  * out[b,c,y,x] = sum_{i,j<K} reflect_pad(img)[b,c,y+i,x+j] * kernel[kb,i,j],
  * kb = b (kernel_batch == B) or 0 (kernel_batch == 1).  K odd, K//2 < min(H,W).
- * `scratch_dev` (otf_filter2d_scratch_words(kernel_batch) 4-byte words; may be NULL =
- * analyse nothing, run every kernel at full K) holds the per-kernel analysis the main
- * kernel consumes without any host round trip: true half-width (largest |offset| with
- * a non-zero tap), launch order of the samples (largest support first), a rank-1 flag
- * and the two rank-1 factors.  With scratch_ready == 0 the call runs the analysis
- * itself (2 small launches); otf_filter2d_analyse_f32 fills the scratch of up to 4
- * kernel tensors (kernel1, kernel2, sinc_kernel) with ONE pair of launches, laid out
+ * `scratch_dev` (otf_filter2d_scratch_words(kernel_batch) 4-byte words, 16-byte aligned;
+ * may be NULL = analyse nothing, run every kernel at full K) holds the per-kernel analysis
+ * the main kernel consumes without any host round trip: true half-width (largest |offset|
+ * with a non-zero tap), launch order of the samples (most expensive first, one packed
+ * record per position), rank-1 / mirror-symmetry flags, and each sample's taps laid out
+ * the way the main kernel keeps them in shared memory (rank-1 factors, or folded / dense
+ * paired taps), fetched by one bulk copy per CTA.  With scratch_ready == 0 the call runs
+ * the analysis itself (1 small launch); otf_filter2d_analyse_f32 fills the scratch of up to
+ * 4 kernel tensors (kernel1, kernel2, sinc_kernel) with ONE launch, laid out
  * back to back (set i at scratch_dev + i * otf_filter2d_scratch_words(kb)), after which
  * the filter calls pass scratch_ready == 1.  K <= 21 runs the register-blocked path
  * specialised on the true support (rank-1 kernels as K + K taps, halo tiles staged by

@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import trainner_redux_b200 as T  # noqa: E402
 from trainner_redux_b200 import synthetic as S  # noqa: E402
-from trainner_redux_b200.kernels import synthesize_kernels  # noqa: E402
+from trainner_redux_b200.kernels import synthesize_kernels
+from trainner_redux_b200.img_process_util import KernelAnalysis  # noqa: E402
 from trainner_redux_b200 import degradations as D  # noqa: E402
 from trainner_redux_b200.realesrgan_feed import clamp_round  # noqa: E402
 from trainner_redux_b200.transforms import crop_pair  # noqa: E402
@@ -120,6 +121,9 @@ for kinds, sp in ((None, 0.1), (("iso",), 0.0), (("aniso",), 0.0), (("generalize
     k = kernels(10, kinds, sp)
     label = "default mix" if kinds is None else ("sinc" if sp == 1.0 else "/".join(kinds))
     add(f"filter2d 256^2 sizes 7..21 {label}", lambda t, k=k: T.filter2d(t, k), 2 * N(x256), 2 * taps(k) * x256.numel(), x=x256)
+    ka = KernelAnalysis([k])  # as the chain runs it: one analysis launch per step for all kernel sets, outside this row
+    add(f"filter2d 256^2 sizes 7..21 {label} (pre-analysed)", lambda t, k=k, ka=ka: T.filter2d(t, k, _analysis=(ka, 0)), 2 * N(x256),
+        2 * taps(k) * x256.numel(), x=x256)
 for ks in (7, 9, 13, 17, 21):
     k = torch.rand(B, ks, ks, device=dev)
     k = k / k.sum((1, 2), keepdim=True)
@@ -128,6 +132,12 @@ k2 = kernels(20, which=1)
 add("filter2d 192^2 mixed", lambda t: T.filter2d(t, k2), 2 * N(x192), 2 * taps(k2) * x192.numel(), x=x192)
 sk = kernels(30, which=2)
 add("filter2d 64^2 final sinc", lambda t: T.filter2d(t, sk), 2 * N(x64), 2 * taps(sk) * x64.numel(), x=x64)
+ka_s = KernelAnalysis([sk])
+add("filter2d 64^2 final sinc (pre-analysed)", lambda t: T.filter2d(t, sk, _analysis=(ka_s, 0)), 2 * N(x64), 2 * taps(sk) * x64.numel(), x=x64)
+k7 = torch.rand(B, 7, 7, device=dev)
+k7 = torch.nn.functional.pad(k7 / k7.sum((1, 2), keepdim=True), (7, 7, 7, 7))
+ka7 = KernelAnalysis([k7])
+add("filter2d 256^2 dense K=7 in 21x21 (pre-analysed)", lambda t: T.filter2d(t, k7, _analysis=(ka7, 0)), 2 * N(x256), 2 * 49 * x256.numel(), x=x256)
 for mode in ("bilinear", "bicubic", "area", "nearest-exact", "lanczos"):
     for s in (0.4, 0.75, 1.25, 1.5):
         oh = round(256 * s)

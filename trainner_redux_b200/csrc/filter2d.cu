@@ -30,11 +30,18 @@ namespace otf {
 //                stored centred in 21 slots; the blur is then evaluated as K + K taps instead of K*K.
 //                Acceptance: |K_ij - u_i v_j| <= 4e-7 |K_ij| + 1e-9 max|K|, i.e. the separable result
 //                differs from the full sum by <= ~4e-7 * sum|K_ij| * max|img| — far inside the 1e-5 bar;
-//   order[0..kb) sample indices sorted by support, largest first: CTAs are launched in that order,
-//                so the CTAs resident on an SM at any time run the same specialisation (instruction-
-//                cache locality) and the expensive tiles go first (LPT scheduling).
+//   order[0..kb) one packed record per launch position (sample | radius << 16 | flags << 24), most expensive
+//                sample first: CTAs are launched in that order, so the CTAs resident on an SM at any time run
+//                the same specialisation (instruction-cache locality) and the expensive tiles go first (LPT).
+//   staged[kb]   the taps exactly as filter2d_kernel wants them in shared memory (22 x 24 float2 slots per sample): the
+//                rank-1 factors (u in words [0,24), v in [24,48)), or the folded / dense PAIRED taps — row i holds
+//                (w[i][.], w[i-1][.]) for the FFMA2 loops.  A CTA then fetches its taps with ONE bulk copy that
+//                completes on the same mbarrier as its tile instead of 4-5 rounds of dependent global loads.
 constexpr int kUVPitch = 24;
-__host__ __device__ inline size_t scratch_words(int kb) { return (size_t)kb * (3 + 2 * kUVPitch); }
+constexpr int kW2Pitch = 24;                      // float2 per paired tap row
+constexpr int kStagedWords = 22 * kW2Pitch * 2;   // per sample
+__host__ __device__ inline size_t staged_offset(int kb) { return ((size_t)3 * kb + 3) & ~(size_t)3; }
+__host__ __device__ inline size_t scratch_words(int kb) { return staged_offset(kb) + (size_t)kb * kStagedWords; }
 
 struct KernelSets {
     const float* ptr[4];  // up to 4 kernel tensors (kernel1, kernel2, sinc_kernel, ...) analysed by one launch
@@ -45,7 +52,7 @@ struct KernelSets {
 // cluster ranks the samples: analysis and launch order in ONE launch with no host-initialised ticket.
 constexpr int kAnalyseWarps = 8, kAnalyseCluster = 8;
 __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnalyseWarps * 32)
-    kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch, int32_t* __restrict__ scratch_base) {
+    kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch, int32_t* __restrict__ scratch_base, int interleave) {
     pdl_enter();
     __shared__ float sk_all[kAnalyseWarps][21 * 21 + 7];
     extern __shared__ int s_sup[];  // [kernel_batch] supports, for the ranking pass (CTA 0 of the cluster)
@@ -53,7 +60,7 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
     int32_t* scratch = scratch_base + (size_t)blockIdx.y * scratch_words(kernel_batch);
     int32_t* support = scratch;
     int32_t* rank1 = scratch + 2 * kernel_batch;
-    float* uv = reinterpret_cast<float*>(scratch + 3 * kernel_batch);
+    float* staged = reinterpret_cast<float*>(scratch + staged_offset(kernel_batch));
     const int c = K / 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = K * K;  // K <= 21 on this path
     float* sk = sk_all[warp];
@@ -94,26 +101,54 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
         }
         ok = __all_sync(0xffffffffu, ok);
         sym = __all_sync(0xffffffffu, sym);
-        if (lane < kUVPitch) {
-            // centred in 21 slots: slot s <-> offset s - 10
-            const int t = lane - 10 + c;  // tap index for this slot
-            const bool in = lane < 21 && t >= 0 && t < K;
-            uv[((size_t)kb * 2 + 0) * kUVPitch + lane] = (ok && in) ? sk[t * K + pj] : 0.0f;
-            uv[((size_t)kb * 2 + 1) * kUVPitch + lane] = (ok && in) ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
+        float* st = staged + (size_t)kb * kStagedWords;
+        if (ok && r >= 2) {
+            if (lane < kUVPitch) {
+                // centred in 21 slots: slot s <-> offset s - 10
+                const int t = lane - 10 + c;  // tap index for this slot
+                const bool in = lane < 21 && t >= 0 && t < K;
+                st[lane] = in ? sk[t * K + pj] : 0.0f;
+                st[kUVPitch + lane] = in ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
+            }
+        } else {
+            // paired taps over the true support: row i holds (w[i][j], w[i-1][j]); mirror-symmetric kernels keep the right
+            // half only, (w[i][r+t], w[i-1][r+t]) for t = 0..r  (accumulate_rows_packed / accumulate_rows_folded)
+            const bool fo = sym && r >= 2;
+            const int kt = 2 * r + 1;
+            auto tap = [&](int i, int j) { return (i >= 0 && i < kt && j >= 0 && j < kt) ? sk[(c - r + i) * K + (c - r + j)] : 0.0f; };
+            float2* st2 = reinterpret_cast<float2*>(st);
+            for (int idx = lane; idx < (kt + 1) * kW2Pitch; idx += 32) {
+                const int i = idx / kW2Pitch, t = idx - i * kW2Pitch;
+                const int j = fo ? (t <= r ? r + t : -1) : t;
+                st2[idx] = make_float2(tap(i, j), tap(i - 1, j));
+            }
         }
         if (lane == 0) { support[kb] = r; rank1[kb] = (ok ? 1 : 0) | (sym ? 2 : 0); }
         __syncwarp();
     }
     cooperative_groups::this_cluster().sync();  // (release / acquire at cluster scope: every CTA's supports are visible)
     if (blockIdx.x != 0) return;
-    for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) s_sup[t] = support[t];
-    __syncthreads();
-    // order[0..kb): sample indices sorted by support, largest first (stable)
+    // order[0..kb): one packed record per launch position — sample index | true radius << 16 | flags << 24 — sorted by the
+    // sample's COST (FP32-pipe operations per output: dense K^2, folded ~K(R+1), rank-1 ~3K), most expensive first, ties by
+    // index: the CTAs resident on an SM at any time run the same specialisation, the expensive tiles go first (LPT), and a
+    // CTA learns its sample, radius and kind from ONE load instead of three dependent ones.
     for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
-        const int mine = s_sup[t];
+        const int r = support[t], fl = rank1[t], kt = 2 * r + 1;
+        const int cost = (r >= 2 && (fl & 1)) ? 3 * kt : (r >= 2 && (fl & 2)) ? kt * (r + 1) + 6 * r : kt * kt;
+        s_sup[t] = (cost << 12) | (r << 4) | (fl & 3);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kernel_batch; t += blockDim.x) {
+        const int mine = s_sup[t] >> 12;
         int rank = 0;
-        for (int u = 0; u < kernel_batch; ++u) rank += (s_sup[u] > mine) || (s_sup[u] == mine && u < t);
-        scratch[kernel_batch + rank] = t;
+        for (int u = 0; u < kernel_batch; ++u) {
+            const int other = s_sup[u] >> 12;
+            rank += (other > mine) || (other == mine && u < t);
+        }
+        // interleave: launch positions alternate between the expensive and the cheap end of the ranking, so FMA-bound
+        // (dense) and latency-bound (rank-1, small K) CTAs share every SM instead of running one kind after the other
+        const int pos = !interleave ? rank : (rank < (kernel_batch + 1) / 2 ? 2 * rank : 2 * (kernel_batch - 1 - rank) + 1);
+        scratch[kernel_batch + pos] = t | (((s_sup[t] >> 4) & 0xff) << 16) | ((s_sup[t] & 3) << 24);
     }
 }
 
@@ -122,7 +157,8 @@ static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch
     OTF_REQUIRE(kernel_batch >= 1 && kernel_batch <= 4096, OTF_ERR_UNSUPPORTED, "filter2d: kernel batch must be 1..4096");
     KernelSets sets;
     for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
-    launch_chain(kernel_analyse_kernel, dim3(dim3(kAnalyseCluster, nsets)), dim3(kAnalyseWarps * 32), kernel_batch * sizeof(int), st, sets, K, kernel_batch, scratch);
+    static const int interleave = getenv("OTF_F2D_INTERLEAVE") ? atoi(getenv("OTF_F2D_INTERLEAVE")) : 0;
+    launch_chain(kernel_analyse_kernel, dim3(dim3(kAnalyseCluster, nsets)), dim3(kAnalyseWarps * 32), kernel_batch * sizeof(int), st, sets, K, kernel_batch, scratch, interleave);
     OTF_LAUNCH_CHECK("kernel_analyse_kernel");
     return OTF_OK;
 }
@@ -193,7 +229,6 @@ __device__ __forceinline__ void accumulate_rows(const float* __restrict__ tile_t
 #ifndef OTF_F2D_MINB
 #define OTF_F2D_MINB 5
 #endif
-constexpr int kW2Pitch = 24;  // float2 per paired tap row
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
     unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
     const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
@@ -372,6 +407,84 @@ __device__ __forceinline__ void accumulate_rank1(const float* __restrict__ tile_
     }
 }
 
+// Rank-1 kernels, CTA-wide two-pass form (the default): the horizontal K-tap pass runs ONCE per tile row for the whole
+// CTA and its result replaces the row in shared memory (in place), then every thread accumulates its register block
+// down the columns.  Per output that is K (TILE_H + 2R) / TILE_H + K FMAs — 48.6 at K = 21 on a 64-row tile — where the
+// per-thread form above recomputes the horizontal pass for each TY-row register block (K (TY + K - 1) / TY + K = 147).
+// Each horizontal sum and each vertical accumulation is the same fmaf chain in the same order as accumulate_rank1, so
+// the results are bit-identical to it.
+//   horizontal pass: lane = 4 consecutive outputs of one tile row (the eight lanes of a quarter-warp read eight
+//   consecutive 16-byte chunks: conflict-free LDS.128); the 32 lanes of a warp cover whole rows, so a row is read and
+//   rewritten by ONE warp — loads, __syncwarp, FMAs, stores — and no block-wide barrier is needed until the pass is over.
+template <int TILE_W, int NT, int KT>
+__device__ __forceinline__ void rank1_hpass(float* __restrict__ tile, int pitch, int rows, const float* __restrict__ v, int tid) {
+    constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
+    constexpr int SEGS = TILE_W / 4, RPI = NT / SEGS;  // segments per row, rows per iteration of the block
+    constexpr int NWIN = 4 + 2 * RA;
+    static_assert(32 % SEGS == 0 && NT % SEGS == 0, "a warp covers whole rows");
+    float vr[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) vr[j] = v[10 - R + j];
+    const int seg = tid % SEGS, rsub = tid / SEGS;
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += RPI) {
+        const int r = r0 + rsub;
+        const bool live = r < rows;
+        float* rowp = tile + min(r, rows - 1) * pitch + 4 * seg;
+        float win[NWIN];
+#pragma unroll
+        for (int q = 0; q < NWIN / 4; ++q) {
+            const float4 t4 = reinterpret_cast<const float4*>(rowp)[q];
+            win[4 * q + 0] = t4.x; win[4 * q + 1] = t4.y; win[4 * q + 2] = t4.z; win[4 * q + 3] = t4.w;
+        }
+        __syncwarp();
+        float h[4];
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox) {
+            float a = vr[0] * win[OFF + ox];
+#pragma unroll
+            for (int j = 1; j < KT; ++j) a = fmaf(vr[j], win[OFF + ox + j], a);
+            h[ox] = a;
+        }
+        if (live) *reinterpret_cast<float4*>(rowp + RA) = make_float4(h[0], h[1], h[2], h[3]);
+    }
+}
+
+//   vertical pass: h sits at tile[row][RA + column]; a thread walks the TY + KT - 1 rows under its TY x TX block.
+template <int TX, int TY, int KT>
+__device__ __forceinline__ void rank1_vpass(const float* __restrict__ tile_thread, int pitch, const float* __restrict__ u,
+                                            float (&acc)[TY][TX]) {
+    constexpr int R = KT / 2, RA = (R + 3) & ~3;
+#pragma unroll 1
+    for (int r = 0; r < TY + KT - 1; ++r) {
+        float h[TX];
+        const float4* rp = reinterpret_cast<const float4*>(tile_thread + r * pitch + RA);
+#pragma unroll
+        for (int q = 0; q < TX / 4; ++q) {
+            const float4 t4 = rp[q];
+            h[4 * q + 0] = t4.x; h[4 * q + 1] = t4.y; h[4 * q + 2] = t4.z; h[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int oy = 0; oy < TY; ++oy) {
+            const int i = r - oy;
+            if (i >= 0 && i < KT) {
+                const float ui = u[10 - R + i];
+#pragma unroll
+                for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(ui, h[ox], acc[oy][ox]);
+            }
+        }
+    }
+}
+
+template <int TX, int TY, int TILE_W, int TILE_H, int NT, int KT>
+__device__ __forceinline__ void rank1_two_pass(float* __restrict__ tile, int pitch, const float* __restrict__ tile_thread,
+                                               const float* __restrict__ u, const float* __restrict__ v, int tid,
+                                               float (&acc)[TY][TX]) {
+    rank1_hpass<TILE_W, NT, KT>(tile, pitch, TILE_H + KT - 1, v, tid);
+    __syncthreads();
+    rank1_vpass<TX, TY, KT>(tile_thread, pitch, u, acc);
+}
+
 // ---- TMA / mbarrier plumbing (sm_100a) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -403,13 +516,40 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+#ifdef OTF_F2D_TRACE
+// profiles/experiments/f2d_trace.cu: per-CTA phase timestamps (globaltimer ns at entry, SM clock at four points)
+__device__ unsigned long long g_f2d_trace[8 * 8192];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define OTF_TRACE(slot) do { if (threadIdx.x == 0) g_f2d_trace[8 * trace_lin + (slot)] = gtime(); } while (0)
+#else
+#define OTF_TRACE(slot) do { } while (0)
+#endif
+
+// L2 prefetch of a tile box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// 1-D bulk copy global -> shared completing on an mbarrier (size and both addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <int TX, int TY, int BX, int BY, bool PACKED>
 __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_kernel(const __grid_constant__ CUtensorMap tmap,
                                                           const float* __restrict__ img, const float* __restrict__ kern,
                                                           const int32_t* __restrict__ scratch, int use_order,
                                                           float* __restrict__ out, int C, int H, int W, int K,
-                                                          int kernel_batch, int vec_ok, int use_tma) {
+                                                          int kernel_batch, int vec_ok, int use_tma, int pf_ahead) {
     pdl_enter();
+#ifdef OTF_F2D_TRACE
+    const int trace_lin = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) & 8191;
+    if (threadIdx.x == 0) g_f2d_trace[8 * trace_lin + 5] = smid();
+    OTF_TRACE(0);
+#endif
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY, NT = BX * BY;
     constexpr int P = TILE_W + 2 * kMaxRA;     // smem row pitch = TMA box width (multiple of 4)
     constexpr int ROWS = TILE_H + 2 * kMaxRT;  // TMA box height
@@ -421,17 +561,23 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + WSM_FLOATS);
 
     const int zb = blockIdx.z / C, zc = blockIdx.z - zb * C;
-    const int b = (scratch && use_order) ? scratch[kernel_batch + zb] : zb;
+    int b = zb, R = K / 2, kflags = 0;  // sample, true radius (block-uniform), rank-1 / mirror-symmetry flags
+    if (scratch && use_order) {
+        const int rec = scratch[kernel_batch + zb];  // packed launch-order record (kernel_analyse_kernel)
+        b = rec & 0xffff;
+        R = min((rec >> 16) & 0xff, K / 2);
+        kflags = rec >> 24;
+    } else if (scratch) {
+        const int kb0 = kernel_batch == 1 ? 0 : zb;
+        R = min(scratch[kb0], K / 2);
+        kflags = scratch[2 * kernel_batch + kb0];
+    }
     const int plane = b * C + zc;
     const int kb = kernel_batch == 1 ? 0 : b;
-    const int32_t* support = scratch;
-    const int R_ = scratch ? min(scratch[kb], K / 2) : K / 2;
-    const int kflags = scratch ? scratch[2 * kernel_batch + kb] : 0;
-    const bool rank1 = R_ >= 2 && (kflags & 1) != 0;
-    const bool fold = PACKED && !rank1 && R_ >= 2 && (kflags & 2) != 0;
+    const bool rank1 = R >= 2 && (kflags & 1) != 0;
+    const bool fold = PACKED && !rank1 && R >= 2 && (kflags & 2) != 0;
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.x;
-    const int R = support ? min(support[kb], K / 2) : K / 2;  // true radius (block-uniform)
     const int KT = 2 * R + 1, RA = (R + 3) & ~3;
     const int c = K / 2;
 
@@ -446,12 +592,35 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     const float* ip = img + (size_t)plane * H * W;
     const int th = TILE_H + 2 * R, nq = (TILE_W + 2 * RA) / 4;
     const int lane = tid & 31;
+    const bool staged_ok = scratch != nullptr && (PACKED || rank1);
+    const float* stg = staged_ok ? reinterpret_cast<const float*>(scratch + staged_offset(kernel_batch)) + (size_t)kb * kStagedWords : nullptr;
+    const uint32_t tap_bytes = rank1 ? 2 * kUVPitch * 4 : (KT + 1) * kW2Pitch * 8;
     if (use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(bar, ROWS * P * 4);
+            mbar_expect_tx(bar, ROWS * P * 4 + (staged_ok ? tap_bytes : 0u));
             tma_load_3d(tile, &tmap, x0 - RA, y0 - R, plane, bar);
+            if (staged_ok) bulk_load(wsm, stg, tap_bytes, bar);
+        } else if (tid == 32 && pf_ahead > 0) {
+            // pull the tile of the CTA that will take this one's place (pf_ahead launch positions later) into L2 now: its
+            // own box load then finds the bytes on chip, and the HBM requests of a whole extra wave are in flight
+            const int per_plane = gridDim.x * gridDim.y;
+            const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + pf_ahead;
+            const int z2 = lin / per_plane, rem = lin - z2 * per_plane;
+            if (z2 < (int)gridDim.z) {
+                const int zb2 = z2 / C, zc2 = z2 - zb2 * C;
+                int b2 = zb2, R2 = K / 2;
+                if (scratch && use_order) {
+                    const int rec = scratch[kernel_batch + zb2];
+                    b2 = rec & 0xffff;
+                    R2 = min((rec >> 16) & 0xff, K / 2);
+                } else if (scratch) {
+                    R2 = min(scratch[kernel_batch == 1 ? 0 : zb2], K / 2);
+                }
+                const int by2 = rem / gridDim.x, bx2 = rem - by2 * gridDim.x;
+                tma_prefetch_3d(&tmap, bx2 * TILE_W - ((R2 + 3) & ~3), by2 * TILE_H - R2, b2 * C + zc2);
+            }
         }
     } else if (lane < nq) {
         const int gx0 = x0 - RA + 4 * lane;
@@ -471,22 +640,13 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
             }
         }
     }
-    // taps -> smem (overlaps with the copies in flight): the two rank-1 factors, or the KT x KT centre
+    // taps -> smem.  With an analysis scratch the taps were laid out for this kernel once per sample (kernel_analyse_kernel:
+    // rank-1 factors, or folded / dense paired taps) and arrive by the bulk copy issued above (TMA path) or a plain
+    // coalesced copy; without one (raw C-ABI call, no scratch) they are paired here from the zero-padded kernel.
     const float* kp = kern + (size_t)kb * K * K;
-    if (rank1) {
-        const float* uv = reinterpret_cast<const float*>(scratch + 3 * kernel_batch) + (size_t)kb * 2 * kUVPitch;
-        for (int idx = tid; idx < 2 * kUVPitch; idx += NT) wsm[idx] = uv[idx];
-    } else if (fold) {
-        // folded paired taps: row i holds (w[i][R+t], w[i-1][R+t]) for t = 0..R (the right half of the mirror-symmetric rows)
-        float2* w2 = reinterpret_cast<float2*>(wsm);
-        auto tap = [&](int i, int t) {
-            const int si = c - R + i, sj = c + t;
-            return (i >= 0 && i < KT && t <= R && si >= 0 && si < K && sj < K) ? kp[si * K + sj] : 0.0f;
-        };
-        for (int idx = tid; idx < 22 * kW2Pitch; idx += NT) {
-            const int i = idx / kW2Pitch, t = idx - i * kW2Pitch;
-            w2[idx] = make_float2(tap(i, t), tap(i - 1, t));
-        }
+    if (staged_ok) {
+        if (!use_tma)
+            for (int idx = tid; idx < (int)(tap_bytes / 4); idx += NT) wsm[idx] = stg[idx];
     } else if (PACKED && R >= 1) {
         // paired taps: row i holds (w[i][j], w[i-1][j]) for i = 0..KT, zeros outside the KT x KT centre
         float2* w2 = reinterpret_cast<float2*>(wsm);
@@ -494,9 +654,10 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
             const int si = c - R + i, sj = c - R + j;
             return (i >= 0 && i < KT && j < KT && si >= 0 && si < K && sj >= 0 && sj < K) ? kp[si * K + sj] : 0.0f;
         };
-        for (int idx = tid; idx < 22 * kW2Pitch; idx += NT) {
-            const int i = idx / kW2Pitch, j = idx - i * kW2Pitch;
-            w2[idx] = make_float2(tap(i, j), tap(i - 1, j));
+        const int nj = KT + 1;  // (rows 0..KT, taps 0..KT: the loops read nothing else)
+        for (int idx = tid; idx < (KT + 1) * nj; idx += NT) {
+            const int i = idx / nj, j = idx - i * nj;
+            w2[i * kW2Pitch + j] = make_float2(tap(i, j), tap(i - 1, j));
         }
     } else
     for (int idx = tid; idx < 21 * kWPitch; idx += NT) {
@@ -513,32 +674,33 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
         // mirror what the box load zero-filled: columns first (rows inside the plane), then whole rows
         const bool fix_x = (x0 - R < 0) || (x0 + TILE_W + R > W);
         const bool fix_y = (y0 - R < 0) || (y0 + TILE_H + R > H);
+        const int warp = tid >> 5;
         if (fix_x) {
             // out-of-plane columns a stored output can reach: R on the left of x = 0, R on the right of x = W-1
-            for (int idx = tid; idx < th * 2 * R; idx += NT) {
-                const int yy = idx / (2 * R), k = idx - yy * (2 * R);
-                const int gx = k < R ? -1 - k : W + (k - R);
-                const int sc = gx - (x0 - RA), gy = y0 - R + yy;
-                if (sc >= 0 && sc < P && gy >= 0 && gy < H) {
-                    const int src = reflect_idx(gx, W) - (x0 - RA);
-                    if (src >= 0 && src < P) tile[yy * P + sc] = tile[yy * P + src];
-                }
+            // (a warp per tile row, a lane per column: no index division)
+            const int k = lane;
+            const int gx = k < R ? -1 - k : W + (k - R);
+            const int sc = gx - (x0 - RA), src = reflect_idx(gx, W) - (x0 - RA);
+            const bool col_ok = k < 2 * R && sc >= 0 && sc < P && src >= 0 && src < P;
+            for (int yy = warp; yy < th; yy += NT / 32) {
+                const int gy = y0 - R + yy;
+                if (col_ok && gy >= 0 && gy < H) tile[yy * P + sc] = tile[yy * P + src];
             }
             __syncthreads();
         }
         if (fix_y) {
-            for (int idx = tid; idx < th * (P / 4); idx += NT) {
-                const int yy = idx / (P / 4), q = idx - yy * (P / 4);
-                const int gy = y0 - R + yy;
-                if (gy < 0 || gy >= H) {
-                    const int src = clampi(clampi(reflect_idx(gy, H), 0, H - 1) - (y0 - R), 0, ROWS - 1);
-                    reinterpret_cast<float4*>(tile + yy * P)[q] = reinterpret_cast<const float4*>(tile + src * P)[q];
-                }
+            // rows above / below the plane only: [0, top) and [bot0, th)
+            const int top = max(0, R - y0), bot0 = min(th, H - (y0 - R));
+            for (int k = warp; k < top + (th - bot0); k += NT / 32) {
+                const int yy = k < top ? k : bot0 + (k - top);
+                const int src = clampi(clampi(reflect_idx(y0 - R + yy, H), 0, H - 1) - (y0 - R), 0, ROWS - 1);
+                if (lane < P / 4) reinterpret_cast<float4*>(tile + yy * P)[lane] = reinterpret_cast<const float4*>(tile + src * P)[lane];
             }
             __syncthreads();
         }
     }
 
+    OTF_TRACE(1);  // tile + taps ready
     const int tx = tid % BX, ty = tid / BX;
     float acc[TY][TX];
 #pragma unroll
@@ -549,17 +711,23 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     const float* tt = tile + (ty * TY) * P + tx * TX;
     if (rank1) {
         const float* u = wsm, *v = wsm + kUVPitch;
+#ifdef OTF_F2D_RANK1_PER_THREAD
+#define OTF_R1(KT_) accumulate_rank1<TX, TY, KT_>(tt, P, u, v, acc)
+#else
+#define OTF_R1(KT_) rank1_two_pass<TX, TY, TILE_W, TILE_H, NT, KT_>(tile, P, tt, u, v, tid, acc)
+#endif
         switch (R) {
-            case 2: accumulate_rank1<TX, TY, 5>(tt, P, u, v, acc); break;
-            case 3: accumulate_rank1<TX, TY, 7>(tt, P, u, v, acc); break;
-            case 4: accumulate_rank1<TX, TY, 9>(tt, P, u, v, acc); break;
-            case 5: accumulate_rank1<TX, TY, 11>(tt, P, u, v, acc); break;
-            case 6: accumulate_rank1<TX, TY, 13>(tt, P, u, v, acc); break;
-            case 7: accumulate_rank1<TX, TY, 15>(tt, P, u, v, acc); break;
-            case 8: accumulate_rank1<TX, TY, 17>(tt, P, u, v, acc); break;
-            case 9: accumulate_rank1<TX, TY, 19>(tt, P, u, v, acc); break;
-            default: accumulate_rank1<TX, TY, 21>(tt, P, u, v, acc); break;
+            case 2: OTF_R1(5); break;
+            case 3: OTF_R1(7); break;
+            case 4: OTF_R1(9); break;
+            case 5: OTF_R1(11); break;
+            case 6: OTF_R1(13); break;
+            case 7: OTF_R1(15); break;
+            case 8: OTF_R1(17); break;
+            case 9: OTF_R1(19); break;
+            default: OTF_R1(21); break;
         }
+#undef OTF_R1
     } else if (fold) {
         if constexpr (PACKED) {
             const float2* w2 = reinterpret_cast<const float2*>(wsm);
@@ -610,6 +778,7 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
         default: accumulate_rows<TX, TY, 21>(tt, P, wsm, acc); break;
     }
 
+    OTF_TRACE(2);  // accumulation done (thread 0's warp)
     float* op = out + (size_t)plane * H * W;
     const int ox0 = x0 + tx * TX;
 #pragma unroll
@@ -628,6 +797,10 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
                 if (ox0 + ox < W) orow[ox] = acc[oy][ox];
         }
     }
+#ifdef OTF_F2D_TRACE
+    OTF_TRACE(3);
+    if (threadIdx.x == 0) g_f2d_trace[8 * trace_lin + 4] = (unsigned long long)R | ((unsigned long long)(rank1 ? 1 : fold ? 2 : 0) << 8);
+#endif
 }
 
 // Generic path for K > 21 (e.g. a 51x51 USM kernel pushed through filter2d): one
@@ -701,7 +874,10 @@ static int launch_blocked(const float* img, int B, int C, int H, int W, const fl
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         use_tma = (r == CUDA_SUCCESS);
     }
-    launch_chain(kfn, dim3(grid), dim3(BX * BY), smem, st, tmap, img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok, use_tma);
+    // OTF_F2D_PREFETCH=n: L2-prefetch the tile n launch positions ahead (A/B switch; 0 = off)
+    static const int pf_ahead = getenv("OTF_F2D_PREFETCH") ? atoi(getenv("OTF_F2D_PREFETCH")) : 0;
+    launch_chain(kfn, dim3(grid), dim3(BX * BY), smem, st, tmap, img, kernel, scratch, use_order, out, C, H, W, K, kernel_batch, vec_ok, use_tma,
+                 pf_ahead);
     OTF_LAUNCH_CHECK("filter2d_kernel");
     return OTF_OK;
 }
@@ -739,7 +915,7 @@ extern "C" int otf_filter2d_f32(const float* img, int B, int C, int H, int W, co
     int use_order = 0;
     if (support_dev) {
         // scratch layout (4-byte words): [0,kb) true radius, [kb,2kb) sample order (largest radius first),
-        // [2kb,3kb) rank-1 flag, then float uv[kb][2][24] rank-1 factors  (otf_filter2d_scratch_words)
+        // [2kb,3kb) rank-1 / symmetry flags, then (16-byte aligned) the per-sample staged taps  (otf_filter2d_scratch_words)
         if (!scratch_ready) {
             if (int rc = analyse_sets(&kernel, 1, kernel_batch, K, support_dev, st)) return rc;
         }
