@@ -109,6 +109,14 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
                 const bool in = lane < 21 && t >= 0 && t < K;
                 st[lane] = in ? sk[t * K + pj] : 0.0f;
                 st[kUVPitch + lane] = in ? __fdiv_rn(sk[pi * K + t], piv) : 0.0f;
+                // the same factors over the true support, packed for the FFMA2 loops of rank1_tile:
+                //   float2 vpair[m] = (v[m-1], v[m])               at words [48, 96)
+                //   float4 upq[m]   = (u[m], u[m-1], u[m-2], u[m-3]) at words [96, 192),   m = 0..23, zero outside [0, kt)
+                const int kt = 2 * r + 1, m = lane;
+                auto uf = [&](int q) { return (q >= 0 && q < kt) ? sk[(c - r + q) * K + pj] : 0.0f; };
+                auto vf = [&](int q) { return (q >= 0 && q < kt) ? __fdiv_rn(sk[pi * K + (c - r + q)], piv) : 0.0f; };
+                reinterpret_cast<float2*>(st)[kUVPitch + m] = make_float2(vf(m - 1), vf(m));
+                reinterpret_cast<float4*>(st)[kUVPitch + m] = make_float4(uf(m), uf(m - 1), uf(m - 2), uf(m - 3));
             }
         } else {
             // paired taps over the true support: row i holds (w[i][j], w[i-1][j]); mirror-symmetric kernels keep the right
@@ -165,6 +173,7 @@ static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch
 
 constexpr int kMaxRT = 10;   // register-blocked path covers radius <= 10 (K <= 21)
 constexpr int kMaxRA = 12;   // halo rounded up to a float4 boundary
+constexpr int kPitchPad = 4;  // makes the row pitch an ODD number of 16-byte chunks (conflict-free two-row LDS.128 phases, rank1_tile)
 constexpr int kWPitch = 24;  // taps row pitch in smem (float4 broadcast loads)
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
@@ -408,81 +417,109 @@ __device__ __forceinline__ void accumulate_rank1(const float* __restrict__ tile_
 }
 
 // Rank-1 kernels, CTA-wide two-pass form (the default): the horizontal K-tap pass runs ONCE per tile row for the whole
-// CTA and its result replaces the row in shared memory (in place), then every thread accumulates its register block
-// down the columns.  Per output that is K (TILE_H + 2R) / TILE_H + K FMAs — 48.6 at K = 21 on a 64-row tile — where the
-// per-thread form above recomputes the horizontal pass for each TY-row register block (K (TY + K - 1) / TY + K = 147).
-// Each horizontal sum and each vertical accumulation is the same fmaf chain in the same order as accumulate_rank1, so
-// the results are bit-identical to it.
-//   horizontal pass: lane = 4 consecutive outputs of one tile row (the eight lanes of a quarter-warp read eight
-//   consecutive 16-byte chunks: conflict-free LDS.128); the 32 lanes of a warp cover whole rows, so a row is read and
-//   rewritten by ONE warp — loads, __syncwarp, FMAs, stores — and no block-wide barrier is needed until the pass is over.
-template <int TILE_W, int NT, int KT>
-__device__ __forceinline__ void rank1_hpass(float* __restrict__ tile, int pitch, int rows, const float* __restrict__ v, int tid) {
+// CTA and its result replaces the row in shared memory (in place), then every thread accumulates a column strip.  Per
+// output that is K (TILE_H + 2R) / TILE_H + K FMAs — 48.6 at K = 21 on a 64-row tile — where the per-thread form above
+// recomputes the horizontal pass for each TY-row register block (K (TY + K - 1) / TY + K = 147).  With so little
+// arithmetic left the pass is bound by SHARED-MEMORY bandwidth (ncu: l1tex 76 %, short-scoreboard the top stall), so
+// both passes are laid out for few, conflict-free wavefronts:
+//   horizontal: a lane produces 8 consecutive outputs of one tile row from a (8 + 2 RA)-pixel window (LDS.128s); the eight
+//     lanes of an LDS phase are 2 rows x 4 segments, and the row pitch is an odd number of 16-byte chunks, so a phase
+//     touches 8 distinct chunks mod 8.  The 32 lanes of a warp cover whole rows: a row is read and rewritten by ONE warp
+//     (loads, __syncwarp, FMAs, stores), no block-wide barrier inside the pass.  FFMA2 over two horizontally adjacent
+//     outputs that share the pixel: (out[2k+1], out[2k]) += p * (v[m-1], v[m]), p = win[OFF + 2k + m], m = 0..KT.
+//   vertical: a thread owns 4 columns x RPT rows (8 consecutive lanes = 8 consecutive chunks), one LDS.128 per tile row,
+//     FFMA2 over two vertically adjacent outputs: (acc[2p], acc[2p+1]) += h * (u[i], u[i-1]), i = r - 2p; the factor pairs of
+//     two output pairs arrive as one broadcast LDS.128 (upq).
+// Every output is still u-major sum of ascending fmaf chains (fma(v0, p, 0) == v0 * p): bit-identical to accumulate_rank1.
+template <int P, int TILE_W, int TILE_H, int NT, int KT>
+__device__ __forceinline__ void rank1_tile(float* __restrict__ tile, const float* __restrict__ wsm, int tid,
+                                           float* __restrict__ op, int x0, int y0, int H, int W, int vec_ok) {
     constexpr int R = KT / 2, RA = (R + 3) & ~3, OFF = RA - R;
-    constexpr int SEGS = TILE_W / 4, RPI = NT / SEGS;  // segments per row, rows per iteration of the block
-    constexpr int NWIN = 4 + 2 * RA;
-    static_assert(32 % SEGS == 0 && NT % SEGS == 0, "a warp covers whole rows");
-    float vr[KT];
+    constexpr int SEGS = TILE_W / 8, RPW = 32 / SEGS, NWARP = NT / 32, NWIN = 8 + 2 * RA, ROWS_H = TILE_H + KT - 1;
+    static_assert(SEGS == 8 || SEGS == 4, "64- or 32-wide tiles");
+    static_assert((P / 4) % 2 == 1, "odd chunk pitch");
+    const int lane = tid & 31, warp = tid >> 5;
+    {
+        const float2* vpair = reinterpret_cast<const float2*>(wsm) + kUVPitch;
+        float2 vp[KT + 1];
 #pragma unroll
-    for (int j = 0; j < KT; ++j) vr[j] = v[10 - R + j];
-    const int seg = tid % SEGS, rsub = tid / SEGS;
+        for (int m = 0; m <= KT; ++m) vp[m] = vpair[m];  // (v[m-1], v[m])
+        const int g = lane >> 3, rowbit = (lane >> 2) & 1, segq = lane & 3;
+        const int rw = SEGS == 8 ? 2 * (g >> 1) + rowbit : 2 * g + rowbit;
+        const int seg = SEGS == 8 ? 4 * (g & 1) + segq : segq;
 #pragma unroll 1
-    for (int r0 = 0; r0 < rows; r0 += RPI) {
-        const int r = r0 + rsub;
-        const bool live = r < rows;
-        float* rowp = tile + min(r, rows - 1) * pitch + 4 * seg;
-        float win[NWIN];
+        for (int r0 = warp * RPW; r0 < ROWS_H; r0 += NWARP * RPW) {
+            const int r = r0 + rw;
+            const bool live = r < ROWS_H;
+            float* rowp = tile + min(r, ROWS_H - 1) * P + 8 * seg;
+            float win[NWIN];
 #pragma unroll
-        for (int q = 0; q < NWIN / 4; ++q) {
-            const float4 t4 = reinterpret_cast<const float4*>(rowp)[q];
-            win[4 * q + 0] = t4.x; win[4 * q + 1] = t4.y; win[4 * q + 2] = t4.z; win[4 * q + 3] = t4.w;
-        }
-        __syncwarp();
-        float h[4];
+            for (int q = 0; q < NWIN / 4; ++q) {
+                const float4 t4 = reinterpret_cast<const float4*>(rowp)[q];
+                win[4 * q + 0] = t4.x; win[4 * q + 1] = t4.y; win[4 * q + 2] = t4.z; win[4 * q + 3] = t4.w;
+            }
+            __syncwarp();
+            float2 a[4];
 #pragma unroll
-        for (int ox = 0; ox < 4; ++ox) {
-            float a = vr[0] * win[OFF + ox];
+            for (int k = 0; k < 4; ++k) a[k] = make_float2(0.0f, 0.0f);  // (out[2k+1], out[2k])
 #pragma unroll
-            for (int j = 1; j < KT; ++j) a = fmaf(vr[j], win[OFF + ox + j], a);
-            h[ox] = a;
-        }
-        if (live) *reinterpret_cast<float4*>(rowp + RA) = make_float4(h[0], h[1], h[2], h[3]);
-    }
-}
-
-//   vertical pass: h sits at tile[row][RA + column]; a thread walks the TY + KT - 1 rows under its TY x TX block.
-template <int TX, int TY, int KT>
-__device__ __forceinline__ void rank1_vpass(const float* __restrict__ tile_thread, int pitch, const float* __restrict__ u,
-                                            float (&acc)[TY][TX]) {
-    constexpr int R = KT / 2, RA = (R + 3) & ~3;
-#pragma unroll 1
-    for (int r = 0; r < TY + KT - 1; ++r) {
-        float h[TX];
-        const float4* rp = reinterpret_cast<const float4*>(tile_thread + r * pitch + RA);
+            for (int m = 0; m <= KT; ++m)
 #pragma unroll
-        for (int q = 0; q < TX / 4; ++q) {
-            const float4 t4 = rp[q];
-            h[4 * q + 0] = t4.x; h[4 * q + 1] = t4.y; h[4 * q + 2] = t4.z; h[4 * q + 3] = t4.w;
-        }
-#pragma unroll
-        for (int oy = 0; oy < TY; ++oy) {
-            const int i = r - oy;
-            if (i >= 0 && i < KT) {
-                const float ui = u[10 - R + i];
-#pragma unroll
-                for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(ui, h[ox], acc[oy][ox]);
+                for (int k = 0; k < 4; ++k) ffma2(a[k], make_float2(win[OFF + 2 * k + m], win[OFF + 2 * k + m]), vp[m]);
+            if (live) {
+                reinterpret_cast<float4*>(rowp + RA)[0] = make_float4(a[0].y, a[0].x, a[1].y, a[1].x);
+                reinterpret_cast<float4*>(rowp + RA)[1] = make_float4(a[2].y, a[2].x, a[3].y, a[3].x);
             }
         }
     }
-}
-
-template <int TX, int TY, int TILE_W, int TILE_H, int NT, int KT>
-__device__ __forceinline__ void rank1_two_pass(float* __restrict__ tile, int pitch, const float* __restrict__ tile_thread,
-                                               const float* __restrict__ u, const float* __restrict__ v, int tid,
-                                               float (&acc)[TY][TX]) {
-    rank1_hpass<TILE_W, NT, KT>(tile, pitch, TILE_H + KT - 1, v, tid);
     __syncthreads();
-    rank1_vpass<TX, TY, KT>(tile_thread, pitch, u, acc);
+    constexpr int QUADS = TILE_W / 4, STRIPS = NT / QUADS, RPT = TILE_H / STRIPS;
+    static_assert(RPT % 4 == 0, "output rows in groups of four");
+    const int quad = tid % QUADS, strip = tid / QUADS;
+    float2 acc2[RPT / 2][4];
+#pragma unroll
+    for (int p = 0; p < RPT / 2; ++p)
+#pragma unroll
+        for (int cx = 0; cx < 4; ++cx) acc2[p][cx] = make_float2(0.0f, 0.0f);
+    const float4* upq = reinterpret_cast<const float4*>(wsm) + kUVPitch;  // (u[i], u[i-1], u[i-2], u[i-3])
+    const float* base = tile + (strip * RPT) * P + RA + 4 * quad;
+#pragma unroll 1
+    for (int r = 0; r < RPT + KT - 1; ++r) {
+        const float4 h4 = *reinterpret_cast<const float4*>(base + r * P);
+        const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int pp = 0; pp < RPT / 4; ++pp) {
+            const int i = r - 4 * pp;  // rows 4pp, 4pp+1 take (u[i], u[i-1]); rows 4pp+2, 4pp+3 take (u[i-2], u[i-3])
+            if (i >= 0 && i <= KT + 2) {
+                const float4 w = upq[i];
+#pragma unroll
+                for (int cx = 0; cx < 4; ++cx) {
+                    ffma2(acc2[2 * pp][cx], make_float2(h[cx], h[cx]), make_float2(w.x, w.y));
+                    ffma2(acc2[2 * pp + 1][cx], make_float2(h[cx], h[cx]), make_float2(w.z, w.w));
+                }
+            }
+        }
+    }
+    const int x = x0 + 4 * quad;
+#pragma unroll
+    for (int p = 0; p < RPT / 2; ++p)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int y = y0 + strip * RPT + 2 * p + half;
+            if (y < H) {
+                float v[4];
+#pragma unroll
+                for (int cx = 0; cx < 4; ++cx) v[cx] = half ? acc2[p][cx].y : acc2[p][cx].x;
+                float* orow = op + (size_t)y * W + x;
+                if (vec_ok && x + 4 <= W) {
+                    *reinterpret_cast<float4*>(orow) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int cx = 0; cx < 4; ++cx)
+                        if (x + cx < W) orow[cx] = v[cx];
+                }
+            }
+        }
 }
 
 // ---- TMA / mbarrier plumbing (sm_100a) ---------------------------------------------------
@@ -551,7 +588,7 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     OTF_TRACE(0);
 #endif
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY, NT = BX * BY;
-    constexpr int P = TILE_W + 2 * kMaxRA;     // smem row pitch = TMA box width (multiple of 4)
+    constexpr int P = TILE_W + 2 * kMaxRA + kPitchPad;  // smem row pitch = TMA box width (multiple of 4, odd number of float4s)
     constexpr int ROWS = TILE_H + 2 * kMaxRT;  // TMA box height
     static_assert(P % 4 == 0 && P / 4 <= 32, "a warp fills one tile row with one float4 per lane");
     extern __shared__ __align__(128) float smem[];
@@ -594,7 +631,7 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
     const int lane = tid & 31;
     const bool staged_ok = scratch != nullptr && (PACKED || rank1);
     const float* stg = staged_ok ? reinterpret_cast<const float*>(scratch + staged_offset(kernel_batch)) + (size_t)kb * kStagedWords : nullptr;
-    const uint32_t tap_bytes = rank1 ? 2 * kUVPitch * 4 : (KT + 1) * kW2Pitch * 8;
+    const uint32_t tap_bytes = rank1 ? 8 * kUVPitch * 4 : (KT + 1) * kW2Pitch * 8;
     if (use_tma) {
         if (tid == 0) {
             mbar_init(bar, 1);
@@ -709,13 +746,32 @@ __global__ void __launch_bounds__(BX* BY, PACKED ? OTF_F2D_MINB : 1) filter2d_ke
         for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = 0.0f;
 
     const float* tt = tile + (ty * TY) * P + tx * TX;
+#ifndef OTF_F2D_RANK1_PER_THREAD
+    if (rank1) {
+        float* opl = out + (size_t)plane * H * W;
+#define OTF_R1(KT_) rank1_tile<P, TILE_W, TILE_H, NT, KT_>(tile, wsm, tid, opl, x0, y0, H, W, vec_ok)
+        switch (R) {
+            case 2: OTF_R1(5); break;
+            case 3: OTF_R1(7); break;
+            case 4: OTF_R1(9); break;
+            case 5: OTF_R1(11); break;
+            case 6: OTF_R1(13); break;
+            case 7: OTF_R1(15); break;
+            case 8: OTF_R1(17); break;
+            case 9: OTF_R1(19); break;
+            default: OTF_R1(21); break;
+        }
+#undef OTF_R1
+#ifdef OTF_F2D_TRACE
+        OTF_TRACE(2); OTF_TRACE(3);
+        if (threadIdx.x == 0) g_f2d_trace[8 * trace_lin + 4] = (unsigned long long)R | (1ull << 8);
+#endif
+        return;
+    }
+#endif
     if (rank1) {
         const float* u = wsm, *v = wsm + kUVPitch;
-#ifdef OTF_F2D_RANK1_PER_THREAD
 #define OTF_R1(KT_) accumulate_rank1<TX, TY, KT_>(tt, P, u, v, acc)
-#else
-#define OTF_R1(KT_) rank1_two_pass<TX, TY, TILE_W, TILE_H, NT, KT_>(tile, P, tt, u, v, tid, acc)
-#endif
         switch (R) {
             case 2: OTF_R1(5); break;
             case 3: OTF_R1(7); break;
@@ -850,7 +906,7 @@ template <int TX, int TY, int BX, int BY, bool PACKED>
 static int launch_blocked(const float* img, int B, int C, int H, int W, const float* kernel, int kernel_batch, int K,
                           const int32_t* scratch, int use_order, float* out, cudaStream_t st) {
     constexpr int TILE_W = TX * BX, TILE_H = TY * BY;
-    constexpr int P = TILE_W + 2 * kMaxRA, ROWS = TILE_H + 2 * kMaxRT;
+    constexpr int P = TILE_W + 2 * kMaxRA + kPitchPad, ROWS = TILE_H + 2 * kMaxRT;
     const size_t smem = ((size_t)ROWS * P + (PACKED ? 22 * kW2Pitch * 2 : 21 * kWPitch)) * sizeof(float) + sizeof(uint64_t);
     auto kfn = filter2d_kernel<TX, TY, BX, BY, PACKED>;
     if (smem > 48 * 1024) {
