@@ -399,8 +399,14 @@ class Arm:
             for i in range(n):
                 yield batches[i % N_ROTATE]
 
+        pf_box: list = []  # ONE prefetcher for warm-up and timed run: its static slots (and the chains captured on them) persist
+
         def run(n: int) -> int:
-            pf = CUDAPrefetcher(loader(n), device=self.dev, slots=2)
+            if pf_box:
+                pf_box[0].reset(loader(n))
+            else:
+                pf_box.append(CUDAPrefetcher(loader(n), device=self.dev, slots=2))
+            pf = pf_box[0]
             h2d = 0
             batch = pf.next()
             while batch is not None:

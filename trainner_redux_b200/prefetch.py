@@ -77,6 +77,10 @@ class CUDAPrefetcher:
         self.preload()
         return batch
 
-    def reset(self) -> None:
+    def reset(self, loader: Iterable[dict] | None = None) -> None:
+        """Restart the loader (prefetch_dataloader.py:495-499); ``loader`` swaps in another one and KEEPS the static
+        slots, so the chains captured against their addresses stay valid from one epoch / loader to the next."""
+        if loader is not None:
+            self.ori_loader = loader
         self.loader = iter(self.ori_loader)
         self.preload()

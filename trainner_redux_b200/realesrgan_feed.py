@@ -415,7 +415,7 @@ class RealESRGANFeed:
         # overwrites (the reference returns fresh tensors); a caller that keeps batches across steps sets
         # ``use_graphs = False`` or clones.  The pool (``use_pool``) copies what it keeps, so it is unaffected.
         self.use_graphs = True
-        self.graphs = ChainGraphCache()
+        self.graphs = ChainGraphCache(capacity=16, credits=8.0)
         self._synth_out: dict[tuple, Tensor] = {}  # kernel-synthesis outputs per upload slot (feed_data, `kernel_params`)
         self._gt_f32: dict[tuple, Tensor] = {}  # normalised fp32 GT per uint8 upload slot
 
