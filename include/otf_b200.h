@@ -113,6 +113,9 @@ int64_t otf_usm_workspace_bytes(int planes, int H, int W);
 int otf_usm_sharp_f32(const float* img, int planes, int H, int W,
                       const float* taps_host, int ntaps, float weight, float threshold,
                       void* workspace_dev, int64_t workspace_bytes, float* out, void* stream);
+/* kernels one otf_usm_sharp_f32 call launches: 4 per L2-sized chunk of planes (the passes run chunk by chunk so that
+ * the three intermediates stay in L2) */
+int otf_usm_launch_count(int planes, int H, int W);
 
 /* ---- a3: resize_pt — traiNNer/data/degradations.py:1004-1021 ------------------
  * Separable resampling with ATen's index/weight rules (SURVEY.md §8a "R"),

@@ -37,6 +37,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_filter2d_f32": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p]),
     "otf_sepconv_reflect_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _p, _p]),
     "otf_usm_workspace_bytes": (_i64, [_i, _i, _i]),
+    "otf_usm_launch_count": (_i, [_i, _i, _i]),
     "otf_usm_sharp_f32": (_i, [_p, _i, _i, _i, _p, _i, _f, _f, _p, _i64, _p, _p]),
     "otf_resize_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "otf_resize_tables_f32": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p]),

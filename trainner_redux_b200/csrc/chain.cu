@@ -187,7 +187,7 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
             case OTF_OP_USM:
                 rc = otf_usm_sharp_f32(cur, B * C, h, w, (const float*)s.p0, s.n, s.f0, s.f1, scratch,
                                        otf_usm_workspace_bytes(B * C, h, w), out, stream);
-                launches += 4;
+                launches += otf_usm_launch_count(B * C, h, w);
                 break;
             case OTF_OP_SEPCONV:
                 rc = otf_sepconv_reflect_f32(cur, B * C, h, w, (const float*)s.p0, s.n, s.mode, out, stream);

@@ -181,6 +181,68 @@ __global__ void __launch_bounds__(256) taps_zero_tile_kernel(const float* __rest
     }
 }
 
+// ---- "oversharpen": 5x5 box (zero padding) + clamp(img + (img - box) * strength) as one streaming pass ---------------
+// The 25 equal taps are evaluated separably with running sums — 5-tap horizontal sums of each source row (from one
+// float4 + two float2 loads), a rolling window of the last five of them down the column strip — instead of 25 LDS + 25
+// FFMA per output through the generic tap list: the pass is a read and a write of the plane (HBM bound).  The sum
+// w * (25 pixels) replaces the reference's sum of 25 products w * p (paragon_otf_degradations.py:472-479): <= 3e-7 apart.
+constexpr int kBoxStrip = 16;
+__global__ void __launch_bounds__(256) box5_sharpen_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
+                                                           float w, float strength) {
+    const int quad = blockIdx.x * 64 + (threadIdx.x & 63), strip = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int x = 4 * quad, y0 = strip * kBoxStrip;
+    if (x >= W || y0 >= H) return;
+    const float* ip = img + (size_t)blockIdx.z * H * W;
+    float* op = out + (size_t)blockIdx.z * H * W;
+    float h[5][4], c[3][4];  // horizontal sums of rows y-2..y+2, centre pixels of rows y..y+2 (y = the row being written)
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[i][k] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[i][k] = 0.0f;
+    const int y_end = min(y0 + kBoxStrip, H);
+#pragma unroll 4
+    for (int yy = y0 - 2; yy < y_end + 2; ++yy) {
+        float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // columns x-2 .. x+5, zero outside the plane
+        if (yy >= 0 && yy < H) {
+            const float* rp = ip + (size_t)yy * W + x;
+            const float4 m = __ldg(reinterpret_cast<const float4*>(rp));
+            p[2] = m.x; p[3] = m.y; p[4] = m.z; p[5] = m.w;
+            if (x >= 2) { const float2 l = __ldg(reinterpret_cast<const float2*>(rp - 2)); p[0] = l.x; p[1] = l.y; }
+            if (x + 4 < W) { const float2 r = __ldg(reinterpret_cast<const float2*>(rp + 4)); p[6] = r.x; p[7] = r.y; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[i][k] = h[i + 1][k];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[i][k] = c[i + 1][k];
+        const float s23 = p[2] + p[3], s45 = p[4] + p[5];
+        h[4][0] = (p[0] + p[1]) + s23 + p[4];
+        h[4][1] = (p[1] + s23) + s45;
+        h[4][2] = (s23 + s45) + p[6];
+        h[4][3] = (p[3] + s45) + (p[6] + p[7]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[2][k] = p[2 + k];
+        const int y = yy - 2;  // rows y-2 .. y+2 are in h[0..4], its centre pixels in c[0]
+        if (y >= y0) {
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float blurred = __fmul_rn(((h[0][k] + h[1][k]) + (h[2][k] + h[3][k])) + h[4][k], w);
+                const float v = c[0][k];
+                o[k] = clamp01(__fadd_rn(v, __fmul_rn(__fsub_rn(v, blurred), strength)));
+            }
+            *reinterpret_cast<float4*>(op + (size_t)y * W + x) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 // ---- x * gain[c], optional clamp --------------------------------------------------------------------
 __global__ void __launch_bounds__(256) channel_gain_kernel(const float4* __restrict__ img, float4* __restrict__ out, int C,
                                                            int64_t quads_per_plane, float g0, float g1, float g2, int clamp_out) {
@@ -329,6 +391,14 @@ extern "C" int otf_taps_zero_f32(const float* img, int planes, int H, int W, int
             ++t.n;
         }
     const int OH = H + 2 * pad - K + 1, OW = W + 2 * pad - K + 1;
+    bool box5 = epilogue == OTF_TAPS_OVERSHARPEN && K == 5 && t.n == 25 && (W & 3) == 0 && (((uintptr_t)img | (uintptr_t)out) & 15) == 0;
+    for (int i = 1; box5 && i < 25; ++i) box5 = t.w[i] == t.w[0];
+    if (box5) {  // the oversharpen stage as the reference configures it: 25 equal taps
+        box5_sharpen_kernel<<<dim3(ceil_div(W / 4, 64), ceil_div(ceil_div(H, kBoxStrip), 4), planes), 256, 0, (cudaStream_t)stream>>>(
+            img, out, H, W, t.w[0], strength);
+        OTF_LAUNCH_CHECK("box5_sharpen_kernel");
+        return OTF_OK;
+    }
     if (pad <= kTapMaxR) {
         const size_t smem = (size_t)(kTapTH + 2 * pad) * (kTapTW + 2 * pad + 1) * sizeof(float);
         taps_zero_tile_kernel<<<dim3(ceil_div(OW, kTapTW), ceil_div(OH, kTapTH), planes), 256, smem, (cudaStream_t)stream>>>(

@@ -5,6 +5,8 @@
 // The USM Gaussian is an exact outer product (cv2.getGaussianKernel(r) x itself), so the
 // 2601-tap 2-D correlation is evaluated as 51 + 51 taps.  HBM-bound: every pass streams the
 // plane once; taps ride in the kernel parameter bank (uniform loads, no LSU traffic).
+#include <stdlib.h>
+
 #include "otf_common.cuh"
 
 namespace otf {
@@ -135,28 +137,47 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
+// Packed FMA form (sm_100a FFMA2, fma.rn.f32x2): two adjacent outputs share the pixel, (out[2k+1], out[2k]) += p * (w[m-1], w[m])
+// with p = win[2k + m], m = 0..NTP and w[-1] = w[NTP] = 0 — NTP + 1 packed instructions per output pair instead of 2 NTP
+// scalar ones, every lane still the ascending fmaf chain of the scalar loop (bit-identical results).  The tap PAIRS ride
+// in the kernel parameter bank as 64-bit constant operands.  ncu on the scalar version: issue slots 58-73 % busy with the
+// FMA pipe at 34-37 % — issue-bound, which is what the packed form halves.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+    const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+    const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+
 template <int NTP>
 struct TapsC {
-    float w[NTP];
+    float2 p[NTP + 1];  // p[m] = (w[m-1], w[m]) over the NTP centred slots
 };
 
 template <int NTP>
 __global__ void __launch_bounds__(256) sepconv_h_kernel(const float* __restrict__ img, float* __restrict__ out, int H, int W,
                                                         const __grid_constant__ TapsC<NTP> taps) {
-    constexpr int CEN = NTP / 2, TW = 256, ROWS = 8, SW = TW + NTP;  // smem col s <-> x = x0 - CEN + s
+    constexpr int CEN = NTP / 2, TW = 256, ROWS = 8, SWR = TW + NTP;  // smem col s <-> x = x0 - CEN + s
+    constexpr int SW = ((SWR / 4) & 1) ? SWR : SWR + 4;                // odd number of 16-byte chunks per row
+    static_assert(NTP % 4 == 0, "window in float4s");
     extern __shared__ __align__(16) float sm[];
     const int plane = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * ROWS;
     const float* ip = img + (size_t)plane * H * W;
     for (int row = threadIdx.x >> 5; row < ROWS; row += 8) {
         const int y = min(y0 + row, H - 1);
-        for (int s = threadIdx.x & 31; s < SW; s += 32) {
+        for (int s = threadIdx.x & 31; s < SWR; s += 32) {
             const int gx = clampi(reflect_idx(x0 - CEN + s, W), 0, W - 1);
             cp_async_f32(&sm[row * SW + s], ip + (size_t)y * W + gx);  // all copies in flight at once
         }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const int row = threadIdx.x >> 5, seg = (threadIdx.x & 31) * 8;
+    // a warp = 2 rows x 16 segments of 8 outputs; the 8 lanes of an LDS.128 phase are 2 rows x 4 segments, which with the
+    // odd chunk pitch touch 8 distinct 16-byte chunks mod 8 (8 lanes of ONE row, 32 bytes apart, would conflict 2-way)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = 2 * (warp >> 1) + ((lane >> 2) & 1);
+    const int seg = (16 * (warp & 1) + 4 * (lane >> 3) + (lane & 3)) * 8;
     const int y = y0 + row;
     if (y >= H || x0 + seg >= W) return;
     float win[8 + NTP];
@@ -166,17 +187,23 @@ __global__ void __launch_bounds__(256) sepconv_h_kernel(const float* __restrict_
         const float4 v = wp[q];
         win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
     }
-    float acc[8];
+    float2 a[4];
 #pragma unroll
-    for (int ox = 0; ox < 8; ++ox) acc[ox] = 0.0f;
+    for (int k = 0; k < 4; ++k) a[k] = make_float2(0.0f, 0.0f);  // (out[2k+1], out[2k])
 #pragma unroll
-    for (int j = 0; j < NTP; ++j)
+    for (int m = 0; m <= NTP; ++m)
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox) acc[ox] = fmaf(taps.w[j], win[ox + j], acc[ox]);
+        for (int k = 0; k < 4; ++k) ffma2(a[k], make_float2(win[2 * k + m], win[2 * k + m]), taps.p[m]);
     float* op = out + (size_t)plane * H * W + (size_t)y * W + x0 + seg;
+    const float acc[8] = {a[0].y, a[0].x, a[1].y, a[1].x, a[2].y, a[2].x, a[3].y, a[3].x};
+    if (x0 + seg + 8 <= W && (W & 3) == 0 && ((uintptr_t)out & 15) == 0) {
+        reinterpret_cast<float4*>(op)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(op)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
 #pragma unroll
-    for (int ox = 0; ox < 8; ++ox)
-        if (x0 + seg + ox < W) op[ox] = acc[ox];
+        for (int ox = 0; ox < 8; ++ox)
+            if (x0 + seg + ox < W) op[ox] = acc[ox];
+    }
 }
 
 template <int NTP, int EPI>
@@ -198,16 +225,19 @@ __global__ void __launch_bounds__(256) sepconv_v_kernel(const float* __restrict_
     __syncthreads();
     const int ys = wy * 8;  // this warp's 8 output rows
     if (x >= W || y0 + ys >= H) return;
+    // (requesting the epilogue's global operands before the tap loop was tried: 60 registers instead of 32 halve the
+    // resident CTAs and the four passes take 0.231 ms instead of 0.185)
     float win[8 + NTP];
 #pragma unroll
     for (int k = 0; k < 8 + NTP; ++k) win[k] = sm[(ys + k) * TWV + lx];
-    float acc[8];
+    float2 a[4];
 #pragma unroll
-    for (int oy = 0; oy < 8; ++oy) acc[oy] = 0.0f;
+    for (int k = 0; k < 4; ++k) a[k] = make_float2(0.0f, 0.0f);  // (out[2k+1], out[2k]) down the column
 #pragma unroll
-    for (int i = 0; i < NTP; ++i)
+    for (int m = 0; m <= NTP; ++m)
 #pragma unroll
-        for (int oy = 0; oy < 8; ++oy) acc[oy] = fmaf(taps.w[i], win[oy + i], acc[oy]);
+        for (int k = 0; k < 4; ++k) ffma2(a[k], make_float2(win[2 * k + m], win[2 * k + m]), taps.p[m]);
+    const float acc[8] = {a[0].y, a[0].x, a[1].y, a[1].x, a[2].y, a[2].x, a[3].y, a[3].x};
 #pragma unroll
     for (int oy = 0; oy < 8; ++oy) {
         const int y = y0 + ys + oy;
@@ -231,10 +261,12 @@ __global__ void __launch_bounds__(256) sepconv_v_kernel(const float* __restrict_
 
 template <int NTP>
 static TapsC<NTP> centre_taps(const Taps& t) {
-    TapsC<NTP> c;
-    for (int i = 0; i < NTP; ++i) c.w[i] = 0.0f;
+    float w[NTP + 2];  // w[1 + slot]; w[0] = w[NTP + 1] = 0
+    for (int i = 0; i < NTP + 2; ++i) w[i] = 0.0f;
     const int r = t.n / 2;
-    for (int i = 0; i < t.n; ++i) c.w[NTP / 2 - r + i] = t.w[i];
+    for (int i = 0; i < t.n; ++i) w[1 + NTP / 2 - r + i] = t.w[i];
+    TapsC<NTP> c;
+    for (int m = 0; m <= NTP; ++m) c.p[m] = make_float2(w[m], w[m + 1]);  // (w[m-1], w[m])
     return c;
 }
 
@@ -246,7 +278,7 @@ static int launch_v_generic(const float* tmp, int planes, int H, int W, const Ta
 template <int NTP>
 static int launch_h_fast(const float* img, int planes, int H, int W, const Taps& t, float* out, cudaStream_t st) {
     const dim3 grid(ceil_div(W, 256), ceil_div(H, 8), planes);
-    sepconv_h_kernel<NTP><<<grid, 256, 8 * (256 + NTP) * sizeof(float), st>>>(img, out, H, W, centre_taps<NTP>(t));
+    sepconv_h_kernel<NTP><<<grid, 256, 8 * (256 + NTP + 4) * sizeof(float), st>>>(img, out, H, W, centre_taps<NTP>(t));
     OTF_LAUNCH_CHECK("sepconv_h_kernel");
     return OTF_OK;
 }
@@ -304,6 +336,22 @@ extern "C" int64_t otf_usm_workspace_bytes(int planes, int H, int W) {
     return (int64_t)planes * H * W * sizeof(float) * 3;  // tmp, mask, sharp
 }
 
+static int usm_chunk_planes(int planes, int H, int W) {
+    // OTF_USM_CHUNK_PLANES=n runs the four passes n planes at a time (A/B switch).  Measured at 64 x 3 x 256^2
+    // (profiles/r02_microbench_usm_chunks.txt): 37 planes 0.224 ms, 48: 0.219, 64: 0.206, 96: 0.200, whole batch 0.185 —
+    // the L2 residency it buys is worth less than the partial waves and launch gaps of 4x more, smaller launches.
+    static const int chunk_planes_env = getenv("OTF_USM_CHUNK_PLANES") ? atoi(getenv("OTF_USM_CHUNK_PLANES")) : 0;
+    (void)H; (void)W;
+    if (chunk_planes_env > 0 && chunk_planes_env < planes) return chunk_planes_env;
+    return planes;
+}
+
+extern "C" int otf_usm_launch_count(int planes, int H, int W) {
+    if (planes <= 0 || H <= 0 || W <= 0) return 0;
+    const int chunk = usm_chunk_planes(planes, H, W);
+    return 4 * ((planes + chunk - 1) / chunk);
+}
+
 extern "C" int otf_usm_sharp_f32(const float* img, int planes, int H, int W, const float* taps_host, int ntaps,
                                  float weight, float threshold, void* workspace_dev, int64_t workspace_bytes,
                                  float* out, void* stream) {
@@ -315,13 +363,21 @@ extern "C" int otf_usm_sharp_f32(const float* img, int planes, int H, int W, con
     if (int rc = fill_taps(t, taps_host, ntaps)) return rc;
     OTF_REQUIRE(ntaps / 2 < H && ntaps / 2 < W, OTF_ERR_BAD_ARG, "usm: reflect pad %d needs H,W > pad (got %dx%d)", ntaps / 2, H, W);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)planes * H * W;
+    // (optionally chunk by chunk, see usm_chunk_planes: the intermediates of every chunk sit at the same workspace addresses)
+    const int chunk = usm_chunk_planes(planes, H, W);
+    const size_t n = (size_t)chunk * H * W;
     float* tmp = (float*)workspace_dev;
     float* mask = tmp + n;
     float* sharp = mask + n;
-    int rc;
-    if ((rc = launch_h(img, planes, H, W, t, tmp, st))) return rc;                                       // blur, rows
-    if ((rc = launch_v<EPI_USM_MASK>(tmp, planes, H, W, t, mask, img, sharp, weight, threshold, st))) return rc;  // blur, cols + mask/sharp
-    if ((rc = launch_h(mask, planes, H, W, t, tmp, st))) return rc;                                      // soft mask, rows
-    return launch_v<EPI_USM_BLEND>(tmp, planes, H, W, t, out, img, sharp, weight, threshold, st);       // soft mask, cols + blend
+    for (int p0 = 0; p0 < planes; p0 += chunk) {
+        const int pc = planes - p0 < chunk ? planes - p0 : chunk;
+        const float* im = img + (size_t)p0 * H * W;
+        float* o = out + (size_t)p0 * H * W;
+        int rc;
+        if ((rc = launch_h(im, pc, H, W, t, tmp, st))) return rc;                                          // blur, rows
+        if ((rc = launch_v<EPI_USM_MASK>(tmp, pc, H, W, t, mask, im, sharp, weight, threshold, st))) return rc;   // blur, cols + mask/sharp
+        if ((rc = launch_h(mask, pc, H, W, t, tmp, st))) return rc;                                        // soft mask, rows
+        if ((rc = launch_v<EPI_USM_BLEND>(tmp, pc, H, W, t, o, im, sharp, weight, threshold, st))) return rc;     // soft mask, cols + blend
+    }
+    return OTF_OK;
 }

@@ -126,5 +126,6 @@ class USMSharp(nn.Module):
         _lib.call(
             "otf_usm_sharp_f32", _lib.ptr(x), b * c, h, w, self._taps.ctypes.data_as(C.c_void_p), n,
             float(weight), float(threshold), _lib.ptr(ws), ws_bytes, _lib.ptr(out), _lib.stream(),
+            launches=lib.otf_usm_launch_count(b * c, h, w),
         )
         return out
