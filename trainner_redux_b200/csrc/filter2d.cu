@@ -52,7 +52,7 @@ struct KernelSets {
 // cluster ranks the samples: analysis and launch order in ONE launch with no host-initialised ticket.
 constexpr int kAnalyseWarps = 8, kAnalyseCluster = 8;
 __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnalyseWarps * 32)
-    kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch, int32_t* __restrict__ scratch_base, int interleave) {
+    kernel_analyse_kernel(const __grid_constant__ KernelSets sets, int K, int kernel_batch, int32_t* __restrict__ scratch_base, int interleave, float trim_tol) {
     pdl_enter();
     __shared__ float sk_all[kAnalyseWarps][21 * 21 + 7];
     extern __shared__ int s_sup[];  // [kernel_batch] supports, for the ranking pass (CTA 0 of the cluster)
@@ -78,6 +78,31 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
             if (fabsf(v) > amax) { amax = fabsf(v); imax = idx; }
         }
         r = __reduce_max_sync(0xffffffffu, r);
+        // EFFECTIVE support: outer rings whose taps add up to less than trim_tol * sum|w| are dropped.  A sigma = 1 Gaussian
+        // drawn into a 21x21 kernel has non-zero taps out to the corners (exp(-50) is representable), but every ring beyond
+        // radius 6 together weighs < 1e-7 of the kernel: leaving them out moves an output by <= trim_tol * sum|w| * max|img|
+        // (2e-7 for a normalised kernel on [0,1] pixels — the size of fp32 summation-order noise, 50x inside the 1e-5 bar)
+        // and shrinks the K^2 loop to the part of the kernel that matters.  trim_tol = 0 (OTF_F2D_TRIM=0) keeps every tap.
+        if (trim_tol > 0.0f && r > 0) {
+            __syncwarp();
+            float tot = 0.0f;
+            for (int idx = lane; idx < n; idx += 32) tot += fabsf(sk[idx]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            float dropped = 0.0f;
+            for (int ring = r; ring >= 1; --ring) {
+                float rs = 0.0f;
+                for (int idx = lane; idx < n; idx += 32) {
+                    const int i = idx / K, j = idx - i * K;
+                    if (max(abs(i - c), abs(j - c)) == ring) rs += fabsf(sk[idx]);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                if (dropped + rs > trim_tol * tot) break;
+                dropped += rs;
+                r = ring - 1;
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {  // pivot = the largest |tap| (ties -> lowest index)
             const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
@@ -166,7 +191,9 @@ static int analyse_sets(const float* const* kernels, int nsets, int kernel_batch
     KernelSets sets;
     for (int i = 0; i < 4; ++i) sets.ptr[i] = kernels[i < nsets ? i : 0];
     static const int interleave = getenv("OTF_F2D_INTERLEAVE") ? atoi(getenv("OTF_F2D_INTERLEAVE")) : 0;
-    launch_chain(kernel_analyse_kernel, dim3(dim3(kAnalyseCluster, nsets)), dim3(kAnalyseWarps * 32), kernel_batch * sizeof(int), st, sets, K, kernel_batch, scratch, interleave);
+    // OTF_F2D_TRIM=<tolerance> (0 = keep every non-zero tap): relative weight of the outer rings the effective support may drop
+    static const float trim_tol = getenv("OTF_F2D_TRIM") ? (float)atof(getenv("OTF_F2D_TRIM")) : 2e-7f;
+    launch_chain(kernel_analyse_kernel, dim3(dim3(kAnalyseCluster, nsets)), dim3(kAnalyseWarps * 32), kernel_batch * sizeof(int), st, sets, K, kernel_batch, scratch, interleave, trim_tol);
     OTF_LAUNCH_CHECK("kernel_analyse_kernel");
     return OTF_OK;
 }
