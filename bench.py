@@ -57,6 +57,16 @@ S1, S2 = 0.75, 1.0
 N_ROTATE = int(os.environ.get("OTF_BENCH_ROTATE", "4"))  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
 
 
+_RECORD_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON record, on the process's real stdout (see main)."""
+    out = _RECORD_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class Workload:
     """c2 (default, the config the metric is quoted on): B=64 x 256^2 GT x4 per GPU, weak scaling.
     c3 (BASELINE.json configs[2]): ONE batch of 32 x 512^2 GT x2 sharded per sample over the ranks, strong scaling."""
@@ -214,7 +224,7 @@ def run_reference(args, wl: Workload) -> None:
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------- clocks ----
@@ -555,7 +565,7 @@ def run_b200(args, wl: Workload) -> None:
     sampler = ClockSampler(local) if rank == 0 else None  # spans warm-up, every timed region and the e2e loops
     numa, numa_why = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
     if world > 1:
-        # NCCL's banner lines go wherever NCCL sends them (stderr); stdout carries the one JSON line, printed last
+        # (NCCL's banner and NCCL_DEBUG lines land on stderr: see main)
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
         torch.cuda.synchronize()
@@ -663,7 +673,7 @@ def run_b200(args, wl: Workload) -> None:
                       "kernels_per_step": launches / args.steps},
             "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "parity": parity, **extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     elif sampler:
         sampler.stop()
     if world > 1:
@@ -683,6 +693,13 @@ def main() -> None:
     ap.add_argument("--streams", type=int, default=4, help="feed_data calls in flight during the timed region")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the per-stage re-capture pass (for ncu launch lists)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record.  Libraries that write to file descriptor 1 on their own (NCCL prints
+    # "NCCL version ..." and, under NCCL_DEBUG, its communicator lines there) are not silenced: for the whole run fd 1 is an
+    # alias of stderr, where those lines stay visible to whoever collects them, and the record goes to the saved stdout.
+    global _RECORD_OUT
+    sys.stdout.flush()
+    _RECORD_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = Workload(args.workload, int(os.environ.get("WORLD_SIZE", "1")), args.noise)
     if args.impl == "reference":

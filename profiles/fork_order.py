@@ -28,6 +28,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=300)
 ap.add_argument("--cpu-steps", type=int, default=3)
 ap.add_argument("--json", default=None)
+ap.add_argument("--profile", action="store_true", help="cProfile the timed loop (host-side cost per stage)")
 ap.add_argument("--order", default="fork", choices=["fork", "classic"],
                 help="fork: the as-shipped order (A); classic: the second-order chain with the same option file's random schedule (:125-146)")
 args = ap.parse_args()
@@ -54,11 +55,20 @@ for _ in range(30):
 torch.cuda.synchronize()
 l0 = _lib.launch_count
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if args.profile:
+    import cProfile
+    import pstats
+
+    pr = cProfile.Profile()
+    pr.enable()
 t0 = time.perf_counter()
 e0.record()
 for _ in range(args.steps):
     feed.feed_data(data)
 e1.record()
+if args.profile:
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(30)
 t_issue = time.perf_counter() - t0
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
