@@ -166,12 +166,13 @@ int otf_philox_uniform_f32(float* out, int64_t n, uint64_t seed, uint64_t offset
  * 8-bit-quantised colour and gray images -> vals = 2^ceil(log2(#distinct));
  * (2) sampling + mixing + tail.  C must be 3.  masks_dev: uint32[B*16] scratch
  * (zeroed by the call).
- * tables_dev (may be NULL): the universal CDF tables filled once per device by
+ * tables_dev (may be NULL): the universal alias tables filled once per device by
  * otf_poisson_build_tables (otf_poisson_tables_bytes() bytes, 16-byte aligned, read-only
  * afterwards).  lambda = (level/255) * vals with vals = 2^v, v <= 8, so only 2304
  * lambdas can ever occur; with the tables and production arguments (no injected
- * counts, no exports) every count is drawn by EXACT INVERSION from one Philox
- * uniform and ~2 table reads.  Without them (or with injected counts, exports,
+ * counts, no exports) every count is drawn from one Philox uniform and ONE 8-byte
+ * table read (Walker / Vose alias method, probabilities right to 2^-24, the
+ * resolution of the uniform).  Without them (or with injected counts, exports,
  * fractional gray flags) counts come from a rejection sampler (sequential inversion
  * below lambda 10, PTRS above).
  * vals_out_dev (fp32[B*2]: colour, gray; may be NULL) and lambda_*_dev (may be

@@ -377,68 +377,70 @@ __global__ void __launch_bounds__(256) poisson_apply_kernel(const float* __restr
         poisson_pixel_generic(ip, op, hw, b, p, vc, vg, sc, gray, gf, counts_c, counts_g, ph, offset, flags, lam_c_out, lam_g_out);
 }
 
-// ---- table inversion (the production path) ----------------------------------------------------------
+// ---- alias tables (the production path) --------------------------------------------------------------
 // lambda = q * vals with q = level / 255 and vals = 2^v, v in 0..8 (a sample has at most 256 distinct levels): only
-// 9 x 256 = 2304 different lambdas can ever occur, whatever the image.  Their exact CDFs are tabulated ONCE per
-// device (otf_poisson_build_tables: 2304 rows x a 256-wide window [k_lo, k_lo + 256) around lambda — >= 7.9 sigma at
-// lambda = 256, tail mass < 1e-14 — 2.96 MB, L2 resident, the 320 KB of one vals mostly L1 resident).  A sample then
-// costs ONE uniform, one guide byte (the first k whose CDF can reach the uniform's 1/256 bucket) and ~1.3 CDF reads:
-// no rejection loop, no divergence, one Philox call per pixel.  The rejection kernel above pays ~2.6 warp-level PTRS
-// attempts per element (85 % acceptance per lane, so nearly every warp retries).  Tables are built in fp64
-// (p(k+1) = p(k) * lambda / (k+1) from p(k_lo) = exp(-lambda + k_lo ln lambda - lgamma(k_lo + 1))) and stored as
-// fp32; with 24-bit uniforms every outcome's probability is exact to 2^-24.
+// 9 x 256 = 2304 different lambdas can ever occur, whatever the image.  For each of them the Poisson pmf on a
+// 256-wide window [k_lo, k_lo + 256) around lambda (>= 7.9 sigma at lambda = 256, tail mass < 1e-14) is turned ONCE per
+// device into a Walker / Vose alias table with 256 columns (fp64 construction, otf_poisson_build_tables): 2304 rows x
+// 256 columns x 8 bytes = 4.7 MB, L2 resident.  A sample then costs ONE 24-bit uniform and ONE 8-byte table read: the top
+// 8 bits pick the column, the low 16 bits are compared with the column's 16-bit threshold and select the column's own
+// count or its alias — no search, no loop, no divergence, one Philox call per pixel, and every outcome's probability is
+// right to 2^-24 (the resolution of the uniform).  Round 1 inverted the CDF instead (a guide byte, k_lo and ~1.3 CDF
+// reads per sample): ncu showed that kernel waiting on its ~3.3 scattered reads per sample (long-scoreboard 8.2) — the
+// alias form makes it one.  The rejection kernel above pays ~2.6 warp-level PTRS attempts per element.
 constexpr int kPoisWin = 256, kPoisRows = 9 * 256;
 
 struct PoissonTables {
-    const int* klo;        // [9][256]
-    const uint8_t* guide;  // [9][256][256]
-    const float* cdf;      // [9][256][256]
+    const uint2* alias;  // [9][256][256]: .x = threshold (0..65536), .y = own count | alias count << 16
 };
-static int64_t poisson_tables_bytes() { return (int64_t)kPoisRows * (4 + kPoisWin + (int64_t)kPoisWin * 4); }
+static int64_t poisson_tables_bytes() { return (int64_t)kPoisRows * kPoisWin * 8; }
 static PoissonTables poisson_tables(const void* dev) {
     PoissonTables t;
-    const char* p = (const char*)dev;
-    t.klo = (const int*)p;
-    p += (size_t)kPoisRows * 4;
-    t.guide = (const uint8_t*)p;
-    p += (size_t)kPoisRows * kPoisWin;
-    t.cdf = (const float*)p;
+    t.alias = (const uint2*)dev;
     return t;
 }
 
 // one thread per (vals exponent, level) row — runs once per device
-__global__ void __launch_bounds__(256) poisson_tables_kernel(int* __restrict__ klo_out, uint8_t* __restrict__ guide_out,
-                                                             float* __restrict__ cdf_out) {
-    const int v = blockIdx.x, level = threadIdx.x;
+__global__ void __launch_bounds__(64) poisson_tables_kernel(uint2* __restrict__ alias_out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= kPoisRows) return;
+    const int v = row >> 8, level = row & 255;
     const float lamf = __fmul_rn(__fdiv_rn((float)level, 255.0f), (float)(1 << v));  // exactly what the apply kernel forms
     const double lam = (double)lamf;
-    const size_t row = (size_t)v * 256 + level;
     int klo = (int)floor(lam - 8.0 * sqrt(lam));
     if (klo < 0) klo = 0;
-    klo_out[row] = klo;
-    float* cdf = cdf_out + row * kPoisWin;
-    uint8_t* guide = guide_out + row * kPoisWin;
+    // scaled pmf: pr[k] = 256 * P(klo + k), renormalised over the window (the mass outside is < 1e-14)
+    double pr[kPoisWin];
+    uint8_t small[kPoisWin], large[kPoisWin];
     double p = lam > 0.0 ? exp(-lam + klo * log(lam) - lgamma((double)klo + 1.0)) : (klo == 0 ? 1.0 : 0.0);
-    double acc = 0.0;
-    int g = 0;  // next guide bucket to fill
+    double tot = 0.0;
     for (int k = 0; k < kPoisWin; ++k) {
-        acc += p;
-        const float c = k == kPoisWin - 1 ? 1.0f : fminf((float)acc, 1.0f);
-        cdf[k] = c;
-        // bucket j holds the uniforms (j*65536 + 1 .. (j+1)*65536) / 2^24: its first admissible k is the first one
-        // whose CDF reaches the bucket's smallest uniform
-        while (g < 256 && c >= (float)(g * 65536 + 1) * (1.0f / 16777216.0f)) guide[g++] = (uint8_t)k;
+        pr[k] = p;
+        tot += p;
         p = p * lam / (double)(klo + k + 1);
     }
+    int ns = 0, nl = 0;
+    for (int k = 0; k < kPoisWin; ++k) {
+        pr[k] = pr[k] / tot * (double)kPoisWin;
+        if (pr[k] < 1.0) small[ns++] = (uint8_t)k; else large[nl++] = (uint8_t)k;
+    }
+    uint2* out = alias_out + (size_t)row * kPoisWin;
+    // Vose: pair a deficient column with a surplus one until one list runs out
+    while (ns > 0 && nl > 0) {
+        const int sidx = small[--ns], lidx = large[nl - 1];
+        const double thr = fmin(fmax(pr[sidx], 0.0), 1.0);
+        out[sidx] = make_uint2((unsigned)llrint(thr * 65536.0), (unsigned)(klo + sidx) | ((unsigned)(klo + lidx) << 16));
+        pr[lidx] = (pr[lidx] + pr[sidx]) - 1.0;
+        if (pr[lidx] < 1.0) { --nl; small[ns++] = (uint8_t)lidx; }
+    }
+    while (nl > 0) { const int k = large[--nl]; out[k] = make_uint2(65536u, (unsigned)(klo + k) | ((unsigned)(klo + k) << 16)); }
+    while (ns > 0) { const int k = small[--ns]; out[k] = make_uint2(65536u, (unsigned)(klo + k) | ((unsigned)(klo + k) << 16)); }  // rounding leftovers
 }
 
 __device__ __forceinline__ float poisson_by_table(const PoissonTables& tab, int row, uint32_t bits) {
     const uint32_t u24 = bits >> 8;
-    const float u = ((float)u24 + 1.0f) * (1.0f / 16777216.0f);  // the same (0,1] uniform as u01()
-    const float* cdf = tab.cdf + (size_t)row * kPoisWin;
-    int k = __ldg(tab.guide + (size_t)row * kPoisWin + (u24 >> 16));
-    while (__ldg(cdf + k) < u) ++k;  // cdf[255] == 1 >= u: terminates
-    return (float)(__ldg(tab.klo + row) + k);
+    const uint2 e = __ldg(tab.alias + (size_t)row * kPoisWin + (u24 >> 16));
+    return (float)(((u24 & 0xffffu) < e.x) ? (e.y & 0xffffu) : (e.y >> 16));
 }
 
 // Pass 2, production flags (no injected counts, no exports, per-sample gray flag exactly 0 or 1): one thread per
@@ -483,27 +485,19 @@ __global__ void __launch_bounds__(256) poisson_apply_table_kernel(const float* _
             // mix with flag 1: noise * 0 + noise_g * 1 == noise_g exactly (degradations.py:808)
             noise[0] = noise[1] = noise[2] = __fsub_rn(__fmul_rn(cnt, inv_vals), s_q[lv]);
         } else {
-            // the three channels' table walks are independent: issue their loads side by side
+            // the three channels' table reads are independent: issue them side by side
             const uint32_t w[3] = {r.x, r.y, r.z};
-            int lv[3], k[3], klo[3];
-            float u[3], c[3];
-            const float* cdf[3];
+            int lv[3];
+            uint2 e[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 lv[ch] = level8(px[ch]);
-                const uint32_t u24 = w[ch] >> 8;
-                u[ch] = ((float)u24 + 1.0f) * (1.0f / 16777216.0f);
-                const size_t row = (size_t)(row0 + lv[ch]);
-                cdf[ch] = tab.cdf + row * kPoisWin;
-                k[ch] = __ldg(tab.guide + row * kPoisWin + (u24 >> 16));
-                klo[ch] = __ldg(tab.klo + row);
+                e[ch] = __ldg(tab.alias + (size_t)(row0 + lv[ch]) * kPoisWin + (w[ch] >> 24));
             }
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) c[ch] = __ldg(cdf[ch] + k[ch]);
-#pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                while (c[ch] < u[ch]) c[ch] = __ldg(cdf[ch] + ++k[ch]);  // cdf[255] == 1 >= u: terminates
-                noise[ch] = __fsub_rn(__fmul_rn((float)(klo[ch] + k[ch]), inv_vals), s_q[lv[ch]]);  // :805-806
+                const float cnt = (float)((((w[ch] >> 8) & 0xffffu) < e[ch].x) ? (e[ch].y & 0xffffu) : (e[ch].y >> 16));
+                noise[ch] = __fsub_rn(__fmul_rn(cnt, inv_vals), s_q[lv[ch]]);  // :805-806
             }
         }
 #pragma unroll
@@ -590,8 +584,7 @@ extern "C" int otf_poisson_build_tables(void* tables_dev, void* stream) {
     using namespace otf;
     OTF_REQUIRE(tables_dev && (((uintptr_t)tables_dev) & 15) == 0, OTF_ERR_BAD_ARG, "poisson_build_tables: null or unaligned pointer");
     char* p = (char*)tables_dev;
-    poisson_tables_kernel<<<9, 256, 0, (cudaStream_t)stream>>>((int*)p, (uint8_t*)(p + (size_t)kPoisRows * 4),
-                                                              (float*)(p + (size_t)kPoisRows * (4 + kPoisWin)));
+    poisson_tables_kernel<<<kPoisRows / 64, 64, 0, (cudaStream_t)stream>>>((uint2*)p);
     OTF_LAUNCH_CHECK("poisson_tables_kernel");
     return OTF_OK;
 }
