@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OTF_ABI_VERSION 2
+#define OTF_ABI_VERSION 3  /* 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
 
 enum {
     OTF_OK = 0,
@@ -301,10 +301,19 @@ int otf_copy_box_f32(const float* src, int Hs, int Ws, int sy, int sx,
  *   OTF_OP_CLAMP_ROUND  -
  *   OTF_OP_CROP_PAIR    terminal: p0 = GT (B,C,H0,W0 of the chain input), oh = top, ow = left, n = lq_patch,
  *                       mode = scale; writes p1 = gt_out, p2 = lq_out; p4 = device int32[2] (top, left) override|NULL
+ *   the fork's extra stages (row f3; the entry points documented under "f3: fork extras" below):
+ *   OTF_OP_WARP         mode = OTF_WARP_*, f0 = parameter                                     (otf_warp_f32)
+ *   OTF_OP_TAPS_ZERO    p0 HOST K x K kernel, K, flags = OTF_TAPS_* epilogue, f0 = strength   (otf_taps_zero_f32; an even K
+ *                       grows the image by one row and column)
+ *   OTF_OP_GAIN         f0, f1, f2 = per-channel gains, flags&1 = clamp01                      (otf_channel_gain_f32)
+ *   OTF_OP_SENSOR       f0 = std, p0 injected N(0,1) field|NULL, seed, offset                  (otf_sensor_noise_f32)
+ *   OTF_OP_DEMOSAIC     -  (C must be 3)                                                       (otf_demosaic_f32)
+ *   OTF_OP_TRUNC8       -                                                                      (otf_trunc8_f32)
  * `final_h/final_w` (host, may be NULL) receive the extent of the last image-producing stage. */
 enum {
     OTF_OP_ANALYSE = 0, OTF_OP_FILTER2D = 1, OTF_OP_USM = 2, OTF_OP_SEPCONV = 3, OTF_OP_RESIZE = 4,
-    OTF_OP_GAUSS = 5, OTF_OP_POISSON = 6, OTF_OP_JPEG = 7, OTF_OP_CLAMP_ROUND = 8, OTF_OP_CROP_PAIR = 9
+    OTF_OP_GAUSS = 5, OTF_OP_POISSON = 6, OTF_OP_JPEG = 7, OTF_OP_CLAMP_ROUND = 8, OTF_OP_CROP_PAIR = 9,
+    OTF_OP_WARP = 10, OTF_OP_TAPS_ZERO = 11, OTF_OP_GAIN = 12, OTF_OP_SENSOR = 13, OTF_OP_DEMOSAIC = 14, OTF_OP_TRUNC8 = 15
 };
 typedef struct OtfStage {
     int32_t op, mode, oh, ow, n, kb, K, flags;
@@ -316,6 +325,8 @@ typedef struct OtfStage {
     const void* p3;
     void* dst;
     const void* p4; /* per-step device parameters of a captured chain (see the op table) */
+    float f2;       /* ABI 3: third scalar (OTF_OP_GAIN) */
+    int32_t reserved;
 } OtfStage;
 int64_t otf_run_stages_workspace_bytes(int B, int C, int H, int W, const OtfStage* stages, int nstages);
 int otf_run_stages_f32(const float* img, int B, int C, int H, int W, const OtfStage* stages, int nstages,

@@ -58,6 +58,41 @@ def test_native_chain_is_bit_identical_to_the_per_stage_path(dev, order, seed):
         assert l2 - l1 <= l1 - l0, "the native chain must never launch more kernels than the per-stage path"
 
 
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_native_fork_chain_with_extras_is_bit_identical_to_the_per_stage_path(dev, seed):
+    """Order (A) with every extra stage of the fork likely (lens / chroma / motion incl. even K / demosaic / sensor noise /
+    shutter / exposure / colour temperature / oversharpen / aliasing / JPEG rounds / editing exposure): one library call
+    per chain (stage ops OTF_OP_WARP .. OTF_OP_TRUNC8) against one Python call per stage."""
+    opt = OTFOptions(order="fork", scale=(4, 2)[seed % 2], gt_size=64, blur_prob=0.7, lens_distort_prob=0.6, chromatic_aberration_prob=0.5,
+                     motion_blur_prob=0.6, sensor_noise_prob=0.6, rolling_shutter_prob=0.5, exposure_prob=0.5, color_temp_prob=0.5,
+                     oversharpen_prob=0.5, aliasing_prob=0.5, demosaic_prob=0.4, recompression_prob=0.5, editing_prob=0.5,
+                     editing_exposure_prob=0.5, compression_formats=("jpeg", "webp"), compression_weights=(0.8, 0.2),
+                     recompression_formats=("jpeg",), recompression_weights=(1.0,), motion_blur_kernel_size=(4, 15), queue_size=12)
+    eager = RealESRGANFeed(opt, device=dev, manual_seed=seed, use_pool=True)
+    native = RealESRGANFeed(opt, device=dev, manual_seed=seed, use_pool=True)
+    eager.native_chain = False
+    seen: set = set()
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # (the webp rounds pass through with a one-time warning)
+        for it in range(6):
+            d = _data(4, 96 + 4 * seed, 10 * seed + it)
+            D._TABLE_CACHE.clear()
+            l0 = _lib.launch_count
+            eager.feed_data(dict(d))
+            l1 = _lib.launch_count
+            D._TABLE_CACHE.clear()
+            native.feed_data(dict(d))
+            l2 = _lib.launch_count
+            assert eager.last_plan.keys() == native.last_plan.keys()
+            seen.update(eager.last_plan.keys())
+            assert torch.equal(eager.lq, native.lq), (seed, it, {k: v for k, v in eager.last_plan.items() if not torch.is_tensor(v)})
+            assert torch.equal(eager.gt, native.gt)
+            assert l2 - l1 <= l1 - l0
+    assert len(seen & {"lens", "chroma", "motion", "demosaic", "sensor", "shutter", "exposure", "color_temp", "oversharpen", "aliasing"}) >= 6
+
+
 @pytest.mark.parametrize("noise", ["gaussian", "poisson"])
 @pytest.mark.parametrize("final_order", ["resize_first", "jpeg_first"])
 def test_fused_launches_are_bit_identical_to_the_unfused_executor(dev, monkeypatch, noise, final_order):

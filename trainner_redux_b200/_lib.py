@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0
-ABI_VERSION = 2  # 2: device-side Philox offset word / crop offsets, OtfStage.p4, OTF_NOISE_RAW_FIELD
+ABI_VERSION = 3  # 3: OtfStage.f2 + the fork-extra ops of the stage executor; 2: device-side Philox offset word / crop offsets, OtfStage.p4
 RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST, RESIZE_LANCZOS = range(7)
 WARP_LENS, WARP_SHUTTER, WARP_CHROMA = range(3)
 TAPS_NONE, TAPS_OVERSHARPEN = 0, 1
@@ -75,7 +75,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
 }
 
 (OP_ANALYSE, OP_FILTER2D, OP_USM, OP_SEPCONV, OP_RESIZE, OP_GAUSS, OP_POISSON, OP_JPEG, OP_CLAMP_ROUND,
- OP_CROP_PAIR) = range(10)
+ OP_CROP_PAIR, OP_WARP, OP_TAPS_ZERO, OP_GAIN, OP_SENSOR, OP_DEMOSAIC, OP_TRUNC8) = range(16)
 
 
 class Stage(C.Structure):
@@ -84,7 +84,7 @@ class Stage(C.Structure):
     _fields_ = [("op", C.c_int32), ("mode", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32), ("n", C.c_int32),
                 ("kb", C.c_int32), ("K", C.c_int32), ("flags", C.c_int32), ("f0", C.c_float), ("f1", C.c_float),
                 ("seed", C.c_uint64), ("offset", C.c_uint64), ("p0", C.c_void_p), ("p1", C.c_void_p), ("p2", C.c_void_p),
-                ("p3", C.c_void_p), ("dst", C.c_void_p), ("p4", C.c_void_p)]
+                ("p3", C.c_void_p), ("dst", C.c_void_p), ("p4", C.c_void_p), ("f2", C.c_float), ("reserved", C.c_int32)]
 
 
 _lib: C.CDLL | None = None

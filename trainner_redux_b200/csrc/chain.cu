@@ -60,7 +60,19 @@ static int plan_layout(int B, int C, int H, int W, const OtfStage* st, int n, La
             case OTF_OP_GAUSS:
             case OTF_OP_JPEG:
             case OTF_OP_CLAMP_ROUND:
+            case OTF_OP_WARP:
+            case OTF_OP_GAIN:
+            case OTF_OP_SENSOR:
+            case OTF_OP_DEMOSAIC:
+            case OTF_OP_TRUNC8:
                 break;
+            case OTF_OP_TAPS_ZERO: {
+                OTF_REQUIRE(s.K > 0 && s.p0, OTF_ERR_BAD_ARG, "run_stages[%d]: taps_zero needs a host kernel", i);
+                const int pad = s.K / 2;  // F.conv2d(padding=K//2): an even K grows the image by one
+                h = h + 2 * pad - s.K + 1;
+                w = w + 2 * pad - s.K + 1;
+                break;
+            }
             case OTF_OP_POISSON:
                 scratch = (int64_t)B * 16 * 4;
                 break;
@@ -224,6 +236,35 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
                 break;
             case OTF_OP_CLAMP_ROUND:
                 rc = otf_clamp_round_f32(cur, (int64_t)B * C * h * w, out, stream);
+                launches += 1;
+                break;
+            case OTF_OP_WARP:
+                rc = otf_warp_f32(cur, B, C, h, w, s.mode, s.f0, out, stream);
+                launches += 1;
+                break;
+            case OTF_OP_TAPS_ZERO: {
+                rc = otf_taps_zero_f32(cur, B * C, h, w, s.K, (const float*)s.p0, s.flags, s.f0, out, stream);
+                const int pad = s.K / 2;
+                h = h + 2 * pad - s.K + 1;
+                w = w + 2 * pad - s.K + 1;
+                launches += 1;
+                break;
+            }
+            case OTF_OP_GAIN:
+                rc = otf_channel_gain_f32(cur, B, C, (int64_t)h * w, s.f0, s.f1, s.f2, s.flags & 1, out, stream);
+                launches += 1;
+                break;
+            case OTF_OP_SENSOR:
+                rc = otf_sensor_noise_f32(cur, (int64_t)B * C * h * w, s.f0, (const float*)s.p0, s.seed, s.offset, out, stream);
+                launches += 1;
+                break;
+            case OTF_OP_DEMOSAIC:
+                OTF_REQUIRE(C == 3, OTF_ERR_BAD_ARG, "run_stages[%d]: demosaic needs 3 channels", i);
+                rc = otf_demosaic_f32(cur, B, h, w, out, stream);
+                launches += 1;
+                break;
+            case OTF_OP_TRUNC8:
+                rc = otf_trunc8_f32(cur, (int64_t)B * C * h * w, out, stream);
                 launches += 1;
                 break;
             case OTF_OP_CROP_PAIR:

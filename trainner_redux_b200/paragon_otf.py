@@ -129,13 +129,18 @@ def exposure(img: Tensor, factor: float) -> Tensor:
     return _gain(img, (factor, factor, factor))
 
 
+def color_temperature_gains(shift: float) -> tuple[float, float, float]:
+    """Per-channel gains of :365-394 — warm: R x(1+0.3s), G x(1+0.1s); cool: B x(1-0.3s), G x(1-0.1s)."""
+    if shift > 0:
+        return (1 + shift * 0.3, 1 + shift * 0.1, 1.0)
+    return (1.0, 1 - shift * 0.1, 1 - shift * 0.3)
+
+
 def color_temperature(img: Tensor, shift: float) -> Tensor:
-    """:365-394 — warm: R x(1+0.3s), G x(1+0.1s); cool: B x(1-0.3s), G x(1-0.1s); clamp."""
+    """:365-394 — the gains above, then clamp."""
     if img.size(1) != 3:
         return img
-    if shift > 0:
-        return _gain(img, (1 + shift * 0.3, 1 + shift * 0.1, 1.0))
-    return _gain(img, (1.0, 1 - shift * 0.1, 1 - shift * 0.3))
+    return _gain(img, color_temperature_gains(shift))
 
 
 def sensor_noise(img: Tensor, std: float, noise: Tensor | None = None, generator: D.PhiloxState | None = None) -> Tensor:
@@ -185,21 +190,29 @@ _JPEGER = DiffJPEG(differentiable=False)
 _WARNED: set[str] = set()
 
 
+def codec_runs_jpeg(format_name: str, quality: float | None, fallback: str = "passthrough") -> bool:
+    """Whether a drawn (format, quality) runs the JPEG round here (see compress_with_format); warns once per host codec
+    that passes through."""
+    if quality is None:
+        return False
+    if format_name == "jpeg" or (fallback == "jpeg" and format_name in ("webp", "avif", "heif")):
+        return True
+    if format_name not in _WARNED:
+        _WARNED.add(format_name)
+        warnings.warn(f"paragon_otf: {format_name!r} is a host codec outside the GPU path; the image passes through unchanged "
+                      "(as the reference does when the codec plugin is missing); set codec_fallback='jpeg' to run a JPEG round "
+                      "at the drawn quality instead", stacklevel=2)
+    return False
+
+
 def compress_with_format(img: Tensor, format_name: str, quality: float | None, fallback: str = "passthrough") -> Tensor:
     """`_compress_with_format` (:95-158) for one drawn (format, quality).  "jpeg" = uint8 truncation, fused DiffJPEG at
     ``int(quality)``, back onto the 8-bit lattice (what a decoded file holds).  WebP / AVIF / HEIF are host codecs:
     ``fallback="passthrough"`` (default) returns the image unchanged with a one-time warning — what the reference does
     when the codec plugin is missing; ``fallback="jpeg"`` runs the JPEG round at the drawn quality instead, so the
     share of compressed batches stays what the option file asks for."""
-    if quality is None:
-        return img
-    if format_name == "jpeg" or (fallback == "jpeg" and format_name in ("webp", "avif", "heif")):
+    if codec_runs_jpeg(format_name, quality, fallback):
         return _JPEGER(trunc8(img), quality=float(int(quality)), _round8=True)
-    if format_name not in _WARNED:
-        _WARNED.add(format_name)
-        warnings.warn(f"paragon_otf: {format_name!r} is a host codec outside the GPU path; the image passes through unchanged "
-                      "(as the reference does when the codec plugin is missing); set codec_fallback='jpeg' to run a JPEG round "
-                      "at the drawn quality instead", stacklevel=2)
     return img
 
 

@@ -488,10 +488,46 @@ class RealESRGANFeed:
             else:
                 sl.clamp_round()
 
-        if fork:
+        if fork:  # realesrgan_model.py:512-616, stage by stage as degrade() runs it
+            from . import paragon_otf as PO
+
+            if "lens" in plan:
+                sl.warp(_lib.WARP_LENS, plan["lens"])
+            if plan.get("chroma") and sl.c == 3:
+                sl.warp(_lib.WARP_CHROMA, 0.0)
+            if "motion" in plan:
+                sl.taps_zero(PO.motion_blur_kernel(*plan["motion"]))
             if plan.get("blur1"):
                 sl.filter2d(kernel1, an(0))
-            tail(plan.get("jpeg"))
+            if plan.get("demosaic"):
+                sl.demosaic()
+            if "sensor" in plan:
+                sl.sensor_noise(plan["sensor"], self.rng.philox, noise=inject.get("sensor_noise"))
+            if "shutter" in plan:
+                sl.warp(_lib.WARP_SHUTTER, plan["shutter"] * sl.h / sl.w)
+            if "exposure" in plan:
+                sl.gain((plan["exposure"],) * 3)
+            if "color_temp" in plan and sl.c == 3:
+                sl.gain(PO.color_temperature_gains(plan["color_temp"]))
+            if "oversharpen" in plan:
+                sl.taps_zero(PO._BOX5, _lib.TAPS_OVERSHARPEN, plan["oversharpen"])
+            if "aliasing" in plan:
+                h, w = sl.h, sl.w
+                sl.resize_raw(_lib.RESIZE_NEAREST, int(h * plan["aliasing"]), int(w * plan["aliasing"]), False)
+                sl.resize_raw(_lib.RESIZE_NEAREST, h, w, False)
+            sl.resize(plan["resize3_mode"], size=(ori_h // sc, ori_w // sc))
+            sl.filter2d(sinc_kernel, an(2))
+            if plan.get("jpeg") is not None:  # per-sample qualities through DiffJPEG (this repo's earlier routing)
+                sl.jpeg(plan["jpeg"], round8=True)
+                return sl
+            fallback = _opt(self.opt, "codec_fallback", "passthrough")
+            for fmt, q in plan.get("compression", []):
+                if PO.codec_runs_jpeg(fmt, q, fallback):  # uint8 truncation, DiffJPEG at int(quality), 8-bit lattice
+                    sl.trunc8()
+                    sl.jpeg(float(int(q)), clamp_in=False, round8=True)
+            if "editing_exposure" in plan:
+                sl.gain((plan["editing_exposure"],) * 3)
+            sl.clamp_round()
             return sl
         if plan.get("usm"):
             r = plan["usm"]["radius"]
@@ -523,14 +559,15 @@ class RealESRGANFeed:
         return sl
 
     def _native(self, plan: dict | None = None) -> bool:
-        # the fork's extra stages are launched per stage from Python (they are not in the native executor's op table)
-        extras = plan is not None and any(k in plan for k in EXTRA_KEYS)
-        return self.native_chain and not (self.time_stages or self.record_stage_fns or self.collect_taps is not None or extras)
+        # (the fork's extra stages are in the native executor's op table too: one library call per chain in both orders)
+        return self.native_chain and not (self.time_stages or self.record_stage_fns or self.collect_taps is not None)
 
     # -- captured chains -------------------------------------------------------------------
     def _graph_key(self, gt: Tensor, kernels: Sequence[Tensor], plan: dict, inject: dict | None) -> tuple | None:
         if not self.use_graphs or inject or not self._native(plan) or torch.cuda.is_current_stream_capturing():
             return None
+        if any(k in plan for k in EXTRA_KEYS):
+            return None  # the fork's extras take their drawn scalars by value and come and go from step to step: run eagerly
         if any(k.dtype != torch.float32 or not k.is_contiguous() or not k.is_cuda for k in kernels):
             return None  # the stage list would work on a converted copy whose address is not the caller's
         sig = plan_signature(plan, gt.size(2), gt.size(3))

@@ -256,6 +256,57 @@ class StageList:
         self.launches += 1
         self.unit_range = True
 
+    # -- the fork's extra stages (paragon_otf.py): same entry points, same arguments ------------
+    def warp(self, mode: int, p0: float) -> None:
+        """paragon_otf._warp: lens distortion / rolling shutter / chromatic aberration."""
+        self._add(_lib.OP_WARP, mode=mode, f0=float(p0))
+        self.launches += 1
+        self.unit_range = mode == _lib.WARP_CHROMA  # (the chromatic warp clamps; the others only interpolate)
+
+    def taps_zero(self, kernel: np.ndarray, epilogue: int = 0, strength: float = 0.0) -> None:
+        """paragon_otf._taps_zero: zero-padded correlation with a small host kernel (motion blur, oversharpen)."""
+        k = int(kernel.shape[0])
+        kh = np.ascontiguousarray(kernel, dtype=np.float32)
+        self._keep.append(kh)
+        self._add(_lib.OP_TAPS_ZERO, p0=kh.ctypes.data, K=k, flags=int(epilogue), f0=float(strength))
+        self.launches += 1
+        pad = k // 2
+        self.h, self.w = self.h + 2 * pad - k + 1, self.w + 2 * pad - k + 1
+        self.unit_range = epilogue == _lib.TAPS_OVERSHARPEN
+
+    def gain(self, g: tuple[float, float, float], clamp: bool = True) -> None:
+        """paragon_otf._gain: exposure / colour temperature."""
+        self._add(_lib.OP_GAIN, f0=float(g[0]), f1=float(g[1]), f2=float(g[2]), flags=int(clamp))
+        self.launches += 1
+        self.unit_range = bool(clamp)
+
+    def sensor_noise(self, std: float, gen: D.PhiloxState, noise: Tensor | None = None) -> None:
+        """paragon_otf.sensor_noise: clamp(img + N * std, 0, 1)."""
+        if noise is not None:
+            if tuple(noise.shape) != (self.b, self.c, self.h, self.w):
+                raise ValueError("sensor_noise: injected field must have the image's shape")
+            self._add(_lib.OP_SENSOR, f0=float(std), p0=self._dev_ptr(noise))
+        else:
+            self._add(_lib.OP_SENSOR, f0=float(std), seed=gen.seed, offset=gen.next_offset())
+        self.launches += 1
+        self.unit_range = True
+
+    def demosaic(self) -> None:
+        if self.c != 3:
+            raise RuntimeError(f"demosaic expects 3 channels, got {self.c}")
+        self._add(_lib.OP_DEMOSAIC)
+        self.launches += 1
+        self.unit_range = True
+
+    def trunc8(self) -> None:
+        self._add(_lib.OP_TRUNC8)
+        self.launches += 1
+        self.unit_range = True
+
+    def resize_raw(self, mode_id: int, oh: int, ow: int, clamp: bool) -> None:
+        """degradations._resize_call with an explicit mode id (the aliasing stage's legacy nearest, no clamp)."""
+        self._resize(mode_id, int(oh), int(ow), clamp)
+
     # -- execution ----------------------------------------------------------------------------
     def run(self, crop: tuple[Tensor, int, int, int, int] | None = None) -> Tensor | tuple[Tensor, Tensor]:
         """Launch the recorded stages.  Returns the final image, or with ``crop=(gt, gt_patch, scale, top, left)``
