@@ -66,16 +66,30 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
     float* sk = sk_all[warp];
     for (int kb = blockIdx.x * kAnalyseWarps + warp; kb < kernel_batch; kb += kAnalyseWarps * kAnalyseCluster) {
         const float* kp = kern + (size_t)kb * n;
+        // a lane's taps (idx = lane + 32 t, t < 14 covers 21 x 21) live in registers: the 14 global loads are independent
+        // (one round trip instead of 14 serialised ones — the launch sits on the chain's critical path in front of blur1)
+        // and the passes below reuse value, ring and position without re-deriving them
+        constexpr int NIT = 14;
+        float tv[NIT];
+        int ti[NIT], tj[NIT];
+#pragma unroll
+        for (int t = 0; t < NIT; ++t) {
+            const int idx = lane + 32 * t;
+            tv[t] = idx < n ? __ldg(kp + idx) : 0.0f;
+            ti[t] = idx / K;
+            tj[t] = idx - ti[t] * K;
+        }
         int r = 0, imax = 0;
-        float amax = 0.0f;
-        for (int idx = lane; idx < n; idx += 32) {
-            const float v = kp[idx];
-            sk[idx] = v;
-            if (v != 0.0f) {
-                const int i = idx / K, j = idx - i * K;
-                r = max(r, max(abs(i - c), abs(j - c)));
+        float amax = 0.0f, tot = 0.0f;
+#pragma unroll
+        for (int t = 0; t < NIT; ++t) {
+            const int idx = lane + 32 * t;
+            if (idx < n) {
+                sk[idx] = tv[t];
+                if (tv[t] != 0.0f) r = max(r, max(abs(ti[t] - c), abs(tj[t] - c)));
+                if (fabsf(tv[t]) > amax) { amax = fabsf(tv[t]); imax = idx; }
+                tot += fabsf(tv[t]);
             }
-            if (fabsf(v) > amax) { amax = fabsf(v); imax = idx; }
         }
         r = __reduce_max_sync(0xffffffffu, r);
         // EFFECTIVE support: outer rings whose taps add up to less than trim_tol * sum|w| are dropped.  A sigma = 1 Gaussian
@@ -84,18 +98,14 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
         // (2e-7 for a normalised kernel on [0,1] pixels — the size of fp32 summation-order noise, 50x inside the 1e-5 bar)
         // and shrinks the K^2 loop to the part of the kernel that matters.  trim_tol = 0 (OTF_F2D_TRIM=0) keeps every tap.
         if (trim_tol > 0.0f && r > 0) {
-            __syncwarp();
-            float tot = 0.0f;
-            for (int idx = lane; idx < n; idx += 32) tot += fabsf(sk[idx]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
             float dropped = 0.0f;
             for (int ring = r; ring >= 1; --ring) {
                 float rs = 0.0f;
-                for (int idx = lane; idx < n; idx += 32) {
-                    const int i = idx / K, j = idx - i * K;
-                    if (max(abs(i - c), abs(j - c)) == ring) rs += fabsf(sk[idx]);
-                }
+#pragma unroll
+                for (int t = 0; t < NIT; ++t)
+                    if (lane + 32 * t < n && max(abs(ti[t] - c), abs(tj[t] - c)) == ring) rs += fabsf(tv[t]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
                 if (dropped + rs > trim_tol * tot) break;
@@ -113,16 +123,19 @@ __global__ void __cluster_dims__(kAnalyseCluster, 1, 1) __launch_bounds__(kAnaly
         const int pi = imax / K, pj = imax - pi * K;
         const float piv = sk[imax];
         bool ok = amax > 0.0f, sym = true;
-        for (int idx = lane; idx < n; idx += 32) {
-            const int i = idx / K, j = idx - i * K;
-            const float kij = sk[idx];
-            if (ok) {
-                const float sep = sk[i * K + pj] * __fdiv_rn(sk[pi * K + j], piv);
-                ok = fabsf(kij - sep) <= 4e-7f * fabsf(kij) + 1e-9f * amax;
+#pragma unroll
+        for (int t = 0; t < NIT; ++t) {
+            if (lane + 32 * t < n) {
+                const int i = ti[t], j = tj[t];
+                const float kij = tv[t];
+                if (ok) {
+                    const float sep = sk[i * K + pj] * __fdiv_rn(sk[pi * K + j], piv);
+                    ok = fabsf(kij - sep) <= 4e-7f * fabsf(kij) + 1e-9f * amax;
+                }
+                // left-right mirror symmetry, K[i][j] == K[i][K-1-j] bit for bit (every isotropic family and the sinc
+                // kernels are: the generators evaluate a function of x^2): such kernels take the horizontal fold
+                sym = sym && (kij == sk[i * K + (K - 1 - j)]);
             }
-            // left-right mirror symmetry, K[i][j] == K[i][K-1-j] bit for bit (every isotropic family and the sinc kernels
-            // are: the generators evaluate a function of x^2): such kernels are evaluated with the horizontal fold
-            sym = sym && (kij == sk[i * K + (K - 1 - j)]);
         }
         ok = __all_sync(0xffffffffu, ok);
         sym = __all_sync(0xffffffffu, sym);
