@@ -173,11 +173,13 @@ def test_degrade_with_injected_fields_matches(dev):
         outs.append(feed.degrade(d["gt"], d["kernel1"], d["kernel2"], d["sinc_kernel"], plan, inject))
     assert outs[0].shape == (b, 3, size // 4, size // 4)
     assert torch.equal(outs[0], outs[1])
-    # and against the oracle, at the chain's end-to-end bar (within 1 LSB on >= 99 % of pixels)
+    # and against the oracle, at the chain's end-to-end bar (within 1 LSB on >= 99.9 % of pixels)
     _, want = O.run_chain_b(d["gt"].cpu(), d["kernel1"].cpu(), d["kernel2"].cpu(), d["sinc_kernel"].cpu(), plan,
                             {k: v.cpu() for k, v in inject.items()})
     diff = (outs[1].cpu()[:, :, :16, :16] - want).abs()
-    assert (diff <= 1 / 255 + 1e-6).float().mean().item() >= 0.99
+    frac_ok = (diff <= 1 / 255 + 1e-6).float().mean().item()
+    print(f"[lsb] native degrade vs oracle: {frac_ok*100:.3f}%")
+    assert frac_ok >= 0.999
 
 
 def test_clean_pass_through_raises_like_the_reference_above_scale_1(dev):

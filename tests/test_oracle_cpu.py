@@ -132,7 +132,7 @@ def test_clamp_round_crop_and_chain(golden):
              "noise2_counts_gray": g["chain_cg2"]}
     gt_c, lq_c = O.run_chain_b(g["chain_gt"], g["chain_k1"], g["chain_k2"], g["chain_sinc"], plan, noise)
     assert torch.equal(gt_c, g["chain_gt_crop"])
-    lsb(lq_c, g["chain_lq"], 0.99)
+    lsb(lq_c, g["chain_lq"], 0.999)
     with pytest.raises(ValueError):
         O.paired_crop(g["chain_gt"], g["chain_lq_full"][:, :, :15], 48, 4, 0, 0)
 

@@ -280,7 +280,7 @@ def test_chain_b_golden_end_to_end(golden, dev):
     assert torch.equal(feed.gt.cpu(), g["chain_gt_crop"])
     # the Poisson counts were drawn for the oracle's lambda; a JPEG rounding flip upstream changes a few
     # pixels, so the end-to-end bar on this 2x3x12x12 crop is "within 1 LSB on >= 99 %" (<= 8 pixels)
-    assert_lsb(feed.lq, g["chain_lq"], what="chain LQ", frac=0.99)
+    assert_lsb(feed.lq, g["chain_lq"], what="chain LQ", frac=0.999)
 
 
 @pytest.mark.parametrize("order", ["classic", "fork"])
@@ -340,7 +340,7 @@ def test_feed_random_plans_vs_oracle(order, seed, dev):
     inject = {k: v.to(dev) for k, v in noise.items()}
     feed = RealESRGANFeed(opt, device=dev, use_pool=False)
     feed.feed_data({"gt": gt, "kernel1": k1, "kernel2": k2, "sinc_kernel": sk}, plan=plan, inject=inject)
-    ok, diff = assert_lsb(feed.lq, want, what=f"{order} seed={seed} plan={ {k: v for k, v in plan.items() if not torch.is_tensor(v)} }", frac=0.99)
+    ok, diff = assert_lsb(feed.lq, want, what=f"{order} seed={seed} plan={ {k: v for k, v in plan.items() if not torch.is_tensor(v)} }", frac=0.999)
     assert tuple(feed.lq.shape) == (b, 3, 24, 24) and tuple(feed.gt.shape) == (b, 3, 96, 96)
 
 
