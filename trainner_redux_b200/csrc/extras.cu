@@ -12,6 +12,8 @@
 // fma(-step, n-1-i, 1) above it; grid_sample's unnormalise = fma(g + 1, size / 2, -0.5); bilinear sum =
 // fma chain nw, ne, sw, se.  One ulp of a source coordinate at x >= 128 is 1.5e-5 of a pixel, so anything
 // looser than that would show up against the 1e-5 bar on noisy images.
+#include <stdlib.h>
+
 #include "otf_common.cuh"
 
 namespace otf {
@@ -41,27 +43,42 @@ struct WarpParams {
     float step_h, step_w;  // linspace steps 2/(H-1), 2/(W-1) as fp32
 };
 
+// The four taps of one bilinear sample with zeros padding, split from the per-channel gather: offsets (clamped into the
+// plane so that every load can issue unconditionally), in-bounds flags and weights are per POSITION, and the C channels
+// of a pixel share them — the loads of all channels are independent and in flight together.
+struct BilinearTaps {
+    int o00, o01, o10, o11;
+    bool m00, m01, m10, m11;
+    float nw, ne, sw, se;
+    __device__ __forceinline__ BilinearTaps(int H, int W, float x, float y) {
+        const float xw = floorf(x), yn = floorf(y);
+        const float xe = __fadd_rn(xw, 1.0f), ys = __fadd_rn(yn, 1.0f);
+        const float wxe = __fsub_rn(xe, x), wxw = __fsub_rn(x, xw), wys = __fsub_rn(ys, y), wyn = __fsub_rn(y, yn);
+        nw = __fmul_rn(wxe, wys), ne = __fmul_rn(wxw, wys), sw = __fmul_rn(wxe, wyn), se = __fmul_rn(wxw, wyn);
+        const int ix = (int)xw, iy = (int)yn;
+        const bool x0 = ix >= 0 && ix < W, x1 = ix + 1 >= 0 && ix + 1 < W, y0 = iy >= 0 && iy < H, y1 = iy + 1 >= 0 && iy + 1 < H;
+        const int cx0 = min(max(ix, 0), W - 1), cx1 = min(max(ix + 1, 0), W - 1);
+        const int cy0 = min(max(iy, 0), H - 1) * W, cy1 = min(max(iy + 1, 0), H - 1) * W;
+        o00 = cy0 + cx0, o01 = cy0 + cx1, o10 = cy1 + cx0, o11 = cy1 + cx1;
+        m00 = x0 && y0, m01 = x1 && y0, m10 = x0 && y1, m11 = x1 && y1;
+    }
+    __device__ __forceinline__ float sample(const float* __restrict__ pl) const {
+        const float va = __ldg(pl + o00), vb = __ldg(pl + o01), vc = __ldg(pl + o10), vd = __ldg(pl + o11);
+        const float a = m00 ? va : 0.0f, b = m01 ? vb : 0.0f, c = m10 ? vc : 0.0f, d = m11 ? vd : 0.0f;
+        float r = __fmul_rn(a, nw);
+        r = __fmaf_rn(b, ne, r);
+        r = __fmaf_rn(c, sw, r);
+        return __fmaf_rn(d, se, r);
+    }
+};
 __device__ __forceinline__ float bilinear_zero(const float* __restrict__ pl, int H, int W, float x, float y) {
-    const float xw = floorf(x), yn = floorf(y);
-    const float xe = __fadd_rn(xw, 1.0f), ys = __fadd_rn(yn, 1.0f);
-    const float wxe = __fsub_rn(xe, x), wxw = __fsub_rn(x, xw), wys = __fsub_rn(ys, y), wyn = __fsub_rn(y, yn);
-    const float nw = __fmul_rn(wxe, wys), ne = __fmul_rn(wxw, wys), sw = __fmul_rn(wxe, wyn), se = __fmul_rn(wxw, wyn);
-    const int ix = (int)xw, iy = (int)yn;
-    const bool x0 = ix >= 0 && ix < W, x1 = ix + 1 >= 0 && ix + 1 < W, y0 = iy >= 0 && iy < H, y1 = iy + 1 >= 0 && iy + 1 < H;
-    const float a = (x0 && y0) ? __ldg(pl + (size_t)iy * W + ix) : 0.0f;
-    const float b = (x1 && y0) ? __ldg(pl + (size_t)iy * W + ix + 1) : 0.0f;
-    const float c = (x0 && y1) ? __ldg(pl + (size_t)(iy + 1) * W + ix) : 0.0f;
-    const float d = (x1 && y1) ? __ldg(pl + (size_t)(iy + 1) * W + ix + 1) : 0.0f;
-    float r = __fmul_rn(a, nw);
-    r = __fmaf_rn(b, ne, r);
-    r = __fmaf_rn(c, sw, r);
-    return __fmaf_rn(d, se, r);
+    return BilinearTaps(H, W, x, y).sample(pl);
 }
 
 // thread = output pixel (j fastest); loops over the C channels of its sample.  One instantiation per mode: the
 // three grids share little code, and a mode-specific kernel needs two thirds of the registers of the combined one.
 template <int MODE>
-__global__ void __launch_bounds__(256, 8) warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W,
+__global__ void __launch_bounds__(256, 6) warp_kernel(const float* __restrict__ img, float* __restrict__ out, int C, int H, int W,
                                                    WarpParams p) {
     // 16 x 16 output tile per CTA: the lens grid samples the TRANSPOSED position (see below), so a flat row of threads
     // would read one source column (32 sectors per load); a square tile touches a square source patch either way
@@ -103,7 +120,63 @@ __global__ void __launch_bounds__(256, 8) warp_kernel(const float* __restrict__ 
         gy = lh;
     }
     const float x = gs_reflect_clip(gs_unnormalise(gx, W), W), y = gs_reflect_clip(gs_unnormalise(gy, H), H);
-    for (int c = 0; c < C; ++c) op[c * plane] = bilinear_zero(ip + c * plane, H, W, x, y);
+    const BilinearTaps taps(H, W, x, y);
+    if (C == 3) {
+        const float v0 = taps.sample(ip), v1 = taps.sample(ip + plane), v2 = taps.sample(ip + 2 * plane);
+        op[0] = v0, op[plane] = v1, op[2 * plane] = v2;
+        return;
+    }
+    for (int c = 0; c < C; ++c) op[c * plane] = taps.sample(ip + c * plane);
+}
+
+// Lens distortion, coalesced on both sides.  The reference's grid samples the TRANSPOSED position (output (i, j) reads the
+// source near column i, row j), so with a thread per output pixel in row-major order a warp reads one source COLUMN
+// (up to 32 sectors per load) — the gather was bound by L1 sector throughput at 0.17 of the HBM roof.  Here a CTA owns a
+// 32 x 32 output tile and walks it column-major for the gathers (lanes = consecutive output ROWS = consecutive source
+// columns: 4 sectors per load), parks the results in a shared-memory tile, and writes the tile out row-major.  The per-pixel
+// arithmetic is warp_kernel<OTF_WARP_LENS>'s, operation for operation.
+// (one output per thread; 32 rows x 16 columns per 512-thread CTA at <= 40 registers, three CTAs = 48 warps resident: the
+// gather is latency-bound — a 256-thread x 4-output version at 94 / 64 registers measured 0.087 / 0.064 ms, 1024 threads
+// capped at 32 registers 0.079 ms)
+constexpr int LENS_TI = 32, LENS_TJ = 16;
+__global__ void __launch_bounds__(LENS_TI * LENS_TJ, 3) warp_lens_tile_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                                                              int C, int H, int W, WarpParams p) {
+    __shared__ float tile[3][LENS_TI][LENS_TJ + 1];
+    const int i0 = blockIdx.y * LENS_TI, j0 = blockIdx.x * LENS_TJ, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const size_t plane = (size_t)H * W;
+    const float* ip = img + (size_t)b * C * plane;
+    float* op = out + (size_t)b * C * plane;
+    float sx, sy;  // source coordinates of output (i0 + lane, j0 + wrp)
+    {
+        const int i = min(i0 + lane, H - 1), j = min(j0 + wrp, W - 1);
+        const float lh = linspace_pm1(i, H, p.step_h), lw = linspace_pm1(j, W, p.step_w);
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(lh, lh), __fmul_rn(lw, lw)));
+        float rd = __fmul_rn(r, __fadd_rn(1.0f, __fmul_rn(p.p0, __fmul_rn(r, r))));
+        float rr = r;
+        if (r == 0.0f) { rd = 0.0f; rr = 1e-6f; }
+        const float ratio = __fdiv_rn(rd, rr);
+        sx = gs_reflect_clip(gs_unnormalise(__fmul_rn(lh, ratio), W), W);
+        sy = gs_reflect_clip(gs_unnormalise(__fmul_rn(lw, ratio), H), H);
+    }
+    const BilinearTaps taps(H, W, sx, sy);
+    const int ti = threadIdx.x / LENS_TJ, tj = threadIdx.x % LENS_TJ;  // store phase: 16 consecutive columns of two rows per warp
+    const int oi = i0 + ti, oj = j0 + tj;
+    const bool store = oi < H && oj < W;
+    for (int c0 = 0; c0 < C; c0 += 3) {  // three channels per barrier pair
+        const int nc = min(3, C - c0);
+        if (nc == 3) {  // twelve independent loads in flight
+            const float* q = ip + c0 * plane;
+            const float v0 = taps.sample(q), v1 = taps.sample(q + plane), v2 = taps.sample(q + 2 * plane);
+            tile[0][lane][wrp] = v0, tile[1][lane][wrp] = v1, tile[2][lane][wrp] = v2;  // [row i][col j]
+        } else {
+            for (int c = 0; c < nc; ++c) tile[c][lane][wrp] = taps.sample(ip + (c0 + c) * plane);
+        }
+        __syncthreads();
+        if (store)
+            for (int c = 0; c < nc; ++c) op[(c0 + c) * plane + (size_t)oi * W + oj] = tile[c][ti][tj];
+        if (c0 + 3 < C) __syncthreads();
+    }
 }
 
 // ---- small correlation with ZERO padding (F.conv2d(padding=K//2, groups=C)) ------------------------
@@ -364,7 +437,10 @@ extern "C" int otf_warp_f32(const float* img, int B, int C, int H, int W, int mo
     p.step_w = 2.0f / (float)(W - 1);
     const dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == OTF_WARP_LENS) warp_kernel<OTF_WARP_LENS><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
+    static const bool lens_flat = getenv("OTF_LENS_FLAT") != nullptr;  // A/B switch: the thread-per-pixel kernel
+    if (mode == OTF_WARP_LENS && !lens_flat)
+        warp_lens_tile_kernel<<<dim3(ceil_div(W, LENS_TJ), ceil_div(H, LENS_TI), B), LENS_TI * LENS_TJ, 0, st>>>(img, out, C, H, W, p);
+    else if (mode == OTF_WARP_LENS) warp_kernel<OTF_WARP_LENS><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
     else if (mode == OTF_WARP_SHUTTER) warp_kernel<OTF_WARP_SHUTTER><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
     else warp_kernel<OTF_WARP_CHROMA><<<grid, 256, 0, st>>>(img, out, C, H, W, p);
     OTF_LAUNCH_CHECK("warp_kernel");
