@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OTF_ABI_VERSION 3  /* 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
+#define OTF_ABI_VERSION 4  /* 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
 
 enum {
     OTF_OK = 0,
@@ -233,6 +233,27 @@ int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
 /* uint8 image -> fp32 / 255 (the host-side normalisation of traiNNer/utils/img_util.py:65-109 `img2tensor`,
  * moved behind a 4x smaller upload). */
 int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* stream);
+
+/* ---- side-stream prefetcher — traiNNer/data/prefetch_dataloader.py:418-499 (`CUDAPrefetcher.preload` / `.next`) ----
+ * One upload step: [ev_consumed is recorded on consumer_stream and copy_stream waits for it — the destination slots
+ * may still be read by what the consumer has issued so far (pass NULL to skip)]; n plain cudaMemcpyAsync host->device
+ * on copy_stream (n <= 64; pinned sources for a truly asynchronous copy); ev_ready recorded on copy_stream.  The
+ * consumer later orders itself behind the upload with otf_stream_wait_event(consumer_stream, ev_ready) — the
+ * `wait_stream` of prefetch_dataloader.py:488-493.  Events are plain CUDA events with timing disabled, owned by the
+ * caller; otf_event_query sets *done to 1 when everything recorded before the event has completed, else 0. */
+int otf_event_create(void** event);
+int otf_event_destroy(void* event);
+int otf_event_query(void* event, int* done);
+int otf_stream_wait_event(void* stream, void* event);
+int otf_upload_async(int n, void* const* dst_dev, const void* const* src_host, const uint64_t* bytes,
+                     void* copy_stream, void* consumer_stream, void* ev_consumed, void* ev_ready);
+/* The mirror image for a step's result (the `.cpu()` / `.item()` reads of a training loop, e.g. the images
+ * traiNNer/models/sr_model.py `get_current_visuals` pulls back): ev_produced is recorded on producer_stream, copy_stream
+ * waits for it, one cudaMemcpyAsync device->host (pinned destination), ev_done recorded on copy_stream.
+ * otf_event_synchronize blocks the calling host thread until the event has completed. */
+int otf_download_async(void* dst_host, const void* src_dev, uint64_t bytes,
+                       void* copy_stream, void* producer_stream, void* ev_produced, void* ev_done);
+int otf_event_synchronize(void* event);
 
 /* Strided (e.g. channels_last) -> dense NCHW copy; strides in elements. */
 int otf_copy_strided_f32(const float* src, const int64_t strides[4],

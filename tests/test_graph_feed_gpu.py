@@ -137,3 +137,23 @@ def test_uint8_gt_through_the_prefetcher(dev):
         ref.feed_data(dict(d, gt=d8["gt"].float() / 255.0))
         assert torch.equal(feed.lq, ref.lq) and torch.equal(feed.gt, ref.gt)
         batch = pf.next()
+
+
+def test_readback_side_stream(dev):
+    """CUDAReadback: the values that land in the pinned ring are the tensor's at the time of the call, even when the
+    producer overwrites the device buffer two calls later (static outputs of a captured chain)."""
+    from trainner_redux_b200.prefetch import CUDAReadback
+
+    rb = CUDAReadback(dev, depth=2)
+    buf = [torch.empty(3, 64, 64, device=dev) for _ in range(2)]
+    hosts = []
+    for i in range(6):
+        buf[i % 2].fill_(float(i))
+        h = rb.read(buf[i % 2])
+        assert h.is_pinned() and h.shape == buf[0].shape
+        hosts.append((i, h))
+        if i >= 1:  # the ring is two deep: the previous result is still intact after this call
+            rb.wait()
+            assert torch.all(hosts[-1][1] == float(i)) and torch.all(hosts[-2][1] == float(i - 1))
+    with pytest.raises(RuntimeError):
+        rb.read(torch.zeros(4))

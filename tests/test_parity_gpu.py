@@ -415,6 +415,14 @@ def test_kernel_synthesis_on_gpu(golden, dev):
     b = RealESRGANFeed(opt, device=dev, manual_seed=1, use_pool=False)
     b.feed_data({"gt": gt, "kernel1": g["ks_ds_k1"], "kernel2": g["ks_ds_k2"], "sinc_kernel": g["ks_ds_sinc"]})
     assert (a.lq - b.lq).abs().max().item() <= 1 / 255 + 1e-6
+    # ... and as ONE stacked (3, B, 8) table (one upload, one synthesis launch): bit-identical to the three tables
+    c = RealESRGANFeed(opt, device=dev, manual_seed=1, use_pool=False)
+    stacked = torch.as_tensor(np.stack(prm), dtype=torch.float64)
+    for _ in range(3):  # host table, then the same device table twice (cached output buffer, captured chain)
+        c.rng = type(c.rng)(1, 0)
+        c.feed_data({"gt": gt, "kernel_params": stacked})
+        assert torch.equal(c.lq, a.lq) and torch.equal(c.gt, a.gt)
+        stacked = stacked.to(dev)
 
 
 def test_paired_feed_second_caller(dev):

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0
-ABI_VERSION = 3  # 3: OtfStage.f2 + the fork-extra ops of the stage executor; 2: device-side Philox offset word / crop offsets, OtfStage.p4
+ABI_VERSION = 4  # 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2 + the fork-extra ops of the stage executor; 2: device-side Philox offset word / crop offsets, OtfStage.p4
 RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST, RESIZE_LANCZOS = range(7)
 WARP_LENS, WARP_SHUTTER, WARP_CHROMA = range(3)
 TAPS_NONE, TAPS_OVERSHARPEN = 0, 1
@@ -56,6 +56,13 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_clamp_round_f32": (_i, [_p, _i64, _p, _p]),
     "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
     "otf_u8_to_f32": (_i, [_p, _i64, _p, _p]),
+    "otf_event_create": (_i, [_p]),
+    "otf_event_destroy": (_i, [_p]),
+    "otf_event_query": (_i, [_p, _p]),
+    "otf_stream_wait_event": (_i, [_p, _p]),
+    "otf_upload_async": (_i, [_i, _p, _p, _p, _p, _p, _p, _p]),
+    "otf_download_async": (_i, [_p, _p, _u64, _p, _p, _p, _p]),
+    "otf_event_synchronize": (_i, [_p]),
     "otf_copy_strided_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "otf_synth_kernels_f32": (_i, [_p, _i, _p, _p]),
     "otf_gather_slots_f32": (_i, [_p, _p, _i, _i64, _p, _p]),

@@ -33,11 +33,12 @@ class ParamBlock:
         # may be refilled for the next step while this step's copy is still queued (a pinned source could not)
         self.host = torch.zeros(nbytes, dtype=torch.uint8)
         self.dev = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        self._off = self.host[:8].view(torch.int64)
-        self._crop = self.host[8:16].view(torch.int32)
         self._rows = self.host[HEADER_BYTES:].view(torch.float32).view(max_rows, b)
+        self._views: tuple | None = None
+        self._hdr = self.host[:HEADER_BYTES].numpy().view("int64"), self.host[:HEADER_BYTES].numpy().view("int32")
         self.rows = 0  # rows in use
         self.noise_stages = 0  # Philox offsets one pass of the chain consumes
+        self.sources: list[Any] = []  # what went into each row, in order (the capture turns it into a fill recipe)
 
     # -- addresses the stage records point at --------------------------------------------------
     @property
@@ -55,6 +56,7 @@ class ParamBlock:
     def begin(self) -> None:
         self.rows = 0
         self.noise_stages = 0
+        self.sources = []
 
     def add_row(self, v: float | Tensor) -> int:
         """Append one per-sample vector (or a scalar broadcast over the batch); returns its device address."""
@@ -66,6 +68,7 @@ class ParamBlock:
         else:
             self._rows[r].copy_(v.reshape(self.b))
         self.rows += 1
+        self.sources.append(v)
         return self.row_ptr(r)
 
     def next_noise_index(self) -> int:
@@ -74,13 +77,23 @@ class ParamBlock:
         return k
 
     def set_header(self, philox_offset: int, top: int, left: int) -> None:
-        self._off[0] = philox_offset
-        self._crop[0] = top
-        self._crop[1] = left
+        q, d = self._hdr  # numpy views of the same bytes (a scalar store into a torch tensor costs ~10x as much)
+        q[0] = philox_offset
+        d[2] = top
+        d[3] = left
 
     def upload(self) -> None:
         n = HEADER_BYTES + 4 * self.b * self.rows
-        self.dev[:n].copy_(self.host[:n], non_blocking=True)
+        if self._views is None or self._views[0] != n:
+            self._views = (n, self.dev[:n], self.host[:n], [self._rows[r] for r in range(self.rows)])
+        self._views[1].copy_(self._views[2], non_blocking=True)
+
+    def row_views(self) -> list[Tensor]:
+        """Host views of the rows in use (built once per layout: indexing a tensor costs more than filling 64 floats)."""
+        n = HEADER_BYTES + 4 * self.b * self.rows
+        if self._views is None or self._views[0] != n:
+            self._views = (n, self.dev[:n], self.host[:n], [self._rows[r] for r in range(self.rows)])
+        return self._views[3]
 
 
 class ParamCollector:
@@ -177,9 +190,32 @@ class ChainGraph:
         self.launches = 0
         self.noise_stages = 0
         self.rows = 0
-        self.last_stream = 0
-        self.done: torch.cuda.Event | None = None
+        self.last_stream: int | None = None  # raw handle of the stream of the last replay (None: never replayed)
         self.keep: Any = None  # the stage list of the capture: owns the host tap arrays / tensors the launches point into
+        # fill recipe: for each row of the parameter block, where in a plan its vector comes from — (key, sub) for
+        # plan[key][sub], (key, None) for plan[key].  None = unknown, walk the chain with a ParamCollector instead
+        self.recipe: list[tuple[str, str | None]] | None = None
+
+
+def fill_recipe(plan: dict, sources: list) -> list[tuple[str, str | None]] | None:
+    """Match the tensors a capture put into its parameter block against the plan they came from (by identity)."""
+    where: dict[int, tuple[str, str | None]] = {}
+    for key in ("noise1", "noise2"):
+        st = plan.get(key)
+        if isinstance(st, dict):
+            for sub, v in st.items():
+                if isinstance(v, Tensor):
+                    where[id(v)] = (key, sub)
+    for key in ("jpeg1", "jpeg2", "jpeg"):
+        v = plan.get(key)
+        if isinstance(v, Tensor):
+            where[id(v)] = (key, None)
+    out = []
+    for v in sources:
+        if not isinstance(v, Tensor) or id(v) not in where:
+            return None
+        out.append(where[id(v)])
+    return out
 
 
 class ChainGraphCache:

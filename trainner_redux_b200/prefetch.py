@@ -12,15 +12,25 @@ the following one, ``reset()`` restarts the loader.  Two differences, both on pu
   * nothing is converted on the way: a ``uint8`` GT batch stays ``uint8`` (a quarter of the PCIe bytes; ``feed_data``
     normalises it on the device), fp32 stays fp32 — the reference's format.
 
+The upload step itself is ONE library call (``otf_upload_async``, csrc/hostrt.cu): order the copy stream behind the
+consumer, one ``cudaMemcpyAsync`` per tensor, record the batch's "ready" event — the Python-level stream context,
+``wait_stream`` pair and per-tensor ``copy_`` of the first version cost more host time than the whole chain's launch.
+Host batches are kept referenced until their copies have completed (the raw copies are invisible to torch's pinned
+memory allocator).
+
 No error swallowing / retry logic: worker failures are the loader's business (out of scope).
 """
 
 from __future__ import annotations
 
+import ctypes as C
+from collections import deque
 from typing import Any, Iterable
 
 import torch
 from torch import Tensor
+
+from . import _lib
 
 
 class CUDAPrefetcher:
@@ -30,50 +40,103 @@ class CUDAPrefetcher:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("CUDAPrefetcher uploads to a CUDA device")
+        _lib.load()
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream(self.device)
+        self._copy_stream = C.c_void_p(self.stream.cuda_stream)
         self.slots = max(2, int(slots))
         self._bufs: dict[tuple, list[Tensor]] = {}
         self._turn = 0
+        with torch.cuda.device(self.device):
+            self._ready = [self._new_event() for _ in range(self.slots)]  # per slot: its upload has been issued up to here
+            self._consumed = self._new_event()
+        self._hold: deque[tuple[int, Any]] = deque()  # (slot, host batch) until the slot's copies have completed
+        self._pending: int | None = None  # slot of the batch waiting to be handed out
         self.batch: dict | None = None
         self.h2d_bytes = 0  # bytes of the batch being handed out (bench.py reports it)
+        self._next_bytes = 0
         self.preload()
 
+    @staticmethod
+    def _new_event() -> C.c_void_p:
+        ev = C.c_void_p()
+        _lib.call("otf_event_create", C.byref(ev))
+        return ev
+
+    def __del__(self) -> None:
+        try:
+            for ev in [*getattr(self, "_ready", []), getattr(self, "_consumed", None)]:
+                if ev is not None:
+                    _lib.call("otf_event_destroy", ev)
+        except Exception:  # noqa: BLE001  interpreter shutdown
+            pass
+
     def _slot(self, key: str, v: Tensor) -> Tensor:
-        k = (key, tuple(v.shape), v.dtype)
+        k = (key, v.shape, v.dtype)
         ring = self._bufs.get(k)
         if ring is None:
             ring = self._bufs[k] = [torch.empty(v.shape, dtype=v.dtype, device=self.device) for _ in range(self.slots)]
         return ring[self._turn % self.slots]
 
-    def _upload(self, key: str, v: Any) -> Any:
+    def _stage(self, key: str, v: Any, todo: list) -> Any:
+        """The device-side stand-in of one batch entry; host tensors are appended to ``todo`` as (dst, src)."""
         if isinstance(v, Tensor):
             if v.is_cuda:
                 return v
-            self._bytes += v.numel() * v.element_size()
-            return self._slot(key, v).copy_(v, non_blocking=True)
+            if not v.is_contiguous():
+                v = v.contiguous()
+            dst = self._slot(key, v)
+            todo.append((dst, v))
+            return dst
         if isinstance(v, (tuple, list)) and v and all(isinstance(t, Tensor) for t in v):
-            return type(v)(self._upload(f"{key}[{i}]", t) for i, t in enumerate(v))
+            return type(v)(self._stage(f"{key}[{i}]", t, todo) for i, t in enumerate(v))
         return v
+
+    def _release_done(self) -> None:
+        done = C.c_int(0)
+        while self._hold:
+            _lib.call("otf_event_query", self._ready[self._hold[0][0]], C.byref(done))
+            if not done.value:
+                break
+            self._hold.popleft()
+
+    def _issue(self, n: int, dst: Any, src: Any, nbytes: Any, slot: int) -> None:
+        self._release_done()
+        _lib.call("otf_upload_async", n, dst, src, nbytes, self._copy_stream, _lib.stream(), self._consumed, self._ready[slot])
 
     def preload(self) -> None:
         try:
             batch = next(self.loader)
         except StopIteration:
             self.batch = None
+            self._pending = None
             return
+        todo: list[tuple[Tensor, Tensor]] = []
+        self.batch = {k: self._stage(k, v, todo) for k, v in batch.items()}
+        n = len(todo)
+        slot = self._turn % self.slots
+        dst = (C.c_void_p * n)(*[d.data_ptr() for d, _ in todo])
+        src = (C.c_void_p * n)(*[s.data_ptr() for _, s in todo])
+        sizes = [s.numel() * s.element_size() for _, s in todo]
+        nbytes = (C.c_uint64 * n)(*sizes)
         # slot reuse: everything the consumer has issued so far (which includes all work on the batch that last used
-        # this slot, handed out `slots` calls ago) must be done before the copy overwrites it
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        self._bytes = 0
-        with torch.cuda.stream(self.stream):
-            self.batch = {k: self._upload(k, v) for k, v in batch.items()}
-        self._next_bytes = self._bytes
+        # this slot, handed out `slots` calls ago) must be done before the copies overwrite it
+        if torch.cuda.current_device() != self.device.index:  # (multi-device processes only: a context costs microseconds)
+            with torch.cuda.device(self.device):
+                self._issue(n, dst, src, nbytes, slot)
+        else:
+            self._issue(n, dst, src, nbytes, slot)
+        self._hold.append((slot, batch))
+        self._pending = slot
+        self._next_bytes = sum(sizes)
         self._turn += 1
 
     def next(self) -> dict | None:
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)  # prefetch_dataloader.py:488-493
+        if self._pending is not None:  # the caller's stream waits for the upload: prefetch_dataloader.py:488-493
+            _lib.call("otf_stream_wait_event", _lib.stream(), self._ready[self._pending])
         batch = self.batch
-        self.h2d_bytes = getattr(self, "_next_bytes", 0)
+        self.h2d_bytes = self._next_bytes
         self.preload()
         return batch
 
@@ -84,3 +147,59 @@ class CUDAPrefetcher:
             self.ori_loader = loader
         self.loader = iter(self.ori_loader)
         self.preload()
+
+
+class CUDAReadback:
+    """Side-stream device-to-host read of a step's result (what a training loop does with ``.cpu()`` on a loss or a
+    visual, e.g. traiNNer/models/sr_model.py ``get_current_visuals``) that does not sit on the compute stream: the copy
+    runs on a private stream behind the producer, into a ring of pinned host buffers.
+
+    ``read(t)`` first makes the CURRENT stream wait for the previous read — at most one read is in flight, so a device
+    buffer the producer rewrites two or more calls later (the static outputs of a captured chain) is never overwritten
+    under a copy — then issues the copy of ``t`` and returns the pinned host tensor it lands in; ``wait()`` blocks the
+    host until the last read has completed."""
+
+    def __init__(self, device: torch.device | str = "cuda", depth: int = 2) -> None:
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDAReadback reads from a CUDA device")
+        _lib.load()
+        self.stream = torch.cuda.Stream(self.device)
+        self._copy_stream = C.c_void_p(self.stream.cuda_stream)
+        self.depth = max(1, int(depth))
+        self._host: dict[tuple, list[Tensor]] = {}
+        self._turn = 0
+        with torch.cuda.device(self.device):
+            self._produced = CUDAPrefetcher._new_event()
+            self._done = CUDAPrefetcher._new_event()
+        self._issued = False
+
+    def __del__(self) -> None:
+        try:
+            for ev in (getattr(self, "_produced", None), getattr(self, "_done", None)):
+                if ev is not None:
+                    _lib.call("otf_event_destroy", ev)
+        except Exception:  # noqa: BLE001  interpreter shutdown
+            pass
+
+    def read(self, t: Tensor) -> Tensor:
+        _lib.require_cuda(t)
+        if not t.is_contiguous():
+            t = t.contiguous()
+        k = (t.shape, t.dtype)
+        ring = self._host.get(k)
+        if ring is None:
+            ring = self._host[k] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for _ in range(self.depth)]
+        dst = ring[self._turn % self.depth]
+        self._turn += 1
+        cur = _lib.stream()
+        if self._issued:
+            _lib.call("otf_stream_wait_event", cur, self._done)
+        _lib.call("otf_download_async", C.c_void_p(dst.data_ptr()), _lib.ptr(t), t.numel() * t.element_size(), self._copy_stream, cur,
+                  self._produced, self._done)
+        self._issued = True
+        return dst
+
+    def wait(self) -> None:
+        if self._issued:
+            _lib.call("otf_event_synchronize", self._done)

@@ -32,7 +32,7 @@ from torch import Tensor
 
 from . import _lib
 from . import degradations as D
-from .chain_graph import ChainGraph, ChainGraphCache, ParamBlock, ParamCollector, plan_signature
+from .chain_graph import ChainGraph, ChainGraphCache, ParamBlock, ParamCollector, fill_recipe, plan_signature
 from .diffjpeg import DiffJPEG
 from .img_process_util import KernelAnalysis, USMSharp, filter2d
 from .stages import StageList
@@ -419,6 +419,25 @@ class RealESRGANFeed:
         self._synth_out: dict[tuple, Tensor] = {}  # kernel-synthesis outputs per upload slot (feed_data, `kernel_params`)
         self._gt_f32: dict[tuple, Tensor] = {}  # normalised fp32 GT per uint8 upload slot
 
+    def _synth_stacked(self, kp: Tensor) -> tuple[Tensor, Tensor, Tensor]:
+        """(3, B, 8) float64 parameter tables -> three (B, 21, 21) fp32 kernels from one launch.  One output buffer per
+        table address (a prefetcher's static slot), so the kernels' addresses repeat and captured chains are replayed."""
+        if not (kp.is_cuda and kp.dtype == torch.float64 and kp.is_contiguous()):
+            kp = kp.to(self.device, dtype=torch.float64, non_blocking=True).contiguous()
+            hit = None
+        else:
+            hit = self._synth_out.get((kp.data_ptr(), 3))
+        if kp.size(2) != 8:
+            raise ValueError("kernel_params must have shape (3, B, 8)")
+        if hit is None or hit[0].size(0) != kp.size(1):
+            buf = torch.empty((3, kp.size(1), 21, 21), dtype=torch.float32, device=self.device)
+            hit = (buf[0], buf[1], buf[2], buf)
+            if len(self._synth_out) > 64:
+                self._synth_out.clear()
+            self._synth_out[(kp.data_ptr(), 3)] = hit
+        _lib.call("otf_synth_kernels_f32", _lib.ptr(kp), 3 * kp.size(1), _lib.ptr(hit[3]), _lib.stream())
+        return hit[0], hit[1], hit[2]
+
     def _timed(self, name: str, fn: Callable[[], Tensor]) -> Tensor:
         if self.record_stage_fns:
             self.stage_fns[name] = fn  # closure over this call's inputs: bench.py re-launches it in a graph
@@ -576,28 +595,44 @@ class RealESRGANFeed:
         return (gt.data_ptr(), tuple(gt.shape), *((k.data_ptr(), tuple(k.shape)) for k in kernels), sig)
 
     def _fill_params(self, entry: ChainGraph, b: int, h: int, w: int, kernels: Sequence[Tensor], plan: dict) -> None:
-        """This step's numbers into the chain's parameter block (walks the same branches as the capture did)."""
-        pc = ParamCollector(entry.params, b, h, w)
-        self._record(pc, *kernels, plan)  # type: ignore[arg-type]
-        if (entry.params.rows, entry.params.noise_stages) != (entry.rows, entry.noise_stages):
-            raise RuntimeError("captured chain and plan disagree about the parameter block layout")  # signature bug
+        """This step's numbers into the chain's parameter block.  A chain whose rows all came from the plan's own
+        per-sample vectors has a fill recipe (chain_graph.fill_recipe): row r <- plan[key][sub]; anything else walks the
+        same branches as the capture did with a ParamCollector."""
+        params = entry.params
+        filled = False
+        if entry.recipe is not None:
+            try:
+                for row, (key, sub) in zip(params.row_views(), entry.recipe):
+                    v = plan[key]
+                    row.copy_(v if sub is None else v[sub])
+                filled = True
+            except (KeyError, TypeError, RuntimeError):  # a hand-made plan with other shapes / scalars: the general walk
+                filled = False
+        if not filled:
+            pc = ParamCollector(params, b, h, w)
+            self._record(pc, *kernels, plan)  # type: ignore[arg-type]
+            if (params.rows, params.noise_stages) != (entry.rows, entry.noise_stages):
+                raise RuntimeError("captured chain and plan disagree about the parameter block layout")  # signature bug
         top, left = plan["crop"]
-        entry.params.set_header(self.rng.philox.offset, top, left)
+        params.set_header(self.rng.philox.offset, top, left)
         self.rng.philox.offset += entry.noise_stages
         cur = _lib.stream().value or 0
-        if entry.done is not None and entry.last_stream != cur:
-            torch.cuda.current_stream().wait_event(entry.done)  # the block must not change under a replay still in flight
-        entry.last_stream = cur
-        entry.params.upload()
+        if entry.last_stream != cur:
+            # the block (and the chain's buffers) must not change under a replay still in flight on another stream: an
+            # event recorded on that stream NOW covers the replay issued there earlier (recording one after every
+            # replay, for the rare caller that hops streams, cost every step a stream lookup and an event record)
+            if entry.last_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.ExternalStream(entry.last_stream, device=self.device) if entry.last_stream
+                          else torch.cuda.default_stream(self.device))
+                torch.cuda.current_stream().wait_event(ev)
+            entry.last_stream = cur
+        params.upload()
 
     def _replay(self, entry: ChainGraph) -> tuple[Tensor, Tensor]:
-        assert entry.graph is not None and entry.gt_out is not None and entry.lq_out is not None
-        entry.graph.replay()
-        if entry.done is None:
-            entry.done = torch.cuda.Event()
-        entry.done.record()
+        entry.graph.replay()  # type: ignore[union-attr]
         _lib.launch_count += entry.launches
-        return entry.gt_out, entry.lq_out
+        return entry.gt_out, entry.lq_out  # type: ignore[return-value]
 
     def _capture(self, key: tuple, gt: Tensor, kernels: Sequence[Tensor], plan: dict) -> ChainGraph | None:
         """Record the chain against a parameter block and capture its launches into a CUDA graph."""
@@ -606,6 +641,7 @@ class RealESRGANFeed:
         try:
             sl = self._record(StageList(gt, params=entry.params), *kernels, plan)  # resize tables are built here, eagerly
             entry.rows, entry.noise_stages = entry.params.rows, entry.params.noise_stages
+            entry.recipe = fill_recipe(plan, entry.params.sources)
             top, left = plan["crop"]
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count
@@ -729,8 +765,14 @@ class RealESRGANFeed:
                         self._synth_out[key] = k
                     return k
 
-                p1, p2, p3 = data["kernel_params"]
-                data = dict(data, kernel1=synth(p1, 0), kernel2=synth(p2, 1), sinc_kernel=synth(p3, 2))
+                kp = data["kernel_params"]
+                if isinstance(kp, Tensor) and kp.dim() == 3 and kp.size(0) == 3:
+                    # the three tables stacked as one (3, B, 8) tensor: one upload, ONE synthesis launch for 3B kernels
+                    k = self._synth_stacked(kp)
+                    data = dict(data, kernel1=k[0], kernel2=k[1], sinc_kernel=k[2])
+                else:
+                    p1, p2, p3 = kp
+                    data = dict(data, kernel1=synth(p1, 0), kernel2=synth(p2, 1), sinc_kernel=synth(p3, 2))
             assert "gt" in data and "kernel1" in data and "kernel2" in data and "sinc_kernel" in data
             gt = data["gt"].to(self.device, non_blocking=True)
             kernel1 = data["kernel1"].to(self.device, non_blocking=True)
