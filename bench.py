@@ -25,9 +25,13 @@ One JSON line on stdout (rank 0):
   value_feed_data              the same loop on ONE stream (what a plain training loop gets);
   value_graph_replay[_one_stream]  bare replays of the same captured chains, no host work per step (upper bounds of the two above);
   pcie_measured_gbs            raw pinned-host <-> device copy bandwidth of this box (the ceiling of e2e);
-  e2e                          feed_data fed by the package's CUDAPrefetcher from pinned HOST fp32 batches (H2D inside the
-                               timed region, LQ read back to the host every step), wall clock;
-  e2e_u8                       the uint8-GT + kernel-parameter upload extension (SURVEY.md §8 f2/f4);
+  e2e                          feed_data fed by the package's CUDAPrefetcher from pinned HOST batches in the dataset's
+                               decoded format — uint8 GT + the (3,B,8) kernel-parameter table (/255 and
+                               kernel synthesis happen on the device) — H2D inside the timed region, LQ read back to pinned
+                               host memory every step (CUDAReadback), `--streams` batches in flight, wall clock;
+  e2e_one_stream               the same loop on ONE stream;
+  e2e_f32                      the same loop fed the reference's host format (fp32 GT + three (B,21,21) kernels,
+                               realesrgan_dataset.py:213-219): 4x the bytes, PCIe-bound;
   roofline                     the dominant kernel (blur1 filter2d) from CUDA-event timings of graph replays;
   cpu_baseline / --impl reference   the oracle port of the reference pipeline on this box's host cores;
   reference_torch_cuda         the same oracle (the reference's own ATen call sequence) run on the CUDA device: PyTorch-eager
@@ -55,7 +59,7 @@ import torch  # noqa: E402
 UNIT = "pairs/s"
 S1, S2 = 0.75, 1.0
 N_ROTATE = int(os.environ.get("OTF_BENCH_ROTATE", "4"))  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
-E2E_SLOTS = int(os.environ.get("OTF_BENCH_E2E_SLOTS", "3"))  # static upload slots of the e2e prefetcher (one captured chain each)
+E2E_SLOTS = int(os.environ.get("OTF_BENCH_E2E_SLOTS", "4"))  # static upload slots of the e2e prefetcher (one captured chain each)
 
 
 _RECORD_OUT = None
@@ -392,7 +396,7 @@ class Arm:
         return self.world * self.wl.batch * steps / (ms_total / 1e3)
 
     # ---- e2e: CUDAPrefetcher (pinned host batches -> static device slots on a copy stream) + feed_data + D2H of the LQ ----
-    def e2e(self, steps: int, warmup: int, u8: bool) -> tuple[float, int, int]:
+    def e2e(self, steps: int, warmup: int, u8: bool, lanes: int = 1) -> tuple[float, int, int]:
         from trainner_redux_b200.prefetch import CUDAPrefetcher, CUDAReadback
 
         wl = self.wl
@@ -413,24 +417,34 @@ class Arm:
 
         pf_box: list = []  # ONE prefetcher for warm-up and timed run: its static slots (and the chains captured on them) persist
 
+        n_slots = lanes * -(-E2E_SLOTS // lanes)  # a multiple of the lane count: a slot (and its captured chain) stays on one lane
+        main = torch.cuda.current_stream()
+        lane = [torch.cuda.Stream(self.dev) for _ in range(lanes)] if lanes > 1 else [main]
+
         def run(n: int) -> int:
             if pf_box:
                 pf_box[0].reset(loader(n))
             else:
-                pf_box.append(CUDAPrefetcher(loader(n), device=self.dev, slots=E2E_SLOTS))
+                pf_box.append(CUDAPrefetcher(loader(n), device=self.dev, slots=n_slots))
             pf = pf_box[0]
-            h2d = 0
+            h2d = t = 0
+            torch.cuda.synchronize()
+            torch.cuda.set_stream(lane[0])  # batch t is handed out, degraded and read back on lane t % lanes
             batch = pf.next()
             while batch is not None:
                 h2d = pf.h2d_bytes
                 self.feed.feed_data(batch, plan=self.plan())
                 rb.read(self.feed.lq)
+                t += 1
+                if lanes > 1:
+                    torch.cuda.set_stream(lane[t % lanes])
                 batch = pf.next()
+            torch.cuda.set_stream(main)
             rb.wait()
             torch.cuda.synchronize()
             return h2d
 
-        run(max(warmup, 2 * E2E_SLOTS))  # (static slots: the chain of each is captured on its second sighting)
+        run(max(warmup, 2 * n_slots))  # (static slots: the chain of each is captured on its second sighting)
         self.barrier()
         t0 = time.perf_counter()
         h2d = run(steps)
@@ -593,8 +607,9 @@ def run_b200(args, wl: Workload) -> None:
     graphs = arm.feed.graphs
     stage_ms = {} if args.no_stage_timing else arm.stage_ms()
 
-    e2e_value, h2d, d2h = arm.e2e(args.steps, args.warmup, u8=False)
-    e2e_u8_value, h2d_u8, _ = arm.e2e(args.steps, args.warmup, u8=True)
+    e2e_f32_value, h2d_f32, d2h = arm.e2e(args.steps, args.warmup, u8=False)
+    e2e_one_value, h2d_u8, _ = arm.e2e(args.steps, args.warmup, u8=True)
+    e2e_value, _, _ = arm.e2e(args.steps, args.warmup, u8=True, lanes=n_streams)
 
     extras = {}
     if not args.no_extras and wl.name == "c2" and wl.noise == "gaussian":
@@ -659,11 +674,14 @@ def run_b200(args, wl: Workload) -> None:
             "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,
             "value_graph_replay_one_stream": arm.pairs_per_s(args.steps, ms_replay1),
             "pcie_measured_gbs": pcie,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "h2d_gbs_per_rank": h2d * e2e_value / world / wl.batch / 1e9},
-            "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
-                       "h2d_gbs_per_rank": h2d_u8 * e2e_u8_value / world / wl.batch / 1e9,
-                       "note": "extension: uint8 GT + kernel-parameter tables uploaded, /255 and kernel synthesis on the device (not the reference's fp32 host format)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                    "h2d_gbs_per_rank": h2d_u8 * e2e_value / world / wl.batch / 1e9,
+                    "feed": "pinned host uint8 GT + (3,B,8) kernel-parameter table (the dataset's decoded format; /255 and kernel "
+                            f"synthesis on the device) -> CUDAPrefetcher -> feed_data -> CUDAReadback of the LQ, {n_streams} batches in flight"},
+            "e2e_one_stream": {"value": e2e_one_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h},
+            "e2e_f32": {"value": e2e_f32_value, "unit": UNIT, "h2d_bytes_per_step": h2d_f32, "d2h_bytes_per_step": d2h,
+                        "h2d_gbs_per_rank": h2d_f32 * e2e_f32_value / world / wl.batch / 1e9,
+                        "feed": "the reference's host format: pinned fp32 GT + three (B,21,21) kernels (PCIe-bound: 4x the bytes)"},
             "gpu_launches": launches,
             "clocks": sampler.stop() if sampler else None,
             "roofline": {"kernel": f"filter2d_kernel (blur1, {wl.batch}x3x{wl.gt}x{wl.gt}, per-sample kernels zero-padded to 21x21: default kernel_list mix, sizes 7..21)",

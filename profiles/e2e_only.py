@@ -14,9 +14,9 @@ import bench  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
 wl = bench.Workload("c2", 1)
 arm = bench.Arm(wl, torch.device("cuda:0"), 0, 1, None)
-for u8 in (True, False):
-    v, h2d, d2h = arm.e2e(steps, 8, u8)
-    print("slots", bench.E2E_SLOTS, "u8" if u8 else "f32", round(v), "pairs/s", round(64e3 / v, 4), "ms/step", flush=True)
+for u8, lanes in ((True, 1), (True, 2), (True, 4), (False, 1)):
+    v, h2d, d2h = arm.e2e(steps, 8, u8, lanes)
+    print("slots", bench.E2E_SLOTS, "lanes", lanes, "u8" if u8 else "f32", round(v), "pairs/s", round(64e3 / v, 4), "ms/step", flush=True)
 
 # no-upload variant of the uint8 loop
 from trainner_redux_b200.prefetch import CUDAPrefetcher, CUDAReadback  # noqa: E402

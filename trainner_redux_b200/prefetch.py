@@ -3,7 +3,8 @@
 
 Same protocol: ``preload()`` takes the next batch from the loader and starts its upload on a private copy stream,
 ``next()`` makes the caller's stream wait for that upload (``wait_stream``, :488-493), hands the batch out and preloads
-the following one, ``reset()`` restarts the loader.  Two differences, both on purpose:
+the following one, ``reset()`` restarts the loader.  The batch is expected to be consumed on the stream that is current
+when ``next()`` returns it (as in the reference's loop).  Two differences, both on purpose:
 
   * the device tensors are STATIC slots (``slots`` per key, reused round-robin) instead of fresh allocations, so the
     addresses ``RealESRGANFeed.feed_data`` sees repeat and its captured chains (chain_graph.py) are replayed instead of
@@ -53,6 +54,7 @@ class CUDAPrefetcher:
             self._consumed = self._new_event()
         self._hold: deque[tuple[int, Any]] = deque()  # (slot, host batch) until the slot's copies have completed
         self._pending: int | None = None  # slot of the batch waiting to be handed out
+        self._slot_stream: list[int | None] = [None] * self.slots  # raw handle of the stream each slot's batch was handed out on
         self.batch: dict | None = None
         self.h2d_bytes = 0  # bytes of the batch being handed out (bench.py reports it)
         self._next_bytes = 0
@@ -103,7 +105,11 @@ class CUDAPrefetcher:
 
     def _issue(self, n: int, dst: Any, src: Any, nbytes: Any, slot: int) -> None:
         self._release_done()
-        _lib.call("otf_upload_async", n, dst, src, nbytes, self._copy_stream, _lib.stream(), self._consumed, self._ready[slot])
+        # the consumer of this slot's previous batch: the stream that was current when ``next()`` handed it out (a loop
+        # that alternates its batches over several streams keeps working: the copy waits for the right one)
+        consumer = self._slot_stream[slot]
+        _lib.call("otf_upload_async", n, dst, src, nbytes, self._copy_stream, _lib.stream() if consumer is None else C.c_void_p(consumer),
+                  self._consumed, self._ready[slot])
 
     def preload(self) -> None:
         try:
@@ -134,7 +140,9 @@ class CUDAPrefetcher:
 
     def next(self) -> dict | None:
         if self._pending is not None:  # the caller's stream waits for the upload: prefetch_dataloader.py:488-493
-            _lib.call("otf_stream_wait_event", _lib.stream(), self._ready[self._pending])
+            cur = _lib.stream()
+            _lib.call("otf_stream_wait_event", cur, self._ready[self._pending])
+            self._slot_stream[self._pending] = cur.value or 0
         batch = self.batch
         self.h2d_bytes = self._next_bytes
         self.preload()
