@@ -494,16 +494,18 @@ class Arm:
                 return sl.run()
             return fn
 
-        def fused_tail():
+        def fused_tail(gt_copy: bool):
             from trainner_redux_b200 import _lib
 
-            x, gt, pch = taps["sinc"], d["gt"], self.wl.crop // sc
-            b = x.size(0)
-            gt_out = torch.empty((b, 3, self.wl.crop, self.wl.crop), dtype=torch.float32, device=self.dev)
-            lq_out = torch.empty((b, 3, pch, pch), dtype=torch.float32, device=self.dev)
-            _lib.call("otf_diffjpeg_crop_pair_f32", _lib.ptr(x), b, x.size(2), x.size(3), _lib.ptr(p["jpeg2"]), 0.0, 1, 0, 1, _lib.ptr(gt),
-                      gt.size(2), gt.size(3), 4, 4, None, pch, sc, _lib.ptr(gt_out), _lib.ptr(lq_out), _lib.stream())
-            return lq_out
+            def fn():
+                x, gt, pch = taps["sinc"], d["gt"], self.wl.crop // sc
+                b = x.size(0)
+                gt_out = torch.empty((b, 3, self.wl.crop, self.wl.crop), dtype=torch.float32, device=self.dev) if gt_copy else None
+                lq_out = torch.empty((b, 3, pch, pch), dtype=torch.float32, device=self.dev)
+                _lib.call("otf_diffjpeg_crop_pair_f32", _lib.ptr(x), b, x.size(2), x.size(3), _lib.ptr(p["jpeg2"]), 0.0, 1, 0, 1, _lib.ptr(gt),
+                          gt.size(2), gt.size(3), 4, 4, None, pch, sc, _lib.ptr(gt_out), _lib.ptr(lq_out), _lib.stream())
+                return lq_out
+            return fn
 
         if p["noise1"]["kind"] == "gaussian" and "blur1" in taps and "blur2" in taps:
             feed.stage_fns["fused resize1+noise1"] = fused_resize_noise(taps["blur1"], p["resize1"], p["noise1"])
@@ -511,7 +513,8 @@ class Arm:
             feed.stage_fns["fused resize2+noise2"] = fused_resize_noise(taps["blur2"], p["resize2"], p["noise2"],
                                                                         size=(int(h0 / sc * s2), int(h0 / sc * s2)))
         if "sinc" in taps and p.get("final_order", "resize_first") == "resize_first":
-            feed.stage_fns["fused jpeg2+round+crop"] = fused_tail
+            feed.stage_fns["fused jpeg2+round+lq_crop"] = fused_tail(False)  # what feed_data launches: the GT window stays a view
+            feed.stage_fns["fused jpeg2+round+crop"] = fused_tail(True)  # with the dense GT copy (pool / MoA / gt_view=False)
         torch.cuda.synchronize()
         from trainner_redux_b200.degradations import pin_resize_tables
 
@@ -669,6 +672,7 @@ def run_b200(args, wl: Workload) -> None:
             "config": wl.config(),  # (the same dict in both arms: the driver compares them)
             "run": {"launch": f"RealESRGANFeed.feed_data, a fresh draw_plan per step, captured chains replayed ({graphs.captures} captures, "
                               f"{graphs.hits} replays so far), {n_streams} calls in flight on {n_streams} streams",
+                    "gt_crop": "the GT half of the pair is the reference's view of the GT batch (transforms.py:124-129: a slice, no copy); the LQ crop is dense",
                     "numa_node_rank0": numa, "numa_note": numa_why},
             "value_feed_data": arm.pairs_per_s(args.steps, ms_single), "ms_per_step_feed_data": ms_single / args.steps,
             "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,

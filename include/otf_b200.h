@@ -208,7 +208,8 @@ int otf_diffjpeg_f32(const float* img, int B, int H, int W,
 /* The chain's usual last three steps in ONE launch: DiffJPEG with the 8-bit lattice on its output (a6 + a7), the LQ crop
  * window stored straight into the dense (B,3,p,p) `lq_out`, and the GT crop window (a8) copied by the CTAs behind the
  * codec's.  Arguments as otf_diffjpeg_f32 (round8_out implied) + otf_crop_pair_f32.  The GT patch must be a multiple of 4
- * pixels wide. */
+ * pixels wide.  gt_out == NULL: no GT copy (the caller keeps the GT window as a strided view of `gt`, which is what the
+ * reference's paired_random_crop returns: transforms.py:124-129). */
 int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
                                const float* factor_dev, float factor_scalar, int factor_is_quality,
                                int differentiable, int clamp_in,
@@ -224,7 +225,8 @@ int otf_clamp_round_f32(const float* x, int64_t n, float* out, void* stream);
  * p*scale...) into dense outputs in one launch.  top_left_dev (int32[2] on the device, may be NULL)
  * overrides (top, left): a captured launch then follows the offsets the caller uploads per step (they are
  * clamped to the valid range on the device; the host validates them when it draws them).  lq_round8 != 0 applies
- * the 8-bit lattice of a7 to the LQ window on the way (clamp/round + crop in one launch). */
+ * the 8-bit lattice of a7 to the LQ window on the way (clamp/round + crop in one launch).  gt_out == NULL skips
+ * the GT window (the caller keeps it as a strided view, as the reference's crop does). */
 int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
                       const float* lq, int Hl, int Wl,
                       int top, int left, const int32_t* top_left_dev, int lq_patch, int scale, int lq_round8,

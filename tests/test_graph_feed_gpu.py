@@ -157,3 +157,30 @@ def test_readback_side_stream(dev):
             assert torch.all(hosts[-1][1] == float(i)) and torch.all(hosts[-2][1] == float(i - 1))
     with pytest.raises(RuntimeError):
         rb.read(torch.zeros(4))
+
+
+def test_gt_window_is_a_view_like_the_reference(dev):
+    """paired_random_crop returns the GT window as a slice of the batch (transforms.py:124-129): feed_data hands out the
+    same view (no bytes move) unless the pool / MoA / ``gt_view = False`` ask for a dense copy — identical values."""
+    b = 4
+    data = _data(b, 96, 3, dev)
+    got = {}
+    for name, kw in (("view", {}), ("copy", {"gt_view": False}), ("pool", {"use_pool": True})):
+        feed = RealESRGANFeed(_opt("gaussian", b), device=dev, manual_seed=11, use_pool=kw.get("use_pool", False))
+        feed.gt_view = kw.get("gt_view", True)
+        steps = []
+        for _ in range(5):  # eager, eager, then replays of the captured chain
+            feed.feed_data(data)
+            top, left = feed.last_plan["crop"]
+            if name == "view":
+                assert not feed.gt.is_contiguous() and feed.gt.untyped_storage().data_ptr() == data["gt"].untyped_storage().data_ptr()
+                assert feed.gt.storage_offset() == 4 * top * 96 + 4 * left and feed.gt.shape == (b, 3, 64, 64)
+            else:
+                assert feed.gt.is_contiguous() and feed.gt.untyped_storage().data_ptr() != data["gt"].untyped_storage().data_ptr()
+            assert feed.lq.is_contiguous()
+            steps.append((feed.gt.clone(), feed.lq.clone()))
+        got[name] = steps
+    for (g0, l0), (g1, l1) in zip(got["view"], got["copy"]):
+        assert torch.equal(g0, g1) and torch.equal(l0, l1)
+    # (the pool hands out its own batches; while it fills, the pair passes through)
+    assert torch.equal(got["pool"][0][0], got["view"][0][0])

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128, 5) diffjpeg_kernel(const float* __restric
             top = clampi(ct.tl_dev[0], 0, H - ct.p);
             left = clampi(ct.tl_dev[1], 0, W - ct.p);
         }
-        if ((int)blockIdx.x >= ct.jpeg_ctas) {  // the GT crop rides in the same launch
+        if ((int)blockIdx.x >= ct.jpeg_ctas) {  // the GT crop rides in the same launch (no such CTAs when gt_out is NULL)
             const int64_t q0 = (int64_t)(blockIdx.x - ct.jpeg_ctas) * blockDim.x + threadIdx.x;
             const int64_t qs = (int64_t)(gridDim.x - ct.jpeg_ctas) * blockDim.x;
             if (ct.vec_gt) copy_window<true>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
@@ -364,11 +364,11 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
                                           int top, int left, const int32_t* top_left_dev, int lq_patch, int scale, float* gt_out,
                                           float* lq_out, void* stream) {
     using namespace otf;
-    OTF_REQUIRE(img && gt && gt_out && lq_out, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: null pointer");
+    OTF_REQUIRE(img && lq_out && (gt || !gt_out), OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: null pointer");
     OTF_REQUIRE(B > 0 && B * 3 <= 65535 && H > 0 && W > 0 && scale > 0 && lq_patch > 0, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: bad extents");
     OTF_REQUIRE(Hg == H * scale && Wg == W * scale, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: GT (%d, %d) is not %dx LQ (%d, %d)", Hg, Wg, scale, H, W);
     OTF_REQUIRE(top >= 0 && left >= 0 && top + lq_patch <= H && left + lq_patch <= W, OTF_ERR_BAD_ARG, "diffjpeg_crop_pair: window outside LQ");
-    OTF_REQUIRE((lq_patch * scale) % 4 == 0 && (((uintptr_t)gt_out) & 15) == 0, OTF_ERR_UNSUPPORTED,
+    OTF_REQUIRE(!gt_out || ((lq_patch * scale) % 4 == 0 && (((uintptr_t)gt_out) & 15) == 0), OTF_ERR_UNSUPPORTED,
                 "diffjpeg_crop_pair: GT patch must be a multiple of 4 pixels wide (use otf_diffjpeg_f32 + otf_crop_pair_f32)");
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
     const int64_t warps = (int64_t)B * ((mcu_x + 1) / 2) * mcu_y;
@@ -385,6 +385,7 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     int copy_ctas = (int)((gquads / 4 + 127) / 128);
     if (copy_ctas > kNumSMs * 8) copy_ctas = kNumSMs * 8;
     if (copy_ctas < 1) copy_ctas = 1;
+    if (!gt_out) copy_ctas = 0;  // the GT window stays a view of the caller's tensor (what the reference's crop returns)
     launch_chain(diffjpeg_kernel, dim3(ct.jpeg_ctas + copy_ctas), dim3(32 * wpc), 0, (cudaStream_t)stream, img, nullptr, B, H, W, mcu_x, mcu_y, factor_dev,
                                                                                   factor_scalar, differentiable, clamp_in, 1, vec_ok,
                                                                                   factor_is_quality, ct);

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict_
         left = clampi(top_left_dev[1], 0, Wl - p);
     }
     const int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, qs = (int64_t)gridDim.x * blockDim.x;
-    copy_window<VEC_GT>(gt, Hg, Wg, top * scale, left * scale, p * scale, gt_out, planes, q0, qs);
+    if (gt_out) copy_window<VEC_GT>(gt, Hg, Wg, top * scale, left * scale, p * scale, gt_out, planes, q0, qs);  // (NULL: the GT window stays a view)
     copy_window<VEC_LQ, ROUND8>(lq, Hl, Wl, top, left, p, lq_out, planes, q0, qs);
 }
 
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) crop_pair_scalar_kernel(const float* __re
         left = clampi(top_left_dev[1], 0, Wl - p);
     }
     const int G = p * scale;
-    const int64_t ng = (int64_t)planes * G * G, nl = (int64_t)planes * p * p;
+    const int64_t ng = gt_out ? (int64_t)planes * G * G : 0, nl = (int64_t)planes * p * p;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ng + nl; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < ng) {
             const int x = (int)(i % G), y = (int)((i / G) % G);
@@ -247,13 +247,13 @@ extern "C" int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg, co
                                  int left, const int32_t* top_left_dev, int lq_patch, int scale, int lq_round8, float* gt_out,
                                  float* lq_out, void* stream) {
     using namespace otf;
-    OTF_REQUIRE(gt && lq && gt_out && lq_out, OTF_ERR_BAD_ARG, "crop_pair: null pointer");
+    OTF_REQUIRE(lq && lq_out && (gt || !gt_out), OTF_ERR_BAD_ARG, "crop_pair: null pointer");
     OTF_REQUIRE(planes > 0 && planes <= 65535 && scale > 0 && lq_patch > 0, OTF_ERR_BAD_ARG, "crop_pair: bad extents");
     OTF_REQUIRE(Hg == Hl * scale && Wg == Wl * scale, OTF_ERR_BAD_ARG, "crop_pair: GT (%d, %d) is not %dx LQ (%d, %d)", Hg, Wg, scale, Hl, Wl);
     OTF_REQUIRE(top >= 0 && left >= 0 && top + lq_patch <= Hl && left + lq_patch <= Wl, OTF_ERR_BAD_ARG, "crop_pair: window outside LQ");
     const int G = lq_patch * scale;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t work = ((int64_t)planes * G * G + (int64_t)planes * lq_patch * lq_patch) / 4;
+    const int64_t work = ((gt_out ? (int64_t)planes * G * G : 0) + (int64_t)planes * lq_patch * lq_patch) / 4;
     int blocks = (int)((work / 4 + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;

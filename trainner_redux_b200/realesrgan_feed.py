@@ -416,6 +416,12 @@ class RealESRGANFeed:
         # ``use_graphs = False`` or clones.  The pool (``use_pool``) copies what it keeps, so it is unaffected.
         self.use_graphs = True
         self.graphs = ChainGraphCache(capacity=16, credits=8.0)
+        # The GT half of the pair as a VIEW of the GT batch, as the reference's paired_random_crop returns it
+        # (transforms.py:124-129: a slice; only the LQ is made contiguous, realesrgan_model.py:627) — no GT bytes move.
+        # The view aliases the batch feed_data was given (a prefetcher's static slot is rewritten `slots` calls
+        # later).  Whenever something downstream needs a dense tensor anyway (pair pool, MoA) the window is copied by
+        # the chain's last launch instead; ``gt_view = False`` forces that copy.
+        self.gt_view = True
         self._synth_out: dict[tuple, Tensor] = {}  # kernel-synthesis outputs per upload slot (feed_data, `kernel_params`)
         self._gt_f32: dict[tuple, Tensor] = {}  # normalised fp32 GT per uint8 upload slot
 
@@ -577,6 +583,15 @@ class RealESRGANFeed:
         tail(None)
         return sl
 
+    def _gt_as_view(self) -> bool:
+        return self.gt_view and self.pool is None and not self.batch_augment
+
+    @staticmethod
+    def _gt_window(gt: Tensor, plan: dict) -> Tensor:
+        top, left = plan["crop"]
+        sc, size = plan["scale"], plan["gt_size"] // plan["scale"] * plan["scale"]
+        return gt[:, :, top * sc : top * sc + size, left * sc : left * sc + size]
+
     def _native(self, plan: dict | None = None) -> bool:
         # (the fork's extra stages are in the native executor's op table too: one library call per chain in both orders)
         return self.native_chain and not (self.time_stages or self.record_stage_fns or self.collect_taps is not None)
@@ -592,7 +607,7 @@ class RealESRGANFeed:
         sig = plan_signature(plan, gt.size(2), gt.size(3))
         if sig is None:
             return None
-        return (gt.data_ptr(), tuple(gt.shape), *((k.data_ptr(), tuple(k.shape)) for k in kernels), sig)
+        return (gt.data_ptr(), tuple(gt.shape), *((k.data_ptr(), tuple(k.shape)) for k in kernels), sig, self._gt_as_view())
 
     def _fill_params(self, entry: ChainGraph, b: int, h: int, w: int, kernels: Sequence[Tensor], plan: dict) -> None:
         """This step's numbers into the chain's parameter block.  A chain whose rows all came from the plan's own
@@ -629,10 +644,11 @@ class RealESRGANFeed:
             entry.last_stream = cur
         params.upload()
 
-    def _replay(self, entry: ChainGraph) -> tuple[Tensor, Tensor]:
+    def _replay(self, entry: ChainGraph, gt: Tensor, plan: dict) -> tuple[Tensor, Tensor]:
         entry.graph.replay()  # type: ignore[union-attr]
         _lib.launch_count += entry.launches
-        return entry.gt_out, entry.lq_out  # type: ignore[return-value]
+        gt_out = entry.gt_out if entry.gt_out is not None else self._gt_window(gt, plan)
+        return gt_out, entry.lq_out  # type: ignore[return-value]
 
     def _capture(self, key: tuple, gt: Tensor, kernels: Sequence[Tensor], plan: dict) -> ChainGraph | None:
         """Record the chain against a parameter block and capture its launches into a CUDA graph."""
@@ -646,7 +662,7 @@ class RealESRGANFeed:
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                entry.gt_out, entry.lq_out = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left))
+                entry.gt_out, entry.lq_out = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left), gt_view=self._gt_as_view())
             entry.launches = _lib.launch_count - l0
             _lib.launch_count = l0  # nothing ran yet: replays are what launches
             entry.graph, entry.keep = g, sl
@@ -810,10 +826,11 @@ class RealESRGANFeed:
                     entry = self._capture(key, gt, kernels, plan)
                 if entry is not None:  # a captured chain: refresh its parameter block, replay
                     self._fill_params(entry, gt.size(0), ori_h, ori_w, kernels, plan)
-                    self.gt, self.lq = self._replay(entry)
+                    self.gt, self.lq = self._replay(entry, gt, plan)
                 else:
                     sl = self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject)
-                    self.gt, self.lq = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left))
+                    gt_out, self.lq = sl.run(crop=(gt, plan["gt_size"], plan["scale"], top, left), gt_view=self._gt_as_view())
+                    self.gt = gt_out if gt_out is not None else self._gt_window(gt, plan)
             else:
                 lq_full = self.degrade(gt, kernel1, kernel2, sinc_kernel, plan, inject)
                 self.gt, self.lq = crop_pair(gt, lq_full, plan["gt_size"], plan["scale"], top, left)

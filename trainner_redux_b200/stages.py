@@ -308,18 +308,19 @@ class StageList:
         self._resize(mode_id, int(oh), int(ow), clamp)
 
     # -- execution ----------------------------------------------------------------------------
-    def run(self, crop: tuple[Tensor, int, int, int, int] | None = None) -> Tensor | tuple[Tensor, Tensor]:
+    def run(self, crop: tuple[Tensor, int, int, int, int] | None = None, gt_view: bool = False) -> Tensor | tuple[Tensor | None, Tensor]:
         """Launch the recorded stages.  Returns the final image, or with ``crop=(gt, gt_patch, scale, top, left)``
-        the (gt_crop, lq_crop) pair of transforms.crop_pair, cropped by the chain's last launch."""
+        the (gt_crop, lq_crop) pair of transforms.crop_pair, cropped by the chain's last launch.  ``gt_view``: no GT
+        copy — the first element is None and the caller slices ``gt`` itself (the reference's crop returns that view)."""
         if not self.stages:
             raise ValueError("empty stage list")
         outs: tuple[Tensor, ...]
         if crop is not None:
             gt, gt_patch, scale, top, left = crop
             p = gt_patch // scale
-            gt_out = torch.empty((self.b, self.c, p * scale, p * scale), dtype=torch.float32, device=self.device)
+            gt_out = None if gt_view else torch.empty((self.b, self.c, p * scale, p * scale), dtype=torch.float32, device=self.device)
             lq_out = torch.empty((self.b, self.c, p, p), dtype=torch.float32, device=self.device)
-            self._add(_lib.OP_CROP_PAIR, p0=self._dev_ptr(gt), p1=gt_out.data_ptr(), p2=lq_out.data_ptr(), oh=top, ow=left, n=p, mode=scale,
+            self._add(_lib.OP_CROP_PAIR, p0=self._dev_ptr(gt), p1=None if gt_out is None else gt_out.data_ptr(), p2=lq_out.data_ptr(), oh=top, ow=left, n=p, mode=scale,
                       p4=None if self.params is None else self.params.crop_ptr)
             self.launches += 1
             outs = (gt_out, lq_out)
