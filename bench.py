@@ -59,7 +59,7 @@ import torch  # noqa: E402
 UNIT = "pairs/s"
 S1, S2 = 0.75, 1.0
 N_ROTATE = int(os.environ.get("OTF_BENCH_ROTATE", "4"))  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
-E2E_SLOTS = int(os.environ.get("OTF_BENCH_E2E_SLOTS", "4"))  # static upload slots of the e2e prefetcher (one captured chain each)
+E2E_SLOTS = int(os.environ.get("OTF_BENCH_E2E_SLOTS", "2"))  # static upload slots of the e2e prefetcher (one captured chain each)
 
 
 _RECORD_OUT = None
@@ -323,6 +323,10 @@ class Arm:
         self.wl, self.dev, self.rank, self.world, self.dist = wl, dev, rank, world, dist
         self.opt = wl.options()
         self.feed = RealESRGANFeed(self.opt, device=dev, manual_seed=0, rank=rank, use_pool=False)
+        # this process builds several prefetchers in a row (three e2e loops, each with its own upload slots, after the
+        # device-resident loops): enough capture credits for all of their chains even in a 20-step run
+        self.feed.graphs.credits = self.feed.graphs.max_credits = 32.0
+        self.feed.graphs.capacity = 32
         self.draw_plan = draw_plan
         self.host = [make_inputs(wl, rank * N_ROTATE + i, dev) for i in range(N_ROTATE)]
         keys = ("gt", "kernel1", "kernel2", "sinc_kernel")
@@ -415,40 +419,39 @@ class Arm:
             for i in range(n):
                 yield batches[i % N_ROTATE]
 
-        pf_box: list = []  # ONE prefetcher for warm-up and timed run: its static slots (and the chains captured on them) persist
-
         n_slots = lanes * -(-E2E_SLOTS // lanes)  # a multiple of the lane count: a slot (and its captured chain) stays on one lane
         main = torch.cuda.current_stream()
         lane = [torch.cuda.Stream(self.dev) for _ in range(lanes)] if lanes > 1 else [main]
+        n_warm = n_slots * -(-max(warmup, 2 * n_slots) // n_slots)  # (static slots: the chain of each is captured on its second sighting)
+        # ONE loader for warm-up and timed steps, as in a training loop: the prefetcher stays one batch ahead, so when the
+        # clock starts the first timed batch is already on its way and every timed step uploads the batch of the step
+        # after it — K steps, K uploads, K read-backs inside the timed region (the loader yields one batch more than is
+        # consumed so that the last step's preload is a real upload too)
+        pf = CUDAPrefetcher(loader(n_warm + steps + 1), device=self.dev, slots=n_slots)
+        state = {"t": 0, "h2d": 0}
 
-        def run(n: int) -> int:
-            if pf_box:
-                pf_box[0].reset(loader(n))
-            else:
-                pf_box.append(CUDAPrefetcher(loader(n), device=self.dev, slots=n_slots))
-            pf = pf_box[0]
-            h2d = t = 0
-            torch.cuda.synchronize()
-            torch.cuda.set_stream(lane[0])  # batch t is handed out, degraded and read back on lane t % lanes
-            batch = pf.next()
-            while batch is not None:
-                h2d = pf.h2d_bytes
+        def run(n: int) -> None:
+            t = state["t"]
+            torch.cuda.set_stream(lane[t % lanes])  # batch t is handed out, degraded and read back on lane t % lanes
+            for _ in range(n):
+                batch = pf.next()
+                state["h2d"] = pf.h2d_bytes
                 self.feed.feed_data(batch, plan=self.plan())
                 rb.read(self.feed.lq)
                 t += 1
                 if lanes > 1:
                     torch.cuda.set_stream(lane[t % lanes])
-                batch = pf.next()
+            state["t"] = t
             torch.cuda.set_stream(main)
             rb.wait()
             torch.cuda.synchronize()
-            return h2d
 
-        run(max(warmup, 2 * n_slots))  # (static slots: the chain of each is captured on its second sighting)
+        run(n_warm)
         self.barrier()
         t0 = time.perf_counter()
-        h2d = run(steps)
+        run(steps)
         dt = time.perf_counter() - t0
+        h2d = state["h2d"]
         t = torch.tensor([dt], device=self.dev)
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
@@ -582,7 +585,7 @@ def run_b200(args, wl: Workload) -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    sampler = ClockSampler(local) if rank == 0 else None  # spans warm-up, every timed region and the e2e loops
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("OTF_BENCH_NO_SAMPLER") else None  # spans warm-up, every timed region and the e2e loops
     numa, numa_why = bind_to_gpu_numa_node(local)  # pinned staging buffers should live next to this rank's GPU
     if world > 1:
         # (NCCL's banner and NCCL_DEBUG lines land on stderr: see main)
