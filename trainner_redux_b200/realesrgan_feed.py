@@ -799,11 +799,12 @@ class RealESRGANFeed:
                 # img2tensor does on the host) — a quarter of the PCIe bytes of the reference's fp32 upload
                 gt8 = gt.contiguous()
                 key = (gt8.data_ptr(), tuple(gt8.shape))
-                gt = self._gt_f32.get(key)  # same reasoning as for the kernels: one fp32 buffer per upload slot
+                gt = self._gt_f32.pop(key, None)  # same reasoning as for the kernels: one fp32 buffer per upload slot
                 if gt is None:
-                    if len(self._gt_f32) >= 4:  # (a handful of slots at most; anything else is not a slot ring)
-                        self._gt_f32.clear()
-                    gt = self._gt_f32[key] = torch.empty(gt8.shape, dtype=torch.float32, device=self.device)
+                    while len(self._gt_f32) >= 8:  # least recently used first (a few slot rings at most are alive at a time)
+                        self._gt_f32.pop(next(iter(self._gt_f32)))
+                    gt = torch.empty(gt8.shape, dtype=torch.float32, device=self.device)
+                self._gt_f32[key] = gt  # (re-inserted: most recently used last)
                 _lib.call("otf_u8_to_f32", _lib.ptr(gt8), gt8.numel(), _lib.ptr(gt), _lib.stream())
             gt = _lib.dense_f32(gt)
             ori_h, ori_w = gt.shape[2:4]
