@@ -133,7 +133,7 @@ class CUDAPrefetcher:
                 self._issue(n, dst, src, nbytes, slot)
         else:
             self._issue(n, dst, src, nbytes, slot)
-        self._hold.append((slot, batch))
+        self._hold.append((slot, (batch, [src_t for _, src_t in todo])))  # (the sources as uploaded: a .contiguous() copy is not in `batch`)
         self._pending = slot
         self._next_bytes = sum(sizes)
         self._turn += 1
