@@ -156,7 +156,10 @@ struct CropTail {
 // the warp's own 1 KB of shared memory (2 STS.128 + 2 LDS.128 per lane and direction) instead of 32 shuffles.
 constexpr int kJpegWarpFloats = 4 * 64 + 32 * 9 + 8;  // chroma staging [4 blocks][8][8] + transpose scratch [32][9] (+ pad to 16 B)
 
-__global__ void __launch_bounds__(128, 5) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
+#ifndef OTF_JPEG_MINB
+#define OTF_JPEG_MINB 5
+#endif
+__global__ void __launch_bounds__(128, OTF_JPEG_MINB) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
                                                        float factor_scalar, int differentiable, int clamp_in,
                                                        int round8_out, int vec_ok, int factor_is_quality,
