@@ -703,7 +703,10 @@ __global__ void __launch_bounds__(256) resize_vh_kernel(const float* __restrict_
 // instructions and no per-tap index arithmetic at all.  Summation order inside a window is unchanged (taps in
 // ascending source order, zeros in between are exact no-ops), so results equal the vertical-first kernel's bit for bit.
 template <int GV, int RV, int GH, int SH, bool VEC, bool NOISE>
-__global__ void __launch_bounds__(128, 4) resize_rb_kernel(const float* __restrict__ img, float* __restrict__ out,
+#ifndef OTF_RB_MINB
+#define OTF_RB_MINB 4
+#endif
+__global__ void __launch_bounds__(128, OTF_RB_MINB) resize_rb_kernel(const float* __restrict__ img, float* __restrict__ out,
                                                            AxisSpec ay, AxisSpec ax, const int* __restrict__ dense,
                                                            const __grid_constant__ RbPlan pl, int clamp_out, int vec_out,
                                                            const __grid_constant__ NoiseEpi ne) {
