@@ -104,6 +104,9 @@ class ParamCollector:
         self.params, self.b, self.h, self.w = params, b, h, w
         params.begin()
 
+    def at(self, name: str) -> "ParamCollector":
+        return self
+
     def analyse(self, kernels: Any) -> None:
         pass
 

@@ -34,7 +34,7 @@ from . import _lib
 from . import degradations as D
 from .chain_graph import ChainGraph, ChainGraphCache, ParamBlock, ParamCollector, fill_recipe, plan_signature
 from .diffjpeg import DiffJPEG
-from .img_process_util import KernelAnalysis, USMSharp, filter2d
+from .img_process_util import USMSharp
 from .stages import StageList
 from .transforms import crop_pair
 
@@ -459,119 +459,101 @@ class RealESRGANFeed:
         self.stage_times.setdefault(name, []).append((e0, e1))
         return out
 
-    # -- stages ---------------------------------------------------------------------------
-    def _noise(self, out: Tensor, st: dict, inject: dict | None, key: str) -> Tensor:
-        inject = inject or {}
-        if inject.get(f"{key}_field") is not None:
-            return D.add_noise_field_pt(out, inject[f"{key}_field"], clip=True, rounds=False)
-        if st["kind"] == "gaussian":
-            return D.add_gaussian_noise_pt(
-                out, st["sigma"].to(self.device, non_blocking=True), st["gray"].to(self.device, non_blocking=True),
-                clip=True, rounds=False, noise=inject.get(f"{key}_color"), noise_gray=inject.get(f"{key}_gray"),
-                generator=self.rng.philox,
-            )
-        return D.add_poisson_noise_pt(
-            out, st["scale"].to(self.device, non_blocking=True), True, False, st["gray"].to(self.device, non_blocking=True),
-            poisson_counts=inject.get(f"{key}_counts_color"), poisson_counts_gray=inject.get(f"{key}_counts_gray"),
-            generator=self.rng.philox,
-        )
-
-    def _jpeg(self, out: Tensor, quality: Tensor, round8: bool) -> Tensor:
-        q = quality.to(self.device, non_blocking=True)  # raw qualities: the kernel converts them, nothing is mutated
-        return self.jpeger(out, quality=q, _clamp_in=True, _round8=round8, _keep_quality=True)
-
-    def _record(self, sl: StageList, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
-                inject: dict | None = None) -> StageList:
-        """The chain of ``degrade`` written as a stage list for the native executor: same branches, same
-        arguments, same order of Philox offsets."""
+    # -- the chain, described once ----------------------------------------------------------
+    def _record(self, sl: Any, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
+                inject: dict | None = None) -> Any:
+        """THE description of the chain: which stages run, in which order, with which arguments and Philox offsets.
+        ``sl`` is whatever consumes it — a ``StageList`` (launch records for the native executor), a
+        ``ParamCollector`` (the per-step numbers of a captured chain) or a ``StageByStage`` (runs each stage at once
+        through the public per-primitive API, behind the stage hooks)."""
         inject = inject or {}
         ori_h, ori_w, sc = sl.h, sl.w, plan["scale"]
         if plan.get("clean"):
-            sl.clamp_round()
+            sl.at("round").clamp_round()
             return sl
         joint = kernel1.shape == kernel2.shape == sinc_kernel.shape and kernel1.size(-1) <= 21 and kernel1.size(0) == sl.b
         fork = plan.get("order") == "fork"
-        if joint:  # one pair of launches analyses all three kernel tensors, as KernelAnalysis does in degrade()
+        if joint:  # ONE launch analyses all three kernel tensors (img_process_util.KernelAnalysis on the per-stage path)
             sl.analyse([kernel1, kernel2, sinc_kernel])
         an = (lambda i: i) if joint else (lambda i: None)
 
         def noise(st: dict, key: str) -> None:
             if inject.get(f"{key}_field") is not None:  # the finished noise field of the reference (parity tests)
-                sl.noise_field(inject[f"{key}_field"])
+                sl.at(key).noise_field(inject[f"{key}_field"])
             elif st["kind"] == "gaussian":
-                sl.gaussian_noise(st["sigma"], st["gray"], self.rng.philox, noise=inject.get(f"{key}_color"),
+                sl.at(key).gaussian_noise(st["sigma"], st["gray"], self.rng.philox, noise=inject.get(f"{key}_color"),
                                   noise_gray=inject.get(f"{key}_gray"))
             else:
-                sl.poisson_noise(st["scale"], st["gray"], self.rng.philox, counts=inject.get(f"{key}_counts_color"),
+                sl.at(key).poisson_noise(st["scale"], st["gray"], self.rng.philox, counts=inject.get(f"{key}_counts_color"),
                                  counts_gray=inject.get(f"{key}_counts_gray"))
 
         def tail(jpeg: Tensor | None) -> None:  # resize3, sinc, then the 8-bit lattice (fused into the last JPEG)
-            sl.resize(plan["resize3_mode"], size=(ori_h // sc, ori_w // sc))
-            sl.filter2d(sinc_kernel, an(2))
+            sl.at("resize3").resize(plan["resize3_mode"], size=(ori_h // sc, ori_w // sc))
+            sl.at("sinc").filter2d(sinc_kernel, an(2))
             if jpeg is not None:
-                sl.jpeg(jpeg, round8=True)
+                sl.at("jpeg2+round").jpeg(jpeg, round8=True)
             else:
-                sl.clamp_round()
+                sl.at("round").clamp_round()
 
         if fork:  # realesrgan_model.py:512-616, stage by stage as degrade() runs it
             from . import paragon_otf as PO
 
             if "lens" in plan:
-                sl.warp(_lib.WARP_LENS, plan["lens"])
+                sl.at("lens").warp(_lib.WARP_LENS, plan["lens"])
             if plan.get("chroma") and sl.c == 3:
-                sl.warp(_lib.WARP_CHROMA, 0.0)
+                sl.at("chroma").warp(_lib.WARP_CHROMA, 0.0)
             if "motion" in plan:
-                sl.taps_zero(PO.motion_blur_kernel(*plan["motion"]))
+                sl.at("motion").taps_zero(PO.motion_blur_kernel(*plan["motion"]))
             if plan.get("blur1"):
-                sl.filter2d(kernel1, an(0))
+                sl.at("blur1").filter2d(kernel1, an(0))
             if plan.get("demosaic"):
-                sl.demosaic()
+                sl.at("demosaic").demosaic()
             if "sensor" in plan:
-                sl.sensor_noise(plan["sensor"], self.rng.philox, noise=inject.get("sensor_noise"))
+                sl.at("sensor").sensor_noise(plan["sensor"], self.rng.philox, noise=inject.get("sensor_noise"))
             if "shutter" in plan:
-                sl.warp(_lib.WARP_SHUTTER, plan["shutter"] * sl.h / sl.w)
+                sl.at("shutter").warp(_lib.WARP_SHUTTER, plan["shutter"] * sl.h / sl.w)
             if "exposure" in plan:
-                sl.gain((plan["exposure"],) * 3)
+                sl.at("exposure").gain((plan["exposure"],) * 3)
             if "color_temp" in plan and sl.c == 3:
-                sl.gain(PO.color_temperature_gains(plan["color_temp"]))
+                sl.at("color_temp").gain(PO.color_temperature_gains(plan["color_temp"]))
             if "oversharpen" in plan:
-                sl.taps_zero(PO._BOX5, _lib.TAPS_OVERSHARPEN, plan["oversharpen"])
+                sl.at("oversharpen").taps_zero(PO._BOX5, _lib.TAPS_OVERSHARPEN, plan["oversharpen"])
             if "aliasing" in plan:
                 h, w = sl.h, sl.w
-                sl.resize_raw(_lib.RESIZE_NEAREST, int(h * plan["aliasing"]), int(w * plan["aliasing"]), False)
-                sl.resize_raw(_lib.RESIZE_NEAREST, h, w, False)
-            sl.resize(plan["resize3_mode"], size=(ori_h // sc, ori_w // sc))
-            sl.filter2d(sinc_kernel, an(2))
+                sl.at("aliasing_down").resize_raw(_lib.RESIZE_NEAREST, int(h * plan["aliasing"]), int(w * plan["aliasing"]), False)
+                sl.at("aliasing").resize_raw(_lib.RESIZE_NEAREST, h, w, False)
+            sl.at("resize3").resize(plan["resize3_mode"], size=(ori_h // sc, ori_w // sc))
+            sl.at("sinc").filter2d(sinc_kernel, an(2))
             if plan.get("jpeg") is not None:  # per-sample qualities through DiffJPEG (this repo's earlier routing)
-                sl.jpeg(plan["jpeg"], round8=True)
+                sl.at("jpeg+round").jpeg(plan["jpeg"], round8=True)
                 return sl
             fallback = _opt(self.opt, "codec_fallback", "passthrough")
             for fmt, q in plan.get("compression", []):
                 if PO.codec_runs_jpeg(fmt, q, fallback):  # uint8 truncation, DiffJPEG at int(quality), 8-bit lattice
-                    sl.trunc8()
-                    sl.jpeg(float(int(q)), clamp_in=False, round8=True)
+                    sl.at(f"compress_{fmt}_trunc8").trunc8()
+                    sl.at(f"compress_{fmt}").jpeg(float(int(q)), clamp_in=False, round8=True)
             if "editing_exposure" in plan:
-                sl.gain((plan["editing_exposure"],) * 3)
-            sl.clamp_round()
+                sl.at("editing_exposure").gain((plan["editing_exposure"],) * 3)
+            sl.at("round").clamp_round()
             return sl
         if plan.get("usm"):
             r = plan["usm"]["radius"]
             if r not in self._usm:
                 self._usm[r] = USMSharp(radius=r)
-            sl.usm(self._usm[r]._taps, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10))
+            sl.at("usm").usm(self._usm[r], plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10))
         if plan.get("blur1"):
-            sl.filter2d(kernel1, an(0))
+            sl.at("blur1").filter2d(kernel1, an(0))
         if plan.get("resize1"):
-            sl.resize(plan["resize1"]["mode"], scale_factor=plan["resize1"]["scale"])
+            sl.at("resize1").resize(plan["resize1"]["mode"], scale_factor=plan["resize1"]["scale"])
         if plan.get("noise1"):
             noise(plan["noise1"], "noise1")
         if plan.get("jpeg1") is not None:
-            sl.jpeg(plan["jpeg1"])
+            sl.at("jpeg1").jpeg(plan["jpeg1"])
         if plan.get("blur2"):
-            sl.filter2d(kernel2, an(1))
+            sl.at("blur2").filter2d(kernel2, an(1))
         if plan.get("resize2"):
             s2 = plan["resize2"]["scale"]
-            sl.resize(plan["resize2"]["mode"], size=(int(ori_h / sc * s2), int(ori_w / sc * s2)))
+            sl.at("resize2").resize(plan["resize2"]["mode"], size=(int(ori_h / sc * s2), int(ori_w / sc * s2)))
         if plan.get("noise2"):
             noise(plan["noise2"], "noise2")
         jpeg2 = plan.get("jpeg2")
@@ -579,7 +561,7 @@ class RealESRGANFeed:
             tail(jpeg2)
             return sl
         if jpeg2 is not None:
-            sl.jpeg(jpeg2)
+            sl.at("jpeg2").jpeg(jpeg2)
         tail(None)
         return sl
 
@@ -678,86 +660,14 @@ class RealESRGANFeed:
     def degrade(self, gt: Tensor, kernel1: Tensor, kernel2: Tensor, sinc_kernel: Tensor, plan: dict,
                 inject: dict | None = None) -> Tensor:
         """Run the chain described by ``plan`` on device tensors; returns the full-size LQ on the
-        8-bit lattice (before the crop)."""
+        8-bit lattice (before the crop).  ONE description of the chain (``_record``) drives both executions: the native
+        stage executor (one library call), or — behind the stage hooks — ``StageByStage``, one public per-primitive
+        call per stage."""
         if self._native(plan):
             return self._record(StageList(gt), kernel1, kernel2, sinc_kernel, plan, inject).run()
-        ori_h, ori_w = gt.shape[2:4]
-        sc = plan["scale"]
-        out = gt
-        if plan.get("clean"):
-            return clamp_round(out)
-        # one pair of launches analyses all three kernel tensors (support, launch order, rank-1 factors)
-        ka = None
-        if kernel1.shape == kernel2.shape == sinc_kernel.shape and kernel1.size(-1) <= 21 and kernel1.size(0) == gt.size(0):
-            ka = KernelAnalysis([kernel1, kernel2, sinc_kernel])
-        an = (lambda i: (ka, i)) if ka is not None else (lambda i: None)
-        if plan.get("order") == "fork":  # realesrgan_model.py:512-616
-            from . import paragon_otf as PO
+        from .stage_by_stage import StageByStage
 
-            inject = inject or {}
-            if "lens" in plan:
-                out = self._timed("lens", lambda o=out: PO.lens_distortion(o, plan["lens"]))
-            if plan.get("chroma"):
-                out = self._timed("chroma", lambda o=out: PO.chromatic_aberration(o))
-            if "motion" in plan:
-                out = self._timed("motion", lambda o=out: PO.motion_blur(o, *plan["motion"]))
-            if plan.get("blur1"):
-                out = self._timed("blur1", lambda o=out: filter2d(o, kernel1, _analysis=an(0) if o.shape == gt.shape else None))
-            if plan.get("demosaic"):
-                out = self._timed("demosaic", lambda o=out: PO.demosaic(o))
-            if "sensor" in plan:
-                out = self._timed("sensor", lambda o=out: PO.sensor_noise(o, plan["sensor"], inject.get("sensor_noise"), self.rng.philox))
-            if "shutter" in plan:
-                out = self._timed("shutter", lambda o=out: PO.rolling_shutter(o, plan["shutter"]))
-            if "exposure" in plan:
-                out = self._timed("exposure", lambda o=out: PO.exposure(o, plan["exposure"]))
-            if "color_temp" in plan:
-                out = self._timed("color_temp", lambda o=out: PO.color_temperature(o, plan["color_temp"]))
-            if "oversharpen" in plan:
-                out = self._timed("oversharpen", lambda o=out: PO.oversharpen(o, plan["oversharpen"]))
-            if "aliasing" in plan:
-                out = self._timed("aliasing", lambda o=out: PO.aliasing(o, plan["aliasing"]))
-            out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-            out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel, _analysis=an(2)))
-            if plan.get("jpeg") is not None:  # per-sample qualities through DiffJPEG (this repo's earlier routing)
-                return self._jpeg(out, plan["jpeg"], round8=True)
-            for fmt, q in plan.get("compression", []):
-                out = self._timed(f"compress_{fmt}", lambda o=out: PO.compress_with_format(o, fmt, q, _opt(self.opt, "codec_fallback", "passthrough")))
-            if "editing_exposure" in plan:
-                out = self._timed("editing_exposure", lambda o=out: PO.exposure(o, plan["editing_exposure"]))
-            return self._timed("round", lambda o=out: clamp_round(o))
-        if plan.get("usm"):
-            r = plan["usm"]["radius"]
-            if r not in self._usm:
-                self._usm[r] = USMSharp(radius=r)
-            out = self._timed("usm", lambda o=out: self._usm[r](o, plan["usm"].get("weight", 0.5), plan["usm"].get("threshold", 10)))
-        if plan.get("blur1"):
-            out = self._timed("blur1", lambda o=out: filter2d(o, kernel1, _analysis=an(0)))
-        if plan.get("resize1"):
-            out = self._timed("resize1", lambda o=out: D.resize_pt(o, scale_factor=plan["resize1"]["scale"], mode=plan["resize1"]["mode"]))
-        if plan.get("noise1"):
-            out = self._timed("noise1", lambda o=out: self._noise(o, plan["noise1"], inject, "noise1"))
-        if plan.get("jpeg1") is not None:
-            out = self._timed("jpeg1", lambda o=out: self._jpeg(o, plan["jpeg1"], round8=False))
-        if plan.get("blur2"):
-            out = self._timed("blur2", lambda o=out: filter2d(o, kernel2, _analysis=an(1)))
-        if plan.get("resize2"):
-            s2 = plan["resize2"]["scale"]
-            out = self._timed("resize2", lambda o=out: D.resize_pt(o, size=(int(ori_h / sc * s2), int(ori_w / sc * s2)), mode=plan["resize2"]["mode"]))
-        if plan.get("noise2"):
-            out = self._timed("noise2", lambda o=out: self._noise(o, plan["noise2"], inject, "noise2"))
-        jpeg2 = plan.get("jpeg2")
-        if plan.get("final_order", "resize_first") == "resize_first":
-            out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-            out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel, _analysis=an(2)))
-            if jpeg2 is not None:  # clamp/round fused into the last kernel
-                return self._timed("jpeg2+round", lambda o=out: self._jpeg(o, jpeg2, round8=True))
-            return self._timed("round", lambda o=out: clamp_round(o))
-        if jpeg2 is not None:
-            out = self._timed("jpeg2", lambda o=out: self._jpeg(o, jpeg2, round8=False))
-        out = self._timed("resize3", lambda o=out: D.resize_pt(o, size=(ori_h // sc, ori_w // sc), mode=plan["resize3_mode"]))
-        out = self._timed("sinc", lambda o=out: filter2d(o, sinc_kernel, _analysis=an(2)))
-        return self._timed("round", lambda o=out: clamp_round(o))
+        return self._record(StageByStage(self, gt), kernel1, kernel2, sinc_kernel, plan, inject).img
 
     # -- the reference entry point --------------------------------------------------------
     @torch.no_grad()

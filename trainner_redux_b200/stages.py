@@ -118,7 +118,12 @@ class StageList:
             self.launches += 1 if k > 21 else 2
             self.unit_range = False
 
-    def usm(self, taps: np.ndarray, weight: float, threshold: float) -> None:
+    def at(self, name: str) -> "StageList":
+        """Stage name (used by the per-stage executor, stage_by_stage.StageByStage); nothing to record here."""
+        return self
+
+    def usm(self, taps: Any, weight: float, threshold: float) -> None:
+        taps = getattr(taps, "_taps", taps)  # a USMSharp module or its 1-D taps
         n = len(taps)
         if n // 2 >= self.h or n // 2 >= self.w:
             raise RuntimeError(f"Padding size should be less than the corresponding input dimension, but got: padding ({n // 2}, {n // 2})")
