@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import random
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Callable, Sequence
 
 import numpy as np

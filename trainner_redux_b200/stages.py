@@ -15,7 +15,6 @@ so a chain run through here is bit-identical to the same chain run call by call
 
 from __future__ import annotations
 
-import ctypes as C
 from typing import Any, Sequence
 
 import numpy as np
