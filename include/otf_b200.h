@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OTF_ABI_VERSION 4  /* 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
+#define OTF_ABI_VERSION 5  /* 5: otf_libjpeg_roundtrip_f32 + OTF_OP_LIBJPEG; 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
 
 enum {
     OTF_OK = 0,
@@ -236,6 +236,17 @@ int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
  * moved behind a 4x smaller upload). */
 int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* stream);
 
+/* ---- f3: the "jpeg" round of the fork's unified compression stage — traiNNer/models/paragon_otf_degradations.py:95-158
+ * (`_compress_with_format`): `(img.clamp(0,1) * 255).astype(uint8)`, `PIL.Image.save(format="JPEG", quality=int(q))`,
+ * `Image.open(...).convert("RGB")`, `/ 255`.  The decoded pixels are those of libjpeg(-turbo)'s baseline round trip with its
+ * defaults (4:2:0, Annex-K tables scaled by `quality`, integer "slow" DCT, fancy chroma up-sampling), reproduced BIT FOR
+ * BIT on the device (entropy coding is lossless and skipped).  img / out: (B,3,H,W) fp32 dense, any H, W >= 1 (libjpeg's
+ * edge expansion included); quality is clamped to 1..100 as jpeg_set_quality does.  workspace: device bytes
+ * (otf_libjpeg_workspace_bytes, 16-byte aligned) holding the decoded Y / Cb / Cr planes between the two launches. */
+int64_t otf_libjpeg_workspace_bytes(int B, int H, int W);
+int otf_libjpeg_roundtrip_f32(const float* img, int B, int H, int W, int quality,
+                              void* workspace, int64_t workspace_bytes, float* out, void* stream);
+
 /* ---- side-stream prefetcher — traiNNer/data/prefetch_dataloader.py:418-499 (`CUDAPrefetcher.preload` / `.next`) ----
  * One upload step: [ev_consumed is recorded on consumer_stream and copy_stream waits for it — the destination slots
  * may still be read by what the consumer has issued so far (pass NULL to skip)]; n plain cudaMemcpyAsync host->device
@@ -332,11 +343,13 @@ int otf_copy_box_f32(const float* src, int Hs, int Ws, int sy, int sx,
  *   OTF_OP_SENSOR       f0 = std, p0 injected N(0,1) field|NULL, seed, offset                  (otf_sensor_noise_f32)
  *   OTF_OP_DEMOSAIC     -  (C must be 3)                                                       (otf_demosaic_f32)
  *   OTF_OP_TRUNC8       -                                                                      (otf_trunc8_f32)
+ *   OTF_OP_LIBJPEG      n = quality (C must be 3; two launches)                                (otf_libjpeg_roundtrip_f32)
  * `final_h/final_w` (host, may be NULL) receive the extent of the last image-producing stage. */
 enum {
     OTF_OP_ANALYSE = 0, OTF_OP_FILTER2D = 1, OTF_OP_USM = 2, OTF_OP_SEPCONV = 3, OTF_OP_RESIZE = 4,
     OTF_OP_GAUSS = 5, OTF_OP_POISSON = 6, OTF_OP_JPEG = 7, OTF_OP_CLAMP_ROUND = 8, OTF_OP_CROP_PAIR = 9,
-    OTF_OP_WARP = 10, OTF_OP_TAPS_ZERO = 11, OTF_OP_GAIN = 12, OTF_OP_SENSOR = 13, OTF_OP_DEMOSAIC = 14, OTF_OP_TRUNC8 = 15
+    OTF_OP_WARP = 10, OTF_OP_TAPS_ZERO = 11, OTF_OP_GAIN = 12, OTF_OP_SENSOR = 13, OTF_OP_DEMOSAIC = 14, OTF_OP_TRUNC8 = 15,
+    OTF_OP_LIBJPEG = 16
 };
 typedef struct OtfStage {
     int32_t op, mode, oh, ow, n, kb, K, flags;

@@ -672,11 +672,13 @@ def run_chain_a(
     if plan.get("jpeg") is not None:
         out = diffjpeg(torch.clamp(out, 0, 1), plan["jpeg"].clone(), differentiable=False).contiguous()
     for fmt, q in plan.get("compression", []):
-        # the unified compression stage (paragon_otf_degradations.py:39-158) with the product's codec substitution for
-        # "jpeg": uint8 truncation (:114-115), DiffJPEG at int(quality), decoded 8-bit lattice; other formats pass through
+        # the unified compression stage (paragon_otf_degradations.py:39-158): "jpeg" is the reference's PIL round — uint8
+        # truncation (:119-120), libjpeg's baseline round trip at int(quality), / 255 (oracle/libjpeg_oracle.py, pinned
+        # bit for bit against PIL); other formats are host codecs and pass through
         if fmt == "jpeg" and q is not None:
-            x8 = torch.floor(torch.clamp(out, 0, 1) * 255.0) / 255.0
-            out = clamp_round(diffjpeg(x8, torch.full((out.size(0),), float(int(q))), differentiable=False).contiguous())
+            from . import libjpeg_oracle
+
+            out = libjpeg_oracle.jpeg_round(out, q)
     lq = clamp_round(out)
     if taps is not None:
         taps["lq_full"] = lq.clone()

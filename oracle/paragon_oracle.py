@@ -178,8 +178,7 @@ def demosaic(img: Tensor) -> Tensor:
 
 def pil_jpeg(img: Tensor, quality: float) -> Tensor:
     """`_compress_with_format(..., "jpeg")` (:95-158): uint8 truncation, libjpeg through PIL, back to [0,1].
-    The product routes this codec choice to the fused DiffJPEG kernel instead (a substitution, not parity:
-    libjpeg's integer DCT, table rounding and fancy chroma up-sampling differ); tests bound the distance."""
+    The product runs libjpeg's round trip on the device (csrc/libjpeg.cu) and must match this bit for bit."""
     from PIL import Image
 
     out = []

@@ -76,6 +76,10 @@ static int plan_layout(int B, int C, int H, int W, const OtfStage* st, int n, La
             case OTF_OP_POISSON:
                 scratch = (int64_t)B * 16 * 4;
                 break;
+            case OTF_OP_LIBJPEG:
+                OTF_REQUIRE(C == 3, OTF_ERR_BAD_ARG, "run_stages[%d]: the JPEG round needs 3 channels", i);
+                scratch = otf_libjpeg_workspace_bytes(B, h, w);
+                break;
             case OTF_OP_RESIZE:
                 OTF_REQUIRE(s.oh > 0 && s.ow > 0, OTF_ERR_BAD_ARG, "run_stages[%d]: resize to (%d, %d)", i, s.oh, s.ow);
                 if (!s.p0) scratch = otf_resize_workspace_bytes(h, w, s.oh, s.ow, s.mode);
@@ -237,6 +241,10 @@ extern "C" int otf_run_stages_f32(const float* img, int B, int C, int H, int W, 
             case OTF_OP_CLAMP_ROUND:
                 rc = otf_clamp_round_f32(cur, (int64_t)B * C * h * w, out, stream);
                 launches += 1;
+                break;
+            case OTF_OP_LIBJPEG:
+                rc = otf_libjpeg_roundtrip_f32(cur, B, h, w, s.n, scratch, otf_libjpeg_workspace_bytes(B, h, w), out, stream);
+                launches += 2;
                 break;
             case OTF_OP_WARP:
                 rc = otf_warp_f32(cur, B, C, h, w, s.mode, s.f0, out, stream);

@@ -10,9 +10,10 @@ Two layers:
     is given.
 
 Out of scope (host codecs): WebP / AVIF / HEIF / ffmpeg video rounds.  The cv2 Bayer demosaic IS
-reproduced on the device (bit for bit).  The unified pipeline's "jpeg" choice is routed to the fused DiffJPEG kernel (a substitution for the PIL
-codec, not bit parity: tests bound the distance); other formats pass through, which is what the reference does
-when a codec plugin is missing (paragon_otf_degradations.py:125-134).
+reproduced on the device (bit for bit), and so is the unified pipeline's "jpeg" choice: ``jpeg_round`` runs libjpeg's
+baseline round trip — what ``PIL.Image.save(format="JPEG")`` + ``Image.open`` decode to — in integer arithmetic on the
+device, bit for bit (csrc/libjpeg.cu; oracle/libjpeg_oracle.py is pinned against PIL itself).  Other formats pass
+through, which is what the reference does when a codec plugin is missing (paragon_otf_degradations.py:125-134).
 """
 
 from __future__ import annotations
@@ -29,7 +30,6 @@ from torch import Tensor
 
 from . import _lib
 from . import degradations as D
-from .diffjpeg import DiffJPEG
 
 _RNG: Any = None
 
@@ -186,8 +186,23 @@ def trunc8(img: Tensor) -> Tensor:
     return out
 
 
-_JPEGER = DiffJPEG(differentiable=False)
 _WARNED: set[str] = set()
+
+
+def jpeg_round(img: Tensor, quality: float) -> Tensor:
+    """The JPEG round of `_compress_with_format` (:119-149) on the device, BIT FOR BIT what the reference gets from PIL:
+    clamp, uint8 truncation, libjpeg's baseline round trip at ``int(quality)`` (4:2:0, Annex-K tables, integer DCT, fancy
+    up-sampling — ``otf_libjpeg_roundtrip_f32``), ``/ 255``.  3-channel images only (the reference turns a 1-channel
+    batch into RGB here; not reproduced)."""
+    x = _f32(img)
+    b, c, h, w = x.shape
+    if c != 3:
+        raise RuntimeError(f"the JPEG round expects 3 channels, got {c}")
+    out = torch.empty_like(x)
+    nbytes = _lib.load().otf_libjpeg_workspace_bytes(b, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _lib.call("otf_libjpeg_roundtrip_f32", _lib.ptr(x), b, h, w, int(quality), _lib.ptr(ws), nbytes, _lib.ptr(out), _lib.stream())
+    return out
 
 
 def codec_runs_jpeg(format_name: str, quality: float | None, fallback: str = "passthrough") -> bool:
@@ -206,17 +221,16 @@ def codec_runs_jpeg(format_name: str, quality: float | None, fallback: str = "pa
 
 
 def compress_with_format(img: Tensor, format_name: str, quality: float | None, fallback: str = "passthrough") -> Tensor:
-    """`_compress_with_format` (:95-158) for one drawn (format, quality).  "jpeg" = uint8 truncation, fused DiffJPEG at
-    ``int(quality)``, back onto the 8-bit lattice (what a decoded file holds).  WebP / AVIF / HEIF are host codecs:
+    """`_compress_with_format` (:95-158) for one drawn (format, quality).  "jpeg" = ``jpeg_round``: the reference's own
+    PIL / libjpeg result, bit for bit (parity, not a stand-in).  WebP / AVIF / HEIF are host codecs:
     ``fallback="passthrough"`` (default) returns the image unchanged with a one-time warning — what the reference does
     when the codec plugin is missing; ``fallback="jpeg"`` runs the JPEG round at the drawn quality instead, so the
     share of compressed batches stays what the option file asks for."""
     if codec_runs_jpeg(format_name, quality, fallback):
-        return _JPEGER(trunc8(img), quality=float(int(quality)), _round8=True)
+        return jpeg_round(img, quality)
     return img
 
 
-# ------------------------------------------------------ the reference's interface ----
 class ParagonOTF:
     """Static methods with the reference's names and draw order (paragon_otf_degradations.py:35-572)."""
 

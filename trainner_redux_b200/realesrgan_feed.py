@@ -529,9 +529,8 @@ class RealESRGANFeed:
                 return sl
             fallback = _opt(self.opt, "codec_fallback", "passthrough")
             for fmt, q in plan.get("compression", []):
-                if PO.codec_runs_jpeg(fmt, q, fallback):  # uint8 truncation, DiffJPEG at int(quality), 8-bit lattice
-                    sl.at(f"compress_{fmt}_trunc8").trunc8()
-                    sl.at(f"compress_{fmt}").jpeg(float(int(q)), clamp_in=False, round8=True)
+                if PO.codec_runs_jpeg(fmt, q, fallback):  # uint8 truncation + libjpeg's round trip at int(quality), bit for bit PIL's
+                    sl.at(f"compress_{fmt}").libjpeg(int(q))
             if "editing_exposure" in plan:
                 sl.at("editing_exposure").gain((plan["editing_exposure"],) * 3)
             sl.at("round").clamp_round()

@@ -131,3 +131,8 @@ class StageByStage:
         from . import paragon_otf as PO
 
         self._do(PO.trunc8)
+
+    def libjpeg(self, quality: int) -> None:
+        from . import paragon_otf as PO
+
+        self._do(lambda o: PO.jpeg_round(o, quality))

@@ -307,6 +307,14 @@ class StageList:
         self.launches += 1
         self.unit_range = True
 
+    def libjpeg(self, quality: int) -> None:
+        """paragon_otf.jpeg_round: uint8 truncation + libjpeg's baseline round trip at ``quality`` + / 255 (two launches)."""
+        if self.c != 3:
+            raise RuntimeError(f"the JPEG round expects 3 channels, got {self.c}")
+        self._add(_lib.OP_LIBJPEG, n=int(quality))
+        self.launches += 2
+        self.unit_range = True
+
     def resize_raw(self, mode_id: int, oh: int, ow: int, clamp: bool) -> None:
         """degradations._resize_call with an explicit mode id (the aliasing stage's legacy nearest, no clamp)."""
         self._resize(mode_id, int(oh), int(ow), clamp)
