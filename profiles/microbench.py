@@ -232,7 +232,8 @@ add("f3 exposure 256^2", lambda t: PO.exposure(t, 1.3), 2 * N(x256), x=x256)
 add("f3 colour temperature 256^2", lambda t: PO.color_temperature(t, 0.1), 2 * N(x256), x=x256)
 add("f3 sensor noise 256^2", lambda t: PO.sensor_noise(t, 0.05), 2 * N(x256), x=x256)
 add("f3 aliasing x0.75 256^2 (2 launches)", lambda t: PO.aliasing(t, 0.75), 2 * N(x256) + 2 * N(x192), x=x256)
-add("f3 jpeg round 64^2 (trunc8 + diffjpeg)", lambda t: PO.compress_with_format(t, "jpeg", 77.0), 4 * N(x64), x=x64)
+add("f3 jpeg round 64^2 (libjpeg round trip, bit-exact PIL: 2 launches)", lambda t: PO.compress_with_format(t, "jpeg", 77.0), 2 * N(x64), x=x64)
+add("f3 jpeg round 192^2 (libjpeg round trip, bit-exact PIL: 2 launches)", lambda t: PO.compress_with_format(t, "jpeg", 77.0), 2 * N(x192), x=x192)
 
 if args.json:
     json.dump({"hbm_peak_gbs": peak, "fma_peak_tflops": FMA_PEAK, "rows": rows}, open(args.json, "w"), indent=1)
