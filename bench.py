@@ -400,7 +400,7 @@ class Arm:
         return self.world * self.wl.batch * steps / (ms_total / 1e3)
 
     # ---- e2e: CUDAPrefetcher (pinned host batches -> static device slots on a copy stream) + feed_data + D2H of the LQ ----
-    def e2e(self, steps: int, warmup: int, u8: bool, lanes: int = 1) -> tuple[float, int, int]:
+    def e2e(self, steps: int, warmup: int, u8: bool, lanes: int = 1, readback: str = "f32") -> tuple[float, int, int]:
         from trainner_redux_b200.prefetch import CUDAPrefetcher, CUDAReadback
 
         wl = self.wl
@@ -413,7 +413,8 @@ class Arm:
                 b = {k: d[k].pin_memory() for k in ("gt", "kernel1", "kernel2", "sinc_kernel")}
             batches.append(b)
         rb = CUDAReadback(self.dev)  # the LQ goes back to pinned host memory on a side stream, every step
-        lq_bytes = 4 * wl.batch * 3 * (wl.crop // wl.scale) ** 2
+        # readback "u8": the LQ lies on the 8-bit lattice, so it crosses PCIe as bytes (CUDAReadback.read(as_u8=True), lossless)
+        lq_bytes = {"f32": 4, "u8": 1, "none": 0}[readback] * wl.batch * 3 * (wl.crop // wl.scale) ** 2
 
         def loader(n):
             for i in range(n):
@@ -437,7 +438,8 @@ class Arm:
                 batch = pf.next()
                 state["h2d"] = pf.h2d_bytes
                 self.feed.feed_data(batch, plan=self.plan())
-                rb.read(self.feed.lq)
+                if readback != "none":  # ("none": profiles/e2e_readback_ab.py only)
+                    rb.read(self.feed.lq, as_u8=readback == "u8")
                 t += 1
                 if lanes > 1:
                     torch.cuda.set_stream(lane[t % lanes])
@@ -615,7 +617,8 @@ def run_b200(args, wl: Workload) -> None:
 
     e2e_f32_value, h2d_f32, d2h = arm.e2e(args.steps, args.warmup, u8=False)
     e2e_one_value, h2d_u8, _ = arm.e2e(args.steps, args.warmup, u8=True)
-    e2e_value, _, _ = arm.e2e(args.steps, args.warmup, u8=True, lanes=n_streams)
+    e2e_rb32_value, _, _ = arm.e2e(args.steps, args.warmup, u8=True, lanes=n_streams)
+    e2e_value, _, d2h_u8 = arm.e2e(args.steps, args.warmup, u8=True, lanes=n_streams, readback="u8")
 
     extras = {}
     if not args.no_extras and wl.name == "c2" and wl.noise == "gaussian":
@@ -681,10 +684,14 @@ def run_b200(args, wl: Workload) -> None:
             "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,
             "value_graph_replay_one_stream": arm.pairs_per_s(args.steps, ms_replay1),
             "pcie_measured_gbs": pcie,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h_u8,
                     "h2d_gbs_per_rank": h2d_u8 * e2e_value / world / wl.batch / 1e9,
                     "feed": "pinned host uint8 GT + (3,B,8) kernel-parameter table (the dataset's decoded format; /255 and kernel "
-                            f"synthesis on the device) -> CUDAPrefetcher -> feed_data -> CUDAReadback of the LQ, {n_streams} batches in flight"},
+                            f"synthesis on the device) -> CUDAPrefetcher -> feed_data -> CUDAReadback of the whole LQ batch as bytes "
+                            f"(it lies on the 8-bit lattice: lossless, u8 / 255 restores it bit for bit), {n_streams} batches in flight"},
+            "e2e_readback_f32": {"value": e2e_rb32_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                                 "note": "same loop with the LQ read back as fp32 (4x the D2H bytes): equal on one GPU, slower when eight "
+                                         "ranks share the host path (profiles/r02_e2e_readback_n8.json)"},
             "e2e_one_stream": {"value": e2e_one_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h},
             "e2e_f32": {"value": e2e_f32_value, "unit": UNIT, "h2d_bytes_per_step": h2d_f32, "d2h_bytes_per_step": d2h,
                         "h2d_gbs_per_rank": h2d_f32 * e2e_f32_value / world / wl.batch / 1e9,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OTF_ABI_VERSION 5  /* 5: otf_libjpeg_roundtrip_f32 + OTF_OP_LIBJPEG; 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
+#define OTF_ABI_VERSION 6  /* 6: otf_f32_to_u8; 5: otf_libjpeg_roundtrip_f32 + OTF_OP_LIBJPEG; 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2, fork-extra ops of the stage executor, otf_usm_launch_count */
 
 enum {
     OTF_OK = 0,
@@ -235,6 +235,12 @@ int otf_crop_pair_f32(const float* gt, int planes, int Hg, int Wg,
 /* uint8 image -> fp32 / 255 (the host-side normalisation of traiNNer/utils/img_util.py:65-109 `img2tensor`,
  * moved behind a 4x smaller upload). */
 int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* stream);
+
+/* ---- the way back — traiNNer/utils/img_util.py:112-181 (`tensor2img`: `(img * 255.0).round()` as uint8, done on the
+ * host after an fp32 read-back) ----  dst[i] = clamp(round(src[i] * 255), 0, 255) (round half to even).  A finished LQ batch
+ * lies on the 8-bit lattice (realesrgan_model.py:616), so its read-back moves one byte per value and
+ * `u8.float() / 255` restores the fp32 tensor bit for bit.  src 16-byte aligned, dst 4-byte aligned. */
+int otf_f32_to_u8(const float* src, int64_t n, uint8_t* dst, void* stream);
 
 /* ---- f3: the "jpeg" round of the fork's unified compression stage — traiNNer/models/paragon_otf_degradations.py:95-158
  * (`_compress_with_format`): `(img.clamp(0,1) * 255).astype(uint8)`, `PIL.Image.save(format="JPEG", quality=int(q))`,

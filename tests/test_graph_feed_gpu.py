@@ -159,6 +159,38 @@ def test_readback_side_stream(dev):
         rb.read(torch.zeros(4))
 
 
+def test_readback_as_bytes_is_lossless_on_the_lattice(dev):
+    """CUDAReadback.read(as_u8=True): an image on the 8-bit lattice (every level, any length incl. a ragged tail) crosses
+    as ``clamp(round(x * 255), 0, 255)`` bytes (`tensor2img`'s conversion, img_util.py:112-181, done on the device) and
+    ``u8.float() / 255`` restores the fp32 tensor bit for bit; off-lattice and out-of-range values round half to even and
+    saturate like the reference's ``(img * 255.0).round()`` + uint8 clamp; a finished LQ batch survives the trip."""
+    from trainner_redux_b200 import _lib as L
+    from trainner_redux_b200.prefetch import CUDAReadback
+
+    rb = CUDAReadback(dev, depth=2)
+    for n in (256, 1027, 64 * 3 * 56 * 56 + 3):
+        lv = (torch.arange(n) * 7919) % 256
+        x = (lv.float() / 255.0).to(dev)
+        h = rb.read(x, as_u8=True)
+        rb.wait()
+        assert h.dtype == torch.uint8 and h.is_pinned() and torch.equal(h, lv.to(torch.uint8))
+        assert torch.equal(h.float() / 255.0, x.cpu())
+    y = torch.tensor([-0.3, 0.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 0.49999, 1.0, 1.7, 254.5 / 255], device=dev)
+    u = torch.empty(y.numel(), dtype=torch.uint8, device=dev)
+    L.call("otf_f32_to_u8", L.ptr(y), y.numel(), L.ptr(u), L.stream())
+    want = torch.clamp(torch.round(y.cpu() * 255.0), 0, 255).to(torch.uint8)
+    assert torch.equal(u.cpu(), want)
+    feed = RealESRGANFeed(_opt("gaussian", 4), device=dev, manual_seed=5, use_pool=False)
+    data = _data(4, 96, 3, dev)
+    for _ in range(3):  # eager, capture, replay: the read-back follows the producer on the current stream each time
+        feed.feed_data(data)
+        h = rb.read(feed.lq, as_u8=True)
+        rb.wait()
+        assert torch.equal(h.float() / 255.0, feed.lq.cpu())
+    with pytest.raises(TypeError):
+        rb.read(torch.zeros(8, dtype=torch.float64, device=dev), as_u8=True)
+
+
 def test_gt_window_is_a_view_like_the_reference(dev):
     """paired_random_crop returns the GT window as a slice of the batch (transforms.py:124-129): feed_data hands out the
     same view (no bytes move) unless the pool / MoA / ``gt_view = False`` ask for a dense copy — identical values."""

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.otf_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.otf_abi_version() == _lib.ABI_VERSION == 6
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (otf_[a-z0-9_]+)", out))
     assert declared <= exported

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("OTF_LIB_PATH") or os.path.join(_HERE, "libotf_b200.so
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "otf_b200.h")
 
 OTF_OK = 0
-ABI_VERSION = 5  # 5: otf_libjpeg_roundtrip_f32 + OP_LIBJPEG; 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2 + the fork-extra ops of the stage executor; 2: device-side Philox offset word / crop offsets, OtfStage.p4
+ABI_VERSION = 6  # 6: otf_f32_to_u8; 5: otf_libjpeg_roundtrip_f32 + OP_LIBJPEG; 4: prefetcher upload step (otf_upload_async + events); 3: OtfStage.f2 + the fork-extra ops of the stage executor; 2: device-side Philox offset word / crop offsets, OtfStage.p4
 RESIZE_BILINEAR_AA, RESIZE_BICUBIC_AA, RESIZE_AREA, RESIZE_NEAREST_EXACT, RESIZE_BICUBIC, RESIZE_NEAREST, RESIZE_LANCZOS = range(7)
 WARP_LENS, WARP_SHUTTER, WARP_CHROMA = range(3)
 TAPS_NONE, TAPS_OVERSHARPEN = 0, 1
@@ -56,6 +56,7 @@ SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "otf_clamp_round_f32": (_i, [_p, _i64, _p, _p]),
     "otf_crop_pair_f32": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p]),
     "otf_u8_to_f32": (_i, [_p, _i64, _p, _p]),
+    "otf_f32_to_u8": (_i, [_p, _i64, _p, _p]),
     "otf_libjpeg_workspace_bytes": (_i64, [_i, _i, _i]),
     "otf_libjpeg_roundtrip_f32": (_i, [_p, _i, _i, _i, _i, _p, _i64, _p, _p]),
     "otf_event_create": (_i, [_p]),
@@ -135,6 +136,7 @@ _LAUNCHES = {
     "otf_trunc8_f32": 1,
     "otf_demosaic_f32": 1,
     "otf_libjpeg_roundtrip_f32": 2,
+    "otf_f32_to_u8": 1,
 }
 
 

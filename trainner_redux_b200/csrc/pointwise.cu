@@ -56,6 +56,22 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restric
     if (tail < n) dst[tail] = __fdiv_rn((float)src[tail], 255.0f);
 }
 
+// ---- the way back: an image on the 8-bit lattice as bytes ------------------------------------
+// What traiNNer/utils/img_util.py:112-181 (`tensor2img`: `(img * 255.0).round()` -> uint8) does on the host after a
+// full-precision read-back: clamp(round(x * 255), 0, 255) on the device, so that a finished LQ batch (which lies on that
+// lattice already, realesrgan_model.py:616) crosses PCIe as one byte per value and `u8.float() / 255` restores it bit for bit.
+__global__ void __launch_bounds__(256) f32_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+    pdl_enter();
+    auto level = [](float v) { return (unsigned)fminf(fmaxf(rintf(__fmul_rn(v, 255.0f)), 0.0f), 255.0f); };
+    const int64_t nq = n >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+        reinterpret_cast<uchar4*>(dst)[q] = make_uchar4(level(v.x), level(v.y), level(v.z), level(v.w));
+    }
+    const int64_t tail = (nq << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tail < n) dst[tail] = (uint8_t)level(src[tail]);
+}
+
 // (copy_window, the quad-per-thread window copy of a8, lives in otf_common.cuh: the fused DiffJPEG + crop launch uses it too)
 template <bool VEC_GT, bool VEC_LQ, bool ROUND8>
 __global__ void __launch_bounds__(256) crop_pair_kernel(const float* __restrict__ gt, int Hg, int Wg,
@@ -240,6 +256,18 @@ extern "C" int otf_u8_to_f32(const uint8_t* src, int64_t n, float* dst, void* st
     if (blocks < 1) blocks = 1;
     launch_chain(u8_to_f32_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, src, dst, n);
     OTF_LAUNCH_CHECK("u8_to_f32_kernel");
+    return OTF_OK;
+}
+
+extern "C" int otf_f32_to_u8(const float* src, int64_t n, uint8_t* dst, void* stream) {
+    using namespace otf;
+    OTF_REQUIRE(src && dst && n > 0, OTF_ERR_BAD_ARG, "f32_to_u8: bad args");
+    OTF_REQUIRE((((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 3) == 0, OTF_ERR_BAD_ARG, "f32_to_u8: misaligned pointers");
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (blocks < 1) blocks = 1;
+    launch_chain(f32_to_u8_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, src, dst, n);
+    OTF_LAUNCH_CHECK("f32_to_u8_kernel");
     return OTF_OK;
 }
 

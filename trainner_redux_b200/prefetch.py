@@ -190,19 +190,34 @@ class CUDAReadback:
         except Exception:  # noqa: BLE001  interpreter shutdown
             pass
 
-    def read(self, t: Tensor) -> Tensor:
+    def read(self, t: Tensor, as_u8: bool = False) -> Tensor:
+        """``as_u8=True``: ``t`` is an fp32 image on the 8-bit lattice (a finished LQ batch, realesrgan_model.py:616) and
+        crosses PCIe as ``clamp(round(t * 255), 0, 255)`` bytes (one launch of ``otf_f32_to_u8`` on the current stream into
+        a device staging buffer of the ring); ``host.float() / 255`` restores ``t`` bit for bit.  A quarter of the bytes: at
+        eight ranks per host the fp32 read-back competes with the uploads for the path to host memory
+        (profiles/r02_e2e_readback_n8.json)."""
         _lib.require_cuda(t)
         if not t.is_contiguous():
             t = t.contiguous()
+        cur = _lib.stream()
+        if self._issued:  # (the copy stream is in order: the last read done = every earlier one done, staging buffers included)
+            _lib.call("otf_stream_wait_event", cur, self._done)
+        if as_u8:
+            if t.dtype != torch.float32:
+                raise TypeError("CUDAReadback.read(as_u8=True) expects a float32 tensor")
+            ku = ("u8dev", t.shape)
+            dring = self._host.get(ku)
+            if dring is None:  # (device-side staging, one per ring position: the copy of call i may still run during call i + 1)
+                dring = self._host[ku] = [torch.empty(t.shape, dtype=torch.uint8, device=t.device) for _ in range(self.depth)]
+            u = dring[self._turn % self.depth]
+            _lib.call("otf_f32_to_u8", _lib.ptr(t), t.numel(), _lib.ptr(u), cur)
+            t = u
         k = (t.shape, t.dtype)
         ring = self._host.get(k)
         if ring is None:
             ring = self._host[k] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for _ in range(self.depth)]
         dst = ring[self._turn % self.depth]
         self._turn += 1
-        cur = _lib.stream()
-        if self._issued:
-            _lib.call("otf_stream_wait_event", cur, self._done)
         _lib.call("otf_download_async", C.c_void_p(dst.data_ptr()), _lib.ptr(t), t.numel() * t.element_size(), self._copy_stream, cur,
                   self._produced, self._done)
         self._issued = True
