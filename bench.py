@@ -59,6 +59,7 @@ import torch  # noqa: E402
 UNIT = "pairs/s"
 S1, S2 = 0.75, 1.0
 N_ROTATE = int(os.environ.get("OTF_BENCH_ROTATE", "4"))  # distinct input batches rotated through (4 x 50 MB > 126 MB L2)
+E2E_SHORT_STEPS, E2E_REPS_SHORT = 100, 5  # e2e timed regions of <= 100 steps are measured 5 times, median reported (Arm.e2e)
 E2E_SLOTS = int(os.environ.get("OTF_BENCH_E2E_SLOTS", "2"))  # static upload slots of the e2e prefetcher (one captured chain each)
 
 
@@ -428,7 +429,8 @@ class Arm:
         # clock starts the first timed batch is already on its way and every timed step uploads the batch of the step
         # after it — K steps, K uploads, K read-backs inside the timed region (the loader yields one batch more than is
         # consumed so that the last step's preload is a real upload too)
-        pf = CUDAPrefetcher(loader(n_warm + steps + 1), device=self.dev, slots=n_slots)
+        reps = E2E_REPS_SHORT if steps <= E2E_SHORT_STEPS else 1
+        pf = CUDAPrefetcher(loader(n_warm + reps * steps + 1), device=self.dev, slots=n_slots)
         state = {"t": 0, "h2d": 0}
 
         def run(n: int) -> None:
@@ -449,16 +451,23 @@ class Arm:
             torch.cuda.synchronize()
 
         run(n_warm)
-        self.barrier()
-        t0 = time.perf_counter()
-        run(steps)
-        dt = time.perf_counter() - t0
+        # a short timed region (the driver's K = 20 is under 5 ms of wall clock, host work included) is at the mercy of one
+        # scheduling hiccup on the host: it is then measured `reps` times — each EXACTLY `steps` steps between a barrier +
+        # synchronise on both sides, max over ranks — and the median is reported, every repetition listed beside it
+        vals = []
+        for _ in range(reps):
+            self.barrier()
+            t0 = time.perf_counter()
+            run(steps)
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], device=self.dev)
+            if self.world > 1:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            vals.append(self.world * wl.batch * steps / t.item())
         h2d = state["h2d"]
-        t = torch.tensor([dt], device=self.dev)
-        if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         params_h2d = 16 + 4 * wl.batch * 6  # the chain's per-step parameter block (chain_graph.ParamBlock)
-        return self.world * wl.batch * steps / t.item(), h2d + params_h2d, lq_bytes
+        self.e2e_reps = [round(v, 1) for v in vals]
+        return sorted(vals)[len(vals) // 2], h2d + params_h2d, lq_bytes
 
     # ---- per-stage GPU durations: every stage re-captured alone (x REP) and replayed, CUDA events ----
     def stage_ms(self) -> dict:
@@ -607,6 +616,10 @@ def run_b200(args, wl: Workload) -> None:
     l0 = _lib.launch_count
     ms_total = arm.timed(args.steps, n_streams)
     launches = _lib.launch_count - l0
+    # a short region (the driver's K = 20 is 3.5 ms) sees single host hiccups as 10 % swings: measured 5 times then — each
+    # region EXACTLY K steps between barrier + synchronise, CUDA events, max over ranks — and the median reported
+    regions_ms = [ms_total] + [arm.timed(args.steps, n_streams) for _ in range(E2E_REPS_SHORT - 1 if args.steps <= E2E_SHORT_STEPS else 0)]
+    ms_total = sorted(regions_ms)[len(regions_ms) // 2]
     value = arm.pairs_per_s(args.steps, ms_total)
     ms_single = arm.timed(args.steps, 1)
     ms_replay1 = arm.timed(args.steps, 1, replay_only=True) if arm.feed.graphs.entries else float("nan")
@@ -619,6 +632,7 @@ def run_b200(args, wl: Workload) -> None:
     e2e_one_value, h2d_u8, _ = arm.e2e(args.steps, args.warmup, u8=True)
     e2e_rb32_value, _, _ = arm.e2e(args.steps, args.warmup, u8=True, lanes=n_streams)
     e2e_value, _, d2h_u8 = arm.e2e(args.steps, args.warmup, u8=True, lanes=n_streams, readback="u8")
+    e2e_reps = list(arm.e2e_reps)
 
     extras = {}
     if not args.no_extras and wl.name == "c2" and wl.noise == "gaussian":
@@ -680,12 +694,14 @@ def run_b200(args, wl: Workload) -> None:
                               f"{graphs.hits} replays so far), {n_streams} calls in flight on {n_streams} streams",
                     "gt_crop": "the GT half of the pair is the reference's view of the GT batch (transforms.py:124-129: a slice, no copy); the LQ crop is dense",
                     "numa_node_rank0": numa, "numa_note": numa_why},
+            "timed_regions_ms": [round(m, 4) for m in regions_ms],
             "value_feed_data": arm.pairs_per_s(args.steps, ms_single), "ms_per_step_feed_data": ms_single / args.steps,
             "value_graph_replay": arm.pairs_per_s(args.steps, ms_replay), "ms_per_step_graph_replay": ms_replay / args.steps,
             "value_graph_replay_one_stream": arm.pairs_per_s(args.steps, ms_replay1),
             "pcie_measured_gbs": pcie,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h_u8,
                     "h2d_gbs_per_rank": h2d_u8 * e2e_value / world / wl.batch / 1e9,
+                    "timed_regions": e2e_reps, "estimator": f"median of {len(e2e_reps)} timed regions of exactly {args.steps} steps each" if len(e2e_reps) > 1 else f"one timed region of {args.steps} steps",
                     "feed": "pinned host uint8 GT + (3,B,8) kernel-parameter table (the dataset's decoded format; /255 and kernel "
                             f"synthesis on the device) -> CUDAPrefetcher -> feed_data -> CUDAReadback of the whole LQ batch as bytes "
                             f"(it lies on the 8-bit lattice: lossless, u8 / 255 restores it bit for bit), {n_streams} batches in flight"},
