@@ -1,5 +1,5 @@
 """Launch each kernel of the path a few times on the bench shapes (B=64) — the command ncu wraps.
-    python profiles/prof_kernels.py [stage ...]     stages: blur1 resize1 resize_up noise1 jpeg1 blur2 sinc poisson usm all
+    python profiles/prof_kernels.py [stage ...]     stages: blur1 resize1 resize_up noise1 jpeg1 libjpeg blur2 sinc poisson usm all
 """
 import os
 import sys
@@ -41,6 +41,10 @@ for it in range(3):
     if want("jpeg1"):
         jp(x192, quality=q.clone(), _clamp_in=True)
         jp(x64, quality=q.clone(), _clamp_in=True, _round8=True)
+    if want("libjpeg"):
+        from trainner_redux_b200 import paragon_otf as PO
+        PO.compress_with_format(x192, "jpeg", 77.0)
+        PO.compress_with_format(x64, "jpeg", 77.0)
     if want("blur2"):
         T.filter2d(x192, k2)
     if want("sinc"):
