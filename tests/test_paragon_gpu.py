@@ -133,7 +133,7 @@ def test_sensor_noise_from_philox_has_the_requested_std(dev):
     assert not torch.equal(out, again)  # the default generator advances
 
 
-@pytest.mark.parametrize("size", [(96, 96), (64, 64), (50, 70), (17, 33), (8, 8), (100, 3), (3, 100), (5, 5), (1, 1), (127, 129)])
+@pytest.mark.parametrize("size", [(96, 96), (64, 64), (50, 70), (17, 33), (8, 8), (100, 3), (3, 100), (5, 5), (1, 1), (127, 129), (256, 256), (250, 301)])
 def test_jpeg_round_is_the_pil_codec_bit_for_bit(size, dev):
     """The unified pipeline's "jpeg" choice (paragon_otf_degradations.py:119-149): uint8 truncation, PIL save / open,
     / 255.  The device runs libjpeg's baseline round trip itself (csrc/libjpeg.cu) — identical to PIL's result, any image
