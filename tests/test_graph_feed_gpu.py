@@ -175,6 +175,10 @@ def test_readback_as_bytes_is_lossless_on_the_lattice(dev):
         rb.wait()
         assert h.dtype == torch.uint8 and h.is_pinned() and torch.equal(h, lv.to(torch.uint8))
         assert torch.equal(h.float() / 255.0, x.cpu())
+    z = (torch.arange(1030) % 256).float().div(255.0).to(dev)[3:]  # a view that does not start on a 16-byte boundary
+    h = rb.read(z, as_u8=True)
+    rb.wait()
+    assert torch.equal(h.float() / 255.0, z.cpu())
     y = torch.tensor([-0.3, 0.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 0.49999, 1.0, 1.7, 254.5 / 255], device=dev)
     u = torch.empty(y.numel(), dtype=torch.uint8, device=dev)
     L.call("otf_f32_to_u8", L.ptr(y), y.numel(), L.ptr(u), L.stream())

@@ -72,14 +72,7 @@ __device__ __forceinline__ void idct8(float (&y)[8]) {
     y[3] = e3 + o3; y[4] = e3 - o3;
 }
 
-// x / 255 with IEEE rounding in three FP32-pipe operations instead of the ~10 of a general division: q = x * RN(1/255),
-// one exact residual, one correction (Markstein).  Equal to __fdiv_rn(x, 255.0f) for EVERY float in [0, 255] — checked
-// exhaustively on the device (profiles/experiments/div255_exact.cu) — which is the whole range this file divides.
-__device__ __forceinline__ float div255(float x) {
-    const float y = 3.9215688593685627e-03f;  // RN(1 / 255) = 0x3B808081
-    const float q = __fmul_rn(x, y);
-    return fmaf(fmaf(-q, 255.0f, x), y, q);
-}
+// (div255 — x / 255 with IEEE rounding in three FP32-pipe operations — lives in otf_common.cuh: the libjpeg round uses it too)
 // clamp(round(x * 255), 0, 255) / 255 for x already in [0, 1] (quantise8 of otf_common.cuh with the cheap division)
 __device__ __forceinline__ float quantise8_unit(float x) { return div255(fminf(fmaxf(rintf(__fmul_rn(x, 255.0f)), 0.0f), 255.0f)); }
 

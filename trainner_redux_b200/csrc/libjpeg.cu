@@ -92,22 +92,31 @@ __device__ __forceinline__ void idct8(int (&v)[8]) {
 __device__ __forceinline__ int level8_trunc(float v) { return (int)__fmul_rn(fminf(fmaxf(v, 0.0f), 1.0f), 255.0f); }
 
 constexpr int kJW = 4;          // warps (MCUs) per CTA
-constexpr int kBP = 9;          // pitch of an 8x8 block row in shared memory (odd: row and column passes both spread over the banks)
-constexpr int kBlk = 8 * kBP;   // words per block
+// Block rows sit on 16-byte boundaries (pitch 12 words), blocks 104 words apart: a row is two 128-bit shared-memory accesses
+// (eight lanes of a block: 16-byte units 3r mod 8, all distinct), and the column pass — lane = (block, column), word
+// 104 * block + column + 12 * k — meets 32 distinct banks (8 * block + column mod 32).  Scalar rows at pitch 9 kept the
+// shared-memory instruction queue full (ncu: mio_throttle 12 stall cycles per issue).
+constexpr int kBP = 12;         // pitch of an 8x8 block row in shared memory
+constexpr int kBlk = 8 * kBP + 8;  // words per block
+__device__ __forceinline__ void row_load(const int* p, int (&d)[8]) {
+    const int4 a = *reinterpret_cast<const int4*>(p), b = *reinterpret_cast<const int4*>(p + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void row_store(int* p, const int (&d)[8]) {
+    *reinterpret_cast<int4*>(p) = make_int4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<int4*>(p + 4) = make_int4(d[4], d[5], d[6], d[7]);
+}
 
 __global__ void __launch_bounds__(32 * kJW) libjpeg_codec_kernel(const float* __restrict__ img, int B, int H, int W, int mcu_x, int mcu_y,
                                                                 const __grid_constant__ JpegQuant qt, uint8_t* __restrict__ yplane,
-                                                                uint8_t* __restrict__ cplane) {
-    __shared__ int s_blk[kJW][6 * kBlk];     // Y00, Y01, Y10, Y11, Cb, Cr
-    __shared__ int s_full[kJW][2][16 * 17];  // full-resolution Cb / Cr of the MCU (pitch 17)
+                                                                uint8_t* __restrict__ cplane, int vec_ok) {
+    __shared__ __align__(16) int s_blk[kJW][6 * kBlk];  // Y00, Y01, Y10, Y11, Cb, Cr
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int64_t mcu = (int64_t)blockIdx.x * kJW + wrp;
     if (mcu >= (int64_t)B * mcu_x * mcu_y) return;  // warp-uniform
     const int b = (int)(mcu / (mcu_x * mcu_y)), m = (int)(mcu - (int64_t)b * mcu_x * mcu_y);
     const int my = m / mcu_x, mx = m - my * mcu_x;
     int* blk = s_blk[wrp];
-    int* cbf = s_full[wrp][0];
-    int* crf = s_full[wrp][1];
     const size_t plane = (size_t)H * W;
     const float* ip = img + (size_t)b * 3 * plane;
     const int ch = (H + 1) >> 1;
@@ -125,30 +134,59 @@ __global__ void __launch_bounds__(32 * kJW) libjpeg_codec_kernel(const float* __
         const float* py = ip + (size_t)ry * W;
         const float* pc = ip + (size_t)rc * W;
         int* yb = blk + ((ly >> 3) * 2 + (lane & 1)) * kBlk + (ly & 7) * kBP;
+        // an MCU inside an aligned image (warp-uniform): six 16-byte loads per lane instead of 24 clamped scalar ones
+        const bool interior = vec_ok && (mx * 16 + 16 <= W) && (my * 16 + 16 <= H);
+        float pr[8], pg[8], pb[8];
+        if (interior) {
+            const float* p0 = py + mx * 16 + lx0;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p0) + hf), g4 = __ldg(reinterpret_cast<const float4*>(p0 + plane) + hf),
+                             b4 = __ldg(reinterpret_cast<const float4*>(p0 + 2 * plane) + hf);
+                pr[4 * hf] = a.x; pr[4 * hf + 1] = a.y; pr[4 * hf + 2] = a.z; pr[4 * hf + 3] = a.w;
+                pg[4 * hf] = g4.x; pg[4 * hf + 1] = g4.y; pg[4 * hf + 2] = g4.z; pg[4 * hf + 3] = g4.w;
+                pb[4 * hf] = b4.x; pb[4 * hf + 1] = b4.y; pb[4 * hf + 2] = b4.z; pb[4 * hf + 3] = b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int x = min(mx * 16 + lx0 + k, W - 1);
+                pr[k] = __ldg(py + x); pg[k] = __ldg(py + plane + x); pb[k] = __ldg(py + 2 * plane + x);
+            }
+        }
+        int cbs[4], crs[4];  // horizontal pair sums of the full-resolution Cb / Cr
+        int yrow[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int x = min(mx * 16 + lx0 + k, W - 1);
-            const int r = level8_trunc(__ldg(py + x)), g = level8_trunc(__ldg(py + plane + x)), bl = level8_trunc(__ldg(py + 2 * plane + x));
-            yb[k] = ((19595 * r + 38470 * g + 7471 * bl + 32768) >> 16) - 128;  // FIX(0.299), FIX(0.587), FIX(0.114); centred
+            const int r = level8_trunc(pr[k]), g = level8_trunc(pg[k]), bl = level8_trunc(pb[k]);
+            yrow[k] = ((19595 * r + 38470 * g + 7471 * bl + 32768) >> 16) - 128;  // FIX(0.299), FIX(0.587), FIX(0.114); centred
             int r2 = r, g2 = g, b2 = bl;
-            if (rc != ry) {
+            if (rc != ry) {  // (never inside an interior MCU)
+                const int x = min(mx * 16 + lx0 + k, W - 1);
                 r2 = level8_trunc(__ldg(pc + x)); g2 = level8_trunc(__ldg(pc + plane + x)); b2 = level8_trunc(__ldg(pc + 2 * plane + x));
             }
             // FIX(0.16874) = 11059, FIX(0.33126) = 21709, FIX(0.5) = 32768, FIX(0.41869) = 27439, FIX(0.08131) = 5329;
             // CBCR_OFFSET + ONE_HALF - 1 = (128 << 16) + 32767
-            cbf[ly * 17 + lx0 + k] = (-11059 * r2 - 21709 * g2 + 32768 * b2 + 8388608 + 32767) >> 16;
-            crf[ly * 17 + lx0 + k] = (32768 * r2 - 27439 * g2 - 5329 * b2 + 8388608 + 32767) >> 16;
+            const int cbv = (-11059 * r2 - 21709 * g2 + 32768 * b2 + 8388608 + 32767) >> 16;
+            const int crv = (32768 * r2 - 27439 * g2 - 5329 * b2 + 8388608 + 32767) >> 16;
+            if (k & 1) { cbs[k >> 1] += cbv; crs[k >> 1] += crv; } else { cbs[k >> 1] = cbv; crs[k >> 1] = crv; }
         }
-    }
-    __syncwarp();
-    // ---- h2v2_downsample: 2x2 box, bias 1, 2, 1, 2 ... along the component row ------------------------------------------
+        row_store(yb, yrow);
+        // ---- h2v2_downsample: 2x2 box, bias 1, 2, 1, 2 ... along the component row.  The horizontal pairs sit in this lane,
+        //      the row below / above in lane ^ 2: one shuffle per pair sum, the even rows store the four chroma samples ----
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int idx = lane + 32 * t;  // 0..127: (component, cy, cx)
-        const int comp = idx >> 6, cy = (idx >> 3) & 7, cx = idx & 7;
-        const int* f = comp ? crf : cbf;
-        const int s = f[(2 * cy) * 17 + 2 * cx] + f[(2 * cy) * 17 + 2 * cx + 1] + f[(2 * cy + 1) * 17 + 2 * cx] + f[(2 * cy + 1) * 17 + 2 * cx + 1];
-        blk[(4 + comp) * kBlk + cy * kBP + cx] = ((s + 1 + (cx & 1)) >> 2) - 128;  // (an MCU starts at an even component column)
+        for (int j = 0; j < 4; ++j) {
+            cbs[j] += __shfl_xor_sync(0xffffffffu, cbs[j], 2);
+            crs[j] += __shfl_xor_sync(0xffffffffu, crs[j], 2);
+        }
+        if (!(ly & 1)) {
+            const int cy = ly >> 1, cx0 = lx0 >> 1;
+            // (an MCU starts at an even component column: the bias alternates with cx)
+            *reinterpret_cast<int4*>(blk + 4 * kBlk + cy * kBP + cx0) =
+                make_int4(((cbs[0] + 1) >> 2) - 128, ((cbs[1] + 2) >> 2) - 128, ((cbs[2] + 1) >> 2) - 128, ((cbs[3] + 2) >> 2) - 128);
+            *reinterpret_cast<int4*>(blk + 5 * kBlk + cy * kBP + cx0) =
+                make_int4(((crs[0] + 1) >> 2) - 128, ((crs[1] + 2) >> 2) - 128, ((crs[2] + 1) >> 2) - 128, ((crs[3] + 2) >> 2) - 128);
+        }
     }
     __syncwarp();
     // ---- forward DCT rows: 48 row tasks (block, row) ----------------------------------------------------------------------
@@ -158,11 +196,9 @@ __global__ void __launch_bounds__(32 * kJW) libjpeg_codec_kernel(const float* __
         if (task < 48) {
             int* p = blk + (task >> 3) * kBlk + (task & 7) * kBP;
             int d[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) d[k] = p[k];
+            row_load(p, d);
             fdct8<true>(d);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) p[k] = d[k];
+            row_store(p, d);
         }
     }
     __syncwarp();
@@ -203,8 +239,7 @@ __global__ void __launch_bounds__(32 * kJW) libjpeg_codec_kernel(const float* __
             const int bi = task >> 3, r = task & 7;
             const int* p = blk + bi * kBlk + r * kBP;
             int d[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) d[k] = p[k];
+            row_load(p, d);
             idct8<false>(d);
             uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -226,9 +261,9 @@ __device__ __forceinline__ void ycc_store(float* __restrict__ op, size_t plane, 
     const int r = y + ((91881 * xr + 32768) >> 16);                         // FIX(1.40200)
     const int bb = y + ((116130 * xb + 32768) >> 16);                       // FIX(1.77200)
     const int g = y + ((-22554 * xb + 32768 - 46802 * xr) >> 16);           // FIX(0.34414), FIX(0.71414)
-    op[off] = __fdiv_rn((float)min(max(r, 0), 255), 255.0f);
-    op[plane + off] = __fdiv_rn((float)min(max(g, 0), 255), 255.0f);
-    op[2 * plane + off] = __fdiv_rn((float)min(max(bb, 0), 255), 255.0f);
+    op[off] = div255((float)min(max(r, 0), 255));  // (== __fdiv_rn(x, 255) on [0, 255], three FP32 operations)
+    op[plane + off] = div255((float)min(max(g, 0), 255));
+    op[2 * plane + off] = div255((float)min(max(bb, 0), 255));
 }
 
 __global__ void __launch_bounds__(256) libjpeg_upsample_kernel(const uint8_t* __restrict__ yplane, const uint8_t* __restrict__ cplane, int B,
@@ -322,7 +357,8 @@ extern "C" int otf_libjpeg_roundtrip_f32(const float* img, int B, int H, int W, 
     uint8_t* cplane = yplane + (size_t)B * Hp * Wp;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t mcus = (int64_t)B * mcu_x * mcu_y;
-    libjpeg_codec_kernel<<<(unsigned)((mcus + kJW - 1) / kJW), 32 * kJW, 0, st>>>(img, B, H, W, mcu_x, mcu_y, qt, yplane, cplane);
+    const int vec_ok = (W % 4 == 0) && ((((uintptr_t)img) & 15) == 0);  // rows, planes and MCU starts on 16-byte boundaries
+    libjpeg_codec_kernel<<<(unsigned)((mcus + kJW - 1) / kJW), 32 * kJW, 0, st>>>(img, B, H, W, mcu_x, mcu_y, qt, yplane, cplane, vec_ok);
     OTF_LAUNCH_CHECK("libjpeg_codec_kernel");
     const int64_t samples = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2);
     libjpeg_upsample_kernel<<<(unsigned)((samples + 255) / 256), 256, 0, st>>>(yplane, cplane, B, H, W, Hp, Wp, out);

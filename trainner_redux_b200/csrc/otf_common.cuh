@@ -95,6 +95,15 @@ __device__ __forceinline__ float noise_tail(float v, int flags) {
     return v;
 }
 
+// x / 255 with IEEE rounding in three FP32-pipe operations instead of the ~10 of a general division: q = x * RN(1/255),
+// one exact residual, one correction (Markstein).  Equal to __fdiv_rn(x, 255.0f) for EVERY float in [0, 255] — checked
+// exhaustively on the device (profiles/experiments/div255_exact.cu) — which is the whole range the codecs divide.
+__device__ __forceinline__ float div255(float x) {
+    const float y = 3.9215688593685627e-03f;  // RN(1 / 255) = 0x3B808081
+    const float q = __fmul_rn(x, y);
+    return fmaf(fmaf(-q, 255.0f, x), y, q);
+}
+
 // ------------------------------------------------------------ Philox4x32-10 -
 struct Philox {
     uint32_t key[2];

@@ -205,6 +205,8 @@ class CUDAReadback:
         if as_u8:
             if t.dtype != torch.float32:
                 raise TypeError("CUDAReadback.read(as_u8=True) expects a float32 tensor")
+            if t.data_ptr() % 16:  # (a view that starts inside a 16-byte group: the kernel reads float4s)
+                t = t.clone()
             ku = ("u8dev", t.shape)
             dring = self._host.get(ku)
             if dring is None:  # (device-side staging, one per ring position: the copy of call i may still run during call i + 1)
