@@ -3,11 +3,8 @@
 //  IDCT -> chroma x2 -> YCbCr2RGB -> clamp -> /255 -> crop), which the reference runs as ~60 ATen
 // launches and ~25 image-sized HBM round trips.  Here the image is read once and written once.
 //
-// Mapping: one warp = two horizontally adjacent 16x16 MCUs (8 Y blocks + 2 Cb + 2 Cr).  Lane l owns the 8-pixel row
-// segment (block yb = l>>3, row r = l&7) of each MCU, i.e. row (yb>>1)*8+r, columns (yb&1)*8..+7 — 32 B per channel per
-// lane, float4-vectorised.  The 8x8 DCT is register resident: an 8-point transform along the lane's own row, an 8x8
-// transpose across the 8 lanes of the block (through the warp's shared-memory scratch), a second 8-point transform;
-// the four chroma blocks of the pair fill one 32-lane pass.
+// Mapping: one warp = one 16x16 MCU (4 Y blocks + Cb + Cr) held in the warp's shared memory; the separable 8x8 DCT runs
+// as (block, row) and (block, column) tasks over the lanes (see diffjpeg_kernel below).
 // Arithmetic order (documented for parity): 1-D DCT-II with the orthonormal matrix
 // C[k][n] = 0.5*alpha_k*cos((2n+1)k*pi/16) evaluated by even/odd decomposition; quantisation divides by
 // fl(table*factor) as the reference does (quotient within 1 ulp of IEEE), torch.round = rintf (half to even).
@@ -76,20 +73,6 @@ __device__ __forceinline__ void idct8(float (&y)[8]) {
 // clamp(round(x * 255), 0, 255) / 255 for x already in [0, 1] (quantise8 of otf_common.cuh with the cheap division)
 __device__ __forceinline__ float quantise8_unit(float x) { return div255(fminf(fmaxf(rintf(__fmul_rn(x, 255.0f)), 0.0f), 255.0f)); }
 
-// 8x8 transpose across the 8 lanes of a group through the warp's shared-memory scratch (pitch 9: both the row
-// writes and the column reads are conflict-free): lane g of a group holds row g in a[0..7]; afterwards column g.
-// 16 shared-memory operations instead of 12 shuffles + 24 selects.
-__device__ __forceinline__ void transpose8(float (&a)[8], float* __restrict__ scratch, int lane) {
-    float* wp = scratch + lane * 9;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) wp[k] = a[k];
-    __syncwarp();
-    const float* rp = scratch + (lane & ~7) * 9 + (lane & 7);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = rp[k * 9];
-    __syncwarp();
-}
-
 // Quantise + dequantise an 8x8 block held as: lane v (within its group of 8) owns coefficients D[u][v], u = register
 // index; t[u] = fl(table[u][v] * factor) (diffjpeg.py:207-212 divides by exactly this product).  The quotient is
 // d * rcp(t) corrected once with the exact residual: within 1 ulp of the IEEE quotient (correctly rounded in all but
@@ -110,21 +93,6 @@ __device__ __forceinline__ void quant_dequant(float (&d)[8], const float (&t)[8]
     }
 }
 
-// Full 2-D DCT -> quantise -> dequantise -> 2-D IDCT on the block whose row `lane&7` is in f[].
-// Input is level-shifted (f-128); output has +128 restored.
-__device__ __forceinline__ void block_codec(float (&f)[8], float* __restrict__ scratch, int lane, const float (&t)[8],
-                                            bool differentiable) {
-    dct8(f);                      // along the row (y index -> v)
-    transpose8(f, scratch, lane); // lane now = v, registers = x (row index)
-    dct8(f);                      // along x -> u
-    quant_dequant(f, t, differentiable);
-    idct8(f);                     // u -> x
-    transpose8(f, scratch, lane); // lane = x, registers = v
-    idct8(f);                     // v -> y
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] += 128.0f;
-}
-
 // diffjpeg.py:57-61 evaluated on fp32 0-d tensors
 __device__ __forceinline__ float quality_to_factor_dev(float v) {
     const float f = v < 50.0f ? __fdiv_rn(5000.0f, v) : __fsub_rn(200.0f, __fmul_rn(v, 2.0f));
@@ -142,147 +110,193 @@ struct CropTail {
     int top, left, p, scale, Hg, Wg, planes, jpeg_ctas, vec_gt;
 };
 
-// One warp = a PAIR of horizontally adjacent 16x16 MCUs (A | B).  Lane l owns, in each MCU, the 8-pixel row segment
-// (block yb = l>>3, row r = l&7): row (yb>>1)*8+r, columns (yb&1)*8..+7.  The eight luma blocks take two codec passes
-// of 32 lanes (MCU A, MCU B); the four chroma blocks (Cb A, Cb B, Cr A, Cr B) take ONE pass — with a single MCU per warp
-// half the lanes of the chroma pass were idle.  Chroma rows travel between the pixel lanes and the chroma lanes through
-// the warp's own 1 KB of shared memory (2 STS.128 + 2 LDS.128 per lane and direction) instead of 32 shuffles.
-constexpr int kJpegWarpFloats = 4 * 64 + 32 * 9 + 8;  // chroma staging [4 blocks][8][8] + transpose scratch [32][9] (+ pad to 16 B)
-
-#ifndef OTF_JPEG_MINB
-#define OTF_JPEG_MINB 5
+// One warp per 16x16 MCU, its six 8x8 blocks (Y00 Y01 Y10 Y11 Cb Cr) resident in the warp's shared memory (pitch 12 words,
+// blocks 104 apart: a row is two 128-bit accesses, the column pass meets 32 distinct banks), the three passes of the
+// separable transform as 48 (block, row) / (block, column) TASKS spread over the lanes:
+//   1  lane = (row of the MCU, left / right 8 columns): 16-byte loads, x255, RGB -> YCbCr, 2x2 chroma mean (one shuffle
+//      with the lane of the row below), rows into the blocks;
+//   2  (block, row):    dct8 along the row;
+//   3  (block, column): dct8 down the column, quantise / dequantise with fl(table * factor), idct8 — the eight
+//      coefficients of a column never leave the lane;
+//   4  (block, row):    idct8 along the row, level shift restored;
+//   5  lane = its 8 pixels again: chroma nearest x2, YCbCr -> RGB, clamp, /255, optional 8-bit lattice, 16-byte stores
+//      (or the LQ crop window only, see CropTail).
+// Round 1-2 kept a lane's pixels, two MCUs' luma rows and the table columns in registers and transposed through shared
+// memory (96 registers, 20 warps per SM, 35 % issue utilisation at 64 x 3 x 192^2: every warp one long serial chain);
+// this layout needs 48 registers (40 warps per SM), runs at 56 % and 0.0169 ms instead of 0.0216 ms — the structure of the
+// integer codec of the fork's JPEG round (libjpeg.cu), which reached 71 %.  Every value goes through the same
+// operations in the same order as before: results are bit-identical to the round-2 kernel.
+constexpr int kDP = 12, kDBlk = 8 * kDP + 8;
+constexpr int kJpegWarpFloats = 6 * kDBlk + 128;  // blocks Y00 Y01 Y10 Y11 Cb Cr + fl(table * factor) [2][8][8]
+__device__ __forceinline__ void row_load8(const float* p, float (&d)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void row_store8(float* p, const float (&d)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(d[4], d[5], d[6], d[7]);
+}
+#ifndef OTF_JPEG_V2_MINB
+#define OTF_JPEG_V2_MINB 10
 #endif
-__global__ void __launch_bounds__(128, OTF_JPEG_MINB) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
+// NM = MCUs per warp (horizontally adjacent).  Shipped with NM = 1.  NM = 2 makes a pass 96 tasks = three FULL rounds of 32
+// lanes (a single MCU's 48 tasks take two rounds, the second half empty: -25 % instructions in the three passes) but
+// measured SLOWER at 64 x 3 x 192^2 — 0.0184 ms (64 registers) / 0.0235 ms (48 registers, spills) against 0.0169 ms: half
+// as many, twice as long warps hide less latency than the idle lanes cost.
+template <bool DIFF, int NM>
+__global__ void __launch_bounds__(128, OTF_JPEG_V2_MINB) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
-                                                       float factor_scalar, int differentiable, int clamp_in,
+                                                       float factor_scalar, int clamp_in,
                                                        int round8_out, int vec_ok, int factor_is_quality,
                                                        const __grid_constant__ CropTail ct) {
     pdl_enter();
-    __shared__ __align__(16) float s_warp[4][kJpegWarpFloats];
+    constexpr int kWarpFloats = NM * 6 * kDBlk + 128, kTasks = NM * 48, kRounds = (kTasks + 31) / 32;
+    extern __shared__ __align__(16) float s_mcu[];  // [warps of the CTA][kWarpFloats]
     int top = ct.top, left = ct.left;
-    if (ct.lq_out) {
-        if (ct.tl_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot leave the image
-            top = clampi(ct.tl_dev[0], 0, H - ct.p);
-            left = clampi(ct.tl_dev[1], 0, W - ct.p);
-        }
-        if ((int)blockIdx.x >= ct.jpeg_ctas) {  // the GT crop rides in the same launch (no such CTAs when gt_out is NULL)
-            const int64_t q0 = (int64_t)(blockIdx.x - ct.jpeg_ctas) * blockDim.x + threadIdx.x;
-            const int64_t qs = (int64_t)(gridDim.x - ct.jpeg_ctas) * blockDim.x;
-            if (ct.vec_gt) copy_window<true>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
-            else copy_window<false>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
-            return;
-        }
+    if (ct.lq_out && ct.tl_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot leave the image
+        top = clampi(ct.tl_dev[0], 0, H - ct.p);
+        left = clampi(ct.tl_dev[1], 0, W - ct.p);
     }
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int pairs_x = (mcu_x + 1) >> 1;
-    const int64_t total = (int64_t)B * pairs_x * mcu_y;
-    if (warp >= total) return;  // warp-uniform
-    float* chroma = s_warp[threadIdx.x >> 5];   // [blk = comp * 2 + mcu][row][col]
-    float* scratch = chroma + 4 * 64;
-    const int b = (int)(warp / ((int64_t)pairs_x * mcu_y));
-    const int m = (int)(warp - (int64_t)b * pairs_x * mcu_y);
-    const int my = m / pairs_x, mx0 = 2 * (m - my * pairs_x);
+    if (ct.lq_out && (int)blockIdx.x >= ct.jpeg_ctas) {  // the GT crop rides in the same launch (no such CTAs when gt_out is NULL)
+        const int64_t q0 = (int64_t)(blockIdx.x - ct.jpeg_ctas) * blockDim.x + threadIdx.x;
+        const int64_t qs = (int64_t)(gridDim.x - ct.jpeg_ctas) * blockDim.x;
+        if (ct.vec_gt) copy_window<true>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
+        else copy_window<false>(ct.gt, ct.Hg, ct.Wg, top * ct.scale, left * ct.scale, ct.p * ct.scale, ct.gt_out, ct.planes, q0, qs);
+        return;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    const int groups_x = (mcu_x + NM - 1) / NM, per_img = groups_x * mcu_y;
+    if (warp >= (int64_t)B * per_img) return;  // warp-uniform
+    const int b = (int)(warp / per_img), m = (int)(warp - (int64_t)b * per_img);
+    const int my = m / groups_x, mx0 = NM * (m - my * groups_x);
+    float* blk = s_mcu + wid * kWarpFloats;
+    float* tab = blk + NM * 6 * kDBlk;
     float factor = factor_dev ? factor_dev[b] : factor_scalar;
     if (factor_is_quality) factor = quality_to_factor_dev(factor);  // diffjpeg.py:57-61 fused (no extra launch)
-    float ty[8], tc[8];  // this lane's column (v = lane & 7) of table * factor
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        ty[u] = __fmul_rn(__ldg(&c_ytab[u][lane & 7]), factor);  // (global, L1-resident: a lane-varying index would serialise the constant bank)
-        tc[u] = __fmul_rn(__ldg(&c_ctab[u][lane & 7]), factor);
+    for (int j = 0; j < 4; ++j) {  // fl(table[u][v] * factor), both tables (diffjpeg.py:207-212 divides by exactly this product)
+        const int idx = lane + 32 * j;
+        const float* t = idx < 64 ? &c_ytab[0][0] + idx : &c_ctab[0][0] + (idx - 64);
+        tab[idx] = __fmul_rn(__ldg(t), factor);
     }
-
-    const int yb = lane >> 3, r = lane & 7;
-    const int by = yb >> 1, bx = yb & 1;
-    const int y = my * 16 + by * 8 + r;
     const size_t hw = (size_t)H * W;
+    const int ly = lane >> 1, half = lane & 1;  // row of the MCU, which 8 of its 16 columns
+    const int y = my * 16 + ly;
     const bool row_ok = y < H;
-
-    // ---- load 2 x 8 px x 3 channels, all twelve 16-byte loads in flight at once (zero padding outside the image:
-    //      diffjpeg.py:515-522).  pair_full is warp-uniform: both MCUs lie inside an aligned image. ----
-    const bool pair_full = vec_ok && (my * 16 + 16 <= H) && ((mx0 + 2) * 16 <= W);
-    float px[2][3][8];
-    {
-        const float* ip0 = img + (size_t)b * 3 * hw + (size_t)y * W + mx0 * 16 + bx * 8;
-        if (pair_full) {
+    const bool rows_in = vec_ok && (my * 16 + 16 <= H);
+    // ---- phase 1: 8 px x 3 channels per lane and MCU (zero padding outside the image: diffjpeg.py:515-522), x255,
+    //      RGB -> YCbCr (:70-91), chroma 2x2 mean (:112-125; the +128 shift and the -128 level shift cancel) ----
 #pragma unroll
-            for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < NM; ++p) {
+        const int x0 = (mx0 + p) * 16 + half * 8;
+        const bool interior = rows_in && ((mx0 + p) * 16 + 16 <= W);  // warp-uniform
+        float* bp = blk + p * 6 * kDBlk;
+        float px[3][8];
+        const float* ip0 = img + (size_t)b * 3 * hw + (size_t)y * W + x0;
+        if (interior) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(ip0 + p * 16 + c * hw));
-                    const float4 d = __ldg(reinterpret_cast<const float4*>(ip0 + p * 16 + c * hw) + 1);
-                    px[p][c][0] = a.x; px[p][c][1] = a.y; px[p][c][2] = a.z; px[p][c][3] = a.w;
-                    px[p][c][4] = d.x; px[p][c][5] = d.y; px[p][c][6] = d.z; px[p][c][7] = d.w;
-                }
+            for (int c = 0; c < 3; ++c) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ip0 + c * hw)), d = __ldg(reinterpret_cast<const float4*>(ip0 + c * hw) + 1);
+                px[c][0] = a.x; px[c][1] = a.y; px[c][2] = a.z; px[c][3] = a.w; px[c][4] = d.x; px[c][5] = d.y; px[c][6] = d.z; px[c][7] = d.w;
+            }
         } else {
 #pragma unroll
-            for (int p = 0; p < 2; ++p)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        px[p][c][k] = (row_ok && (mx0 + p) * 16 + bx * 8 + k < W) ? __ldg(ip0 + p * 16 + c * hw + k) : 0.0f;
+                for (int k = 0; k < 8; ++k) px[c][k] = (row_ok && x0 + k < W) ? __ldg(ip0 + c * hw + k) : 0.0f;
         }
-    }
-    float yv[2][8];
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        // ---- x255, RGB -> YCbCr (diffjpeg.py:70-91), level shift for Y folded in ----
-        float cb[8], cr[8];
+        float yrow[8], cb[8], cr[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float R = px[p][0][k], G = px[p][1][k], Bc = px[p][2][k];
+            float R = px[0][k], G = px[1][k], Bc = px[2][k];
             if (clamp_in) { R = clamp01(R); G = clamp01(G); Bc = clamp01(Bc); }
             R = __fmul_rn(R, 255.0f); G = __fmul_rn(G, 255.0f); Bc = __fmul_rn(Bc, 255.0f);
-            yv[p][k] = fmaf(Bc, 0.114f, fmaf(G, 0.587f, R * 0.299f)) - 128.0f;
-            cb[k] = fmaf(Bc, 0.5f, fmaf(G, -0.331264f, R * -0.168736f));  // the +128 shift is folded away, see below
+            yrow[k] = fmaf(Bc, 0.114f, fmaf(G, 0.587f, R * 0.299f)) - 128.0f;
+            cb[k] = fmaf(Bc, 0.5f, fmaf(G, -0.331264f, R * -0.168736f));
             cr[k] = fmaf(Bc, -0.081312f, fmaf(G, -0.418688f, R * 0.5f));
         }
-        // ---- chroma 2x2 mean (diffjpeg.py:112-125); the +128 shift and the -128 level shift cancel ----
+        row_store8(bp + ((ly >> 3) * 2 + half) * kDBlk + (ly & 7) * kDP, yrow);
         float cbs[4], crs[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 4; ++k) {  // the row below / above sits in lane ^ 2
             float s0 = cb[2 * k] + cb[2 * k + 1], s1 = cr[2 * k] + cr[2 * k + 1];
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
             cbs[k] = s0 * 0.25f;
             crs[k] = s1 * 0.25f;
         }
-        if (!(r & 1)) {  // chroma row by*4 + r/2, columns bx*4..+3 of blocks (Cb, p) and (Cr, p)
-            const int off = (by * 4 + (r >> 1)) * 8 + bx * 4;
-            *reinterpret_cast<float4*>(chroma + (0 * 2 + p) * 64 + off) = make_float4(cbs[0], cbs[1], cbs[2], cbs[3]);
-            *reinterpret_cast<float4*>(chroma + (1 * 2 + p) * 64 + off) = make_float4(crs[0], crs[1], crs[2], crs[3]);
+        if (!(ly & 1)) {  // chroma row ly / 2, columns half * 4 .. + 3
+            *reinterpret_cast<float4*>(bp + 4 * kDBlk + (ly >> 1) * kDP + half * 4) = make_float4(cbs[0], cbs[1], cbs[2], cbs[3]);
+            *reinterpret_cast<float4*>(bp + 5 * kDBlk + (ly >> 1) * kDP + half * 4) = make_float4(crs[0], crs[1], crs[2], crs[3]);
         }
     }
     __syncwarp();
-    // ---- codec: the four luma blocks of A, of B, then Cb A | Cb B | Cr A | Cr B (lane>>3 = chroma block) ----
-    block_codec(yv[0], scratch, lane, ty, differentiable);
-    block_codec(yv[1], scratch, lane, ty, differentiable);
-    {
-        float ch[8];
-        const float4 c0 = *reinterpret_cast<const float4*>(chroma + lane * 8), c1 = *reinterpret_cast<const float4*>(chroma + lane * 8 + 4);
-        ch[0] = c0.x; ch[1] = c0.y; ch[2] = c0.z; ch[3] = c0.w; ch[4] = c1.x; ch[5] = c1.y; ch[6] = c1.z; ch[7] = c1.w;
-        block_codec(ch, scratch, lane, tc, differentiable);
-        __syncwarp();
-        *reinterpret_cast<float4*>(chroma + lane * 8) = make_float4(ch[0], ch[1], ch[2], ch[3]);
-        *reinterpret_cast<float4*>(chroma + lane * 8 + 4) = make_float4(ch[4], ch[5], ch[6], ch[7]);
-        __syncwarp();
+    // ---- phase 2: 1-D DCT along the rows (column index -> v), (block, row) tasks ----
+#pragma unroll
+    for (int rnd = 0; rnd < kRounds; ++rnd) {
+        const int task = lane + 32 * rnd;
+        if (kTasks % 32 == 0 || task < kTasks) {
+            float* p = blk + (task >> 3) * kDBlk + (task & 7) * kDP;
+            float f[8];
+            row_load8(p, f);
+            dct8(f);
+            row_store8(p, f);
+        }
     }
+    __syncwarp();
+    // ---- phase 3: per (block, column v): DCT along the rows' index (-> u), quantise, dequantise, IDCT (u -> row) ----
+#pragma unroll
+    for (int rnd = 0; rnd < kRounds; ++rnd) {
+        const int task = lane + 32 * rnd;
+        if (kTasks % 32 == 0 || task < kTasks) {
+            const int bi = task >> 3, c = task & 7;
+            float* p = blk + bi * kDBlk + c;
+            const float* tp = tab + ((bi % 6) >= 4 ? 64 : 0) + c;
+            float f[8], t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { f[k] = p[k * kDP]; t[k] = tp[8 * k]; }
+            dct8(f);
+            quant_dequant(f, t, DIFF);
+            idct8(f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) p[k * kDP] = f[k];
+        }
+    }
+    __syncwarp();
+    // ---- phase 4: 1-D IDCT along the rows (v -> column), level shift restored ----
+#pragma unroll
+    for (int rnd = 0; rnd < kRounds; ++rnd) {
+        const int task = lane + 32 * rnd;
+        if (kTasks % 32 == 0 || task < kTasks) {
+            float* p = blk + (task >> 3) * kDBlk + (task & 7) * kDP;
+            float f[8];
+            row_load8(p, f);
+            idct8(f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += 128.0f;
+            row_store8(p, f);
+        }
+    }
+    __syncwarp();
+    // ---- phase 5: chroma nearest x2 (diffjpeg.py:397-402), YCbCr -> RGB (:415-431), clamp, /255 (:476-479), optional 8-bit
+    //      lattice; the lane's own 8 pixels of each MCU again ----
     if (!row_ok) return;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int x0 = (mx0 + p) * 16 + bx * 8;
+    for (int p = 0; p < NM; ++p) {
+        const int x0 = (mx0 + p) * 16 + half * 8;
         if (x0 >= W) break;
-        // ---- chroma back to the pixel lanes: nearest x2 (diffjpeg.py:397-402) ----
-        const int off = (by * 4 + (r >> 1)) * 8 + bx * 4;
-        const float4 vb = *reinterpret_cast<const float4*>(chroma + (0 * 2 + p) * 64 + off);
-        const float4 vr = *reinterpret_cast<const float4*>(chroma + (1 * 2 + p) * 64 + off);
+        const bool interior = rows_in && ((mx0 + p) * 16 + 16 <= W);
+        const float* bp = blk + p * 6 * kDBlk;
+        float yrow[8];
+        row_load8(bp + ((ly >> 3) * 2 + half) * kDBlk + (ly & 7) * kDP, yrow);
+        const float4 vb = *reinterpret_cast<const float4*>(bp + 4 * kDBlk + (ly >> 1) * kDP + half * 4);
+        const float4 vr = *reinterpret_cast<const float4*>(bp + 5 * kDBlk + (ly >> 1) * kDP + half * 4);
         const float cbv[4] = {vb.x, vb.y, vb.z, vb.w}, crv[4] = {vr.x, vr.y, vr.z, vr.w};
-        // ---- YCbCr -> RGB (diffjpeg.py:415-431), clamp, /255 (:476-479), optional 8-bit lattice ----
         float res[3][8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float Y = yv[p][k], Cb = cbv[k >> 1] - 128.0f, Cr = crv[k >> 1] - 128.0f;   // block_codec restored +128 on every plane
+            const float Y = yrow[k], Cb = cbv[k >> 1] - 128.0f, Cr = crv[k >> 1] - 128.0f;   // (+128 was restored on every plane)
             float R = fmaf(Cr, 1.402f, Y);
             float G = fmaf(Cr, -0.714136f, fmaf(Cb, -0.344136f, Y));
             float Bc = fmaf(Cb, 1.772f, Y);
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(128, OTF_JPEG_MINB) diffjpeg_kernel(const floa
         float* op = out + (size_t)b * 3 * hw + (size_t)y * W + x0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (pair_full) {
+            if (interior) {
                 reinterpret_cast<float4*>(op + c * hw)[0] = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
                 reinterpret_cast<float4*>(op + c * hw)[1] = make_float4(res[c][4], res[c][5], res[c][6], res[c][7]);
             } else {
@@ -318,6 +332,27 @@ __global__ void __launch_bounds__(128, OTF_JPEG_MINB) diffjpeg_kernel(const floa
             }
         }
     }
+}
+
+// Host side of the v2 launch: MCUs per warp, warps per CTA, grid, dynamic shared memory.
+struct JpegLaunchV2 {
+    int nm, wpc, ctas;
+    size_t smem;
+};
+static JpegLaunchV2 jpeg_launch_v2(int B, int mcu_x, int mcu_y, int force_wpc) {
+    JpegLaunchV2 l;
+    l.nm = 1;
+    const int64_t warps = (int64_t)B * ((mcu_x + l.nm - 1) / l.nm) * mcu_y;
+    l.wpc = force_wpc ? force_wpc : (warps >= (int64_t)kNumSMs * 16 ? 4 : 1);  // few MCUs -> one-warp CTAs so they spread over all 148 SMs
+    l.ctas = (int)ceil_div(warps, l.wpc);
+    l.smem = (size_t)l.wpc * (l.nm * 6 * kDBlk + 128) * sizeof(float);
+    return l;
+}
+template <typename... Args>
+static cudaError_t launch_jpeg_v2(const JpegLaunchV2& l, int differentiable, int extra_ctas, cudaStream_t st, Args... args) {
+    const dim3 grid(l.ctas + extra_ctas), block(32 * l.wpc);
+    return differentiable ? launch_chain(diffjpeg_kernel<true, 1>, grid, block, l.smem, st, args...)
+                          : launch_chain(diffjpeg_kernel<false, 1>, grid, block, l.smem, st, args...);
 }
 
 __global__ void quality_to_factor_kernel(float* q, int B) {
@@ -342,15 +377,13 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     OTF_REQUIRE(img && out, OTF_ERR_BAD_ARG, "diffjpeg: null pointer");
     OTF_REQUIRE(B > 0 && H > 0 && W > 0, OTF_ERR_BAD_ARG, "diffjpeg: bad extents");
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
-    const int64_t warps = (int64_t)B * ((mcu_x + 1) / 2) * mcu_y;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
-    // one warp per pair of MCUs; few MCUs (64^2 LQ stage) -> one-warp CTAs so they spread over all 148 SMs
-    const int wpc = warps >= (int64_t)kNumSMs * 8 ? 4 : 1;
     CropTail ct;
     memset(&ct, 0, sizeof(ct));
-    launch_chain(diffjpeg_kernel, dim3(ceil_div(warps, wpc)), dim3(32 * wpc), 0, (cudaStream_t)stream, img, out, B, H, W, mcu_x, mcu_y, factor_dev,
-                                                                             factor_scalar, differentiable, clamp_in,
-                                                                             round8_out, vec_ok, factor_is_quality, ct);
+    const JpegLaunchV2 l = jpeg_launch_v2(B, mcu_x, mcu_y, 0);
+    ct.jpeg_ctas = l.ctas;
+    launch_jpeg_v2(l, differentiable, 0, (cudaStream_t)stream, img, out, B, H, W, mcu_x, mcu_y, factor_dev, factor_scalar, clamp_in, round8_out,
+                   vec_ok, factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel");
     return OTF_OK;
 }
@@ -367,7 +400,8 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     OTF_REQUIRE(!gt_out || ((lq_patch * scale) % 4 == 0 && (((uintptr_t)gt_out) & 15) == 0), OTF_ERR_UNSUPPORTED,
                 "diffjpeg_crop_pair: GT patch must be a multiple of 4 pixels wide (use otf_diffjpeg_f32 + otf_crop_pair_f32)");
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
-    const int64_t warps = (int64_t)B * ((mcu_x + 1) / 2) * mcu_y;
+    const JpegLaunchV2 l2 = jpeg_launch_v2(B, mcu_x, mcu_y, 4);
+    const int64_t warps = (int64_t)l2.ctas * 4;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
     const int wpc = 4;  // (the GT copy behind the codec wants full CTAs)
     CropTail ct;
@@ -382,9 +416,8 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     if (copy_ctas > kNumSMs * 8) copy_ctas = kNumSMs * 8;
     if (copy_ctas < 1) copy_ctas = 1;
     if (!gt_out) copy_ctas = 0;  // the GT window stays a view of the caller's tensor (what the reference's crop returns)
-    launch_chain(diffjpeg_kernel, dim3(ct.jpeg_ctas + copy_ctas), dim3(32 * wpc), 0, (cudaStream_t)stream, img, nullptr, B, H, W, mcu_x, mcu_y, factor_dev,
-                                                                                  factor_scalar, differentiable, clamp_in, 1, vec_ok,
-                                                                                  factor_is_quality, ct);
+    launch_jpeg_v2(l2, differentiable, copy_ctas, (cudaStream_t)stream, img, (float*)nullptr, B, H, W, mcu_x, mcu_y, factor_dev, factor_scalar,
+                   clamp_in, 1, vec_ok, factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel (fused crop)");
     return OTF_OK;
 }
