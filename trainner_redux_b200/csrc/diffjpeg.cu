@@ -127,7 +127,6 @@ struct CropTail {
 // integer codec of the fork's JPEG round (libjpeg.cu), which reached 71 %.  Every value goes through the same
 // operations in the same order as before: results are bit-identical to the round-2 kernel.
 constexpr int kDP = 12, kDBlk = 8 * kDP + 8;
-constexpr int kJpegWarpFloats = 6 * kDBlk + 128;  // blocks Y00 Y01 Y10 Y11 Cb Cr + fl(table * factor) [2][8][8]
 __device__ __forceinline__ void row_load8(const float* p, float (&d)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
@@ -136,21 +135,22 @@ __device__ __forceinline__ void row_store8(float* p, const float (&d)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(d[4], d[5], d[6], d[7]);
 }
-#ifndef OTF_JPEG_V2_MINB
-#define OTF_JPEG_V2_MINB 10
+#ifndef OTF_JPEG_MINB
+#define OTF_JPEG_MINB 10
 #endif
 // NM = MCUs per warp (horizontally adjacent).  Shipped with NM = 1.  NM = 2 makes a pass 96 tasks = three FULL rounds of 32
 // lanes (a single MCU's 48 tasks take two rounds, the second half empty: -25 % instructions in the three passes) but
 // measured SLOWER at 64 x 3 x 192^2 — 0.0184 ms (64 registers) / 0.0235 ms (48 registers, spills) against 0.0169 ms: half
 // as many, twice as long warps hide less latency than the idle lanes cost.
 template <bool DIFF, int NM>
-__global__ void __launch_bounds__(128, OTF_JPEG_V2_MINB) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
+__global__ void __launch_bounds__(128, OTF_JPEG_MINB) diffjpeg_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int H,
                                                        int W, int mcu_x, int mcu_y, const float* __restrict__ factor_dev,
                                                        float factor_scalar, int clamp_in,
                                                        int round8_out, int vec_ok, int factor_is_quality,
                                                        const __grid_constant__ CropTail ct) {
     pdl_enter();
-    constexpr int kWarpFloats = NM * 6 * kDBlk + 128, kTasks = NM * 48, kRounds = (kTasks + 31) / 32;
+    constexpr int kWarpFloats = NM * 6 * kDBlk + 128;  // blocks Y00 Y01 Y10 Y11 Cb Cr of each MCU + fl(table * factor) [2][8][8]
+    constexpr int kTasks = NM * 48, kRounds = (kTasks + 31) / 32;
     extern __shared__ __align__(16) float s_mcu[];  // [warps of the CTA][kWarpFloats]
     int top = ct.top, left = ct.left;
     if (ct.lq_out && ct.tl_dev) {  // per-step offsets of a captured chain, clamped so that a bad upload cannot leave the image
@@ -334,13 +334,13 @@ __global__ void __launch_bounds__(128, OTF_JPEG_V2_MINB) diffjpeg_kernel(const f
     }
 }
 
-// Host side of the v2 launch: MCUs per warp, warps per CTA, grid, dynamic shared memory.
-struct JpegLaunchV2 {
+// Host side of the launch: MCUs per warp, warps per CTA, grid, dynamic shared memory.
+struct JpegLaunch {
     int nm, wpc, ctas;
     size_t smem;
 };
-static JpegLaunchV2 jpeg_launch_v2(int B, int mcu_x, int mcu_y, int force_wpc) {
-    JpegLaunchV2 l;
+static JpegLaunch jpeg_launch(int B, int mcu_x, int mcu_y, int force_wpc) {
+    JpegLaunch l;
     l.nm = 1;
     const int64_t warps = (int64_t)B * ((mcu_x + l.nm - 1) / l.nm) * mcu_y;
     l.wpc = force_wpc ? force_wpc : (warps >= (int64_t)kNumSMs * 16 ? 4 : 1);  // few MCUs -> one-warp CTAs so they spread over all 148 SMs
@@ -349,7 +349,7 @@ static JpegLaunchV2 jpeg_launch_v2(int B, int mcu_x, int mcu_y, int force_wpc) {
     return l;
 }
 template <typename... Args>
-static cudaError_t launch_jpeg_v2(const JpegLaunchV2& l, int differentiable, int extra_ctas, cudaStream_t st, Args... args) {
+static cudaError_t launch_jpeg(const JpegLaunch& l, int differentiable, int extra_ctas, cudaStream_t st, Args... args) {
     const dim3 grid(l.ctas + extra_ctas), block(32 * l.wpc);
     return differentiable ? launch_chain(diffjpeg_kernel<true, 1>, grid, block, l.smem, st, args...)
                           : launch_chain(diffjpeg_kernel<false, 1>, grid, block, l.smem, st, args...);
@@ -380,9 +380,9 @@ extern "C" int otf_diffjpeg_f32(const float* img, int B, int H, int W, const flo
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)out & 15) == 0);
     CropTail ct;
     memset(&ct, 0, sizeof(ct));
-    const JpegLaunchV2 l = jpeg_launch_v2(B, mcu_x, mcu_y, 0);
+    const JpegLaunch l = jpeg_launch(B, mcu_x, mcu_y, 0);
     ct.jpeg_ctas = l.ctas;
-    launch_jpeg_v2(l, differentiable, 0, (cudaStream_t)stream, img, out, B, H, W, mcu_x, mcu_y, factor_dev, factor_scalar, clamp_in, round8_out,
+    launch_jpeg(l, differentiable, 0, (cudaStream_t)stream, img, out, B, H, W, mcu_x, mcu_y, factor_dev, factor_scalar, clamp_in, round8_out,
                    vec_ok, factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel");
     return OTF_OK;
@@ -400,7 +400,7 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     OTF_REQUIRE(!gt_out || ((lq_patch * scale) % 4 == 0 && (((uintptr_t)gt_out) & 15) == 0), OTF_ERR_UNSUPPORTED,
                 "diffjpeg_crop_pair: GT patch must be a multiple of 4 pixels wide (use otf_diffjpeg_f32 + otf_crop_pair_f32)");
     const int mcu_x = ceil_div(W, 16), mcu_y = ceil_div(H, 16);
-    const JpegLaunchV2 l2 = jpeg_launch_v2(B, mcu_x, mcu_y, 4);
+    const JpegLaunch l2 = jpeg_launch(B, mcu_x, mcu_y, 4);
     const int64_t warps = (int64_t)l2.ctas * 4;
     const int vec_ok = (W % 4 == 0) && (((uintptr_t)img & 15) == 0);
     const int wpc = 4;  // (the GT copy behind the codec wants full CTAs)
@@ -416,7 +416,7 @@ extern "C" int otf_diffjpeg_crop_pair_f32(const float* img, int B, int H, int W,
     if (copy_ctas > kNumSMs * 8) copy_ctas = kNumSMs * 8;
     if (copy_ctas < 1) copy_ctas = 1;
     if (!gt_out) copy_ctas = 0;  // the GT window stays a view of the caller's tensor (what the reference's crop returns)
-    launch_jpeg_v2(l2, differentiable, copy_ctas, (cudaStream_t)stream, img, (float*)nullptr, B, H, W, mcu_x, mcu_y, factor_dev, factor_scalar,
+    launch_jpeg(l2, differentiable, copy_ctas, (cudaStream_t)stream, img, (float*)nullptr, B, H, W, mcu_x, mcu_y, factor_dev, factor_scalar,
                    clamp_in, 1, vec_ok, factor_is_quality, ct);
     OTF_LAUNCH_CHECK("diffjpeg_kernel (fused crop)");
     return OTF_OK;
