@@ -27,12 +27,16 @@ One JSON line on stdout (rank 0):
   pcie_measured_gbs            raw pinned-host <-> device copy bandwidth of this box (the ceiling of e2e);
   e2e                          feed_data fed by the package's CUDAPrefetcher from pinned HOST batches in the dataset's
                                decoded format — uint8 GT + the (3,B,8) kernel-parameter table (/255 and
-                               kernel synthesis happen on the device) — H2D inside the timed region, LQ read back to pinned
-                               host memory every step (CUDAReadback), `--streams` batches in flight, wall clock;
-  e2e_one_stream               the same loop on ONE stream;
+                               kernel synthesis happen on the device) — H2D inside the timed region, the whole LQ batch read
+                               back to pinned host memory every step as bytes (CUDAReadback.read(as_u8=True): the LQ lies on the
+                               8-bit lattice, lossless), `--streams` batches in flight, wall clock;
+  e2e_readback_f32             the same loop with the LQ read back as fp32 (4x the D2H bytes);
+  e2e_one_stream               the same loop on ONE stream (fp32 read-back);
+  timed_regions_ms, e2e.timed_regions   K <= 100: five timed regions of exactly K steps each, the median is reported;
   e2e_f32                      the same loop fed the reference's host format (fp32 GT + three (B,21,21) kernels,
                                realesrgan_dataset.py:213-219): 4x the bytes, PCIe-bound;
   roofline                     the dominant kernel (blur1 filter2d) from CUDA-event timings of graph replays;
+  chain                        stage-sum bytes per pair, per-launch times (`stage_ms`) and their fractions of the HBM roof;
   cpu_baseline / --impl reference   the oracle port of the reference pipeline on this box's host cores;
   reference_torch_cuda         the same oracle (the reference's own ATen call sequence) run on the CUDA device: PyTorch-eager
                                on the same B200, the GPU path a user of the reference has today;
@@ -111,6 +115,17 @@ class Workload:
             jpeg_range2=(30, 95), resize_prob=(0, 0, 1), resize_mode_list=["bicubic"], resize_mode_prob=[1.0], resize_prob2=(0, 0, 1),
             resize_mode_list2=["bilinear"], resize_mode_prob2=[1.0], resize_mode_list3=["area"], resize_mode_prob3=[1.0],
             final_jpeg_first_prob=0.0)
+
+    def stage_bytes_per_pair(self) -> dict:
+        """Algorithmic bytes of each launch of the step (unique input + unique output at fp32; a fused launch counts
+        its external input and final output), keyed like `stage_ms`."""
+        a = 3 * self.gt * self.gt * 4
+        b1 = int(round(self.gt * S1)) ** 2 * 3 * 4
+        c = (self.gt // self.scale) ** 2 * 3 * 4
+        b2 = int(self.gt / self.scale * S2) ** 2 * 3 * 4
+        crop = 3 * (self.crop // self.scale) ** 2 * 4
+        return {"blur1": 2 * a, "fused resize1+noise1": a + b1, "jpeg1": 2 * b1, "blur2": 2 * b1, "fused resize2+noise2": b1 + b2,
+                "sinc": 2 * c, "fused jpeg2+round+lq_crop": c + crop}
 
     def algorithmic_bytes_per_pair(self) -> int:
         """Stage-sum model of SURVEY.md §8d."""
@@ -721,6 +736,8 @@ def run_b200(args, wl: Workload) -> None:
                                  **ex, "note": "filter2d is FP32-FMA bound above K~9 (SURVEY.md H1); executed FP32-pipe operations, not nominal K^2 taps"}},
             "chain": {"algorithmic_bytes_per_pair": chain_bytes, "achieved_gbs": chain_bytes * value / world / 1e9,
                       "frac_of_hbm_peak": chain_bytes * value / world / 1e9 / pk["hbm_gbs"], "stage_ms": stage_ms,
+                      "stage_frac_of_hbm_peak": {k: round(wl.batch * nb / (stage_ms[k] * 1e-3) / 1e9 / pk["hbm_gbs"], 4)
+                                                 for k, nb in wl.stage_bytes_per_pair().items() if stage_ms.get(k)},
                       "kernels_per_step": launches / args.steps},
             "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "parity": parity, **extras,
         }
